@@ -1,0 +1,3 @@
+/* Forwarding header: the declarations the reference keeps in include/srp/arena.h live in srp/api.h. */
+#pragma once
+#include "srp/api.h"

@@ -1,0 +1,3 @@
+/* Forwarding header: the declarations the reference keeps in include/srp/vertex.h live in srp/api.h. */
+#pragma once
+#include "srp/api.h"

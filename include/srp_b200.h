@@ -1,0 +1,103 @@
+/* srp-b200 -- the additive extension surface next to the srp C API (include/srp/api.h).
+ *
+ * Existing srp programs keep using the srpNew..., srp...CopyData and srpDraw...Buffer calls unchanged.  What
+ * they add is one CUDA translation unit with the __device__ twins of their shaders
+ * (include/srp_b200_device.cuh), which registers the twins here.  Everything else in
+ * this header is optional: synchronisation policy, zero-copy / batched entry points
+ * used by the benchmarks and the multi-GPU modes, and counters.
+ *
+ * All functions are plain C ABI (pointers and sizes only). */
+#ifndef SRP_B200_H_
+#define SRP_B200_H_
+#include "srp/api.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- shader registry ---------------------------------------------------------------
+ * Replaces the reference's direct calls through sp->vs->shader / sp->fs->shader
+ * (src/pipeline/vertex_processing.c:73, src/raster/fragment.c:98): at draw time the
+ * host function pointers found in SRPShaderProgram are looked up here and the draw
+ * runs device program `deviceProgramId` of the program table linked into the
+ * executable.  `uniformSize` is sizeof the user's uniform struct (the API passes it
+ * un-sized); it is copied to the device at every draw.  Returns 0 on success.
+ * A draw whose program is not registered reports a HIGH error through the message
+ * callback and draws nothing -- there is no CPU fallback. */
+typedef void (*SRPVertexShaderFunc)(SRPVertexShaderIn*, SRPVertexShaderOut*);
+typedef void (*SRPFragmentShaderFunc)(SRPFragmentShaderIn*, SRPFragmentShaderOut*);
+int srpB200RegisterProgram(SRPVertexShaderFunc hostVS, SRPFragmentShaderFunc hostFS,
+                           int deviceProgramId, size_t uniformSize);
+
+/* ---- synchronisation policy --------------------------------------------------------
+ * The device planes of a framebuffer are authoritative; fb->color/depth/stencil are a
+ * pinned host mirror.
+ *   SRP_B200_SYNC_DRAW      (default) every srpDraw*Buffer returns with the mirror up to
+ *                           date, like the reference.  srpFramebufferClear is deferred
+ *                           and fused into the next draw (or download).
+ *   SRP_B200_SYNC_EXPLICIT  draws only enqueue work; the mirror is refreshed by
+ *                           srpB200FramebufferDownload() / srpB200Finish(). */
+typedef enum { SRP_B200_SYNC_DRAW = 0, SRP_B200_SYNC_EXPLICIT = 1 } SRPB200SyncMode;
+void srpB200SetSyncMode(SRPB200SyncMode mode);
+SRPB200SyncMode srpB200GetSyncMode(void);
+void srpB200Finish(void);                                   /* wait for all enqueued work */
+void srpB200FramebufferDownload(const SRPFramebuffer* fb);  /* device planes -> host mirror (synchronous) */
+void srpB200FramebufferUpload(const SRPFramebuffer* fb);    /* host mirror -> device planes */
+
+/* ---- device-resident objects -------------------------------------------------------
+ * Framebuffer on caller-owned device memory (e.g. planes of a torch tensor that NCCL
+ * gathers); color/depth/stencil of the returned struct still point to a host mirror. */
+SRPFramebuffer* srpB200NewFramebufferOnDevice(size_t width, size_t height,
+                                              void* deviceColor, void* deviceDepth, void* deviceStencil);
+/* device pointers of the planes: which = 0 colour (u32), 1 depth (f32), 2 stencil (u8) */
+void* srpB200FramebufferDevicePlane(const SRPFramebuffer* fb, int which);
+/* texture from RGB8 texels in memory (the file loader srpNewTexture only reads PNG) */
+SRPTexture* srpB200NewTextureFromMemory(const uint8_t* rgb, int width, int height,
+                                        SRPTextureWrappingMode wrappingModeX, SRPTextureWrappingMode wrappingModeY);
+
+/* ---- frame-parallel batch ----------------------------------------------------------
+ * One call = nFrames independent srpFramebufferClear + srpDrawIndexBuffer pairs that
+ * share buffers, program and context state and differ in uniform and target:
+ * frame f reads uniform block `(char*) uniforms + f * uniformStride` and renders into
+ * fbs[f].  `clearFirst` != 0 applies srpFramebufferClear semantics to every target
+ * first.  ib may be NULL (vertex-buffer draw). */
+void srpB200DrawBatch(const SRPIndexBuffer* ib, const SRPVertexBuffer* vb,
+                      SRPFramebuffer* const* fbs, size_t nFrames,
+                      const SRPShaderProgram* sp, const void* uniforms, size_t uniformStride,
+                      SRPPrimitive primitive, size_t startIndex, size_t count, int clearFirst);
+
+/* ---- sort-first strips -------------------------------------------------------------
+ * Restrict rasterisation (not geometry processing, so primitive ids are unchanged) to
+ * framebuffer rows [row0, row1); row0 is rounded down and row1 up to the tile height
+ * (srpB200TileHeight()).  Pass (0, SIZE_MAX) to reset. */
+void srpB200SetRowRange(size_t row0, size_t row1);
+size_t srpB200TileWidth(void);
+size_t srpB200TileHeight(void);
+
+/* ---- counters ----------------------------------------------------------------------
+ * Accumulated since the last reset over all draws (deterministic; equal to the
+ * reference's emitFragment / fragment-shader call counts for the same input). */
+typedef struct SRPB200Stats
+{
+	unsigned long long draws;
+	unsigned long long primsIn, primsEmitted, primsStored;
+	unsigned long long fragsEmitted, fragsShaded;
+	unsigned long long kernelLaunches;     /* kernels of this library launched            */
+	unsigned long long h2dBytes, d2hBytes; /* bytes this library copied across PCIe       */
+	unsigned long long overflow;           /* draws dropped because a pool was too small  */
+} SRPB200Stats;
+void srpB200GetStats(SRPB200Stats* out);   /* synchronises */
+void srpB200ResetStats(void);
+
+/* device / build identification, e.g. "srp-b200 sm_100a tile 32x16" */
+const char* srpB200Version(void);
+/* select the CUDA device for the calling process (before any other call); default:
+ * environment SRP_B200_DEVICE, else LOCAL_RANK, else 0 */
+void srpB200SetDevice(int device);
+/* raw CUDA stream (cudaStream_t) all work is enqueued on, for event timing */
+void* srpB200Stream(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRP_B200_H_ */

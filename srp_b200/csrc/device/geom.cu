@@ -1,0 +1,569 @@
+/* srp-b200 -- geometry front-end kernel (sm_100a).
+ *
+ * One CTA = one batch of 256 consecutive input primitives of one frame.  Replaces, for
+ * that batch, the reference's per-primitive loop in
+ *   src/pipeline/primitive_assembly.c:37-135 (assembleTrianglesGeneric),
+ *   :137-178 (assembleLines), :221-254 (assemblePoints)
+ * and everything it calls: topology.c:24-83, core/buffer.c:102-128 (typed index fetch),
+ * vertex_processing.c:38-74 (post-VS cache + vertex shader), clipping.c:68-258,
+ * raster/triangle.c:113-160 / line.c:79-86 / point.c:76-79 (setup).
+ *
+ * Stages inside the CTA:
+ *   1. topology + index fetch: every thread resolves the 1..3 vertex indices of its
+ *      input primitive;
+ *   2. post-VS cache = index de-duplication in shared memory: the indices are inserted
+ *      into a 1024-slot open-addressing table, the distinct ones are numbered by a CTA
+ *      scan, and the user vertex shader runs ONCE per distinct index of the batch with
+ *      its outputs (clip position + varyings blob) kept in shared memory;
+ *   3. per primitive: outcodes, trivial accept/reject, Sutherland-Hodgman (triangles) or
+ *      Liang-Barsky (lines) clipping on the rare path, polygon-mode expansion, setup,
+ *      face / degenerate culling -- first only counting how many primitive ids the input
+ *      primitive consumes and how many records it stores;
+ *   4. order-preserving compaction: CTA exclusive scan of both counts + a decoupled
+ *      look-back across the batches of the frame (batches are handed out by an atomic
+ *      ticket so a predecessor is always resident) gives every input primitive the
+ *      reference's serial `primitiveID++` base (primitive_assembly.c:64,90-91) and its
+ *      record slot;
+ *   5. the primitives are set up again and their records written in id order.
+ *
+ * HBM traffic per input triangle: 3 indices + (amortised) its vertices in, one record
+ * (80 B header + 3 blobs) + one 8-byte bbox out. */
+#include "kernels.cuh"
+
+namespace {
+
+struct ClipVert
+{
+	SrpdPos p;
+	alignas(8) unsigned char vary[SRPD_MAX_VARYING_BYTES];
+};
+
+__device__ __forceinline__ uint32_t fetchIndex(const SrpdDraw& d, uint64_t streamIndex)
+{
+	if (d.ib == nullptr)
+		return (uint32_t) streamIndex;
+	switch (d.ibElemSize)
+	{
+		case 1:  return ((const uint8_t*) d.ib)[streamIndex];
+		case 2:  return ((const uint16_t*) d.ib)[streamIndex];
+		case 4:  return ((const uint32_t*) d.ib)[streamIndex];
+		default: return (uint32_t) ((const uint64_t*) d.ib)[streamIndex];
+	}
+}
+
+/* stream indices of input primitive k, reference topology.c:24-48,62-83 */
+__device__ __forceinline__ void resolveTopology(const SrpdDraw& d, uint32_t k, uint64_t s[3])
+{
+	const uint64_t base = d.startIndex;
+	switch (d.topology)
+	{
+		case SRPD_TOPO_TRIANGLES:
+			s[0] = base + 3ull * k; s[1] = s[0] + 1; s[2] = s[0] + 2; break;
+		case SRPD_TOPO_TRIANGLE_STRIP:
+		{
+			const uint64_t odd = k & 1u;   /* odd triangles swap their first two vertices */
+			s[0] = base + k + odd; s[1] = base + k + (1 - odd); s[2] = base + k + 2; break;
+		}
+		case SRPD_TOPO_TRIANGLE_FAN:
+			s[0] = base; s[1] = base + k + 1; s[2] = base + k + 2; break;
+		case SRPD_TOPO_LINES:
+			s[0] = base + 2ull * k; s[1] = s[0] + 1; s[2] = 0; break;
+		case SRPD_TOPO_LINE_STRIP:
+			s[0] = base + k; s[1] = base + k + 1; s[2] = 0; break;
+		case SRPD_TOPO_LINE_LOOP:
+			s[0] = base + k; s[1] = base + ((uint64_t) (k + 1) % d.count); s[2] = 0; break;
+		default:   /* points */
+			s[0] = base + k; s[1] = 0; s[2] = 0; break;
+	}
+}
+
+__device__ __forceinline__ uint32_t hashInsert(uint32_t* keys, uint32_t key)
+{
+	uint32_t h = (key * 2654435761u) >> 22;
+	for (;;)
+	{
+		const uint32_t prev = atomicCAS(&keys[h], SRPD_HASH_EMPTY, key);
+		if (prev == SRPD_HASH_EMPTY || prev == key)
+			return h;
+		h = (h + 1) & (SRPD_HASH_SLOTS - 1);
+	}
+}
+
+/* Sutherland-Hodgman against one plane, reference clipping.c:199-242 (note it emits
+ * `next`, so the polygon's starting vertex rotates from plane to plane). */
+__device__ int clipAgainstPlane(const SrpdState& st, const ClipVert* in, int n, int plane, ClipVert* out)
+{
+	int o = 0;
+	for (int i = 0; i < n; i++)
+	{
+		const ClipVert& cur = in[i];
+		const ClipVert& nxt = in[(i + 1) % n];
+		const float da = srpdPlaneDistance(cur.p, plane);
+		const float db = srpdPlaneDistance(nxt.p, plane);
+		const bool ci = da >= 0, ni = db >= 0;
+		if (ci && ni)
+		{
+			if (o < SRPD_CLIP_MAX_VERTS) out[o++] = nxt;
+		}
+		else if (ci || ni)
+		{
+			const float diff = SRP_FSUB(da, db);
+			if (srpdRoughlyZero(diff))
+				continue;
+			const float t = SRP_FDIV(da, diff);
+			if (o < SRPD_CLIP_MAX_VERTS)
+			{
+				out[o].p = srpdBlendPos(cur.p, nxt.p, t);
+				srpdBlendVaryings(st, cur.vary, nxt.vary, SRP_FSUB(1.0f, t), t, out[o].vary);
+				o++;
+			}
+			if (!ci && ni)
+				if (o < SRPD_CLIP_MAX_VERTS) out[o++] = nxt;
+		}
+	}
+	return o;
+}
+
+/* Where a thread's outputs go.  WRITE = false: count only. */
+struct Emitter
+{
+	const SrpdGeomArgs* a;
+	unsigned char* records;     /* frame base */
+	uint2* bboxes;              /* frame base */
+	uint32_t idBase, storeBase; /* global bases of this input primitive (valid when writing) */
+	uint32_t nEmit, nStore;
+	bool overflow;
+};
+
+__device__ __forceinline__ void copyBlobWords(const unsigned char* src, unsigned char* dst, int bytes)
+{
+	/* both sides are 8-byte aligned and `bytes` is a multiple of 8 */
+	const uint2* s = (const uint2*) src;
+	uint2* d = (uint2*) dst;
+	for (int i = 0; i < bytes / 8; i++)
+		d[i] = s[i];
+}
+
+__device__ void storeBlob(const SrpdState& st, const unsigned char* src, float invW, bool persp, unsigned char* dst)
+{
+	copyBlobWords(src, dst, st.slotSize);
+	if (!persp)
+		return;
+	for (int ai = 0; ai < st.nVaryings; ai++)
+	{
+		const SrpdVarying& at = st.varyings[ai];
+		if (at.mode != SRP_INTERPOLATION_MODE_PERSPECTIVE)
+			continue;
+		if (at.type == SRP_FLOAT)
+			for (int e = 0; e < at.nItems; e++)
+				srpdStore<float>(dst + at.offset + 4 * e, SRP_FMUL(srpdLoad<float>(src + at.offset + 4 * e), invW));
+		else if (at.type == SRP_DOUBLE)
+			for (int e = 0; e < at.nItems; e++)
+				srpdStore<double>(dst + at.offset + 8 * e, SRP_DMUL(srpdLoad<double>(src + at.offset + 8 * e), (double) invW));
+	}
+}
+
+template <bool WRITE>
+__device__ __forceinline__ unsigned char* beginRecord(Emitter& em, const uint32_t w[SRPD_REC_HEADER_WORDS],
+                                                       uint16_t x0, uint16_t y0, uint16_t x1, uint16_t y1)
+{
+	if (!WRITE)
+		return nullptr;
+	const uint32_t slot = em.storeBase + em.nStore;
+	if (slot >= em.a->recCapacity)
+	{
+		em.overflow = true;
+		return nullptr;
+	}
+	unsigned char* rec = em.records + (size_t) slot * em.a->recStride;
+	uint4* h = (uint4*) rec;
+	h[0] = make_uint4(w[0], w[1], w[2], w[3]);
+	h[1] = make_uint4(w[4], w[5], w[6], w[7]);
+	h[2] = make_uint4(w[8], w[9], w[10], w[11]);
+	h[3] = make_uint4(w[12], w[13], w[14], em.idBase + em.nEmit);
+	h[4] = make_uint4(w[16], w[17], w[18], w[19]);
+	em.bboxes[slot] = make_uint2((uint32_t) x0 | ((uint32_t) y0 << 16), (uint32_t) x1 | ((uint32_t) y1 << 16));
+	return rec + SRPD_REC_HEADER_BYTES;
+}
+
+template <bool WRITE>
+__device__ void emitTriangle(Emitter& em, const SrpdState& st, const SrpdPos p[3], const unsigned char* const vary[3])
+{
+	SrpdTriSetup s;
+	bool stored;
+	if (!srpdSetupTriangle(st, p, s, stored))
+		return;
+	if (stored)
+	{
+		unsigned char* blobs = beginRecord<WRITE>(em, s.w, s.minX, s.minY, s.maxX, s.maxY);
+		if (WRITE && blobs)
+			for (int i = 0; i < 3; i++)
+				storeBlob(st, vary[s.order[i]], s.invW[i], true, blobs + i * st.slotSize);
+		em.nStore++;
+	}
+	em.nEmit++;
+}
+
+template <bool WRITE>
+__device__ void emitLine(Emitter& em, const SrpdState& st, const SrpdPos p[2], const unsigned char* const vary[2])
+{
+	SrpdLineSetup s;
+	srpdSetupLine(st, p, s);
+	unsigned char* blobs = beginRecord<WRITE>(em, s.w, s.minX, s.minY, s.maxX, s.maxY);
+	if (WRITE && blobs)
+		for (int i = 0; i < 2; i++)
+			storeBlob(st, vary[i], s.invW[i], true, blobs + i * st.slotSize);
+	em.nStore++;
+	em.nEmit++;
+}
+
+template <bool WRITE>
+__device__ void emitPoint(Emitter& em, const SrpdState& st, const SrpdPos& p, const unsigned char* vary)
+{
+	SrpdPointSetup s;
+	if (srpdSetupPoint(st, p, s))
+	{
+		unsigned char* blob = beginRecord<WRITE>(em, s.w, s.minX, s.minY, s.maxX, s.maxY);
+		if (WRITE && blob)
+			storeBlob(st, vary, 1.0f, false, blob);
+		em.nStore++;
+	}
+	em.nEmit++;
+}
+
+/* one (possibly clip-generated) triangle through the polygon mode,
+ * reference primitive_assembly.c:80-129 */
+template <bool WRITE>
+__device__ void emitPolygonModeTriangle(Emitter& em, const SrpdState& st, const SrpdPos p[3], const unsigned char* const vary[3])
+{
+	if (st.polygonMode == SRP_POLYGON_MODE_FILL)
+		emitTriangle<WRITE>(em, st, p, vary);
+	else if (st.polygonMode == SRP_POLYGON_MODE_LINE)
+		for (int j = 0; j < 3; j++)
+		{
+			const SrpdPos lp[2] = { p[j], p[(j + 1) % 3] };
+			const unsigned char* const lv[2] = { vary[j], vary[(j + 1) % 3] };
+			emitLine<WRITE>(em, st, lp, lv);
+		}
+	else
+		for (int j = 0; j < 3; j++)
+			emitPoint<WRITE>(em, st, p[j], vary[j]);
+}
+
+/* clipTriangle + expansion, reference clipping.c:68-119 */
+template <bool WRITE>
+__device__ void processTriangle(Emitter& em, const SrpdState& st, const SrpdPos p[3], const unsigned char* const vary[3])
+{
+	const uint32_t c0 = srpdClipCode(p[0]), c1 = srpdClipCode(p[1]), c2 = srpdClipCode(p[2]);
+	if ((c0 | c1 | c2) == 0)
+	{
+		emitPolygonModeTriangle<WRITE>(em, st, p, vary);
+		return;
+	}
+	if ((c0 & c1 & c2) != 0)
+		return;
+
+	ClipVert bufA[SRPD_CLIP_MAX_VERTS], bufB[SRPD_CLIP_MAX_VERTS];
+	ClipVert* src = bufA;
+	ClipVert* dst = bufB;
+	for (int i = 0; i < 3; i++)
+	{
+		src[i].p = p[i];
+		copyBlobWords(vary[i], src[i].vary, st.slotSize);
+	}
+	int n = 3;
+	for (int plane = 0; plane < 6; plane++)
+	{
+		n = clipAgainstPlane(st, src, n, plane, dst);
+		if (n == 0)
+			return;
+		ClipVert* t = src; src = dst; dst = t;
+	}
+	for (int i = 1; i + 1 < n; i++)   /* fan (0, i, i+1) */
+	{
+		const SrpdPos tp[3] = { src[0].p, src[i].p, src[i + 1].p };
+		const unsigned char* const tv[3] = { src[0].vary, src[i].vary, src[i + 1].vary };
+		emitPolygonModeTriangle<WRITE>(em, st, tp, tv);
+	}
+}
+
+/* clipLine (Liang-Barsky) + setup, reference clipping.c:139-183 */
+template <bool WRITE>
+__device__ void processLine(Emitter& em, const SrpdState& st, const SrpdPos p[2], const unsigned char* const vary[2])
+{
+	const uint32_t c0 = srpdClipCode(p[0]), c1 = srpdClipCode(p[1]);
+	if ((c0 | c1) == 0)
+	{
+		emitLine<WRITE>(em, st, p, vary);
+		return;
+	}
+	if ((c0 & c1) != 0)
+		return;
+
+	float t0 = 0.f, t1 = 1.f;
+	for (int plane = 0; plane < 6; plane++)
+	{
+		const float da = srpdPlaneDistance(p[0], plane);
+		const float db = srpdPlaneDistance(p[1], plane);
+		if (da < 0 && db < 0)
+			return;
+		if (da < 0 || db < 0)
+		{
+			const float diff = SRP_FSUB(da, db);
+			if (srpdRoughlyZero(diff))
+				continue;
+			const float t = SRP_FDIV(da, diff);
+			if (da < 0)
+				t0 = (t0 > t) ? t0 : t;     /* MAX(t0, t) */
+			else
+				t1 = (t1 > t) ? t : t1;     /* MIN(t1, t) */
+			if (t0 > t1)
+				return;
+		}
+	}
+	ClipVert a, b;
+	SrpdPos cp[2] = { p[0], p[1] };
+	const unsigned char* cv[2] = { vary[0], vary[1] };
+	if (t0 > 0)
+	{
+		a.p = srpdBlendPos(p[0], p[1], t0);
+		srpdBlendVaryings(st, vary[0], vary[1], SRP_FSUB(1.0f, t0), t0, a.vary);
+		cp[0] = a.p; cv[0] = a.vary;
+	}
+	if (t1 < 1)
+	{
+		b.p = srpdBlendPos(p[0], p[1], t1);
+		srpdBlendVaryings(st, vary[0], vary[1], SRP_FSUB(1.0f, t1), t1, b.vary);
+		cp[1] = b.p; cv[1] = b.vary;
+	}
+	const unsigned char* const cvc[2] = { cv[0], cv[1] };
+	emitLine<WRITE>(em, st, cp, cvc);
+}
+
+template <bool WRITE>
+__device__ __forceinline__ void processPrimitive(Emitter& em, const SrpdDraw& d, int nv,
+                                                 const SrpdPos p[3], const unsigned char* const vary[3])
+{
+	if (nv == 3)
+		processTriangle<WRITE>(em, d.st, p, vary);
+	else if (nv == 2)
+		processLine<WRITE>(em, d.st, p, vary);
+	else if (!srpdClipPoint(p[0]))
+		emitPoint<WRITE>(em, d.st, p[0], vary[0]);
+}
+
+__device__ __forceinline__ uint32_t warpInclusiveScan(uint32_t v, int lane)
+{
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, v, o);
+		if (lane >= o) v += n;
+	}
+	return v;
+}
+
+} // namespace
+
+__global__ void __launch_bounds__(SRPD_GEOM_THREADS, 1)
+srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	uint32_t* hashKey   = (uint32_t*) smem;                                   /* 4096 B */
+	uint16_t* hashDense = (uint16_t*) (smem + 4 * SRPD_HASH_SLOTS);           /* 2048 B */
+	uint32_t* uniq      = (uint32_t*) (smem + 6 * SRPD_HASH_SLOTS);           /* 3072 B */
+	float4*   vpos      = (float4*) (smem + 6 * SRPD_HASH_SLOTS + 4 * SRPD_GEOM_MAX_VERTS);
+	unsigned char* vvary = (unsigned char*) (vpos + SRPD_GEOM_MAX_VERTS);
+
+	__shared__ uint32_t sBatch;
+	__shared__ uint32_t sWarpSum[2][SRPD_GEOM_THREADS / 32];
+	__shared__ uint32_t sNUniq;
+	__shared__ uint32_t sPrefix[2];
+
+	const SrpdDraw& d = a.d;
+	const SrpdState& st = d.st;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+	/* batches are handed out in order so that look-back predecessors are always scheduled */
+	if (tid == 0)
+		sBatch = atomicAdd(a.ticket, 1u);
+	for (int i = tid; i < SRPD_HASH_SLOTS; i += SRPD_GEOM_THREADS)
+		hashKey[i] = SRPD_HASH_EMPTY;
+	__syncthreads();
+	const uint32_t batch = sBatch;
+	const uint32_t frame = batch / a.batchesPerFrame;
+	const uint32_t b = batch - frame * a.batchesPerFrame;
+	const SrpdFrame fr = a.frames ? a.frames[frame] : a.frame0;
+
+	const uint32_t k = b * SRPD_GEOM_THREADS + tid;
+	const bool active = k < d.nInputPrims;
+	const int nv = (d.topology >= SRPD_TOPO_TRIANGLES) ? 3 : (d.topology == SRPD_TOPO_POINTS ? 1 : 2);
+
+	/* 1. topology + typed index fetch */
+	uint32_t vi[3] = { 0, 0, 0 };
+	uint32_t slot[3] = { 0, 0, 0 };
+	if (active)
+	{
+		uint64_t s[3];
+		resolveTopology(d, k, s);
+		for (int i = 0; i < nv; i++)
+			vi[i] = fetchIndex(d, s[i]);
+	}
+
+	/* 2. post-VS cache: de-duplicate the batch's indices, shade each distinct one once.
+	 * Points bypass the cache like the reference (primitive_assembly.c:239-240). */
+	uint32_t nUniq;
+	if (nv > 1)
+	{
+		if (active)
+			for (int i = 0; i < nv; i++)
+				slot[i] = hashInsert(hashKey, vi[i]);
+		__syncthreads();
+		/* number the occupied slots: thread t owns slots 4t..4t+3 */
+		uint32_t occ = 0;
+		for (int i = 0; i < SRPD_HASH_SLOTS / SRPD_GEOM_THREADS; i++)
+			occ += hashKey[tid * (SRPD_HASH_SLOTS / SRPD_GEOM_THREADS) + i] != SRPD_HASH_EMPTY;
+		const uint32_t inc = warpInclusiveScan(occ, lane);
+		if (lane == 31) sWarpSum[0][warp] = inc;
+		__syncthreads();
+		uint32_t base = 0;
+		for (int w = 0; w < warp; w++) base += sWarpSum[0][w];
+		if (tid == SRPD_GEOM_THREADS - 1) sNUniq = base + inc;
+		uint32_t dense = base + inc - occ;
+		for (int i = 0; i < SRPD_HASH_SLOTS / SRPD_GEOM_THREADS; i++)
+		{
+			const int h = tid * (SRPD_HASH_SLOTS / SRPD_GEOM_THREADS) + i;
+			if (hashKey[h] != SRPD_HASH_EMPTY)
+			{
+				hashDense[h] = (uint16_t) dense;
+				uniq[dense] = hashKey[h];
+				dense++;
+			}
+		}
+		__syncthreads();
+		nUniq = sNUniq;
+		for (int i = 0; i < nv; i++)
+			slot[i] = hashDense[slot[i]];
+	}
+	else
+	{
+		nUniq = min((uint32_t) SRPD_GEOM_THREADS, d.nInputPrims - b * SRPD_GEOM_THREADS);
+		if (active) uniq[tid] = vi[0];
+		slot[0] = tid;
+		__syncthreads();
+	}
+
+	for (uint32_t u = tid; u < nUniq; u += SRPD_GEOM_THREADS)
+	{
+		const uint32_t vertexIndex = uniq[u];
+		SRPVertexShaderIn in;
+		in.uniform = (SRPUniform*) fr.uniform;
+		in.vertex = (SRPVertex*) (d.vb + (size_t) vertexIndex * d.vbStride);
+		in.vertexID = vertexIndex;
+		SRPVertexShaderOut out;
+		out.clipPosition[0] = 0.f; out.clipPosition[1] = 0.f; out.clipPosition[2] = 0.f; out.clipPosition[3] = 0.f;
+		out.varyings = (SRPVarying*) (vvary + (size_t) u * st.slotSize);
+		srpB200DeviceVS(st.programId, &in, &out);
+		vpos[u] = make_float4(out.clipPosition[0], out.clipPosition[1], out.clipPosition[2], out.clipPosition[3]);
+	}
+	__syncthreads();
+
+	/* 3. count */
+	SrpdPos p[3];
+	const unsigned char* vary[3];
+	for (int i = 0; i < 3; i++)
+	{
+		const float4 q = vpos[active && i < nv ? slot[i] : 0];
+		p[i].x = q.x; p[i].y = q.y; p[i].z = q.z; p[i].w = q.w;
+		vary[i] = vvary + (size_t) (active && i < nv ? slot[i] : 0) * st.slotSize;
+	}
+	Emitter em;
+	em.a = &a;
+	em.records = a.records + (size_t) frame * a.recCapacity * a.recStride;
+	em.bboxes = a.bboxes + (size_t) frame * a.recCapacity;
+	em.idBase = 0; em.storeBase = 0; em.nEmit = 0; em.nStore = 0; em.overflow = false;
+	if (active)
+		processPrimitive<false>(em, d, nv, p, vary);
+	const uint32_t myEmit = em.nEmit, myStore = em.nStore;
+
+	/* 4. CTA scan + decoupled look-back over the frame's batches */
+	const uint32_t incE = warpInclusiveScan(myEmit, lane);
+	const uint32_t incS = warpInclusiveScan(myStore, lane);
+	if (lane == 31) { sWarpSum[0][warp] = incE; sWarpSum[1][warp] = incS; }
+	__syncthreads();
+	uint32_t baseE = 0, baseS = 0, totE = 0, totS = 0;
+	for (int w = 0; w < SRPD_GEOM_THREADS / 32; w++)
+	{
+		if (w < warp) { baseE += sWarpSum[0][w]; baseS += sWarpSum[1][w]; }
+		totE += sWarpSum[0][w]; totS += sWarpSum[1][w];
+	}
+	if (tid == 0)
+	{
+		const unsigned long long agg = ((unsigned long long) totE << 31) | (unsigned long long) totS;
+		volatile unsigned long long* state = a.scanState;
+		unsigned long long prefix = 0;
+		if (b == 0)
+			state[batch] = SRPD_SCAN_PREFIX | agg;
+		else
+		{
+			state[batch] = SRPD_SCAN_AGG | agg;
+			uint32_t j = batch - 1;
+			for (;;)
+			{
+				const unsigned long long s = state[j];
+				const unsigned long long flag = s >> 62;
+				if (flag == 0)
+					continue;                          /* predecessor has not published yet */
+				prefix += s & SRPD_SCAN_VALUE_MASK;
+				if (flag == 2)
+					break;
+				j--;                                   /* the frame's batch 0 always publishes a prefix */
+			}
+			state[batch] = SRPD_SCAN_PREFIX | (prefix + agg);
+		}
+		sPrefix[0] = (uint32_t) (prefix >> 31);
+		sPrefix[1] = (uint32_t) (prefix & 0x7FFFFFFFull);
+		if (b == a.batchesPerFrame - 1)
+		{
+			const uint32_t e = sPrefix[0] + totE, s = sPrefix[1] + totS;
+			a.frameCounts[2 * frame + 0] = e;
+			a.frameCounts[2 * frame + 1] = s < a.recCapacity ? s : a.recCapacity;
+			atomicAdd(&a.stats->primsIn, (unsigned long long) d.nInputPrims);
+			atomicAdd(&a.stats->primsEmitted, (unsigned long long) e);
+			atomicAdd(&a.stats->primsStored, (unsigned long long) s);
+		}
+	}
+	__syncthreads();
+
+	/* 5. write, in id order */
+	if (active && myStore > 0)
+	{
+		em.idBase = sPrefix[0] + baseE + incE - myEmit;
+		em.storeBase = sPrefix[1] + baseS + incS - myStore;
+		em.nEmit = 0; em.nStore = 0;
+		processPrimitive<true>(em, d, nv, p, vary);
+		if (em.overflow)
+		{
+			atomicAdd(&a.stats->overflow, 1ull);
+			atomicExch(a.abortFlag, 1u);
+		}
+	}
+}
+
+static int gGeomLaunches = 0;
+int srpdGeomLaunchCount(void) { return gGeomLaunches; }
+
+void srpdLaunchGeom(const SrpdGeomArgs& a, cudaStream_t stream)
+{
+	const size_t smemBytes = 6 * SRPD_HASH_SLOTS + 4 * SRPD_GEOM_MAX_VERTS
+		+ (size_t) SRPD_GEOM_MAX_VERTS * (16 + a.d.st.slotSize);
+	static bool configured = false;
+	if (!configured)
+	{
+		cudaFuncSetAttribute(srpdGeomKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+		configured = true;
+	}
+	const unsigned grid = a.batchesPerFrame * a.d.nFrames;
+	srpdGeomKernel<<<grid, SRPD_GEOM_THREADS, smemBytes, stream>>>(a);
+	gGeomLaunches++;
+}

@@ -1,0 +1,95 @@
+/* srp-b200 internal -- kernel argument blocks and launch geometry shared by the CUDA
+ * translation units (geom.cu, bin.cu, raster.cu, runtime.cu). */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "core.cuh"
+
+/* User program table (defined by SRP_B200_DEFINE_PROGRAM_TABLE in the executable's
+ * shader translation unit, resolved at device-link time). */
+extern "C" __device__ void srpB200DeviceVS(int programId, SRPVertexShaderIn* in, SRPVertexShaderOut* out);
+extern "C" __device__ void srpB200DeviceFS(int programId, SRPFragmentShaderIn* in, SRPFragmentShaderOut* out);
+
+/* ---- launch geometry -------------------------------------------------------------- */
+constexpr int SRPD_TILE_W = 32;          /* pixels; one 128-byte colour row per tile row   */
+constexpr int SRPD_TILE_H = 16;
+constexpr int SRPD_BLK_W = 8;            /* pixels owned by one warp: 8 x 4                */
+constexpr int SRPD_BLK_H = 4;
+constexpr int SRPD_TILE_THREADS = SRPD_TILE_W * SRPD_TILE_H;       /* one thread per pixel */
+constexpr int SRPD_TILE_WARPS = SRPD_TILE_THREADS / 32;
+constexpr int SRPD_SUPER_W = 8;          /* tiles per supertile (coarse bin), x            */
+constexpr int SRPD_SUPER_H = 8;          /* tiles per supertile, y                         */
+
+constexpr int SRPD_GEOM_THREADS = 256;   /* input primitives per geometry batch            */
+constexpr int SRPD_GEOM_MAX_VERTS = 3 * SRPD_GEOM_THREADS;
+constexpr int SRPD_HASH_SLOTS = 1024;    /* post-VS cache: open-addressing table in smem   */
+constexpr uint32_t SRPD_HASH_EMPTY = 0xFFFFFFFFu;
+constexpr int SRPD_CLIP_MAX_VERTS = 10;  /* a triangle against 6 planes has <= 9 vertices  */
+
+constexpr int SRPD_STATS_SLOTS = 1024;   /* SrpdStats[slots]: counters are spread to avoid same-address atomics */
+
+constexpr int SRPD_BIN_THREADS = 256;
+constexpr int SRPD_BIN_CHUNK = 2048;     /* records per coarse-binning CTA                  */
+
+/* Decoupled look-back word: [63:62] status, [61:31] emitted ids, [30:0] stored records */
+constexpr unsigned long long SRPD_SCAN_AGG = 1ull << 62;
+constexpr unsigned long long SRPD_SCAN_PREFIX = 2ull << 62;
+constexpr unsigned long long SRPD_SCAN_VALUE_MASK = (1ull << 62) - 1;
+
+struct SrpdGeomArgs
+{
+	SrpdDraw d;
+	SrpdFrame frame0;                 /* used when frames == nullptr (single draw)       */
+	const SrpdFrame* frames;          /* device array [nFrames]                          */
+	unsigned char* records;           /* [nFrames][recCapacity] records of recStride B   */
+	uint2* bboxes;                    /* [nFrames][recCapacity] x0|y0<<16, x1|y1<<16 (half-open, pixels) */
+	uint32_t recCapacity;
+	uint32_t recStride;
+	unsigned long long* scanState;    /* [nFrames * batchesPerFrame], zeroed per draw    */
+	uint32_t* ticket;                 /* zeroed per draw                                 */
+	uint32_t* abortFlag;              /* zeroed per draw; set when a scratch pool overflows: the
+	                                     tile kernel then leaves the framebuffer untouched  */
+	uint32_t batchesPerFrame;
+	uint32_t* frameCounts;            /* [nFrames][2]: ids emitted, records stored       */
+	SrpdStats* stats;
+};
+
+struct SrpdBinArgs
+{
+	const uint2* bboxes;
+	const uint32_t* frameCounts;      /* [0][1] = number of stored records               */
+	uint32_t nChunksMax;              /* grid size of the chunk kernels                  */
+	uint32_t superX, superY;          /* supertile grid                                  */
+	uint32_t* chunkCounts;            /* [nChunksMax][nSuper]                            */
+	uint32_t* superOffsets;           /* [nSuper + 1]                                    */
+	uint32_t* listIds;                /* [listCapacity] record indices, id order per supertile */
+	uint32_t listCapacity;
+	uint32_t* abortFlag;
+	SrpdStats* stats;
+};
+
+struct SrpdTileArgs
+{
+	SrpdDraw d;
+	SrpdFrame frame0;
+	const SrpdFrame* frames;
+	const unsigned char* records;
+	const uint2* bboxes;
+	uint32_t recCapacity;
+	uint32_t recStride;
+	const uint32_t* frameCounts;
+	const uint32_t* superOffsets;     /* nullptr: direct path, every tile scans all records */
+	const uint32_t* listIds;
+	uint32_t superX;
+	uint32_t tilesX, tilesY;
+	const uint32_t* abortFlag;
+	SrpdStats* stats;
+};
+
+/* launchers (defined next to their kernels) */
+void srpdLaunchGeom(const SrpdGeomArgs& a, cudaStream_t stream);
+void srpdLaunchBin(const SrpdBinArgs& a, cudaStream_t stream);
+void srpdLaunchTiles(const SrpdTileArgs& a, cudaStream_t stream);
+void srpdLaunchClear(uint32_t* color, float* depth, size_t nPixels, cudaStream_t stream);
+int srpdGeomLaunchCount(void);
+int srpdBinLaunchCount(void);

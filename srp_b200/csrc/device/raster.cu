@@ -1,0 +1,484 @@
+/* srp-b200 -- tile kernel: coverage, interpolation, fragment shading and the whole
+ * per-fragment test sequence, one CTA per 32x16-pixel framebuffer tile (sm_100a).
+ *
+ * Replaces the reference's immediate-mode inner loops
+ *   src/raster/triangle.c:73-111 (rasterizeTriangle), line.c:34-77 (rasterizeLine),
+ *   point.c:32-74 (rasterizePoint), fragment.c:63-125 (emitFragment),
+ *   pipeline/interpolation.c:34-163, core/color.c:14-23 (colorPack)
+ * and srpFramebufferClear (core/framebuffer.c:57-62), which is fused in here.
+ *
+ * Ownership model: every thread owns ONE pixel of the tile for the whole draw and keeps
+ * its colour / depth / stencil in registers; the tile's primitives are visited in
+ * primitive-id order, so the reference's "later primitive wins" semantics (no blending,
+ * depth EQUAL/ALWAYS, stencil counters) hold with no atomics.  A warp owns an 8x4 pixel
+ * block.  Work distribution:
+ *   - the CTA scans its candidate list (all records of the frame, or the coarse bin of
+ *     its supertile) 512 records at a time and compacts the ones whose bounding box
+ *     touches the tile into shared memory with a ballot + warp-scan (order preserved);
+ *   - each warp walks that list 32 entries per step, ballots "touches my 8x4 block" and
+ *     visits only those, in order.
+ * Exact arithmetic: a pixel's barycentrics are NOT evaluated in closed form; the thread
+ * replays the reference's incremental chain -- (y - minY) float additions of dlambda/dy
+ * from the value at the bounding-box corner, then (x - minX) additions of dlambda/dx
+ * (triangle.c:102-109) -- which is what makes depth bit-exact.
+ * Lines replay the DDA chain of line.c:56-76 the same way.
+ *
+ * Framebuffer traffic per tile: at most one read and one write of 9 B/px; with a
+ * pending clear no read at all.  Stores go through shared memory and leave as 16-byte
+ * vectors, one 128-byte row segment per 8 threads. */
+#include "kernels.cuh"
+
+namespace {
+
+struct Pixel
+{
+	uint32_t color;
+	float depth;
+	uint32_t stencil;
+	uint32_t dirty;      /* bit0 colour, bit1 depth, bit2 stencil */
+};
+
+struct FragCounters { uint32_t emitted, shaded; };
+
+/* emitFragment, reference src/raster/fragment.c:63-125.  `sx, sy` are the (unwrapped)
+ * integer fragment coordinates the scissor test sees; interpolation of the varyings is
+ * deferred until the early tests have passed (it is pure). */
+template <int NV>
+__device__ __forceinline__ void emitFragment(
+	const SrpdState& st, const SrpdFrame& fr, Pixel& px, FragCounters& cnt,
+	int sx, int sy, float fragX, float fragY, float depth, float rec, float fragW,
+	bool frontFacing, uint32_t primitiveID,
+	const unsigned char* blobs, const float* wgt)
+{
+	cnt.emitted++;
+	if (!srpdScissor(st, sx, sy))
+		return;
+
+	const SrpdStencilFace& sf = frontFacing ? st.stencilFront : st.stencilBack;
+	const float storedDepth = px.depth;
+	const uint8_t storedStencil = (uint8_t) px.stencil;
+
+	if (st.stencilEnabled)
+	{
+		if (!srpdCompareU8(sf.func, (uint8_t) (sf.ref & sf.mask), (uint8_t) (storedStencil & sf.mask)))
+		{
+			px.stencil = srpdStencilWrite(storedStencil, srpdStencilOp(sf.sfailOp, storedStencil, sf.ref), sf.writeMask);
+			px.dirty |= 4u;
+			return;
+		}
+	}
+	if (st.earlyDepth && st.depthTest && !srpdCompare(st.depthOp, depth, storedDepth))
+	{
+		if (st.stencilEnabled)
+		{
+			px.stencil = srpdStencilWrite(storedStencil, srpdStencilOp(sf.dfailOp, storedStencil, sf.ref), sf.writeMask);
+			px.dirty |= 4u;
+		}
+		return;
+	}
+
+	alignas(8) unsigned char interpolated[SRPD_MAX_VARYING_BYTES];
+	if (NV == 1)
+	{
+		for (int k = 0; k < st.slotSize; k++)
+			interpolated[k] = blobs[k];
+	}
+	else
+	{
+		const unsigned char* b[NV];
+		for (int i = 0; i < NV; i++)
+			b[i] = blobs + i * st.slotSize;
+		srpdInterpolate<NV>(st, b, wgt, rec, interpolated);
+	}
+
+	SRPFragmentShaderIn in;
+	in.uniform = (SRPUniform*) fr.uniform;
+	in.varyings = (SRPInterpolated*) interpolated;
+	in.fragCoord[0] = fragX; in.fragCoord[1] = fragY; in.fragCoord[2] = depth; in.fragCoord[3] = fragW;
+	in.frontFacing = frontFacing;
+	in.primitiveID = primitiveID;
+	SRPFragmentShaderOut out;
+	out.color[0] = 0.f; out.color[1] = 0.f; out.color[2] = 0.f; out.color[3] = 0.f;
+	out.fragDepth = __int_as_float(0x7FC00000);   /* NAN */
+	srpB200DeviceFS(st.programId, &in, &out);
+	cnt.shaded++;
+
+	if (!st.earlyDepth)
+	{
+		if (!isnan(out.fragDepth))
+			depth = out.fragDepth;
+		if (st.depthTest && !srpdCompare(st.depthOp, depth, storedDepth))
+		{
+			if (st.stencilEnabled)
+			{
+				px.stencil = srpdStencilWrite(storedStencil, srpdStencilOp(sf.dfailOp, storedStencil, sf.ref), sf.writeMask);
+				px.dirty |= 4u;
+			}
+			return;
+		}
+	}
+	if (st.stencilEnabled)
+	{
+		px.stencil = srpdStencilWrite(storedStencil, srpdStencilOp(sf.passOp, storedStencil, sf.ref), sf.writeMask);
+		px.dirty |= 4u;
+	}
+	px.color = srpdColorPack(out.color);
+	px.dirty |= 1u;
+	if (st.depthTest && st.depthWrite)
+	{
+		px.depth = depth;
+		px.dirty |= 2u;
+	}
+}
+
+/* rasterizeTriangle for one pixel, reference triangle.c:73-111 */
+__device__ __forceinline__ void visitTriangle(
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, Pixel& px, FragCounters& cnt,
+	int x, int y, bool valid)
+{
+	const uint4* h = (const uint4*) rec;
+	const uint4 q0 = __ldg(h + 0), q1 = __ldg(h + 1);
+	const int minX = (int) (q0.w & 0xFFFFu), maxX = (int) (q0.w >> 16);
+	const int minY = (int) (q1.w & 0xFFFFu), maxY = (int) (q1.w >> 16);
+	if (!valid || x < minX || x >= maxX || y < minY || y >= maxY)
+		return;
+	const uint4 q2 = __ldg(h + 2);
+	float l0 = __uint_as_float(q0.x), l1 = __uint_as_float(q0.y), l2 = __uint_as_float(q0.z);
+	{
+		const float dy0 = __uint_as_float(q2.x), dy1 = __uint_as_float(q2.y), dy2 = __uint_as_float(q2.z);
+		const int ny = y - minY;
+		for (int i = 0; i < ny; i++)
+		{
+			l0 = __fadd_rn(l0, dy0); l1 = __fadd_rn(l1, dy1); l2 = __fadd_rn(l2, dy2);
+		}
+		const float dx0 = __uint_as_float(q1.x), dx1 = __uint_as_float(q1.y), dx2 = __uint_as_float(q1.z);
+		const int nx = x - minX;
+		for (int i = 0; i < nx; i++)
+		{
+			l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
+		}
+	}
+	/* top-left rule: lambda > 0 || (|lambda| <= 1e-9 && edgeTL), triangle.c:82-87 */
+	const uint32_t flags = q2.w;
+	const bool in0 = (l0 > 0.f) || (srpdRoughlyZero(l0) && (flags & 1u));
+	const bool in1 = (l1 > 0.f) || (srpdRoughlyZero(l1) && (flags & 2u));
+	const bool in2 = (l2 > 0.f) || (srpdRoughlyZero(l2) && (flags & 4u));
+	if (!(in0 && in1 && in2))
+		return;
+
+	const uint4 q3 = __ldg(h + 3), q4 = __ldg(h + 4);
+	const float wgt[3] = { l0, l1, l2 };
+	/* interpolateDepthAndWTriangle, interpolation.c:34-47 */
+	const float iwSum = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(q4.x), l0), __fmul_rn(__uint_as_float(q4.y), l1)),
+	                              __fmul_rn(__uint_as_float(q4.z), l2));
+	const float recW = __fdiv_rn(1.0f, iwSum);
+	const float depth = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(q3.x), l0), __fmul_rn(__uint_as_float(q3.y), l1)),
+	                              __fmul_rn(__uint_as_float(q3.z), l2));
+	emitFragment<3>(a.d.st, fr, px, cnt, x, y, (float) ((double) x + 0.5), (float) ((double) y + 0.5),
+	                depth, recW, recW, (flags & 8u) != 0, q3.w, rec + SRPD_REC_HEADER_BYTES, wgt);
+}
+
+/* round half away from zero of a float-valued double; exact because x + 0.5 is exact */
+__device__ __forceinline__ int roundToInt(float v)
+{
+	const double d = (double) v;
+	return (int) trunc(d + copysign(0.5, d));
+}
+
+/* rasterizeLine for one pixel, reference line.c:34-77: every lane replays the whole DDA
+ * chain and keeps the fragments that land on its own linear index y*W + x -- including
+ * the ones the reference's unchecked indexing wraps to the next row (App. B-1). */
+__device__ __forceinline__ void visitLine(
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, Pixel& px, FragCounters& cnt,
+	int x, int y, bool valid)
+{
+	const uint4* h = (const uint4*) rec;
+	const uint4 q0 = __ldg(h + 0), q1 = __ldg(h + 1), q2 = __ldg(h + 2), q3 = __ldg(h + 3);
+	float fx = __uint_as_float(q0.x), fy = __uint_as_float(q0.y);
+	const float xInc = __uint_as_float(q0.z), yInc = __uint_as_float(q0.w);
+	const float tInc = __uint_as_float(q1.x);
+	const int steps = (int) q1.y;
+	const float zw0 = __uint_as_float(q1.z), zw1 = __uint_as_float(q1.w);
+	const float iw0 = __uint_as_float(q2.x), iw1 = __uint_as_float(q2.y);
+	const long long W = a.d.st.width;
+	const long long mine = valid ? (long long) y * W + x : -1;
+	float t = 0.f;
+	for (int i = 0; i <= steps; i++)
+	{
+		const int ipx = roundToInt(fx), ipy = roundToInt(fy);
+		if ((long long) ipy * W + ipx == mine)
+		{
+			const float w0 = __fsub_rn(1.0f, t);
+			const float wgt[2] = { w0, t };
+			/* interpolateDepthAndWLine, interpolation.c:49-60 */
+			const float recW = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(iw0, w0), __fmul_rn(iw1, t)));
+			const float depth = __fadd_rn(__fmul_rn(zw0, w0), __fmul_rn(zw1, t));
+			emitFragment<2>(a.d.st, fr, px, cnt, ipx, ipy, (float) ((double) ipx + 0.5), (float) ((double) ipy + 0.5),
+			                depth, recW, recW, true, q3.w, rec + SRPD_REC_HEADER_BYTES, wgt);
+		}
+		fx = __fadd_rn(fx, xInc);
+		fy = __fadd_rn(fy, yInc);
+		t = __fadd_rn(t, tInc);
+	}
+}
+
+/* rasterizePoint for one pixel, reference point.c:32-74 */
+__device__ __forceinline__ void visitPoint(
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, Pixel& px, FragCounters& cnt,
+	int x, int y, bool valid)
+{
+	const uint4* h = (const uint4*) rec;
+	const uint4 q1 = __ldg(h + 1);
+	if (!valid || x < (int) q1.x || x > (int) q1.y || y < (int) q1.z || y > (int) q1.w)
+		return;
+	const uint4 q0 = __ldg(h + 0);
+	const float pcx = (float) ((double) x + 0.5), pcy = (float) ((double) y + 0.5);
+	if (pcx < __uint_as_float(q0.x) || pcx >= __uint_as_float(q0.z) || pcy < __uint_as_float(q0.y) || pcy >= __uint_as_float(q0.w))
+		return;
+	const uint4 q2 = __ldg(h + 2), q3 = __ldg(h + 3);
+	emitFragment<1>(a.d.st, fr, px, cnt, x, y, pcx, pcy, __uint_as_float(q2.x), 0.f, __uint_as_float(q2.y),
+	                true, q3.w, rec + SRPD_REC_HEADER_BYTES, nullptr);
+}
+
+/* Tile plane -> framebuffer: threads cooperatively emit 16-byte stores from the staged
+ * tile (row-major TILE_W x TILE_H elements of T in shared memory). */
+template <typename T>
+__device__ __forceinline__ void storePlane(const T* staged, T* plane, int W, int H, int tx0, int ty0, int tid)
+{
+	constexpr int PER_VEC = 16 / (int) sizeof(T);
+	constexpr int VECS_PER_ROW = SRPD_TILE_W / PER_VEC;
+	constexpr int NVEC = VECS_PER_ROW * SRPD_TILE_H;
+	const bool vectorOk = (W % PER_VEC) == 0 && ((uintptr_t) plane % 16) == 0;
+	for (int v = tid; v < NVEC; v += SRPD_TILE_THREADS)
+	{
+		const int row = v / VECS_PER_ROW, cv = v % VECS_PER_ROW;
+		const int gy = ty0 + row, gx = tx0 + cv * PER_VEC;
+		if (gy >= H || gx >= W)
+			continue;
+		T* dst = plane + (size_t) gy * W + gx;
+		const T* src = staged + row * SRPD_TILE_W + cv * PER_VEC;
+		if (vectorOk && gx + PER_VEC <= W)
+			*(uint4*) dst = *(const uint4*) src;
+		else
+			for (int e = 0; e < PER_VEC && gx + e < W; e++)
+				dst[e] = src[e];
+	}
+}
+
+} // namespace
+
+/* Register budget: both launch-bound arguments are given explicitly (under device LTO a
+ * missing minimum makes the linker's code generator cap the kernel at 64 registers and
+ * spill).  Triangles and points fit two 512-thread CTAs per SM; the line walker does not. */
+template <int KIND>
+__global__ void __launch_bounds__(SRPD_TILE_THREADS, KIND == SRPD_KIND_LINE ? 1 : 2)
+srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
+{
+	__shared__ __align__(16) uint32_t sIds[SRPD_TILE_THREADS];     /* reused as the colour staging tile */
+	__shared__ __align__(16) uint2 sBox[SRPD_TILE_THREADS];        /* reused as depth (+ stencil) staging */
+	__shared__ uint32_t sWarpCnt[SRPD_TILE_WARPS];
+	__shared__ uint32_t sDirty;
+
+	const SrpdState& st = a.d.st;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t frame = blockIdx.y;
+	const int tileX = blockIdx.x % a.tilesX;
+	const int tileY = a.d.tileRow0 + blockIdx.x / a.tilesX;
+	const SrpdFrame fr = a.frames ? a.frames[frame] : a.frame0;
+
+	/* candidate list of this tile */
+	uint32_t begin = 0, end;
+	const uint32_t* ids = nullptr;
+	if (a.superOffsets)
+	{
+		const uint32_t s = (uint32_t) (tileY / SRPD_SUPER_H) * a.superX + (uint32_t) (tileX / SRPD_SUPER_W);
+		begin = a.superOffsets[s];
+		end = a.superOffsets[s + 1];
+		ids = a.listIds;
+	}
+	else
+		end = a.frameCounts[2 * frame + 1];
+	if (begin == end && !fr.clearPending)
+		return;
+	if (*a.abortFlag)      /* a scratch pool overflowed: the host repeats the draw with larger pools */
+		return;
+
+	const unsigned char* records = a.records + (size_t) frame * a.recCapacity * a.recStride;
+	const uint2* bboxes = a.bboxes + (size_t) frame * a.recCapacity;
+
+	/* pixel ownership: warp w -> 8x4 block (w % 4, w / 4); lane -> (lane % 8, lane / 8) */
+	const int tx0 = tileX * SRPD_TILE_W, ty0 = tileY * SRPD_TILE_H;
+	const int bx0 = tx0 + (warp % (SRPD_TILE_W / SRPD_BLK_W)) * SRPD_BLK_W;
+	const int by0 = ty0 + (warp / (SRPD_TILE_W / SRPD_BLK_W)) * SRPD_BLK_H;
+	const int x = bx0 + (lane % SRPD_BLK_W), y = by0 + (lane / SRPD_BLK_W);
+	const bool valid = x < st.width && y < st.height;
+	const size_t pixelIndex = (size_t) y * st.width + x;
+
+	Pixel px;
+	px.color = 0u; px.depth = -1.0f; px.stencil = 0u; px.dirty = 0u;
+	if (valid)
+	{
+		if (!fr.clearPending)
+		{
+			px.color = fr.color[pixelIndex];
+			if (st.depthTest)
+				px.depth = fr.depth[pixelIndex];
+		}
+		if (st.stencilEnabled)
+			px.stencil = fr.stencil[pixelIndex];
+	}
+	if (tid == 0)
+		sDirty = 0u;
+	__syncthreads();
+
+	FragCounters cnt;
+	cnt.emitted = 0; cnt.shaded = 0;
+
+	for (uint32_t c = begin; c < end; c += SRPD_TILE_THREADS)
+	{
+		/* CTA: keep the candidates whose bbox touches the tile, in order */
+		const uint32_t i = c + tid;
+		bool hit = false;
+		uint32_t rid = 0;
+		uint2 bb = make_uint2(0u, 0u);
+		if (i < end)
+		{
+			rid = ids ? ids[i] : i;
+			bb = bboxes[rid];
+			const int x0 = (int) (bb.x & 0xFFFFu), y0 = (int) (bb.x >> 16);
+			const int x1 = (int) (bb.y & 0xFFFFu), y1 = (int) (bb.y >> 16);
+			hit = x0 < tx0 + SRPD_TILE_W && x1 > tx0 && y0 < ty0 + SRPD_TILE_H && y1 > ty0;
+		}
+		const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+		if (lane == 0)
+			sWarpCnt[warp] = __popc(ballot);
+		__syncthreads();
+		uint32_t base = 0, total = 0;
+		#pragma unroll
+		for (int w = 0; w < SRPD_TILE_WARPS; w++)
+		{
+			const uint32_t n = sWarpCnt[w];
+			if (w < warp) base += n;
+			total += n;
+		}
+		if (hit)
+		{
+			const uint32_t pos = base + __popc(ballot & ((1u << lane) - 1u));
+			sIds[pos] = rid;
+			sBox[pos] = bb;
+		}
+		__syncthreads();
+
+		/* warp: visit, in order, the entries that touch this warp's 8x4 block */
+		for (uint32_t j0 = 0; j0 < total; j0 += 32)
+		{
+			const uint32_t j = j0 + lane;
+			bool mine = false;
+			if (j < total)
+			{
+				const uint2 b2 = sBox[j];
+				const int x0 = (int) (b2.x & 0xFFFFu), y0 = (int) (b2.x >> 16);
+				const int x1 = (int) (b2.y & 0xFFFFu), y1 = (int) (b2.y >> 16);
+				mine = x0 < bx0 + SRPD_BLK_W && x1 > bx0 && y0 < by0 + SRPD_BLK_H && y1 > by0;
+			}
+			uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
+			while (m)
+			{
+				const int bit = __ffs(m) - 1;
+				m &= m - 1;
+				const unsigned char* rec = records + (size_t) sIds[j0 + bit] * a.recStride;
+				if (KIND == SRPD_KIND_TRIANGLE)
+					visitTriangle(a, fr, rec, px, cnt, x, y, valid);
+				else if (KIND == SRPD_KIND_LINE)
+					visitLine(a, fr, rec, px, cnt, x, y, valid);
+				else
+					visitPoint(a, fr, rec, px, cnt, x, y, valid);
+			}
+		}
+		__syncthreads();
+	}
+
+	/* counters: warp reduction, then one atomic per warp into one of 64 slots chosen by
+	 * the tile index, so the atomics of a frame do not serialise on one L2 address */
+	{
+		uint32_t e = cnt.emitted, s = cnt.shaded;
+		#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
+			s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+		}
+		if (lane == 0 && e)
+		{
+			SrpdStats* slot = a.stats + ((blockIdx.x * SRPD_TILE_WARPS + warp) & (SRPD_STATS_SLOTS - 1));
+			atomicAdd(&slot->fragsEmitted, (unsigned long long) e);
+			atomicAdd(&slot->fragsShaded, (unsigned long long) s);
+		}
+	}
+
+	/* write-back: stage the tile in shared memory, leave as 16-byte vectors */
+	uint32_t dirty = px.dirty;
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		dirty |= __shfl_xor_sync(0xFFFFFFFFu, dirty, o);
+	if (lane == 0 && dirty)
+		atomicOr(&sDirty, dirty);
+	uint32_t* sColor = sIds;
+	float* sDepth = (float*) sBox;
+	uint8_t* sStencil = (uint8_t*) (sDepth + SRPD_TILE_THREADS);
+	const int local = (y - ty0) * SRPD_TILE_W + (x - tx0);
+	sColor[local] = px.color;
+	sDepth[local] = px.depth;
+	sStencil[local] = (uint8_t) px.stencil;
+	__syncthreads();
+	const uint32_t tileDirty = sDirty | (fr.clearPending ? 3u : 0u);
+	if (tileDirty & 1u)
+		storePlane<uint32_t>(sColor, fr.color, st.width, st.height, tx0, ty0, tid);
+	if (tileDirty & 2u)
+		storePlane<float>(sDepth, fr.depth, st.width, st.height, tx0, ty0, tid);
+	if (tileDirty & 4u)
+		storePlane<uint8_t>(sStencil, fr.stencil, st.width, st.height, tx0, ty0, tid);
+}
+
+/* srpFramebufferClear as a real memory operation (only needed when a pending clear has
+ * to be materialised without a draw), reference core/framebuffer.c:57-62 */
+__global__ void __launch_bounds__(256) srpdClearKernel(uint4* color, uint4* depth, size_t nVec, uint32_t* colorTail, float* depthTail, int nTail)
+{
+	const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+	const uint32_t m1 = 0xBF800000u;   /* -1.0f */
+	const uint4 minusOne = make_uint4(m1, m1, m1, m1);
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < nVec; i += (size_t) gridDim.x * blockDim.x)
+	{
+		color[i] = zero;
+		depth[i] = minusOne;
+	}
+	if (blockIdx.x == 0 && (int) threadIdx.x < nTail)
+	{
+		colorTail[threadIdx.x] = 0u;
+		depthTail[threadIdx.x] = -1.0f;
+	}
+}
+
+void srpdLaunchClear(uint32_t* color, float* depth, size_t nPixels, cudaStream_t stream)
+{
+	const size_t nVec = nPixels / 4;
+	const int nTail = (int) (nPixels % 4);
+	unsigned grid = (unsigned) ((nVec + 255) / 256);
+	if (grid > 148u * 16u) grid = 148u * 16u;
+	if (grid == 0) grid = 1;
+	srpdClearKernel<<<grid, 256, 0, stream>>>((uint4*) color, (uint4*) depth, nVec, color + nVec * 4, depth + nVec * 4, nTail);
+}
+
+void srpdLaunchTiles(const SrpdTileArgs& a, cudaStream_t stream)
+{
+	const uint32_t rows = a.d.tileRow1 - a.d.tileRow0;
+	if (rows == 0 || a.tilesX == 0)
+		return;
+	const dim3 grid(a.tilesX * rows, a.d.nFrames);
+	if (a.d.kind == SRPD_KIND_TRIANGLE)
+		srpdTileKernel<SRPD_KIND_TRIANGLE><<<grid, SRPD_TILE_THREADS, 0, stream>>>(a);
+	else if (a.d.kind == SRPD_KIND_LINE)
+		srpdTileKernel<SRPD_KIND_LINE><<<grid, SRPD_TILE_THREADS, 0, stream>>>(a);
+	else
+		srpdTileKernel<SRPD_KIND_POINT><<<grid, SRPD_TILE_THREADS, 0, stream>>>(a);
+}

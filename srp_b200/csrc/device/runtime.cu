@@ -1,0 +1,425 @@
+/* srp-b200 -- CUDA runtime layer behind the thin C ABI of srpcu.h.
+ *
+ * Owns what the reference's src/memory (per-draw bump arena, src/memory/arena.c:69-116)
+ * owned, re-designed for the device: one stream, grow-only scratch pools in HBM that
+ * every draw re-uses (primitive records, bounding boxes, scan state, coarse-bin lists,
+ * uniform ring), and the submission of the kernels of one draw:
+ *
+ *   memset(scan state)  ->  geometry  ->  [count, scan, fill coarse bins]  ->  tiles
+ *
+ * Nothing here falls back to the CPU: without a usable sm_100 device every entry point
+ * fails and says why. */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include "kernels.cuh"
+#include "srpcu.h"
+
+namespace {
+
+struct Pool
+{
+	void* ptr = nullptr;
+	size_t bytes = 0;
+};
+
+struct Runtime
+{
+	bool ready = false;
+	bool failed = false;
+	int device = -1;
+	cudaStream_t stream = nullptr;
+	std::string lastError;
+	Pool records, bboxes, scan, frameCounts, chunkCounts, superOffsets, listIds, uniforms, frames;
+	SrpdStats* stats = nullptr;            /* device, SRPD_STATS_SLOTS slots */
+	SrpdStats* statsHost = nullptr;        /* pinned */
+	unsigned long long launches = 0, h2d = 0, d2h = 0;
+	int forceBinning = -1;                 /* SRP_B200_BINNING=0/1 overrides the heuristic */
+	uint32_t binThreshold = 4096;
+};
+
+Runtime g;
+int gRequestedDevice = -1;
+int gWorstCasePools = 0;
+
+bool fail(const char* what, cudaError_t e)
+{
+	char buf[512];
+	snprintf(buf, sizeof buf, "srp-b200: %s failed: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+	g.lastError = buf;
+	return false;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(#call, e_); return 1; } } while (0)
+
+bool grow(Pool& p, size_t bytes)
+{
+	if (bytes <= p.bytes)
+		return true;
+	if (p.ptr)
+	{
+		cudaStreamSynchronize(g.stream);
+		cudaFree(p.ptr);
+		p.ptr = nullptr; p.bytes = 0;
+	}
+	size_t want = bytes + bytes / 4;
+	want = (want + 255) & ~(size_t) 255;
+	cudaError_t e = cudaMalloc(&p.ptr, want);
+	if (e != cudaSuccess)
+	{
+		e = cudaMalloc(&p.ptr, bytes);
+		want = bytes;
+	}
+	if (e != cudaSuccess)
+		return fail("cudaMalloc(scratch pool)", e);
+	p.bytes = want;
+	return true;
+}
+
+int envInt(const char* name, int fallback)
+{
+	const char* v = getenv(name);
+	return (v && *v) ? atoi(v) : fallback;
+}
+
+} // namespace
+
+extern "C" {
+
+void srpcuSetDevice(int device) { gRequestedDevice = device; }
+void srpcuSetWorstCasePools(int on) { gWorstCasePools = on; }
+const char* srpcuLastError(void) { return g.lastError.c_str(); }
+void* srpcuStream(void) { return srpcuInit() == 0 ? (void*) g.stream : nullptr; }
+int srpcuTileWidth(void) { return SRPD_TILE_W; }
+int srpcuTileHeight(void) { return SRPD_TILE_H; }
+
+const char* srpcuVersion(void)
+{
+	static char buf[128];
+	snprintf(buf, sizeof buf, "srp-b200 sm_100a tile %dx%d supertile %dx%d geom-batch %d",
+	         SRPD_TILE_W, SRPD_TILE_H, SRPD_SUPER_W, SRPD_SUPER_H, SRPD_GEOM_THREADS);
+	return buf;
+}
+
+int srpcuInit(void)
+{
+	if (g.ready)
+		return 0;
+	if (g.failed)
+		return 1;
+	g.failed = true;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+	{
+		g.lastError = std::string("srp-b200: no CUDA device available (") + cudaGetErrorString(e)
+			+ "); this library has no CPU path";
+		return 1;
+	}
+	int dev = gRequestedDevice;
+	if (dev < 0) dev = envInt("SRP_B200_DEVICE", -1);
+	if (dev < 0) dev = envInt("LOCAL_RANK", 0);
+	if (dev >= count) dev = dev % count;
+	CU(cudaSetDevice(dev));
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, dev));
+	if (prop.major != 10)
+	{
+		char buf[256];
+		snprintf(buf, sizeof buf, "srp-b200: device %d (%s, sm_%d%d) is not an sm_100 part; the kernels are built for sm_100a only",
+		         dev, prop.name, prop.major, prop.minor);
+		g.lastError = buf;
+		return 1;
+	}
+	g.device = dev;
+	CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+	CU(cudaMalloc(&g.stats, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
+	CU(cudaMemset(g.stats, 0, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
+	CU(cudaMallocHost(&g.statsHost, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
+	g.forceBinning = envInt("SRP_B200_BINNING", -1);
+	g.binThreshold = (uint32_t) envInt("SRP_B200_BIN_THRESHOLD", 4096);
+	g.failed = false;
+	g.ready = true;
+	return 0;
+}
+
+void* srpcuMalloc(size_t bytes)
+{
+	if (srpcuInit()) return nullptr;
+	void* p = nullptr;
+	if (bytes == 0) bytes = 16;
+	cudaError_t e = cudaMalloc(&p, bytes);
+	if (e != cudaSuccess) { fail("cudaMalloc", e); return nullptr; }
+	cudaMemsetAsync(p, 0, bytes, g.stream);
+	return p;
+}
+void srpcuFree(void* p)
+{
+	if (p && g.ready) { cudaStreamSynchronize(g.stream); cudaFree(p); }
+}
+void* srpcuMallocHost(size_t bytes)
+{
+	if (srpcuInit()) return nullptr;
+	void* p = nullptr;
+	if (bytes == 0) bytes = 16;
+	cudaError_t e = cudaMallocHost(&p, bytes);
+	if (e != cudaSuccess) { fail("cudaMallocHost", e); return nullptr; }
+	memset(p, 0, bytes);
+	return p;
+}
+void srpcuFreeHost(void* p)
+{
+	if (p && g.ready) { cudaStreamSynchronize(g.stream); cudaFreeHost(p); }
+}
+void* srpcuMallocManaged(size_t bytes)
+{
+	if (srpcuInit()) return nullptr;
+	void* p = nullptr;
+	if (bytes == 0) bytes = 16;
+	cudaError_t e = cudaMallocManaged(&p, bytes);
+	if (e != cudaSuccess) { fail("cudaMallocManaged", e); return nullptr; }
+	return p;
+}
+void srpcuFreeManaged(void* p)
+{
+	if (p && g.ready) { cudaStreamSynchronize(g.stream); cudaFree(p); }
+}
+void srpcuPrefetchToDevice(void* p, size_t bytes)
+{
+	if (!g.ready || !p) return;
+	cudaMemAdvise(p, bytes, cudaMemAdviseSetReadMostly, g.device);
+	cudaMemPrefetchAsync(p, bytes, g.device, g.stream);
+}
+
+int srpcuUpload(void* dst, const void* src, size_t bytes)
+{
+	if (srpcuInit()) return 1;
+	if (bytes == 0) return 0;
+	CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, g.stream));
+	g.h2d += bytes;
+	return 0;
+}
+int srpcuDownload(void* dstHost, const void* srcDevice, size_t bytes)
+{
+	if (srpcuInit()) return 1;
+	if (bytes == 0) return 0;
+	CU(cudaMemcpyAsync(dstHost, srcDevice, bytes, cudaMemcpyDeviceToHost, g.stream));
+	g.d2h += bytes;
+	return 0;
+}
+int srpcuSynchronize(void)
+{
+	if (!g.ready) return 0;
+	CU(cudaStreamSynchronize(g.stream));
+	CU(cudaGetLastError());
+	return 0;
+}
+
+int srpcuClearPlanes(uint32_t* color, float* depth, size_t nPixels)
+{
+	if (srpcuInit()) return 1;
+	srpdLaunchClear(color, depth, nPixels, g.stream);
+	g.launches++;
+	CU(cudaGetLastError());
+	return 0;
+}
+
+int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
+              const void* uniforms, size_t uniformBytes, size_t uniformStride)
+{
+	if (srpcuInit()) return 1;
+	SrpdDraw d = *dIn;
+	const SrpdState& st = d.st;
+	const uint32_t nFrames = d.nFrames;
+	if (nFrames == 0 || d.nInputPrims == 0)
+		return 0;
+
+	/* uniforms: one 256-byte aligned block per frame */
+	const size_t ublock = (uniformBytes + 255) & ~(size_t) 255;
+	unsigned char* uniDev = nullptr;
+	if (uniforms && uniformBytes)
+	{
+		if (!grow(g.uniforms, ublock * nFrames)) return 1;
+		uniDev = (unsigned char*) g.uniforms.ptr;
+		if (nFrames == 1)
+			CU(cudaMemcpyAsync(uniDev, uniforms, uniformBytes, cudaMemcpyDefault, g.stream));
+		else
+			CU(cudaMemcpy2DAsync(uniDev, ublock, uniforms, uniformStride, uniformBytes, nFrames, cudaMemcpyDefault, g.stream));
+		g.h2d += uniformBytes * nFrames;
+	}
+
+	/* frame bindings */
+	SrpdFrame frame0 = framesHost[0];
+	frame0.uniform = uniDev;
+	const SrpdFrame* framesDev = nullptr;
+	if (nFrames > 1)
+	{
+		if (!grow(g.frames, sizeof(SrpdFrame) * nFrames)) return 1;
+		SrpdFrame* tmp = (SrpdFrame*) malloc(sizeof(SrpdFrame) * nFrames);
+		for (uint32_t f = 0; f < nFrames; f++)
+		{
+			tmp[f] = framesHost[f];
+			tmp[f].uniform = uniDev ? uniDev + (size_t) f * ublock : nullptr;
+		}
+		cudaError_t e = cudaMemcpyAsync(g.frames.ptr, tmp, sizeof(SrpdFrame) * nFrames, cudaMemcpyHostToDevice, g.stream);
+		/* pageable source: the copy has been staged when the call returns */
+		free(tmp);
+		if (e != cudaSuccess) { fail("cudaMemcpyAsync(frames)", e); return 1; }
+		g.h2d += sizeof(SrpdFrame) * nFrames;
+		framesDev = (const SrpdFrame*) g.frames.ptr;
+	}
+
+	/* scratch sizing.  Worst case per input primitive is d.maxOutPerInput records; the
+	 * pools are sized for 2x the input (+ slack) and a draw that would exceed them sets
+	 * the overflow counter, which the host turns into a retry at the worst-case size. */
+	const int nVerts = srpdVertsOfKind(d.kind);
+	const uint32_t recStride = srpdRecordStride(st, nVerts);
+	const uint64_t worst = (uint64_t) d.nInputPrims * d.maxOutPerInput;
+	uint64_t cap = (d.maxOutPerInput == 1) ? worst : (uint64_t) d.nInputPrims * 2 + 4096;
+	if (d.st.polygonMode != SRP_POLYGON_MODE_FILL && d.maxOutPerInput > 1)
+		cap = (uint64_t) d.nInputPrims * 4 + 4096;
+	if (gWorstCasePools || getenv("SRP_B200_WORST_CASE_POOLS") || cap > worst) cap = worst;
+	if (cap > 0x7FFFFFF0ull) cap = 0x7FFFFFF0ull;
+	const uint32_t recCapacity = (uint32_t) cap;
+	const uint32_t batchesPerFrame = (d.nInputPrims + SRPD_GEOM_THREADS - 1) / SRPD_GEOM_THREADS;
+
+	if (!grow(g.records, (size_t) recCapacity * recStride * nFrames)) return 1;
+	if (!grow(g.bboxes, (size_t) recCapacity * sizeof(uint2) * nFrames)) return 1;
+	const size_t scanBytes = 16 + sizeof(unsigned long long) * (size_t) batchesPerFrame * nFrames;
+	if (!grow(g.scan, scanBytes)) return 1;
+	if (!grow(g.frameCounts, sizeof(uint32_t) * 2 * nFrames)) return 1;
+	CU(cudaMemsetAsync(g.scan.ptr, 0, scanBytes, g.stream));
+
+	SrpdGeomArgs ga;
+	memset(&ga, 0, sizeof ga);
+	ga.d = d;
+	ga.frame0 = frame0;
+	ga.frames = framesDev;
+	ga.records = (unsigned char*) g.records.ptr;
+	ga.bboxes = (uint2*) g.bboxes.ptr;
+	ga.recCapacity = recCapacity;
+	ga.recStride = recStride;
+	ga.ticket = (uint32_t*) g.scan.ptr;
+	ga.abortFlag = (uint32_t*) g.scan.ptr + 1;
+	ga.scanState = (unsigned long long*) ((unsigned char*) g.scan.ptr + 16);
+	ga.batchesPerFrame = batchesPerFrame;
+	ga.frameCounts = (uint32_t*) g.frameCounts.ptr;
+	ga.stats = g.stats;
+	srpdLaunchGeom(ga, g.stream);
+	g.launches++;
+	CU(cudaGetLastError());
+
+	const uint32_t tilesX = (st.width + SRPD_TILE_W - 1) / SRPD_TILE_W;
+	const uint32_t tilesY = (st.height + SRPD_TILE_H - 1) / SRPD_TILE_H;
+	const uint32_t superX = (tilesX + SRPD_SUPER_W - 1) / SRPD_SUPER_W;
+	const uint32_t superY = (tilesY + SRPD_SUPER_H - 1) / SRPD_SUPER_H;
+	const uint32_t nSuper = superX * superY;
+
+	bool binned = nFrames == 1 && recCapacity > g.binThreshold && nSuper > 1 && nSuper <= 8192
+		&& superX <= 256 && superY <= 256;
+	if (g.forceBinning == 0) binned = false;
+	if (g.forceBinning == 1 && nFrames == 1 && nSuper <= 8192 && superX <= 256 && superY <= 256) binned = true;
+
+	SrpdTileArgs ta;
+	memset(&ta, 0, sizeof ta);
+	ta.d = d;
+	ta.frame0 = frame0;
+	ta.frames = framesDev;
+	ta.records = ga.records;
+	ta.bboxes = ga.bboxes;
+	ta.recCapacity = recCapacity;
+	ta.recStride = recStride;
+	ta.frameCounts = ga.frameCounts;
+	ta.superX = superX;
+	ta.tilesX = tilesX;
+	ta.tilesY = tilesY;
+	ta.abortFlag = ga.abortFlag;
+	ta.stats = g.stats;
+	if (ta.d.tileRow1 > tilesY) ta.d.tileRow1 = tilesY;
+	if (ta.d.tileRow0 > ta.d.tileRow1) ta.d.tileRow0 = ta.d.tileRow1;
+
+	if (binned)
+	{
+		SrpdBinArgs ba;
+		memset(&ba, 0, sizeof ba);
+		ba.bboxes = ga.bboxes;
+		ba.frameCounts = ga.frameCounts;
+		ba.nChunksMax = (recCapacity + SRPD_BIN_CHUNK - 1) / SRPD_BIN_CHUNK;
+		ba.superX = superX;
+		ba.superY = superY;
+		uint64_t listCap = (uint64_t) recCapacity * 2 + (uint64_t) nSuper * 64 + 65536;
+		if (gWorstCasePools || getenv("SRP_B200_WORST_CASE_POOLS")) listCap = (uint64_t) recCapacity * nSuper;
+		if (listCap > 0x7FFFFFF0ull) listCap = 0x7FFFFFF0ull;
+		ba.listCapacity = (uint32_t) listCap;
+		if (!grow(g.chunkCounts, sizeof(uint32_t) * (size_t) ba.nChunksMax * nSuper)) return 1;
+		if (!grow(g.superOffsets, sizeof(uint32_t) * (nSuper + 1))) return 1;
+		if (!grow(g.listIds, sizeof(uint32_t) * (size_t) ba.listCapacity)) return 1;
+		ba.chunkCounts = (uint32_t*) g.chunkCounts.ptr;
+		ba.superOffsets = (uint32_t*) g.superOffsets.ptr;
+		ba.listIds = (uint32_t*) g.listIds.ptr;
+		ba.abortFlag = ga.abortFlag;
+		ba.stats = g.stats;
+		srpdLaunchBin(ba, g.stream);
+		g.launches += 3;
+		CU(cudaGetLastError());
+		ta.superOffsets = ba.superOffsets;
+		ta.listIds = ba.listIds;
+	}
+
+	srpdLaunchTiles(ta, g.stream);
+	g.launches++;
+	CU(cudaGetLastError());
+	return 0;
+}
+
+void srpcuGetStats(SrpdStats* out, unsigned long long* launches, unsigned long long* h2d, unsigned long long* d2h)
+{
+	memset(out, 0, sizeof *out);
+	if (launches) *launches = g.launches;
+	if (h2d) *h2d = g.h2d;
+	if (d2h) *d2h = g.d2h;
+	if (!g.ready)
+		return;
+	cudaMemcpyAsync(g.statsHost, g.stats, sizeof(SrpdStats) * SRPD_STATS_SLOTS, cudaMemcpyDeviceToHost, g.stream);
+	cudaStreamSynchronize(g.stream);
+	for (int i = 0; i < SRPD_STATS_SLOTS; i++)
+	{
+		out->primsIn += g.statsHost[i].primsIn;
+		out->primsEmitted += g.statsHost[i].primsEmitted;
+		out->primsStored += g.statsHost[i].primsStored;
+		out->fragsEmitted += g.statsHost[i].fragsEmitted;
+		out->fragsShaded += g.statsHost[i].fragsShaded;
+		out->overflow += g.statsHost[i].overflow;
+	}
+}
+
+/* Number of scratch-pool overflows since the previous call (synchronises; 8-byte copy).
+ * Only slot 0 of the counter array is used for overflow accounting. */
+int srpcuTakeOverflow(void)
+{
+	static unsigned long long seen = 0;
+	if (!g.ready)
+		return 0;
+	cudaMemcpyAsync(&g.statsHost[0].overflow, &g.stats[0].overflow, sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream);
+	cudaStreamSynchronize(g.stream);
+	const unsigned long long now = g.statsHost[0].overflow;
+	const int fresh = now > seen;
+	seen = now;
+	return fresh;
+}
+
+void srpcuResetStats(void)
+{
+	g.launches = 0; g.h2d = 0; g.d2h = 0;
+	if (g.ready)
+	{
+		/* keep the overflow counter monotonic (srpcuTakeOverflow compares against the
+		 * last value it saw), zero everything else */
+		srpcuTakeOverflow();
+		cudaMemsetAsync(g.stats, 0, sizeof(SrpdStats) * SRPD_STATS_SLOTS, g.stream);
+		cudaMemcpyAsync(&g.stats[0].overflow, &g.statsHost[0].overflow, sizeof(unsigned long long), cudaMemcpyHostToDevice, g.stream);
+		cudaStreamSynchronize(g.stream);
+	}
+}
+
+} // extern "C"

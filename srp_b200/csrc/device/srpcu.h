@@ -1,0 +1,58 @@
+/* srp-b200 internal -- the thin C ABI between the host C layer (csrc/host) and the
+ * CUDA layer (csrc/device).  Host code never includes CUDA headers; it sees device
+ * memory as opaque pointers and submits one SrpdDraw per draw call. */
+#ifndef SRPCU_H_
+#define SRPCU_H_
+#include <stddef.h>
+#include <stdint.h>
+#include "draw_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Lazily creates the per-process runtime (device selection, stream, scratch pools).
+ * Returns 0 on success; on failure srpcuLastError() explains (no GPU / wrong arch /
+ * extension built without its program table ...).  There is no CPU fallback. */
+int srpcuInit(void);
+void srpcuSetDevice(int device);
+const char* srpcuLastError(void);
+const char* srpcuVersion(void);
+void* srpcuStream(void);
+
+void* srpcuMalloc(size_t bytes);                 /* device memory, zero-filled           */
+void srpcuFree(void* p);
+void* srpcuMallocHost(size_t bytes);             /* pinned host memory, zero-filled      */
+void srpcuFreeHost(void* p);
+void* srpcuMallocManaged(size_t bytes);          /* managed memory (textures)            */
+void srpcuFreeManaged(void* p);
+void srpcuPrefetchToDevice(void* p, size_t bytes);
+/* stream-ordered copy of caller memory of any kind (host, pinned, device) to the device */
+int srpcuUpload(void* dst, const void* src, size_t bytes);
+int srpcuDownload(void* dstHost, const void* srcDevice, size_t bytes);   /* enqueue only */
+int srpcuSynchronize(void);
+
+/* Apply a pending clear to real memory: colour 0, depth -1 (stencil untouched). */
+int srpcuClearPlanes(uint32_t* color, float* depth, size_t nPixels);
+
+/* Enqueue one draw (all its kernels) for d->nFrames frames.  `frames` is a host array
+ * of nFrames bindings whose `uniform` fields are ignored: frame f uses the uniform
+ * block at uniforms + f*uniformStride (uniformBytes each; NULL / 0 = no uniform). */
+int srpcuDraw(const SrpdDraw* d, const SrpdFrame* frames,
+              const void* uniforms, size_t uniformBytes, size_t uniformStride);
+
+/* 1 if a scratch pool overflowed since the previous call (the affected draw was
+ * incomplete); the host then repeats the draw with worst-case pools. */
+int srpcuTakeOverflow(void);
+void srpcuSetWorstCasePools(int on);
+
+void srpcuGetStats(SrpdStats* out, unsigned long long* launches, unsigned long long* h2d, unsigned long long* d2h);
+void srpcuResetStats(void);
+
+int srpcuTileWidth(void);
+int srpcuTileHeight(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

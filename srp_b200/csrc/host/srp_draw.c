@@ -1,0 +1,333 @@
+/* srp-b200 host layer -- the draw entry points: validation, dispatch, state snapshot.
+ *
+ * This is the drop-in seam.  It mirrors reference src/pipeline/draw.c:63-189 (drawBuffer,
+ * drawTriangles/Lines/Points, checkOOB) and the warnings of primitive_assembly.c:180-196,
+ * then -- instead of assembling and rasterising on the CPU -- snapshots the context, the
+ * varyings layout and the uniform into one SrpdDraw and submits it to the CUDA layer.
+ *
+ * Messages (type, severity, wording) follow the reference so that programs inspecting the
+ * callback keep working; conditions that only exist here (unregistered program, varyings
+ * larger than the device limit, no GPU) are reported HIGH through the callback and on
+ * stderr, and the draw is skipped.  Nothing is ever rendered on the CPU. */
+#include <stdlib.h>
+#include <string.h>
+#include "srp_internal.h"
+
+static size_t gRow0 = 0, gRow1 = SIZE_MAX;
+static unsigned long long gDraws = 0;
+
+void srpB200SetRowRange(size_t row0, size_t row1) { gRow0 = row0; gRow1 = row1; }
+size_t srpB200TileWidth(void) { return (size_t) srpcuTileWidth(); }
+size_t srpB200TileHeight(void) { return (size_t) srpcuTileHeight(); }
+const char* srpB200Version(void) { return srpcuVersion(); }
+void srpB200SetDevice(int device) { srpcuSetDevice(device); }
+void* srpB200Stream(void) { return srpcuStream(); }
+
+void srpB200GetStats(SRPB200Stats* out)
+{
+	SrpdStats s;
+	unsigned long long launches, h2d, d2h;
+	srpcuGetStats(&s, &launches, &h2d, &d2h);
+	out->draws = gDraws;
+	out->primsIn = s.primsIn;
+	out->primsEmitted = s.primsEmitted;
+	out->primsStored = s.primsStored;
+	out->fragsEmitted = s.fragsEmitted;
+	out->fragsShaded = s.fragsShaded;
+	out->kernelLaunches = launches;
+	out->h2dBytes = h2d;
+	out->d2hBytes = d2h;
+	out->overflow = s.overflow;
+}
+void srpB200ResetStats(void) { gDraws = 0; srpcuResetStats(); }
+
+/* ---- validation, reference draw.c:167-189 and primitive_assembly.c:180-196 ---- */
+static bool checkOOB(const SRPIndexBuffer* ib, const SRPVertexBuffer* vb, size_t startIndex, size_t count)
+{
+	const size_t endIndex = startIndex + count - 1;
+	const size_t bufferSize = ib ? ib->nIndices : vb->nVertices;
+	if (endIndex >= bufferSize)
+	{
+		srpMessage(SRP_MESSAGE_ERROR, SRP_MESSAGE_SEVERITY_HIGH, __func__,
+			ib ? "Attempt to OOB access index buffer (read) at indices %zu-%zu (size: %zu)\n"
+			   : "Attempt to OOB access vertex buffer (read) at indices %zu-%zu (size: %zu)\n",
+			startIndex, endIndex, bufferSize);
+		return true;
+	}
+	return false;
+}
+
+static void warnOnExcessVertexCount(SRPPrimitive prim, size_t vertexCount)
+{
+	if (prim == SRP_PRIM_LINES && vertexCount % 2 != 0)
+		srpMessage(SRP_MESSAGE_WARNING, SRP_MESSAGE_SEVERITY_LOW, __func__,
+			"Odd vertex count when drawing SRP_PRIM_LINES. The last vertex will be ignored\n");
+	if (prim == SRP_PRIM_TRIANGLES && vertexCount % 3 != 0)
+		srpMessage(SRP_MESSAGE_WARNING, SRP_MESSAGE_SEVERITY_LOW, __func__,
+			"Vertex count not divisible by 3 when drawing SRP_PRIM_TRIANGLES. The last %i vertex/vertices will be ignored\n",
+			(int) (vertexCount % 3));
+}
+
+/* primitive counts, reference topology.c:14-22,50-60 */
+static size_t inputPrimitiveCount(SRPPrimitive prim, size_t n)
+{
+	switch (prim)
+	{
+		case SRP_PRIM_TRIANGLES:      return n / 3;
+		case SRP_PRIM_TRIANGLE_STRIP:
+		case SRP_PRIM_TRIANGLE_FAN:   return n >= 3 ? n - 2 : 0;
+		case SRP_PRIM_LINES:          return n / 2;
+		case SRP_PRIM_LINE_STRIP:     return n != 1 ? n - 1 : 0;
+		case SRP_PRIM_LINE_LOOP:      return n != 1 ? n : 0;
+		case SRP_PRIM_POINTS:         return n;
+	}
+	return 0;
+}
+
+static void snapshotStencilFace(SrpdStencilFace* d, const SRPStencilFaceState* s)
+{
+	d->func = (uint8_t) s->func; d->ref = s->ref; d->mask = s->mask; d->writeMask = s->writeMask;
+	d->sfailOp = (uint8_t) s->sfailOp; d->dfailOp = (uint8_t) s->dfailOp; d->passOp = (uint8_t) s->passOp; d->pad = 0;
+}
+
+/* varyings layout: attribute after attribute, tightly packed (interpolation.c:104-161).
+ * The slot reserved per blob covers both what the program declared and what its
+ * attribute list spans (tests/scenes/interpolation/flat.c declares 3 floats over a
+ * 1-byte struct). */
+static bool snapshotVaryings(SrpdState* st, const SRPVertexShader* vs)
+{
+	if (vs->nVaryings > SRPD_MAX_VARYINGS)
+	{
+		srpFatalMessage("srpDraw", "%zu varyings exceed the device limit of %d", vs->nVaryings, SRPD_MAX_VARYINGS);
+		return false;
+	}
+	size_t offset = 0;
+	for (size_t i = 0; i < vs->nVaryings; i++)
+	{
+		const SRPVaryingInfo* info = &vs->varyingsInfo[i];
+		size_t elem;
+		switch (info->type)
+		{
+			case SRP_FLOAT: case SRP_INT32: case SRP_UINT32: elem = 4; break;
+			case SRP_DOUBLE: case SRP_INT64: case SRP_UINT64: elem = 8; break;
+			case SRP_INT16: case SRP_UINT16: elem = 2; break;
+			case SRP_INT8: case SRP_UINT8: elem = 1; break;
+			default:
+				srpMessage(SRP_MESSAGE_ERROR, SRP_MESSAGE_SEVERITY_HIGH, "interpolateAttributes",
+					"Unexpected type (%i)", info->type);
+				elem = 0;
+		}
+		st->varyings[i].offset = (uint16_t) offset;
+		st->varyings[i].nItems = (uint16_t) (elem ? info->nItems : 0);
+		st->varyings[i].type = (uint8_t) info->type;
+		st->varyings[i].mode = (uint8_t) info->interpolationMode;
+		st->varyings[i].elemSize = (uint8_t) elem;
+		st->varyings[i].pad = 0;
+		offset += elem * info->nItems;
+		if (offset > SRPD_MAX_VARYING_BYTES)
+			break;
+	}
+	size_t slot = vs->varyingsSize > offset ? vs->varyingsSize : offset;
+	slot = (slot + 7) & ~(size_t) 7;
+	if (slot > SRPD_MAX_VARYING_BYTES)
+	{
+		srpFatalMessage("srpDraw", "varyings of %zu bytes exceed the device limit of %d bytes", slot, SRPD_MAX_VARYING_BYTES);
+		return false;
+	}
+	st->nVaryings = (int32_t) vs->nVaryings;
+	st->varyingsSize = (int32_t) vs->varyingsSize;
+	st->slotSize = (int32_t) slot;
+	return true;
+}
+
+static bool buildDraw(
+	SrpdDraw* d, const SRPIndexBuffer* ib, const SRPVertexBuffer* vb, const SRPFramebuffer* fb,
+	const SRPShaderProgram* sp, SRPPrimitive primitive, size_t startIndex, size_t count,
+	const SRPProgramEntry** outProgram)
+{
+	memset(d, 0, sizeof *d);
+	const SRPContext* c = &srpContext;
+
+	const bool isTriangle = primitive == SRP_PRIM_TRIANGLES || primitive == SRP_PRIM_TRIANGLE_STRIP || primitive == SRP_PRIM_TRIANGLE_FAN;
+	const bool isLine = primitive == SRP_PRIM_LINES || primitive == SRP_PRIM_LINE_STRIP || primitive == SRP_PRIM_LINE_LOOP;
+	const bool isPoint = primitive == SRP_PRIM_POINTS;
+	if (!isTriangle && !isLine && !isPoint)
+	{
+		srpMessage(SRP_MESSAGE_ERROR, SRP_MESSAGE_SEVERITY_HIGH, "drawBuffer", "Unknown primitive type: %i", primitive);
+		return false;
+	}
+	if (isTriangle && c->raster.cullFace == SRP_FACE_FRONT_AND_BACK)
+		return false;                                   /* draw.c:89 */
+	if (isTriangle && c->raster.polygonMode != SRP_POLYGON_MODE_FILL && c->raster.polygonMode != SRP_POLYGON_MODE_LINE
+	    && c->raster.polygonMode != SRP_POLYGON_MODE_POINT)
+	{
+		srpMessage(SRP_MESSAGE_ERROR, SRP_MESSAGE_SEVERITY_HIGH, "assembleTrianglesGeneric",
+			"Unexpected srpContext.raster.polygonMode (%i)", c->raster.polygonMode);
+		return false;
+	}
+	if (!isPoint)
+		warnOnExcessVertexCount(primitive, count);
+	if (isPoint && c->raster.pointSize <= 0.)
+		return false;                                   /* primitive_assembly.c:227-228 */
+	const size_t nPrims = inputPrimitiveCount(primitive, count);
+	if (nPrims == 0)
+		return false;
+	if (nPrims > 100000000u)
+	{
+		srpFatalMessage("srpDraw", "%zu input primitives exceed the per-draw limit", nPrims);
+		return false;
+	}
+
+	const SRPProgramEntry* prog = srpLookupProgram(sp->vs->shader, sp->fs->shader);
+	if (prog == NULL)
+	{
+		srpFatalMessage("srpDraw",
+			"shader program (vs %p, fs %p) has no registered __device__ twins (srpB200RegisterProgram); "
+			"nothing is drawn -- this library has no CPU path", (void*) sp->vs->shader, (void*) sp->fs->shader);
+		return false;
+	}
+	*outProgram = prog;
+
+	SrpdState* st = &d->st;
+	st->width = (int32_t) fb->width;
+	st->height = (int32_t) fb->height;
+	st->frontFaceCW = c->raster.frontFace == SRP_WINDING_CW;
+	st->cullFace = (uint8_t) c->raster.cullFace;
+	st->polygonMode = isTriangle ? (uint8_t) c->raster.polygonMode : (uint8_t) SRP_POLYGON_MODE_FILL;
+	st->provokingFirst = c->provokingVertexMode == SRP_PROVOKING_VERTEX_FIRST;
+	st->pointSize = c->raster.pointSize;
+	st->scissorEnabled = c->scissor.enabled;
+	st->scissorX0 = c->scissor.x;
+	st->scissorX1 = c->scissor.x + c->scissor.width;
+	st->scissorY0 = c->scissor.y;
+	st->scissorY1 = c->scissor.y + c->scissor.height;
+	st->stencilEnabled = c->stencil.enabled;
+	snapshotStencilFace(&st->stencilFront, &c->stencil.front);
+	snapshotStencilFace(&st->stencilBack, &c->stencil.back);
+	st->depthTest = c->depth.testEnable;
+	st->depthWrite = c->depth.writeEnable;
+	st->depthOp = (uint8_t) c->depth.compareOp;
+	st->earlyDepth = !sp->fs->mayOverwriteDepth;
+	st->programId = prog->deviceId;
+	if (!snapshotVaryings(st, sp->vs))
+		return false;
+
+	d->vb = vb->data;
+	d->vbStride = vb->nBytesPerVertex;
+	d->ib = ib ? ib->data : NULL;
+	d->ibElemSize = ib ? (uint32_t) ib->nBytesPerIndex : 0;
+	d->topology = (uint32_t) primitive;
+	d->startIndex = startIndex;
+	d->count = count;
+	d->nInputPrims = (uint32_t) nPrims;
+	if (isTriangle)
+	{
+		d->kind = st->polygonMode == SRP_POLYGON_MODE_FILL ? SRPD_KIND_TRIANGLE
+		        : st->polygonMode == SRP_POLYGON_MODE_LINE ? SRPD_KIND_LINE : SRPD_KIND_POINT;
+		d->maxOutPerInput = st->polygonMode == SRP_POLYGON_MODE_FILL ? 7 : 21;
+	}
+	else
+	{
+		d->kind = isLine ? SRPD_KIND_LINE : SRPD_KIND_POINT;
+		d->maxOutPerInput = 1;
+	}
+	const size_t th = (size_t) srpcuTileHeight();
+	const size_t tilesY = (fb->height + th - 1) / th;
+	size_t r0 = gRow0 / th, r1 = gRow1 == SIZE_MAX ? tilesY : (gRow1 + th - 1) / th;
+	if (r1 > tilesY) r1 = tilesY;
+	if (r0 > r1) r0 = r1;
+	d->tileRow0 = (uint32_t) r0;
+	d->tileRow1 = (uint32_t) r1;
+	return true;
+}
+
+static void submit(
+	const SRPIndexBuffer* ib, const SRPVertexBuffer* vb, SRPFramebuffer* const* fbs, size_t nFrames,
+	const SRPShaderProgram* sp, const void* uniforms, size_t uniformStride,
+	SRPPrimitive primitive, size_t startIndex, size_t count, bool clearFirst)
+{
+	if (count == 0 || nFrames == 0 || checkOOB(ib, vb, startIndex, count))
+		return;
+
+	SRPFramebufferImpl** impls = malloc(nFrames * sizeof *impls);
+	SrpdFrame* frames = malloc(nFrames * sizeof *frames);
+	if (!impls || !frames) abort();
+	bool ok = true;
+	for (size_t f = 0; f < nFrames; f++)
+	{
+		impls[f] = srpFramebufferImpl(fbs[f]);
+		if (impls[f] == NULL || impls[f]->pub.width != fbs[0]->width || impls[f]->pub.height != fbs[0]->height)
+		{
+			srpFatalMessage("srpDraw", "framebuffer %zu is not a live srp framebuffer of the batch's size", f);
+			ok = false;
+			break;
+		}
+		if (clearFirst)
+			srpFramebufferClear(fbs[f]);
+	}
+
+	SrpdDraw d;
+	const SRPProgramEntry* prog = NULL;
+	if (ok && buildDraw(&d, ib, vb, fbs[0], sp, primitive, startIndex, count, &prog))
+	{
+		d.nFrames = (uint32_t) nFrames;
+		for (int attempt = 0; attempt < 2; attempt++)
+		{
+			for (size_t f = 0; f < nFrames; f++)
+			{
+				frames[f].uniform = NULL;
+				frames[f].color = impls[f]->dColor;
+				frames[f].depth = impls[f]->dDepth;
+				frames[f].stencil = impls[f]->dStencil;
+				frames[f].clearPending = impls[f]->clearPending;
+				frames[f].pad = 0;
+			}
+			const size_t ubytes = uniforms ? prog->uniformSize : 0;
+			if (srpcuDraw(&d, frames, uniforms, ubytes, uniformStride))
+			{
+				srpFatalMessage("srpDraw", "%s", srpcuLastError());
+				break;
+			}
+			gDraws++;
+			if (srpB200GetSyncMode() != SRP_B200_SYNC_DRAW || !srpcuTakeOverflow())
+			{
+				srpFramebufferAfterDraw(impls, nFrames, d.st.stencilEnabled);
+				break;
+			}
+			/* A scratch pool was too small for this draw (heavy clipping / huge primitives).
+			 * The kernels raised the draw's abort flag, so the tile kernel left the
+			 * framebuffer (and a pending clear) untouched: repeat once with worst-case pools. */
+			if (attempt == 1)
+			{
+				srpFatalMessage("srpDraw", "scratch pools overflowed even at worst-case size; draw is incomplete");
+				srpFramebufferAfterDraw(impls, nFrames, d.st.stencilEnabled);
+				break;
+			}
+			srpcuSetWorstCasePools(1);
+		}
+	}
+	free(frames);
+	free(impls);
+}
+
+void srpDrawVertexBuffer(const SRPVertexBuffer* vb, const SRPFramebuffer* fb, const SRPShaderProgram* sp,
+                         SRPPrimitive primitive, size_t startIndex, size_t count)
+{
+	SRPFramebuffer* target = (SRPFramebuffer*) fb;
+	submit(NULL, vb, &target, 1, sp, sp->uniform, 0, primitive, startIndex, count, false);
+}
+
+void srpDrawIndexBuffer(const SRPIndexBuffer* ib, const SRPVertexBuffer* vb, const SRPFramebuffer* fb,
+                        const SRPShaderProgram* sp, SRPPrimitive primitive, size_t startIndex, size_t count)
+{
+	SRPFramebuffer* target = (SRPFramebuffer*) fb;
+	submit(ib, vb, &target, 1, sp, sp->uniform, 0, primitive, startIndex, count, false);
+}
+
+void srpB200DrawBatch(const SRPIndexBuffer* ib, const SRPVertexBuffer* vb,
+                      SRPFramebuffer* const* fbs, size_t nFrames,
+                      const SRPShaderProgram* sp, const void* uniforms, size_t uniformStride,
+                      SRPPrimitive primitive, size_t startIndex, size_t count, int clearFirst)
+{
+	submit(ib, vb, fbs, nFrames, sp, uniforms, uniformStride, primitive, startIndex, count, clearFirst != 0);
+}

@@ -1,0 +1,177 @@
+/* srp-b200 host layer -- framebuffer objects and the host/device synchronisation policy.
+ *
+ * Public behaviour of reference src/core/framebuffer.c:17-62: three row-major planes
+ * (u32 RGBA8888 with R in the top byte, f32 depth, u8 stencil); srpFramebufferClear sets
+ * colour 0 and depth -1 and leaves stencil alone; the stencil plane starts as zeros (the
+ * reference never initialises it and relies on fresh pages).
+ *
+ * Here the planes live in HBM.  The pointers in the public struct address a pinned host
+ * mirror that is refreshed by a device-to-host copy: after every draw (default policy)
+ * or on request (include/srp_b200.h).  A clear only sets a flag; the next draw's tile
+ * kernel starts from the clear values instead of loading the planes, and writes every
+ * tile, so clear + draw costs one write of the planes and no read. */
+#include <stdlib.h>
+#include <string.h>
+#include "srp_internal.h"
+
+static SRPB200SyncMode gSyncMode = SRP_B200_SYNC_DRAW;
+
+void srpB200SetSyncMode(SRPB200SyncMode mode) { gSyncMode = mode; }
+SRPB200SyncMode srpB200GetSyncMode(void) { return gSyncMode; }
+
+SRPFramebufferImpl* srpFramebufferImpl(const SRPFramebuffer* fb)
+{
+	SRPFramebufferImpl* impl = (SRPFramebufferImpl*) fb;
+	if (impl == NULL || impl->magic != SRP_FB_MAGIC)
+		return NULL;
+	return impl;
+}
+
+static SRPFramebuffer* newFramebuffer(size_t width, size_t height, void* dColor, void* dDepth, void* dStencil)
+{
+	if (width == 0 || height == 0 || width > 16384 || height > 16384)
+	{
+		srpFatalMessage("srpNewFramebuffer", "unsupported framebuffer size %zux%zu (1..16384 per side)", width, height);
+		return NULL;
+	}
+	SRPFramebufferImpl* fb = calloc(1, sizeof *fb);
+	if (!fb) abort();
+	fb->magic = SRP_FB_MAGIC;
+	fb->pub.width = width;
+	fb->pub.height = height;
+	fb->pub.size = width * height;
+	const size_t n = fb->pub.size;
+	fb->ownsDevicePlanes = dColor == NULL;
+	fb->dColor = dColor ? dColor : srpcuMalloc(n * sizeof(uint32_t));
+	fb->dDepth = dDepth ? dDepth : srpcuMalloc(n * sizeof(float));
+	fb->dStencil = dStencil ? dStencil : srpcuMalloc(n * sizeof(uint8_t));
+	fb->pub.color = srpcuMallocHost(n * sizeof(uint32_t));
+	fb->pub.depth = srpcuMallocHost(n * sizeof(float));
+	fb->pub.stencil = srpcuMallocHost(n * sizeof(uint8_t));
+	if (!fb->dColor || !fb->dDepth || !fb->dStencil || !fb->pub.color || !fb->pub.depth || !fb->pub.stencil)
+	{
+		srpFatalMessage("srpNewFramebuffer", "%s", srpcuLastError());
+		srpFreeFramebuffer(&fb->pub);
+		return NULL;
+	}
+	return &fb->pub;
+}
+
+SRPFramebuffer* srpNewFramebuffer(size_t width, size_t height)
+{
+	return newFramebuffer(width, height, NULL, NULL, NULL);
+}
+
+SRPFramebuffer* srpB200NewFramebufferOnDevice(size_t width, size_t height,
+                                              void* deviceColor, void* deviceDepth, void* deviceStencil)
+{
+	if (!deviceColor || !deviceDepth || !deviceStencil)
+	{
+		srpFatalMessage(__func__, "all three device planes must be provided");
+		return NULL;
+	}
+	return newFramebuffer(width, height, deviceColor, deviceDepth, deviceStencil);
+}
+
+void srpFreeFramebuffer(SRPFramebuffer* pub)
+{
+	SRPFramebufferImpl* fb = srpFramebufferImpl(pub);
+	if (!fb) return;
+	if (fb->ownsDevicePlanes)
+	{
+		srpcuFree(fb->dColor);
+		srpcuFree(fb->dDepth);
+		srpcuFree(fb->dStencil);
+	}
+	srpcuFreeHost(fb->pub.color);
+	srpcuFreeHost(fb->pub.depth);
+	srpcuFreeHost(fb->pub.stencil);
+	fb->magic = 0;
+	free(fb);
+}
+
+void srpFramebufferClear(const SRPFramebuffer* pub)
+{
+	SRPFramebufferImpl* fb = srpFramebufferImpl(pub);
+	if (!fb) return;
+	fb->clearPending = true;
+	fb->mirrorStale = true;
+}
+
+void* srpB200FramebufferDevicePlane(const SRPFramebuffer* pub, int which)
+{
+	SRPFramebufferImpl* fb = srpFramebufferImpl(pub);
+	if (!fb) return NULL;
+	return which == 0 ? (void*) fb->dColor : which == 1 ? (void*) fb->dDepth : which == 2 ? (void*) fb->dStencil : NULL;
+}
+
+/* make a deferred clear real (needed when somebody wants the planes without a draw) */
+static void materializeClear(SRPFramebufferImpl* fb)
+{
+	if (!fb->clearPending)
+		return;
+	if (srpcuClearPlanes(fb->dColor, fb->dDepth, fb->pub.size))
+		srpFatalMessage("srpFramebufferClear", "%s", srpcuLastError());
+	fb->clearPending = false;
+}
+
+static void enqueueDownload(SRPFramebufferImpl* fb)
+{
+	materializeClear(fb);
+	const size_t n = fb->pub.size;
+	int err = srpcuDownload(fb->pub.color, fb->dColor, n * sizeof(uint32_t));
+	err |= srpcuDownload(fb->pub.depth, fb->dDepth, n * sizeof(float));
+	if (fb->stencilTouched)
+		err |= srpcuDownload(fb->pub.stencil, fb->dStencil, n * sizeof(uint8_t));
+	if (err)
+		srpFatalMessage("srpB200FramebufferDownload", "%s", srpcuLastError());
+	fb->stencilTouched = false;
+	fb->mirrorStale = false;
+}
+
+void srpB200FramebufferDownload(const SRPFramebuffer* pub)
+{
+	SRPFramebufferImpl* fb = srpFramebufferImpl(pub);
+	if (!fb) return;
+	fb->stencilTouched = true;      /* explicit request: bring everything */
+	enqueueDownload(fb);
+	if (srpcuSynchronize())
+		srpFatalMessage(__func__, "%s", srpcuLastError());
+}
+
+void srpB200FramebufferUpload(const SRPFramebuffer* pub)
+{
+	SRPFramebufferImpl* fb = srpFramebufferImpl(pub);
+	if (!fb) return;
+	const size_t n = fb->pub.size;
+	fb->clearPending = false;
+	int err = srpcuUpload(fb->dColor, fb->pub.color, n * sizeof(uint32_t));
+	err |= srpcuUpload(fb->dDepth, fb->pub.depth, n * sizeof(float));
+	err |= srpcuUpload(fb->dStencil, fb->pub.stencil, n * sizeof(uint8_t));
+	if (err || srpcuSynchronize())
+		srpFatalMessage(__func__, "%s", srpcuLastError());
+}
+
+void srpB200Finish(void)
+{
+	if (srpcuSynchronize())
+		srpFatalMessage(__func__, "%s", srpcuLastError());
+}
+
+/* called by the draw entry points once the draw's kernels are enqueued */
+void srpFramebufferAfterDraw(SRPFramebufferImpl* const* fbs, size_t n, bool stencilEnabled)
+{
+	for (size_t i = 0; i < n; i++)
+	{
+		fbs[i]->clearPending = false;
+		fbs[i]->mirrorStale = true;
+		if (stencilEnabled)
+			fbs[i]->stencilTouched = true;
+	}
+	if (gSyncMode != SRP_B200_SYNC_DRAW)
+		return;
+	for (size_t i = 0; i < n; i++)
+		enqueueDownload(fbs[i]);
+	if (srpcuSynchronize())
+		srpFatalMessage("srpDraw", "%s", srpcuLastError());
+}

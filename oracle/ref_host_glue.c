@@ -6,6 +6,7 @@
 #include <string.h>
 #include <stdint.h>
 #include "srp/srp.h"
+#include "oracle_alloc.h"
 #include "core/texture_p.h"   /* the reference's private texture layout, src/core/texture_p.h:15-24 */
 
 /* texture from RGB8 texels in memory: what stbi_load() would have produced for a file
@@ -13,9 +14,9 @@
 SRPTexture* srpB200NewTextureFromMemory(const uint8_t* rgb, int width, int height,
                                         SRPTextureWrappingMode wrappingModeX, SRPTextureWrappingMode wrappingModeY)
 {
-	SRPTexture* t = malloc(sizeof *t);
+	SRPTexture* t = oracleMalloc(sizeof *t);   /* released by the reference's SRP_FREE */
 	const size_t n = (size_t) width * height * 3;
-	t->data = malloc(n);
+	t->data = malloc(n);                       /* released by stbi_image_free() = free() */
 	memcpy(t->data, rgb, n);
 	t->width = width;
 	t->height = height;

@@ -1,0 +1,352 @@
+#!/usr/bin/env python3
+"""Benchmark of the srp draw path on B200 (one JSON line on stdout, rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json: "frames/s & Gfrag/s (teapot 4K, 1M-tri mesh)"): cfg3, the synthetic
+1 002 528-triangle shell at 3840x2160 with the camera inside the mesh, Gouraud shader, depth
+test.  A step = srpFramebufferClear + srpDrawIndexBuffer of one frame per
+GPU.  With N GPUs the work is frame-parallel (every rank renders its own frames of the same
+scene; rank 0 builds the mesh and broadcasts vertex / index buffers over NCCL once, no
+collective in the timed region): weak scaling, value = N * K / max-over-ranks time.
+
+  value      frames/s with inputs resident in HBM: device time of the K steps, measured with
+             CUDA events on the library's own stream; L2 is flushed between steps
+  e2e        the same metric through the public C API with HOST buffers: every step uploads
+             the vertex and index buffers from pinned host memory (srp*BufferCopyData),
+             clears, draws and returns with the colour + depth planes copied back into the
+             host-visible framebuffer (default synchronisation policy), wall clock
+  roofline   the dominant kernel's algorithmic bytes / its measured duration vs the measured
+             HBM copy bandwidth (MEASURED_PEAKS.json), plus the whole-frame figure
+  cpu_baseline  the unmodified reference (oracle/_ref) on the host cores, bounded sample
+
+`--impl reference` times that reference instead (frame-parallel over all host cores).
+The oracle is only used as the CPU baseline / reference arm here, never on the product path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    "cfg3": dict(desc="cfg3: 1,002,528-triangle sphere shell, camera inside, 3840x2160, Gouraud VS, depth test",
+                 width=3840, height=2160),
+    "cfg2": dict(desc="cfg2: Utah teapot 1920x1080, Gouraud VS, depth test + back-face culling", width=1920, height=1080),
+    "cfg1": dict(desc="cfg1: textured cube 800x600, depth test, perspective-correct UVs", width=800, height=600),
+}
+
+
+def make_scene(workload):
+    from srp_b200 import scenes as S
+    if workload == "cfg3":
+        return S.cfg3_shell()
+    if workload == "cfg2":
+        return S.cfg2_teapot()
+    if workload == "cfg1":
+        return S.cfg1_textured_cube()
+    raise SystemExit(f"unknown workload {workload}")
+
+
+def algorithmic_bytes(scene):
+    """indices + referenced vertices + uniform + touched texels + one write of
+    the three planes (9 B/px; the frame starts with a clear, so no read)"""
+    d = scene.draws[0]
+    n_idx = len(d.indices) if d.indices is not None else 0
+    idx_bytes = n_idx * (d.indices.dtype.itemsize if d.indices is not None else 0)
+    v_ref = len(np.unique(d.indices)) if d.indices is not None else d.vertices.nbytes // d.stride
+    tex = sum(t[0].nbytes for t in scene.textures.values())
+    uni = len(d.uniform) if isinstance(d.uniform, (bytes, bytearray)) else 200
+    fb = scene.width * scene.height * 9
+    return {"indices": idx_bytes, "vertices": v_ref * d.stride, "uniform": uni, "texture": tex, "framebuffer": fb,
+            "total": idx_bytes + v_ref * d.stride + uni + tex + fb}
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU reference
+def _ref_worker(args):
+    workload, frames, warm = args
+    from srp_b200 import host as H, scenes as S
+    ref = H.load_oracle_reference()
+    p = S.Prepared(ref, make_scene(workload))
+    for _ in range(warm):
+        p.draw_all()
+    t0 = time.perf_counter()
+    for _ in range(frames):
+        p.draw_all()
+    dt = time.perf_counter() - t0
+    covered = int((p.planes()[0] != 0).sum())
+    p.free()
+    return dt, covered
+
+
+def run_reference(workload, frames_per_worker, workers, warm=1):
+    """frame-parallel CPU run of the unmodified reference: `workers` processes (the library is
+    single-threaded with global state), each renders `frames_per_worker` frames"""
+    from srp_b200 import host as H
+    if not H.REFERENCE_SO.exists():
+        return None
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(workers) as pool:
+        res = pool.map(_ref_worker, [(workload, frames_per_worker, warm)] * workers)
+    wall = time.perf_counter() - t0
+    slowest = max(r[0] for r in res)
+    return {"frames": frames_per_worker * workers, "seconds": slowest, "wall_with_setup": wall, "covered": res[0][1]}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W = max(args.warmup, 3)
+    K = args.steps
+    wl = WORKLOADS[args.workload]
+    config = {"workload": wl["desc"], "frames_per_step_per_gpu": 1, "partition": "frame-parallel" if world > 1 else "single GPU",
+              "l2": "flushed between timed steps (256 MiB fill)", "data": "synthetic"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from srp_b200 import host as H
+        if not H.REFERENCE_SO.exists():
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_host.so was not built (needs /root/reference at build time)"}))
+            return
+        cores = host_cores()
+        workers = min(cores, 64)
+        r = run_reference(args.workload, K, workers, warm=min(W, 1))
+        value = r["frames"] / r["seconds"]
+        line = {"impl": "reference", "metric": f"frames_per_s_{args.workload}", "value": value, "unit": "frames/s",
+                "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * r["seconds"] / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(config, partition=f"frame-parallel over {workers} host processes"),
+                "cpu_baseline": {"value": value, "unit": "frames/s", "cores": workers, "kind": "reference",
+                                 "sample": f"{r['frames']} frames of the same workload ({K} per process), unmodified reference built by oracle/Makefile"},
+                "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------- ours
+    os.environ["SRP_B200_DEVICE"] = str(local_rank)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from srp_b200 import host as H, scenes as S
+    lib = H.load_product()
+    scene = make_scene(args.workload)
+    draw = scene.draws[0]
+    alg = algorithmic_bytes(scene)
+
+    # rank 0's vertex / index buffers are broadcast over NVLink once; every rank then uploads
+    # from the device copy (srp*BufferCopyData accepts device memory through unified addressing)
+    vraw = np.ascontiguousarray(draw.vertices).view(np.uint8).reshape(-1)
+    iraw = np.ascontiguousarray(draw.indices).view(np.uint8).reshape(-1)
+    vpin = torch.from_numpy(vraw.copy()).pin_memory()
+    ipin = torch.from_numpy(iraw.copy()).pin_memory()
+    if world > 1:
+        vdev, idev = vpin.cuda(), ipin.cuda()
+        if rank != 0:
+            vdev.zero_(); idev.zero_()
+        dist.broadcast(vdev, 0); dist.broadcast(idev, 0)
+        torch.cuda.synchronize()
+
+    prep = S.Prepared(lib, scene)
+    _, prog, vb, ib, count = prep.items[0]
+    if world > 1:
+        lib.dll.srpVertexBufferCopyData(vb, draw.stride, vdev.numel(), vdev.data_ptr())
+        lib.dll.srpIndexBufferCopyData(ib, H.SRP_UINT32, idev.numel(), idev.data_ptr())
+    stream = torch.cuda.ExternalStream(lib.dll.srpB200Stream())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- kernel-only: inputs resident, explicit synchronisation, CUDA events on the library stream
+    lib.dll.srpB200SetSyncMode(H.SRP_B200_SYNC_EXPLICIT)
+    for _ in range(W):
+        prep.draw_all()
+    lib.dll.srpB200Finish()
+    lib.dll.srpB200ResetStats()
+    lib.dll.srpB200SetProfiling(1)
+    lib.stage_times()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    with torch.cuda.stream(stream):
+        for k in range(K):
+            flush.fill_(k & 0xFF)                 # L2 flush, outside the timed interval
+            starts[k].record(stream)
+            prep.draw_all()
+            ends[k].record(stream)
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    stages = lib.stage_times()
+    lib.dll.srpB200SetProfiling(0)
+    stats = lib.stats()
+    frags_per_frame = stats["fragsEmitted"] / max(1, stats["draws"])
+    shaded_per_frame = stats["fragsShaded"] / max(1, stats["draws"])
+    launches = stats["kernelLaunches"]
+
+    # ---- end to end: host buffers in, host-visible framebuffer out, default policy, wall clock
+    lib.dll.srpB200SetSyncMode(H.SRP_B200_SYNC_DRAW)
+    def e2e_step():
+        lib.dll.srpVertexBufferCopyData(vb, draw.stride, vpin.numel(), vpin.data_ptr())
+        lib.dll.srpIndexBufferCopyData(ib, H.SRP_UINT32, ipin.numel(), ipin.data_ptr())
+        prep.draw_all()                           # returns with colour + depth mirrored on the host
+    for _ in range(W):
+        e2e_step()
+    lib.dll.srpB200ResetStats()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    st2 = lib.stats()
+    checksum = int(np.ctypeslib.as_array(prep.fb.ptr.contents.color, shape=(scene.width * scene.height,))[::4099].sum())
+
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(t[0]), float(t[1]) / 1e3
+
+    if rank == 0:
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+        value = world * K / (dev_ms / 1e3)
+        n = max(1, stages["draws"])
+        per = {k: stages[k] / n for k in ("geometry_ms", "binning_ms", "tiles_ms")}
+        # dominant kernel and its algorithmic bytes per launch (DESIGN.md "Kernels"):
+        #   geometry: indices + referenced vertices in; tiles: one write of the three planes
+        dom = max(per, key=per.get)
+        dom_bytes = {"geometry_ms": alg["indices"] + alg["vertices"] + alg["uniform"], "binning_ms": 0,
+                     "tiles_ms": alg["framebuffer"] + alg["texture"]}[dom]
+        achieved = dom_bytes / (per[dom] / 1e3) / 1e9 if per[dom] > 0 else 0.0
+        frame_gbs = alg["total"] * (value / world) / 1e9
+        line = {
+            "metric": f"frames_per_s_{args.workload}", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config,
+            "gfrag_per_s": world * frags_per_frame * K / (dev_ms / 1e3) / 1e9,
+            "fragments_per_frame": frags_per_frame, "shaded_fragments_per_frame": shaded_per_frame,
+            "input_triangles_per_s": world * (count // 3) * K / (dev_ms / 1e3),
+            "stage_ms_per_frame": per,
+            "roofline": {"bound": "hbm", "kernel": {"geometry_ms": "srpdGeomKernel", "binning_ms": "srpdBin*Kernel", "tiles_ms": "srpdTileKernel"}[dom],
+                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                         "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_src,
+                         "frame": {"algorithmic_bytes": alg, "achieved": frame_gbs, "frac": frame_gbs / hbm}},
+            "e2e": {"value": world * K / e2e_s, "unit": "frames/s",
+                    "h2d_bytes_per_step": st2["h2dBytes"] // K, "d2h_bytes_per_step": st2["d2hBytes"] // K,
+                    "ms_per_step": 1e3 * e2e_s / K, "result_checksum": checksum},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "version": lib.dll.srpB200Version().decode(),
+        }
+        if world == 1:
+            cores = host_cores()
+            workers = min(cores, 64)
+            per_frame_guess = 0.6 if args.workload == "cfg3" else 0.03
+            fpw = max(1, int(args.cpu_seconds / per_frame_guess))
+            r = run_reference(args.workload, fpw, workers)
+            if r is not None:
+                line["cpu_baseline"] = {"value": r["frames"] / r["seconds"], "unit": "frames/s", "cores": workers, "kind": "reference",
+                                        "single_core_value": (r["frames"] / workers) / r["seconds"],
+                                        "sample": f"{r['frames']} frames of the same workload ({fpw} per process, {workers} single-threaded processes), "
+                                                  "unmodified reference built by oracle/Makefile"}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference",
+                                        "sample": "oracle/_ref not present on this box"}
+        print(json.dumps(line))
+    prep.free()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -89,6 +89,13 @@ typedef struct SRPB200Stats
 void srpB200GetStats(SRPB200Stats* out);   /* synchronises */
 void srpB200ResetStats(void);
 
+/* Per-stage device time.  While enabled every draw records four CUDA events on the
+ * submission stream (before geometry, after geometry, after binning, after the tiles);
+ * collecting synchronises, returns the number of draws measured and the summed
+ * milliseconds of {geometry, binning, tiles} since the previous collection. */
+void srpB200SetProfiling(int enable);
+unsigned long long srpB200CollectStageTimes(double outMs[3]);
+
 /* device / build identification, e.g. "srp-b200 sm_100a tile 32x16" */
 const char* srpB200Version(void);
 /* select the CUDA device for the calling process (before any other call); default:

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 #include "kernels.cuh"
 #include "srpcu.h"
 
@@ -37,6 +38,13 @@ struct Runtime
 	unsigned long long launches = 0, h2d = 0, d2h = 0;
 	int forceBinning = -1;                 /* SRP_B200_BINNING=0/1 overrides the heuristic */
 	uint32_t binThreshold = 4096;
+	/* optional per-stage timing: 4 events per draw (start, after geometry, after binning,
+	 * after tiles) on the submission stream, summed when collected */
+	bool profile = false;
+	std::vector<cudaEvent_t> freeEvents;
+	std::vector<cudaEvent_t> pendingEvents;   /* groups of 4 */
+	double stageMs[3] = { 0, 0, 0 };
+	unsigned long long stageDraws = 0;
 };
 
 Runtime g;
@@ -74,6 +82,21 @@ bool grow(Pool& p, size_t bytes)
 		return fail("cudaMalloc(scratch pool)", e);
 	p.bytes = want;
 	return true;
+}
+
+cudaEvent_t takeEvent()
+{
+	cudaEvent_t e = nullptr;
+	if (!g.freeEvents.empty()) { e = g.freeEvents.back(); g.freeEvents.pop_back(); }
+	else cudaEventCreate(&e);
+	return e;
+}
+void mark()
+{
+	if (!g.profile) return;
+	cudaEvent_t e = takeEvent();
+	cudaEventRecord(e, g.stream);
+	g.pendingEvents.push_back(e);
 }
 
 int envInt(const char* name, int fallback)
@@ -290,6 +313,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	if (!grow(g.frameCounts, sizeof(uint32_t) * 2 * nFrames)) return 1;
 	CU(cudaMemsetAsync(g.scan.ptr, 0, scanBytes, g.stream));
 
+	mark();
 	SrpdGeomArgs ga;
 	memset(&ga, 0, sizeof ga);
 	ga.d = d;
@@ -308,6 +332,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	srpdLaunchGeom(ga, g.stream);
 	g.launches++;
 	CU(cudaGetLastError());
+	mark();
 
 	const uint32_t tilesX = (st.width + SRPD_TILE_W - 1) / SRPD_TILE_W;
 	const uint32_t tilesY = (st.height + SRPD_TILE_H - 1) / SRPD_TILE_H;
@@ -366,9 +391,11 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		ta.listIds = ba.listIds;
 	}
 
+	mark();
 	srpdLaunchTiles(ta, g.stream);
 	g.launches++;
 	CU(cudaGetLastError());
+	mark();
 	return 0;
 }
 
@@ -406,6 +433,35 @@ int srpcuTakeOverflow(void)
 	const int fresh = now > seen;
 	seen = now;
 	return fresh;
+}
+
+/* per-stage device time: enable, run draws, collect {geometry, binning, tiles} in ms */
+void srpcuSetProfiling(int on)
+{
+	g.profile = on != 0;
+}
+unsigned long long srpcuCollectStageTimes(double outMs[3])
+{
+	if (g.ready)
+	{
+		cudaStreamSynchronize(g.stream);
+		for (size_t i = 0; i + 3 < g.pendingEvents.size(); i += 4)
+		{
+			for (int k = 0; k < 3; k++)
+			{
+				float ms = 0.f;
+				if (cudaEventElapsedTime(&ms, g.pendingEvents[i + k], g.pendingEvents[i + k + 1]) == cudaSuccess)
+					g.stageMs[k] += ms;
+			}
+			g.stageDraws++;
+		}
+		for (cudaEvent_t e : g.pendingEvents) g.freeEvents.push_back(e);
+		g.pendingEvents.clear();
+	}
+	for (int k = 0; k < 3; k++) { outMs[k] = g.stageMs[k]; g.stageMs[k] = 0; }
+	const unsigned long long n = g.stageDraws;
+	g.stageDraws = 0;
+	return n;
 }
 
 void srpcuResetStats(void)

@@ -46,6 +46,9 @@ int srpcuDraw(const SrpdDraw* d, const SrpdFrame* frames,
 int srpcuTakeOverflow(void);
 void srpcuSetWorstCasePools(int on);
 
+void srpcuSetProfiling(int on);
+unsigned long long srpcuCollectStageTimes(double outMs[3]);
+
 void srpcuGetStats(SrpdStats* out, unsigned long long* launches, unsigned long long* h2d, unsigned long long* d2h);
 void srpcuResetStats(void);
 

@@ -40,6 +40,8 @@ void srpB200GetStats(SRPB200Stats* out)
 	out->overflow = s.overflow;
 }
 void srpB200ResetStats(void) { gDraws = 0; srpcuResetStats(); }
+void srpB200SetProfiling(int enable) { srpcuSetProfiling(enable); }
+unsigned long long srpB200CollectStageTimes(double outMs[3]) { return srpcuCollectStageTimes(outMs); }
 
 /* ---- validation, reference draw.c:167-189 and primitive_assembly.c:180-196 ---- */
 static bool checkOOB(const SRPIndexBuffer* ib, const SRPVertexBuffer* vb, size_t startIndex, size_t count)

@@ -220,6 +220,8 @@ class SrpLibrary:
             "srpB200SetRowRange": (None, [sz, sz]),
             "srpB200TileWidth": (sz, []), "srpB200TileHeight": (sz, []),
             "srpB200GetStats": (None, [C.POINTER(SRPB200Stats)]), "srpB200ResetStats": (None, []),
+            "srpB200SetProfiling": (None, [i32]),
+            "srpB200CollectStageTimes": (C.c_ulonglong, [C.POINTER(C.c_double)]),
             "srpB200Version": (C.c_char_p, []), "srpB200SetDevice": (None, [i32]),
             "srpB200Stream": (vp, []),
         }
@@ -294,6 +296,11 @@ class SrpLibrary:
         return getattr(self.dll, fn)(*[float(a) for a in args]).numpy()
 
     # -- product-only ---------------------------------------------------------------------
+    def stage_times(self) -> dict:
+        ms = (C.c_double * 3)()
+        n = int(self.dll.srpB200CollectStageTimes(ms))
+        return {"draws": n, "geometry_ms": ms[0], "binning_ms": ms[1], "tiles_ms": ms[2]}
+
     def stats(self) -> dict:
         s = SRPB200Stats()
         self.dll.srpB200GetStats(C.byref(s))

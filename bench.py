@@ -164,7 +164,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample (0: skip, e.g. under ncu)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -328,7 +328,7 @@ def main():
             "clocks": clocks,
             "version": lib.dll.srpB200Version().decode(),
         }
-        if world == 1:
+        if world == 1 and args.cpu_seconds > 0:
             cores = host_cores()
             workers = min(cores, 64)
             per_frame_guess = 0.6 if args.workload == "cfg3" else 0.03

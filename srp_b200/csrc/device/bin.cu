@@ -12,11 +12,11 @@
  *   scan  : per supertile an exclusive scan over the chunks, then an exclusive scan over
  *           the supertiles' totals                -> superOffsets[s] + chunkCounts[c][s] is
  *                                                    the write cursor of (chunk c, supertile s)
- *   fill  : one warp per chunk walks its records 32 at a time; a record's slot in a
- *           supertile list is cursor + (number of EARLIER lanes whose box also covers that
- *           supertile) -- a warp-scan compaction, evaluated through ballot/match for the
- *           common one-supertile case -- so every list comes out sorted by record index
- *           without atomics or a sort.
+ *   fill  : one CTA per chunk, each warp walks its share of the records 32 at a time; a
+ *           record's slot in a supertile list is cursor + (number of EARLIER lanes whose box
+ *           also covers that supertile) -- a warp-scan compaction, evaluated through
+ *           ballot/match for the common one-supertile case -- so every list comes out sorted
+ *           by record index without global atomics or a sort.
  * A tile then filters its supertile's list against its own rectangle in shared memory
  * (raster.cu). */
 #include "kernels.cuh"
@@ -131,69 +131,109 @@ srpdBinScanKernel(const __grid_constant__ SrpdBinArgs a)
 	}
 }
 
-__global__ void __launch_bounds__(32)
+/* Fill: one CTA per chunk, FILL_WARPS warps; warp w owns the chunk's records
+ * [w*SPAN, (w+1)*SPAN) with SPAN = SRPD_BIN_CHUNK / FILL_WARPS.
+ *   1. every lane loads its SPAN/32 bounding boxes up front (the loads overlap) and the warp
+ *      counts its records per supertile                     -> sCnt[w][s]
+ *   2. exclusive scan over the warps for every supertile, seeded with the chunk's global
+ *      cursor                                               -> sCnt[w][s] = first slot of warp w
+ *   3. every warp walks its records 32 at a time in record order; a record's slot is the
+ *      warp cursor + the number of EARLIER lanes of the step that cover the same supertile
+ *      (ballot/match warp-scan), then the cursors advance.
+ * Lists therefore come out sorted by record index with no atomics on global memory. */
+template <int FILL_WARPS>
+__global__ void __launch_bounds__(FILL_WARPS * 32, 1)
 srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 {
-	extern __shared__ uint32_t sCursor[];          /* [nSuper] write cursors of this chunk, then [32] lane rects */
+	constexpr int SPAN = SRPD_BIN_CHUNK / FILL_WARPS;     /* records per warp      */
+	constexpr int ROUNDS = SPAN / 32;                     /* steps of 32 per warp  */
+	extern __shared__ uint32_t sFill[];                   /* [FILL_WARPS][nSuper] cursors, then [FILL_WARPS][32] rects */
 	const uint32_t nSuper = a.superX * a.superY;
-	uint32_t* sRect = sCursor + nSuper;
 	const uint32_t nStored = a.frameCounts[1];
 	const uint32_t first = blockIdx.x * SRPD_BIN_CHUNK;
 	if (first >= nStored)
 		return;
-	const int lane = threadIdx.x;
-	for (uint32_t s = lane; s < nSuper; s += 32)
-		sCursor[s] = a.superOffsets[s] + a.chunkCounts[(size_t) blockIdx.x * nSuper + s];
-	__syncwarp();
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	uint32_t* sCnt = sFill + (size_t) warp * nSuper;
+	uint32_t* sRect = sFill + (size_t) FILL_WARPS * nSuper + warp * 32;
 
-	for (uint32_t o = 0; o < SRPD_BIN_CHUNK; o += 32)
+	for (uint32_t i = tid; i < FILL_WARPS * nSuper; i += FILL_WARPS * 32)
+		sFill[i] = 0;
+	uint32_t rect[ROUNDS];
+	const uint32_t warpFirst = first + warp * SPAN;
+	#pragma unroll
+	for (int r = 0; r < ROUNDS; r++)
 	{
-		const uint32_t r = first + o + lane;
-		if (first + o >= nStored)
-			break;
-		uint32_t rect = 0x00000101u;
-		if (r < nStored)
-			rect = superRect(a.bboxes[r], a.superX, a.superY);
-		const bool empty = rectEmpty(rect);
-		const uint32_t anyMulti = __ballot_sync(0xFFFFFFFFu, !empty && !rectSingle(rect));
+		const uint32_t rec = warpFirst + r * 32 + lane;
+		rect[r] = rec < nStored ? superRect(a.bboxes[rec], a.superX, a.superY) : 0x00000101u;
+	}
+	__syncthreads();
+	#pragma unroll
+	for (int r = 0; r < ROUNDS; r++)
+		if (!rectEmpty(rect[r]))
+			for (uint32_t sy = (rect[r] >> 8) & 0xFFu; sy <= (rect[r] >> 24); sy++)
+				for (uint32_t sx = rect[r] & 0xFFu; sx <= ((rect[r] >> 16) & 0xFFu); sx++)
+					atomicAdd(&sCnt[sy * a.superX + sx], 1u);
+	__syncthreads();
+	for (uint32_t s = tid; s < nSuper; s += FILL_WARPS * 32)
+	{
+		uint32_t run = a.superOffsets[s] + a.chunkCounts[(size_t) blockIdx.x * nSuper + s];
+		for (int w = 0; w < FILL_WARPS; w++)
+		{
+			const uint32_t c = sFill[(size_t) w * nSuper + s];
+			sFill[(size_t) w * nSuper + s] = run;
+			run += c;
+		}
+	}
+	__syncthreads();
+
+	#pragma unroll
+	for (int r = 0; r < ROUNDS; r++)
+	{
+		const uint32_t rec = warpFirst + r * 32 + lane;
+		const uint32_t rc = rect[r];
+		const bool empty = rectEmpty(rc);
+		const uint32_t anyLive = __ballot_sync(0xFFFFFFFFu, !empty);
+		if (anyLive == 0)
+			continue;
+		const uint32_t anyMulti = __ballot_sync(0xFFFFFFFFu, !empty && !rectSingle(rc));
 		if (anyMulti == 0)
 		{
 			/* every record of this step covers exactly one supertile: rank among the lanes
 			 * that picked the same supertile = position in that supertile's list */
-			const uint32_t s = empty ? 0xFFFFFFFFu : ((rect >> 8) & 0xFFu) * a.superX + (rect & 0xFFu);
+			const uint32_t s = empty ? 0xFFFFFFFFu : ((rc >> 8) & 0xFFu) * a.superX + (rc & 0xFFu);
 			const uint32_t peers = __match_any_sync(0xFFFFFFFFu, s);
 			if (!empty)
 			{
-				const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-				const uint32_t pos = sCursor[s] + rank;
+				const uint32_t pos = sCnt[s] + __popc(peers & ((1u << lane) - 1u));
 				if (pos < a.listCapacity)
-					a.listIds[pos] = r;
+					a.listIds[pos] = rec;
 			}
 			__syncwarp();
 			if (!empty && (peers >> lane) == 1u)     /* highest lane of the group advances the cursor */
-				sCursor[s] += __popc(peers);
+				sCnt[s] += __popc(peers);
 			__syncwarp();
 		}
 		else
 		{
 			/* general step: a record may cover a rectangle of supertiles */
-			sRect[lane] = rect;
+			sRect[lane] = rc;
 			__syncwarp();
 			if (!empty)
-				for (uint32_t sy = (rect >> 8) & 0xFFu; sy <= (rect >> 24); sy++)
-					for (uint32_t sx = rect & 0xFFu; sx <= ((rect >> 16) & 0xFFu); sx++)
+				for (uint32_t sy = (rc >> 8) & 0xFFu; sy <= (rc >> 24); sy++)
+					for (uint32_t sx = rc & 0xFFu; sx <= ((rc >> 16) & 0xFFu); sx++)
 					{
 						uint32_t rank = 0;
 						for (int l = 0; l < lane; l++)
 							rank += rectContains(sRect[l], sx, sy);
-						const uint32_t pos = sCursor[sy * a.superX + sx] + rank;
+						const uint32_t pos = sCnt[sy * a.superX + sx] + rank;
 						if (pos < a.listCapacity)
-							a.listIds[pos] = r;
+							a.listIds[pos] = rec;
 					}
 			__syncwarp();
 			if (!empty)
-				for (uint32_t sy = (rect >> 8) & 0xFFu; sy <= (rect >> 24); sy++)
-					for (uint32_t sx = rect & 0xFFu; sx <= ((rect >> 16) & 0xFFu); sx++)
+				for (uint32_t sy = (rc >> 8) & 0xFFu; sy <= (rc >> 24); sy++)
+					for (uint32_t sx = rc & 0xFFu; sx <= ((rc >> 16) & 0xFFu); sx++)
 					{
 						uint32_t before = 0;
 						bool last = true;
@@ -204,7 +244,7 @@ srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 							if (l > lane && c) last = false;
 						}
 						if (last)
-							sCursor[sy * a.superX + sx] += before + 1;
+							sCnt[sy * a.superX + sx] += before + 1;
 					}
 			__syncwarp();
 		}
@@ -219,6 +259,21 @@ void srpdLaunchBin(const SrpdBinArgs& a, cudaStream_t stream)
 	const uint32_t nSuper = a.superX * a.superY;
 	srpdBinCountKernel<<<a.nChunksMax, SRPD_BIN_THREADS, nSuper * sizeof(uint32_t), stream>>>(a);
 	srpdBinScanKernel<<<1, 1024, 0, stream>>>(a);
-	srpdBinFillKernel<<<a.nChunksMax, 32, (nSuper + 32) * sizeof(uint32_t), stream>>>(a);
+	/* as many warps per chunk as the cursor matrix allows in shared memory */
+	const size_t budget = 160 * 1024;
+	if ((8 * (size_t) nSuper + 8 * 32) * sizeof(uint32_t) <= budget)
+	{
+		const size_t bytes = (8 * (size_t) nSuper + 8 * 32) * sizeof(uint32_t);
+		static bool configured8 = false;
+		if (!configured8) { cudaFuncSetAttribute(srpdBinFillKernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget); configured8 = true; }
+		srpdBinFillKernel<8><<<a.nChunksMax, 8 * 32, bytes, stream>>>(a);
+	}
+	else
+	{
+		const size_t bytes = (2 * (size_t) nSuper + 2 * 32) * sizeof(uint32_t);
+		static bool configured2 = false;
+		if (!configured2) { cudaFuncSetAttribute(srpdBinFillKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget); configured2 = true; }
+		srpdBinFillKernel<2><<<a.nChunksMax, 2 * 32, bytes, stream>>>(a);
+	}
 	gBinLaunches += 3;
 }

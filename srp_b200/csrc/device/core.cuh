@@ -52,8 +52,10 @@ SRP_HD uint32_t srpdRecordStride(const SrpdState& st, int nVerts)
 }
 SRP_HD int srpdVertsOfKind(uint32_t kind) { return kind == SRPD_KIND_TRIANGLE ? 3 : (kind == SRPD_KIND_LINE ? 2 : 1); }
 
-/* |x| <= 1e-9 evaluated in double, reference ROUGHLY_ZERO (src/math/utils.h:40-42) */
-SRP_HD bool srpdRoughlyZero(float x) { return fabs((double) x) <= SRPD_EPS; }
+/* reference ROUGHLY_ZERO (src/math/utils.h:40-42): fabs((double) x) <= 1e-9.  For a float
+ * argument that is the same predicate as |x| <= F with F the largest float not above 1e-9,
+ * F = 0x3089705F = 9.999999717180685e-10 (the next float, 1.0000000605e-09, is above). */
+SRP_HD bool srpdRoughlyZero(float x) { return fabsf(x) <= srpdU2F(0x3089705Fu); }
 
 /* ---------------------------------------------------------------------------------
  * applyPerspectiveDivide, reference src/pipeline/vertex_processing.c:76-88.
@@ -469,9 +471,9 @@ SRP_HD uint8_t srpdStencilWrite(uint8_t current, uint8_t val, uint8_t writeMask)
 SRP_HD uint32_t srpdPackChannel(float c)
 {
 	float v = SRP_FMUL(c, 255.0f);
-	if (v < 0) return 0u;
-	if (v > 255) return 255u;
-	return (uint32_t) (uint8_t) (int) v;   /* NaN is UB in the reference (unpinned); gives 0 here */
+	/* v < 0 -> 0, v > 255 -> 255, else truncate; NaN is UB in the reference (unpinned): 0 here */
+	const uint32_t t = (uint32_t) (int) v & 0xFFu;
+	return (v < 0) ? 0u : ((v > 255) ? 255u : t);
 }
 SRP_HD uint32_t srpdColorPack(const float c[4])
 {

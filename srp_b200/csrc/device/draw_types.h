@@ -53,6 +53,10 @@ typedef struct SrpdState
 	int32_t varyingsSize;            /* what the program declared                        */
 	int32_t slotSize;                /* bytes reserved per blob: max(declared, sum of attributes), rounded up to 8 */
 	int32_t programId;               /* device program table index                       */
+	/* fast path: every attribute is SRP_FLOAT and 4-byte aligned (the usual case): the blob
+	 * is nFloats consecutive floats, floatModes holds 2 bits of SRPInterpolationMode each */
+	uint32_t floatModes;
+	uint8_t  allFloat, nFloats, pad2, pad3;
 	SrpdVarying varyings[SRPD_MAX_VARYINGS];
 } SrpdState;
 

@@ -497,40 +497,59 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 		if (w < warp) { baseE += sWarpSum[0][w]; baseS += sWarpSum[1][w]; }
 		totE += sWarpSum[0][w]; totS += sWarpSum[1][w];
 	}
-	if (tid == 0)
+	if (warp == 0)
 	{
+		/* Decoupled look-back by one warp: lane l inspects predecessor (batch - 1 - l); the
+		 * window slides back 32 batches at a time until a batch that already knows its
+		 * inclusive prefix is found.  Batch 0 of every frame publishes a prefix at once, so
+		 * the walk never leaves the frame. */
 		const unsigned long long agg = ((unsigned long long) totE << 31) | (unsigned long long) totS;
 		volatile unsigned long long* state = a.scanState;
+		const uint32_t frameFirst = frame * a.batchesPerFrame;
 		unsigned long long prefix = 0;
-		if (b == 0)
-			state[batch] = SRPD_SCAN_PREFIX | agg;
-		else
+		if (lane == 0)
+			state[batch] = (b == 0 ? SRPD_SCAN_PREFIX : SRPD_SCAN_AGG) | agg;
+		if (b != 0)
 		{
-			state[batch] = SRPD_SCAN_AGG | agg;
-			uint32_t j = batch - 1;
+			long long window = (long long) batch - 1;
 			for (;;)
 			{
-				const unsigned long long s = state[j];
-				const unsigned long long flag = s >> 62;
-				if (flag == 0)
-					continue;                          /* predecessor has not published yet */
-				prefix += s & SRPD_SCAN_VALUE_MASK;
-				if (flag == 2)
+				const long long j = window - lane;
+				unsigned long long sv = SRPD_SCAN_PREFIX;            /* before the frame: prefix 0 */
+				if (j >= (long long) frameFirst)
+					sv = state[j];
+				const unsigned flag = (unsigned) (sv >> 62);
+				const uint32_t notReady = __ballot_sync(0xFFFFFFFFu, flag == 0);
+				const uint32_t isPrefix = __ballot_sync(0xFFFFFFFFu, flag == 2);
+				const int p = isPrefix ? __ffs(isPrefix) - 1 : 32;    /* nearest lane that holds a prefix */
+				const uint32_t need = p >= 31 ? 0xFFFFFFFFu : ((1u << (p + 1)) - 1u);
+				if (notReady & need)
+					continue;                                          /* a needed predecessor has not published yet */
+				unsigned long long v = (lane <= p) ? (sv & SRPD_SCAN_VALUE_MASK) : 0ull;
+				#pragma unroll
+				for (int o = 16; o > 0; o >>= 1)
+					v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+				prefix += v;
+				if (p < 32)
 					break;
-				j--;                                   /* the frame's batch 0 always publishes a prefix */
+				window -= 32;
 			}
-			state[batch] = SRPD_SCAN_PREFIX | (prefix + agg);
+			if (lane == 0)
+				state[batch] = SRPD_SCAN_PREFIX | (prefix + agg);
 		}
-		sPrefix[0] = (uint32_t) (prefix >> 31);
-		sPrefix[1] = (uint32_t) (prefix & 0x7FFFFFFFull);
-		if (b == a.batchesPerFrame - 1)
+		if (lane == 0)
 		{
-			const uint32_t e = sPrefix[0] + totE, s = sPrefix[1] + totS;
-			a.frameCounts[2 * frame + 0] = e;
-			a.frameCounts[2 * frame + 1] = s < a.recCapacity ? s : a.recCapacity;
-			atomicAdd(&a.stats->primsIn, (unsigned long long) d.nInputPrims);
-			atomicAdd(&a.stats->primsEmitted, (unsigned long long) e);
-			atomicAdd(&a.stats->primsStored, (unsigned long long) s);
+			sPrefix[0] = (uint32_t) (prefix >> 31);
+			sPrefix[1] = (uint32_t) (prefix & 0x7FFFFFFFull);
+			if (b == a.batchesPerFrame - 1)
+			{
+				const uint32_t e = sPrefix[0] + totE, st2 = sPrefix[1] + totS;
+				a.frameCounts[2 * frame + 0] = e;
+				a.frameCounts[2 * frame + 1] = st2 < a.recCapacity ? st2 : a.recCapacity;
+				atomicAdd(&a.stats->primsIn, (unsigned long long) d.nInputPrims);
+				atomicAdd(&a.stats->primsEmitted, (unsigned long long) e);
+				atomicAdd(&a.stats->primsStored, (unsigned long long) st2);
+			}
 		}
 	}
 	__syncthreads();

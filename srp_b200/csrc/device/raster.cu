@@ -80,8 +80,34 @@ __device__ __forceinline__ void emitFragment(
 	alignas(8) unsigned char interpolated[SRPD_MAX_VARYING_BYTES];
 	if (NV == 1)
 	{
-		for (int k = 0; k < st.slotSize; k++)
-			interpolated[k] = blobs[k];
+		for (int k = 0; k < st.slotSize / 4; k++)
+			((uint32_t*) interpolated)[k] = __ldg((const uint32_t*) blobs + k);
+	}
+	else if (st.allFloat)
+	{
+		/* all attributes are floats: the blob is an array of st.nFloats floats, two bits of
+		 * interpolation mode each; same operation order as srpdInterpolate (interpolation.c:63-83) */
+		const int slotWords = st.slotSize / 4;
+		const float* b = (const float*) blobs;
+		const int prov = st.provokingFirst ? 0 : NV - 1;
+		uint32_t modes = st.floatModes;
+		for (int e = 0; e < st.nFloats; e++, modes >>= 2)
+		{
+			const uint32_t m = modes & 3u;
+			float v;
+			if (m == SRP_INTERPOLATION_MODE_FLAT)
+				v = __ldg(b + prov * slotWords + e);
+			else
+			{
+				v = 0.f;
+				#pragma unroll
+				for (int i = 0; i < NV; i++)
+					v = __fadd_rn(v, __fmul_rn(__ldg(b + i * slotWords + e), wgt[i]));
+				if (m == SRP_INTERPOLATION_MODE_PERSPECTIVE)
+					v = __fmul_rn(v, rec);
+			}
+			((float*) interpolated)[e] = v;
+		}
 	}
 	else
 	{
@@ -147,13 +173,30 @@ __device__ __forceinline__ void visitTriangle(
 	{
 		const float dy0 = __uint_as_float(q2.x), dy1 = __uint_as_float(q2.y), dy2 = __uint_as_float(q2.z);
 		const int ny = y - minY;
-		for (int i = 0; i < ny; i++)
+		int i = 0;
+		for (; i + 4 <= ny; i += 4)
+		{
+			#pragma unroll
+			for (int u = 0; u < 4; u++)
+			{
+				l0 = __fadd_rn(l0, dy0); l1 = __fadd_rn(l1, dy1); l2 = __fadd_rn(l2, dy2);
+			}
+		}
+		for (; i < ny; i++)
 		{
 			l0 = __fadd_rn(l0, dy0); l1 = __fadd_rn(l1, dy1); l2 = __fadd_rn(l2, dy2);
 		}
 		const float dx0 = __uint_as_float(q1.x), dx1 = __uint_as_float(q1.y), dx2 = __uint_as_float(q1.z);
 		const int nx = x - minX;
-		for (int i = 0; i < nx; i++)
+		for (i = 0; i + 4 <= nx; i += 4)
+		{
+			#pragma unroll
+			for (int u = 0; u < 4; u++)
+			{
+				l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
+			}
+		}
+		for (; i < nx; i++)
 		{
 			l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
 		}

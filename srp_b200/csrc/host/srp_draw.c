@@ -139,6 +139,23 @@ static bool snapshotVaryings(SrpdState* st, const SRPVertexShader* vs)
 	st->nVaryings = (int32_t) vs->nVaryings;
 	st->varyingsSize = (int32_t) vs->varyingsSize;
 	st->slotSize = (int32_t) slot;
+
+	/* all-float layouts (<= 16 floats) take the word-wise interpolation path of the tile kernel */
+	st->allFloat = 1;
+	st->floatModes = 0;
+	size_t nFloats = 0;
+	for (size_t i = 0; i < vs->nVaryings && st->allFloat; i++)
+	{
+		if (st->varyings[i].type != SRP_FLOAT || st->varyings[i].mode > SRP_INTERPOLATION_MODE_FLAT)
+			st->allFloat = 0;
+		else
+			for (unsigned e = 0; e < st->varyings[i].nItems; e++, nFloats++)
+				if (nFloats < 16)
+					st->floatModes |= (uint32_t) st->varyings[i].mode << (2 * nFloats);
+	}
+	if (nFloats > 16 || nFloats * 4 > slot)
+		st->allFloat = 0;
+	st->nFloats = (uint8_t) (st->allFloat ? nFloats : 0);
 	return true;
 }
 

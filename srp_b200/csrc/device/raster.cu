@@ -157,10 +157,67 @@ __device__ __forceinline__ void emitFragment(
 	}
 }
 
-/* rasterizeTriangle for one pixel, reference triangle.c:73-111 */
+/* Barycentric chain, part 1 (one LANE per TRIANGLE): the reference reaches pixel (x, y) of a
+ * triangle by (y - minY) float additions of dlambda/dy from the value at the bounding-box
+ * corner, then (x - minX) additions of dlambda/dx (triangle.c:102-109).  All 32 pixels of a
+ * warp's 8x4 block share most of that chain, so before a warp visits the up-to-32 triangles
+ * of a list step, lane k walks triangle k's chain once: down to each of the block's four
+ * rows, then right to the block's first column (clamped to the bounding box).  The twelve
+ * row-start values go to shared memory; a pixel then only adds its <= 7 remaining x steps.
+ * The sequence of additions each pixel's value goes through is unchanged => bit-exact. */
+__device__ __forceinline__ void prepareTriangle(const unsigned char* rec, int bx0, int by0, float* out)
+{
+	const uint4* h = (const uint4*) rec;
+	const uint4 q0 = __ldg(h + 0), q1 = __ldg(h + 1), q2 = __ldg(h + 2);
+	const int minX = (int) (q0.w & 0xFFFFu), minY = (int) (q1.w & 0xFFFFu);
+	float l0 = __uint_as_float(q0.x), l1 = __uint_as_float(q0.y), l2 = __uint_as_float(q0.z);
+	const float dy0 = __uint_as_float(q2.x), dy1 = __uint_as_float(q2.y), dy2 = __uint_as_float(q2.z);
+	const float dx0 = __uint_as_float(q1.x), dx1 = __uint_as_float(q1.y), dx2 = __uint_as_float(q1.z);
+	const int sy = by0 - minY;                 /* chain steps down to the block's first row (may be < 0) */
+	const int n0 = sy > 0 ? sy : 0;
+	int i = 0;
+	for (; i + 4 <= n0; i += 4)
+	{
+		#pragma unroll
+		for (int u = 0; u < 4; u++)
+		{
+			l0 = __fadd_rn(l0, dy0); l1 = __fadd_rn(l1, dy1); l2 = __fadd_rn(l2, dy2);
+		}
+	}
+	for (; i < n0; i++)
+	{
+		l0 = __fadd_rn(l0, dy0); l1 = __fadd_rn(l1, dy1); l2 = __fadd_rn(l2, dy2);
+	}
+	float r[SRPD_BLK_H][3];
+	#pragma unroll
+	for (int k = 0; k < SRPD_BLK_H; k++)
+	{
+		r[k][0] = l0; r[k][1] = l1; r[k][2] = l2;
+		if (sy + k >= 0)                       /* rows above the bounding box do not advance the chain */
+		{
+			l0 = __fadd_rn(l0, dy0); l1 = __fadd_rn(l1, dy1); l2 = __fadd_rn(l2, dy2);
+		}
+	}
+	const int nx = bx0 > minX ? bx0 - minX : 0;   /* steps right to the block's first column */
+	for (i = 0; i < nx; i++)
+	{
+		#pragma unroll
+		for (int k = 0; k < SRPD_BLK_H; k++)
+		{
+			r[k][0] = __fadd_rn(r[k][0], dx0); r[k][1] = __fadd_rn(r[k][1], dx1); r[k][2] = __fadd_rn(r[k][2], dx2);
+		}
+	}
+	float4* o = (float4*) out;
+	o[0] = make_float4(r[0][0], r[0][1], r[0][2], r[1][0]);
+	o[1] = make_float4(r[1][1], r[1][2], r[2][0], r[2][1]);
+	o[2] = make_float4(r[2][2], r[3][0], r[3][1], r[3][2]);
+}
+
+/* rasterizeTriangle for one pixel, reference triangle.c:73-111; `rowStart` = the prepared
+ * row-start barycentrics of this triangle for the warp's block (prepareTriangle) */
 __device__ __forceinline__ void visitTriangle(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, Pixel& px, FragCounters& cnt,
-	int x, int y, bool valid)
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, const float* rowStart,
+	Pixel& px, FragCounters& cnt, int x, int y, int bx0, int ly, bool valid)
 {
 	const uint4* h = (const uint4*) rec;
 	const uint4 q0 = __ldg(h + 0), q1 = __ldg(h + 1);
@@ -168,40 +225,17 @@ __device__ __forceinline__ void visitTriangle(
 	const int minY = (int) (q1.w & 0xFFFFu), maxY = (int) (q1.w >> 16);
 	if (!valid || x < minX || x >= maxX || y < minY || y >= maxY)
 		return;
-	const uint4 q2 = __ldg(h + 2);
-	float l0 = __uint_as_float(q0.x), l1 = __uint_as_float(q0.y), l2 = __uint_as_float(q0.z);
+	float l0 = rowStart[ly * 3 + 0], l1 = rowStart[ly * 3 + 1], l2 = rowStart[ly * 3 + 2];
 	{
-		const float dy0 = __uint_as_float(q2.x), dy1 = __uint_as_float(q2.y), dy2 = __uint_as_float(q2.z);
-		const int ny = y - minY;
-		int i = 0;
-		for (; i + 4 <= ny; i += 4)
-		{
-			#pragma unroll
-			for (int u = 0; u < 4; u++)
-			{
-				l0 = __fadd_rn(l0, dy0); l1 = __fadd_rn(l1, dy1); l2 = __fadd_rn(l2, dy2);
-			}
-		}
-		for (; i < ny; i++)
-		{
-			l0 = __fadd_rn(l0, dy0); l1 = __fadd_rn(l1, dy1); l2 = __fadd_rn(l2, dy2);
-		}
 		const float dx0 = __uint_as_float(q1.x), dx1 = __uint_as_float(q1.y), dx2 = __uint_as_float(q1.z);
-		const int nx = x - minX;
-		for (i = 0; i + 4 <= nx; i += 4)
-		{
-			#pragma unroll
-			for (int u = 0; u < 4; u++)
-			{
-				l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
-			}
-		}
-		for (; i < nx; i++)
+		const int nx = x - (bx0 > minX ? bx0 : minX);      /* 0..7 remaining steps */
+		for (int i = 0; i < nx; i++)
 		{
 			l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
 		}
 	}
 	/* top-left rule: lambda > 0 || (|lambda| <= 1e-9 && edgeTL), triangle.c:82-87 */
+	const uint4 q2 = __ldg(h + 2);
 	const uint32_t flags = q2.w;
 	const bool in0 = (l0 > 0.f) || (srpdRoughlyZero(l0) && (flags & 1u));
 	const bool in1 = (l1 > 0.f) || (srpdRoughlyZero(l1) && (flags & 2u));
@@ -321,6 +355,8 @@ srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 	__shared__ __align__(16) uint2 sBox[SRPD_TILE_THREADS];        /* reused as depth (+ stencil) staging */
 	__shared__ uint32_t sWarpCnt[SRPD_TILE_WARPS];
 	__shared__ uint32_t sDirty;
+	/* per warp: row-start barycentrics of the (up to) 32 triangles of the current list step */
+	__shared__ __align__(16) float sPrep[KIND == SRPD_KIND_TRIANGLE ? SRPD_TILE_WARPS * 32 * SRPD_BLK_H * 3 : 4];
 
 	const SrpdState& st = a.d.st;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -425,18 +461,27 @@ srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 				mine = x0 < bx0 + SRPD_BLK_W && x1 > bx0 && y0 < by0 + SRPD_BLK_H && y1 > by0;
 			}
 			uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
+			if (KIND == SRPD_KIND_TRIANGLE && m)
+			{
+				float* prep = sPrep + (size_t) warp * 32 * SRPD_BLK_H * 3;
+				if (mine)
+					prepareTriangle(records + (size_t) sIds[j] * a.recStride, bx0, by0, prep + lane * SRPD_BLK_H * 3);
+				__syncwarp();
+			}
 			while (m)
 			{
 				const int bit = __ffs(m) - 1;
 				m &= m - 1;
 				const unsigned char* rec = records + (size_t) sIds[j0 + bit] * a.recStride;
 				if (KIND == SRPD_KIND_TRIANGLE)
-					visitTriangle(a, fr, rec, px, cnt, x, y, valid);
+					visitTriangle(a, fr, rec, sPrep + ((size_t) warp * 32 + bit) * SRPD_BLK_H * 3, px, cnt,
+					              x, y, bx0, lane / SRPD_BLK_W, valid);
 				else if (KIND == SRPD_KIND_LINE)
 					visitLine(a, fr, rec, px, cnt, x, y, valid);
 				else
 					visitPoint(a, fr, rec, px, cnt, x, y, valid);
 			}
+			__syncwarp();      /* the next step overwrites this warp's prepared values */
 		}
 		__syncthreads();
 	}

@@ -35,15 +35,7 @@ __device__ __forceinline__ uint32_t superRect(uint2 bb, uint32_t superX, uint32_
 	if (sy1 >= superY) sy1 = superY - 1;
 	return sx0 | (sy0 << 8) | (sx1 << 16) | (sy1 << 24);
 }
-__device__ __forceinline__ bool rectContains(uint32_t r, uint32_t sx, uint32_t sy)
-{
-	return sx >= (r & 0xFFu) && sx <= ((r >> 16) & 0xFFu) && sy >= ((r >> 8) & 0xFFu) && sy <= (r >> 24);
-}
 __device__ __forceinline__ bool rectEmpty(uint32_t r) { return (r & 0xFFu) > ((r >> 16) & 0xFFu); }
-__device__ __forceinline__ bool rectSingle(uint32_t r)
-{
-	return (r & 0xFFu) == ((r >> 16) & 0xFFu) && ((r >> 8) & 0xFFu) == (r >> 24);
-}
 
 } // namespace
 
@@ -137,9 +129,10 @@ srpdBinScanKernel(const __grid_constant__ SrpdBinArgs a)
  *      counts its records per supertile                     -> sCnt[w][s]
  *   2. exclusive scan over the warps for every supertile, seeded with the chunk's global
  *      cursor                                               -> sCnt[w][s] = first slot of warp w
- *   3. every warp walks its records 32 at a time in record order; a record's slot is the
- *      warp cursor + the number of EARLIER lanes of the step that cover the same supertile
- *      (ballot/match warp-scan), then the cursors advance.
+ *   3. every warp walks its records 32 at a time in record order: the lanes of a step OR
+ *      their lane bit into a per-supertile mask, a record's slot is the warp cursor + the
+ *      population count of the mask below its own lane (a warp-scan compaction keyed by
+ *      supertile), then the last covering lane advances the cursor.
  * Lists therefore come out sorted by record index with no atomics on global memory. */
 template <int FILL_WARPS>
 __global__ void __launch_bounds__(FILL_WARPS * 32, 1)
@@ -147,7 +140,7 @@ srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 {
 	constexpr int SPAN = SRPD_BIN_CHUNK / FILL_WARPS;     /* records per warp      */
 	constexpr int ROUNDS = SPAN / 32;                     /* steps of 32 per warp  */
-	extern __shared__ uint32_t sFill[];                   /* [FILL_WARPS][nSuper] cursors, then [FILL_WARPS][32] rects */
+	extern __shared__ uint32_t sFill[];                   /* [FILL_WARPS][nSuper] cursors, then [FILL_WARPS][nSuper] lane masks */
 	const uint32_t nSuper = a.superX * a.superY;
 	const uint32_t nStored = a.frameCounts[1];
 	const uint32_t first = blockIdx.x * SRPD_BIN_CHUNK;
@@ -155,9 +148,9 @@ srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 		return;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	uint32_t* sCnt = sFill + (size_t) warp * nSuper;
-	uint32_t* sRect = sFill + (size_t) FILL_WARPS * nSuper + warp * 32;
+	uint32_t* sMask = sFill + (size_t) (FILL_WARPS + warp) * nSuper;
 
-	for (uint32_t i = tid; i < FILL_WARPS * nSuper; i += FILL_WARPS * 32)
+	for (uint32_t i = tid; i < 2 * FILL_WARPS * nSuper; i += FILL_WARPS * 32)
 		sFill[i] = 0;
 	uint32_t rect[ROUNDS];
 	const uint32_t warpFirst = first + warp * SPAN;
@@ -193,61 +186,40 @@ srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 		const uint32_t rec = warpFirst + r * 32 + lane;
 		const uint32_t rc = rect[r];
 		const bool empty = rectEmpty(rc);
-		const uint32_t anyLive = __ballot_sync(0xFFFFFFFFu, !empty);
-		if (anyLive == 0)
+		if (__ballot_sync(0xFFFFFFFFu, !empty) == 0)
 			continue;
-		const uint32_t anyMulti = __ballot_sync(0xFFFFFFFFu, !empty && !rectSingle(rc));
-		if (anyMulti == 0)
-		{
-			/* every record of this step covers exactly one supertile: rank among the lanes
-			 * that picked the same supertile = position in that supertile's list */
-			const uint32_t s = empty ? 0xFFFFFFFFu : ((rc >> 8) & 0xFFu) * a.superX + (rc & 0xFFu);
-			const uint32_t peers = __match_any_sync(0xFFFFFFFFu, s);
-			if (!empty)
-			{
-				const uint32_t pos = sCnt[s] + __popc(peers & ((1u << lane) - 1u));
-				if (pos < a.listCapacity)
-					a.listIds[pos] = rec;
-			}
-			__syncwarp();
-			if (!empty && (peers >> lane) == 1u)     /* highest lane of the group advances the cursor */
-				sCnt[s] += __popc(peers);
-			__syncwarp();
-		}
-		else
-		{
-			/* general step: a record may cover a rectangle of supertiles */
-			sRect[lane] = rc;
-			__syncwarp();
-			if (!empty)
-				for (uint32_t sy = (rc >> 8) & 0xFFu; sy <= (rc >> 24); sy++)
-					for (uint32_t sx = rc & 0xFFu; sx <= ((rc >> 16) & 0xFFu); sx++)
+		const uint32_t sx0 = rc & 0xFFu, sy0 = (rc >> 8) & 0xFFu, sx1 = (rc >> 16) & 0xFFu, sy1 = rc >> 24;
+		/* which lanes of this step cover supertile s: one bit per lane */
+		if (!empty)
+			for (uint32_t sy = sy0; sy <= sy1; sy++)
+				for (uint32_t sx = sx0; sx <= sx1; sx++)
+					atomicOr(&sMask[sy * a.superX + sx], 1u << lane);
+		__syncwarp();
+		/* slot = cursor + number of EARLIER lanes covering the same supertile */
+		if (!empty)
+			for (uint32_t sy = sy0; sy <= sy1; sy++)
+				for (uint32_t sx = sx0; sx <= sx1; sx++)
+				{
+					const uint32_t s = sy * a.superX + sx;
+					const uint32_t pos = sCnt[s] + __popc(sMask[s] & ((1u << lane) - 1u));
+					if (pos < a.listCapacity)
+						a.listIds[pos] = rec;
+				}
+		__syncwarp();
+		/* the last covering lane advances the cursor and clears the mask for the next step */
+		if (!empty)
+			for (uint32_t sy = sy0; sy <= sy1; sy++)
+				for (uint32_t sx = sx0; sx <= sx1; sx++)
+				{
+					const uint32_t s = sy * a.superX + sx;
+					const uint32_t m = sMask[s];
+					if ((m >> lane) == 1u)
 					{
-						uint32_t rank = 0;
-						for (int l = 0; l < lane; l++)
-							rank += rectContains(sRect[l], sx, sy);
-						const uint32_t pos = sCnt[sy * a.superX + sx] + rank;
-						if (pos < a.listCapacity)
-							a.listIds[pos] = rec;
+						sCnt[s] += __popc(m);
+						sMask[s] = 0;
 					}
-			__syncwarp();
-			if (!empty)
-				for (uint32_t sy = (rc >> 8) & 0xFFu; sy <= (rc >> 24); sy++)
-					for (uint32_t sx = rc & 0xFFu; sx <= ((rc >> 16) & 0xFFu); sx++)
-					{
-						uint32_t before = 0;
-						bool last = true;
-						for (int l = 0; l < 32; l++)
-						{
-							const bool c = rectContains(sRect[l], sx, sy);
-							if (l < lane) before += c;
-							if (l > lane && c) last = false;
-						}
-						if (last)
-							sCnt[sy * a.superX + sx] += before + 1;
-					}
-			__syncwarp();
-		}
+				}
+		__syncwarp();
 	}
 }
 
@@ -261,16 +233,16 @@ void srpdLaunchBin(const SrpdBinArgs& a, cudaStream_t stream)
 	srpdBinScanKernel<<<1, 1024, 0, stream>>>(a);
 	/* as many warps per chunk as the cursor matrix allows in shared memory */
 	const size_t budget = 160 * 1024;
-	if ((8 * (size_t) nSuper + 8 * 32) * sizeof(uint32_t) <= budget)
+	if (2 * 8 * (size_t) nSuper * sizeof(uint32_t) <= budget)
 	{
-		const size_t bytes = (8 * (size_t) nSuper + 8 * 32) * sizeof(uint32_t);
+		const size_t bytes = 2 * 8 * (size_t) nSuper * sizeof(uint32_t);
 		static bool configured8 = false;
 		if (!configured8) { cudaFuncSetAttribute(srpdBinFillKernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget); configured8 = true; }
 		srpdBinFillKernel<8><<<a.nChunksMax, 8 * 32, bytes, stream>>>(a);
 	}
 	else
 	{
-		const size_t bytes = (2 * (size_t) nSuper + 2 * 32) * sizeof(uint32_t);
+		const size_t bytes = 2 * 2 * (size_t) nSuper * sizeof(uint32_t);
 		static bool configured2 = false;
 		if (!configured2) { cudaFuncSetAttribute(srpdBinFillKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget); configured2 = true; }
 		srpdBinFillKernel<2><<<a.nChunksMax, 2 * 32, bytes, stream>>>(a);

@@ -229,10 +229,12 @@ __device__ __forceinline__ void visitTriangle(
 	{
 		const float dx0 = __uint_as_float(q1.x), dx1 = __uint_as_float(q1.y), dx2 = __uint_as_float(q1.z);
 		const int nx = x - (bx0 > minX ? bx0 : minX);      /* 0..7 remaining steps */
-		for (int i = 0; i < nx; i++)
-		{
-			l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
-		}
+		#pragma unroll
+		for (int i = 0; i < SRPD_BLK_W - 1; i++)
+			if (i < nx)
+			{
+				l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
+			}
 	}
 	/* top-left rule: lambda > 0 || (|lambda| <= 1e-9 && edgeTL), triangle.c:82-87 */
 	const uint4 q2 = __ldg(h + 2);

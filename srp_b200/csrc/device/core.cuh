@@ -314,6 +314,36 @@ SRP_HD int srpdSetupTriangle(const SrpdState& st, const SrpdPos clip[3], SrpdTri
 	return 1;
 }
 
+/* Exact coverage pre-test for small triangles: replays rasterizeTriangle's loop
+ * (triangle.c:78-110) over the bounding box with the same incremental barycentrics and the
+ * same top-left inside test, and reports whether ANY pixel would emit a fragment. */
+SRP_HD bool srpdTriangleIsSmall(const SrpdTriSetup& s)
+{
+	return (int) (s.maxX - s.minX) <= 4 && (int) (s.maxY - s.minY) <= 4;
+}
+SRP_HD bool srpdSmallTriangleCoversAnyPixel(const SrpdTriSetup& s)
+{
+	float row0 = srpdU2F(s.w[0]), row1 = srpdU2F(s.w[1]), row2 = srpdU2F(s.w[2]);
+	const float dx0 = srpdU2F(s.w[4]), dx1 = srpdU2F(s.w[5]), dx2 = srpdU2F(s.w[6]);
+	const float dy0 = srpdU2F(s.w[8]), dy1 = srpdU2F(s.w[9]), dy2 = srpdU2F(s.w[10]);
+	const uint32_t flags = s.w[11];
+	for (int y = s.minY; y < s.maxY; y++)
+	{
+		float l0 = row0, l1 = row1, l2 = row2;
+		for (int x = s.minX; x < s.maxX; x++)
+		{
+			const bool in0 = (l0 > 0.f) || (srpdRoughlyZero(l0) && (flags & 1u));
+			const bool in1 = (l1 > 0.f) || (srpdRoughlyZero(l1) && (flags & 2u));
+			const bool in2 = (l2 > 0.f) || (srpdRoughlyZero(l2) && (flags & 4u));
+			if (in0 && in1 && in2)
+				return true;
+			l0 = SRP_FADD(l0, dx0); l1 = SRP_FADD(l1, dx1); l2 = SRP_FADD(l2, dx2);
+		}
+		row0 = SRP_FADD(row0, dy0); row1 = SRP_FADD(row1, dy1); row2 = SRP_FADD(row2, dy2);
+	}
+	return false;
+}
+
 /* ---------------------------------------------------------------------------------
  * Line setup, reference src/raster/line.c:34-55,79-86 (the loop-invariant part of
  * rasterizeLine is hoisted here).  Both endpoints are clip-space positions. */

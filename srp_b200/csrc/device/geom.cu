@@ -130,6 +130,7 @@ struct Emitter
 	const SrpdGeomArgs* a;
 	unsigned char* records;     /* frame base */
 	uint2* bboxes;              /* frame base */
+	uint32_t* occupancy;        /* frame base */
 	uint32_t idBase, storeBase; /* global bases of this input primitive (valid when writing) */
 	uint32_t nEmit, nStore;
 	bool overflow;
@@ -183,6 +184,23 @@ __device__ __forceinline__ unsigned char* beginRecord(Emitter& em, const uint32_
 	h[3] = make_uint4(w[12], w[13], w[14], em.idBase + em.nEmit);
 	h[4] = make_uint4(w[16], w[17], w[18], w[19]);
 	em.bboxes[slot] = make_uint2((uint32_t) x0 | ((uint32_t) y0 << 16), (uint32_t) x1 | ((uint32_t) y1 << 16));
+	/* occupancy bitmap: one bit per tile the box touches (row-wise word masks) */
+	if (x1 > x0 && y1 > y0)
+	{
+		const uint32_t tx0 = x0 / SRPD_TILE_W, tx1 = (uint32_t) (x1 - 1) / SRPD_TILE_W;
+		const uint32_t ty0 = y0 / SRPD_TILE_H, ty1 = (uint32_t) (y1 - 1) / SRPD_TILE_H;
+		for (uint32_t ty = ty0; ty <= ty1 && ty < em.a->tilesY; ty++)
+		{
+			const uint32_t b0 = ty * em.a->tilesX + tx0, b1 = ty * em.a->tilesX + (tx1 < em.a->tilesX ? tx1 : em.a->tilesX - 1);
+			for (uint32_t w = b0 >> 5; w <= (b1 >> 5); w++)
+			{
+				const uint32_t lo = w == (b0 >> 5) ? (b0 & 31u) : 0u, hi = w == (b1 >> 5) ? (b1 & 31u) : 31u;
+				const uint32_t mask = (hi == 31u ? 0xFFFFFFFFu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+				if ((em.occupancy[w] & mask) != mask)
+					atomicOr(&em.occupancy[w], mask);
+			}
+		}
+	}
 	return rec + SRPD_REC_HEADER_BYTES;
 }
 
@@ -193,6 +211,11 @@ __device__ void emitTriangle(Emitter& em, const SrpdState& st, const SrpdPos p[3
 	bool stored;
 	if (!srpdSetupTriangle(st, p, s, stored))
 		return;
+	/* A triangle whose bounding box is a few pixels (sub-pixel geometry, cfg4) usually covers
+	 * no pixel centre at all.  Walking the reference's own chain over the box here decides
+	 * that exactly; such a triangle keeps its primitive id but needs no record. */
+	if (stored && srpdTriangleIsSmall(s) && !srpdSmallTriangleCoversAnyPixel(s))
+		stored = false;
 	if (stored)
 	{
 		unsigned char* blobs = beginRecord<WRITE>(em, s.w, s.minX, s.minY, s.maxX, s.maxY);
@@ -483,6 +506,7 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	em.a = &a;
 	em.records = a.records + (size_t) frame * a.recCapacity * a.recStride;
 	em.bboxes = a.bboxes + (size_t) frame * a.recCapacity;
+	em.occupancy = a.occupancy + (size_t) frame * a.occWordsPerFrame;
 	em.idBase = 0; em.storeBase = 0; em.nEmit = 0; em.nStore = 0; em.overflow = false;
 	if (active)
 		processPrimitive<false>(em, d, nv, p, vary);

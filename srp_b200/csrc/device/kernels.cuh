@@ -51,6 +51,9 @@ struct SrpdGeomArgs
 	                                     tile kernel then leaves the framebuffer untouched  */
 	uint32_t batchesPerFrame;
 	uint32_t* frameCounts;            /* [nFrames][2]: ids emitted, records stored       */
+	uint32_t* occupancy;              /* [nFrames][occWordsPerFrame], zeroed per draw: tiles touched by a stored record */
+	uint32_t occWordsPerFrame;
+	uint32_t tilesX, tilesY;
 	SrpdStats* stats;
 };
 
@@ -83,6 +86,11 @@ struct SrpdTileArgs
 	uint32_t superX;
 	uint32_t tilesX, tilesY;
 	const uint32_t* abortFlag;
+	const uint32_t* occupancy;        /* [nFrames][occWordsPerFrame] bit per tile: some record's box touches it */
+	uint32_t occWordsPerFrame;
+	uint32_t* workCounter;            /* zeroed per draw: next work item of the persistent tile kernel */
+	uint32_t tilesPerItem;            /* consecutive tiles of one frame per work item */
+	uint32_t smCount;
 	SrpdStats* stats;
 };
 

@@ -346,26 +346,14 @@ __device__ __forceinline__ void storePlane(const T* staged, T* plane, int W, int
 
 } // namespace
 
-/* Register budget: both launch-bound arguments are given explicitly (under device LTO a
- * missing minimum makes the linker's code generator cap the kernel at 64 registers and
- * spill).  Triangles and points fit two 512-thread CTAs per SM; the line walker does not. */
+/* One tile: filter the candidate list, visit the primitives in order, write the tile back. */
 template <int KIND>
-__global__ void __launch_bounds__(SRPD_TILE_THREADS, KIND == SRPD_KIND_LINE ? 1 : 2)
-srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
+__device__ __forceinline__ void processTile(
+	const SrpdTileArgs& a, const SrpdFrame& fr, uint32_t frame, int tileX, int tileY,
+	uint32_t* sIds, uint2* sBox, uint32_t* sWarpCnt, uint32_t* sDirty, float* sPrep, FragCounters& cnt)
 {
-	__shared__ __align__(16) uint32_t sIds[SRPD_TILE_THREADS];     /* reused as the colour staging tile */
-	__shared__ __align__(16) uint2 sBox[SRPD_TILE_THREADS];        /* reused as depth (+ stencil) staging */
-	__shared__ uint32_t sWarpCnt[SRPD_TILE_WARPS];
-	__shared__ uint32_t sDirty;
-	/* per warp: row-start barycentrics of the (up to) 32 triangles of the current list step */
-	__shared__ __align__(16) float sPrep[KIND == SRPD_KIND_TRIANGLE ? SRPD_TILE_WARPS * 32 * SRPD_BLK_H * 3 : 4];
-
 	const SrpdState& st = a.d.st;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t frame = blockIdx.y;
-	const int tileX = blockIdx.x % a.tilesX;
-	const int tileY = a.d.tileRow0 + blockIdx.x / a.tilesX;
-	const SrpdFrame fr = a.frames ? a.frames[frame] : a.frame0;
 
 	/* candidate list of this tile */
 	uint32_t begin = 0, end;
@@ -379,10 +367,6 @@ srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 	}
 	else
 		end = a.frameCounts[2 * frame + 1];
-	if (begin == end && !fr.clearPending)
-		return;
-	if (*a.abortFlag)      /* a scratch pool overflowed: the host repeats the draw with larger pools */
-		return;
 
 	const unsigned char* records = a.records + (size_t) frame * a.recCapacity * a.recStride;
 	const uint2* bboxes = a.bboxes + (size_t) frame * a.recCapacity;
@@ -409,11 +393,8 @@ srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 			px.stencil = fr.stencil[pixelIndex];
 	}
 	if (tid == 0)
-		sDirty = 0u;
+		*sDirty = 0u;
 	__syncthreads();
-
-	FragCounters cnt;
-	cnt.emitted = 0; cnt.shaded = 0;
 
 	for (uint32_t c = begin; c < end; c += SRPD_TILE_THREADS)
 	{
@@ -488,8 +469,107 @@ srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 		__syncthreads();
 	}
 
-	/* counters: warp reduction, then one atomic per warp into one of 64 slots chosen by
-	 * the tile index, so the atomics of a frame do not serialise on one L2 address */
+	/* write-back: stage the tile in shared memory, leave as 16-byte vectors */
+	uint32_t dirty = px.dirty;
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+		dirty |= __shfl_xor_sync(0xFFFFFFFFu, dirty, o);
+	if (lane == 0 && dirty)
+		atomicOr(sDirty, dirty);
+	uint32_t* sColor = sIds;
+	float* sDepth = (float*) sBox;
+	uint8_t* sStencil = (uint8_t*) (sDepth + SRPD_TILE_THREADS);
+	const int local = (y - ty0) * SRPD_TILE_W + (x - tx0);
+	sColor[local] = px.color;
+	sDepth[local] = px.depth;
+	sStencil[local] = (uint8_t) px.stencil;
+	__syncthreads();
+	const uint32_t tileDirty = *sDirty | (fr.clearPending ? 3u : 0u);
+	if (tileDirty & 1u)
+		storePlane<uint32_t>(sColor, fr.color, st.width, st.height, tx0, ty0, tid);
+	if (tileDirty & 2u)
+		storePlane<float>(sDepth, fr.depth, st.width, st.height, tx0, ty0, tid);
+	if (tileDirty & 4u)
+		storePlane<uint8_t>(sStencil, fr.stencil, st.width, st.height, tx0, ty0, tid);
+	__syncthreads();      /* the staging arrays are reused by the next tile */
+}
+
+/* A tile no primitive touches while a clear is pending: just write the clear values
+ * (colour 0, depth -1; reference core/framebuffer.c:57-62), one 128-byte row per warp. */
+__device__ __forceinline__ void clearTile(const SrpdState& st, const SrpdFrame& fr, int tileX, int tileY)
+{
+	const int x = tileX * SRPD_TILE_W + (threadIdx.x % SRPD_TILE_W);
+	const int y = tileY * SRPD_TILE_H + (threadIdx.x / SRPD_TILE_W);
+	if (x < st.width && y < st.height)
+	{
+		const size_t i = (size_t) y * st.width + x;
+		fr.color[i] = 0u;
+		fr.depth[i] = -1.0f;
+	}
+}
+
+/* Persistent tile kernel: the grid is sized to the machine (CTAs per SM x SM count) and the
+ * CTAs pull work items -- groups of `tilesPerItem` consecutive tiles of one frame -- from an
+ * atomic counter, so neither empty tiles (skipped through the occupancy bitmap the geometry
+ * kernel filled) nor hundreds of frames of a batch cost a CTA launch each.
+ *
+ * Register budget: both launch-bound arguments are given explicitly (under device LTO a
+ * missing minimum makes the linker's code generator cap the kernel at 64 registers and
+ * spill).  Triangles and points fit two 512-thread CTAs per SM; the line walker does not. */
+template <int KIND>
+__global__ void __launch_bounds__(SRPD_TILE_THREADS, KIND == SRPD_KIND_LINE ? 1 : 2)
+srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
+{
+	__shared__ __align__(16) uint32_t sIds[SRPD_TILE_THREADS];     /* reused as the colour staging tile */
+	__shared__ __align__(16) uint2 sBox[SRPD_TILE_THREADS];        /* reused as depth (+ stencil) staging */
+	__shared__ uint32_t sWarpCnt[SRPD_TILE_WARPS];
+	__shared__ uint32_t sDirty;
+	__shared__ uint32_t sItem[2];
+	/* per warp: row-start barycentrics of the (up to) 32 triangles of the current list step */
+	__shared__ __align__(16) float sPrep[KIND == SRPD_KIND_TRIANGLE ? SRPD_TILE_WARPS * 32 * SRPD_BLK_H * 3 : 4];
+
+	if (*a.abortFlag)      /* a scratch pool overflowed: the host repeats the draw with larger pools */
+		return;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t rows = a.d.tileRow1 - a.d.tileRow0;
+	const uint32_t tilesPerFrame = a.tilesX * rows;
+	const uint32_t itemsPerFrame = (tilesPerFrame + a.tilesPerItem - 1) / a.tilesPerItem;
+	const uint32_t nItems = itemsPerFrame * a.d.nFrames;
+
+	FragCounters cnt;
+	cnt.emitted = 0; cnt.shaded = 0;
+
+	if (tid == 0)
+		sItem[0] = atomicAdd(a.workCounter, 1u);
+	__syncthreads();
+	for (uint32_t it = 0;; it++)
+	{
+		const uint32_t item = sItem[it & 1];
+		if (item >= nItems)
+			break;
+		if (tid == 0)      /* fetch the next item while this one is processed */
+			sItem[(it + 1) & 1] = atomicAdd(a.workCounter, 1u);
+		const uint32_t frame = item / itemsPerFrame;
+		const uint32_t first = (item - frame * itemsPerFrame) * a.tilesPerItem;
+		const uint32_t last = min(first + a.tilesPerItem, tilesPerFrame);
+		const SrpdFrame fr = a.frames ? a.frames[frame] : a.frame0;
+		const uint32_t* occ = a.occupancy + (size_t) frame * a.occWordsPerFrame;
+		for (uint32_t t = first; t < last; t++)
+		{
+			const int tileX = (int) (t % a.tilesX);
+			const int tileY = (int) (a.d.tileRow0 + t / a.tilesX);
+			const uint32_t tileIndex = (uint32_t) tileY * a.tilesX + (uint32_t) tileX;
+			const bool occupied = (occ[tileIndex >> 5] >> (tileIndex & 31u)) & 1u;
+			if (occupied)
+				processTile<KIND>(a, fr, frame, tileX, tileY, sIds, sBox, sWarpCnt, &sDirty, sPrep, cnt);
+			else if (fr.clearPending)
+				clearTile(a.d.st, fr, tileX, tileY);
+		}
+		__syncthreads();   /* sItem[(it + 1) & 1] is visible; sItem[it & 1] may be overwritten next round */
+	}
+
+	/* counters: warp reduction, then one atomic per warp into one of the slots, so the atomics
+	 * of a frame do not serialise on one L2 address */
 	{
 		uint32_t e = cnt.emitted, s = cnt.shaded;
 		#pragma unroll
@@ -505,29 +585,6 @@ srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 			atomicAdd(&slot->fragsShaded, (unsigned long long) s);
 		}
 	}
-
-	/* write-back: stage the tile in shared memory, leave as 16-byte vectors */
-	uint32_t dirty = px.dirty;
-	#pragma unroll
-	for (int o = 16; o > 0; o >>= 1)
-		dirty |= __shfl_xor_sync(0xFFFFFFFFu, dirty, o);
-	if (lane == 0 && dirty)
-		atomicOr(&sDirty, dirty);
-	uint32_t* sColor = sIds;
-	float* sDepth = (float*) sBox;
-	uint8_t* sStencil = (uint8_t*) (sDepth + SRPD_TILE_THREADS);
-	const int local = (y - ty0) * SRPD_TILE_W + (x - tx0);
-	sColor[local] = px.color;
-	sDepth[local] = px.depth;
-	sStencil[local] = (uint8_t) px.stencil;
-	__syncthreads();
-	const uint32_t tileDirty = sDirty | (fr.clearPending ? 3u : 0u);
-	if (tileDirty & 1u)
-		storePlane<uint32_t>(sColor, fr.color, st.width, st.height, tx0, ty0, tid);
-	if (tileDirty & 2u)
-		storePlane<float>(sDepth, fr.depth, st.width, st.height, tx0, ty0, tid);
-	if (tileDirty & 4u)
-		storePlane<uint8_t>(sStencil, fr.stencil, st.width, st.height, tx0, ty0, tid);
 }
 
 /* srpFramebufferClear as a real memory operation (only needed when a pending clear has
@@ -564,11 +621,17 @@ void srpdLaunchTiles(const SrpdTileArgs& a, cudaStream_t stream)
 	const uint32_t rows = a.d.tileRow1 - a.d.tileRow0;
 	if (rows == 0 || a.tilesX == 0)
 		return;
-	const dim3 grid(a.tilesX * rows, a.d.nFrames);
+	/* persistent grid: resident CTAs per SM x SM count (no more CTAs than work items) */
+	const uint32_t tilesPerFrame = a.tilesX * rows;
+	const uint64_t nItems = (uint64_t) ((tilesPerFrame + a.tilesPerItem - 1) / a.tilesPerItem) * a.d.nFrames;
+	const uint32_t perSm = a.d.kind == SRPD_KIND_LINE ? 1u : 2u;
+	uint64_t grid = (uint64_t) a.smCount * perSm;
+	if (grid > nItems) grid = nItems;
+	if (grid == 0) return;
 	if (a.d.kind == SRPD_KIND_TRIANGLE)
-		srpdTileKernel<SRPD_KIND_TRIANGLE><<<grid, SRPD_TILE_THREADS, 0, stream>>>(a);
+		srpdTileKernel<SRPD_KIND_TRIANGLE><<<(unsigned) grid, SRPD_TILE_THREADS, 0, stream>>>(a);
 	else if (a.d.kind == SRPD_KIND_LINE)
-		srpdTileKernel<SRPD_KIND_LINE><<<grid, SRPD_TILE_THREADS, 0, stream>>>(a);
+		srpdTileKernel<SRPD_KIND_LINE><<<(unsigned) grid, SRPD_TILE_THREADS, 0, stream>>>(a);
 	else
-		srpdTileKernel<SRPD_KIND_POINT><<<grid, SRPD_TILE_THREADS, 0, stream>>>(a);
+		srpdTileKernel<SRPD_KIND_POINT><<<(unsigned) grid, SRPD_TILE_THREADS, 0, stream>>>(a);
 }

@@ -33,6 +33,7 @@ struct Runtime
 	cudaStream_t stream = nullptr;
 	std::string lastError;
 	Pool records, bboxes, scan, frameCounts, chunkCounts, superOffsets, listIds, uniforms, frames;
+	int smCount = 148;
 	SrpdStats* stats = nullptr;            /* device, SRPD_STATS_SLOTS slots */
 	SrpdStats* statsHost = nullptr;        /* pinned */
 	unsigned long long launches = 0, h2d = 0, d2h = 0;
@@ -155,6 +156,7 @@ int srpcuInit(void)
 		return 1;
 	}
 	g.device = dev;
+	g.smCount = prop.multiProcessorCount;
 	CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
 	CU(cudaMalloc(&g.stats, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
 	CU(cudaMemset(g.stats, 0, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
@@ -308,7 +310,12 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 
 	if (!grow(g.records, (size_t) recCapacity * recStride * nFrames)) return 1;
 	if (!grow(g.bboxes, (size_t) recCapacity * sizeof(uint2) * nFrames)) return 1;
-	const size_t scanBytes = 16 + sizeof(unsigned long long) * (size_t) batchesPerFrame * nFrames;
+	/* one zero-filled block per draw: [ticket, abort flag, tile work counter, pad] [scan state] [tile occupancy bitmap] */
+	const uint32_t tilesX = (st.width + SRPD_TILE_W - 1) / SRPD_TILE_W;
+	const uint32_t tilesY = (st.height + SRPD_TILE_H - 1) / SRPD_TILE_H;
+	const uint32_t occWords = (tilesX * tilesY + 31) / 32;
+	const size_t scanStateBytes = sizeof(unsigned long long) * (size_t) batchesPerFrame * nFrames;
+	const size_t scanBytes = 16 + scanStateBytes + sizeof(uint32_t) * (size_t) occWords * nFrames;
 	if (!grow(g.scan, scanBytes)) return 1;
 	if (!grow(g.frameCounts, sizeof(uint32_t) * 2 * nFrames)) return 1;
 	CU(cudaMemsetAsync(g.scan.ptr, 0, scanBytes, g.stream));
@@ -328,14 +335,16 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ga.scanState = (unsigned long long*) ((unsigned char*) g.scan.ptr + 16);
 	ga.batchesPerFrame = batchesPerFrame;
 	ga.frameCounts = (uint32_t*) g.frameCounts.ptr;
+	ga.occupancy = (uint32_t*) ((unsigned char*) g.scan.ptr + 16 + scanStateBytes);
+	ga.occWordsPerFrame = occWords;
+	ga.tilesX = tilesX;
+	ga.tilesY = tilesY;
 	ga.stats = g.stats;
 	srpdLaunchGeom(ga, g.stream);
 	g.launches++;
 	CU(cudaGetLastError());
 	mark();
 
-	const uint32_t tilesX = (st.width + SRPD_TILE_W - 1) / SRPD_TILE_W;
-	const uint32_t tilesY = (st.height + SRPD_TILE_H - 1) / SRPD_TILE_H;
 	const uint32_t superX = (tilesX + SRPD_SUPER_W - 1) / SRPD_SUPER_W;
 	const uint32_t superY = (tilesY + SRPD_SUPER_H - 1) / SRPD_SUPER_H;
 	const uint32_t nSuper = superX * superY;
@@ -359,6 +368,10 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ta.tilesX = tilesX;
 	ta.tilesY = tilesY;
 	ta.abortFlag = ga.abortFlag;
+	ta.occupancy = ga.occupancy;
+	ta.occWordsPerFrame = occWords;
+	ta.workCounter = (uint32_t*) g.scan.ptr + 2;
+	ta.smCount = (uint32_t) g.smCount;
 	ta.stats = g.stats;
 	if (ta.d.tileRow1 > tilesY) ta.d.tileRow1 = tilesY;
 	if (ta.d.tileRow0 > ta.d.tileRow1) ta.d.tileRow0 = ta.d.tileRow1;
@@ -391,6 +404,16 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		ta.listIds = ba.listIds;
 	}
 
+	{
+		/* work-item granularity: enough items for dynamic load balance (>= ~32 per CTA), but not
+		 * one atomic per tile when a batch has millions of mostly empty tiles */
+		const uint32_t rows = ta.d.tileRow1 - ta.d.tileRow0;
+		const uint64_t tiles = (uint64_t) tilesX * rows * nFrames;
+		const uint64_t target = (uint64_t) g.smCount * 2 * 32;
+		uint32_t per = 1;
+		while (per < 32 && tiles / (per * 2) >= target) per *= 2;
+		ta.tilesPerItem = per;
+	}
 	mark();
 	srpdLaunchTiles(ta, g.stream);
 	g.launches++;

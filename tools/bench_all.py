@@ -1,0 +1,99 @@
+#!/usr/bin/env python3
+"""Secondary measurements (not the driver's JSON line): kernel-only frame times and stage
+split of every BASELINE config on one GPU, incl. the frame-parallel batch (cfg5).
+Run under gpurun; writes gpurun_out/bench_all.json."""
+import ctypes as C
+import json
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import numpy as np
+import torch
+from srp_b200 import host as H, scenes as S
+
+
+def time_scene(lib, scene, steps=10, warm=3):
+    lib.dll.srpB200SetSyncMode(H.SRP_B200_SYNC_EXPLICIT)
+    p = S.Prepared(lib, scene)
+    for _ in range(warm):
+        p.draw_all()
+    lib.dll.srpB200Finish()
+    lib.dll.srpB200ResetStats(); lib.dll.srpB200SetProfiling(1); lib.stage_times()
+    stream = torch.cuda.ExternalStream(lib.dll.srpB200Stream())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    with torch.cuda.stream(stream):
+        for a, b in ev:
+            flush.fill_(1)
+            a.record(stream); p.draw_all(); b.record(stream)
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    st = lib.stage_times(); lib.dll.srpB200SetProfiling(0)
+    stats = lib.stats()
+    t0 = time.perf_counter()
+    lib.dll.srpB200SetSyncMode(H.SRP_B200_SYNC_DRAW)
+    for _ in range(steps):
+        p.draw_all()
+    e2e = (time.perf_counter() - t0) / steps * 1e3
+    p.free()
+    n = max(1, st["draws"])
+    return {"scene": scene.name, "ms_per_frame": ms, "frames_per_s": 1e3 / ms, "e2e_ms_per_frame_sync_draw": e2e,
+            "draws_per_frame": len(scene.draws), "stage_ms_per_draw": {k: st[k] / n for k in ("geometry_ms", "binning_ms", "tiles_ms")},
+            "frags_emitted_per_frame": stats["fragsEmitted"] / steps, "frags_shaded_per_frame": stats["fragsShaded"] / steps,
+            "gfrag_per_s": stats["fragsEmitted"] / steps / ms / 1e6, "launches_per_frame": stats["kernelLaunches"] / steps}
+
+
+def time_batch(lib, n_frames=1024, size=1024, steps=3):
+    mesh = S.teapot_mesh()
+    draws = [S.teapot_draw(f, mesh) for f in range(n_frames)]
+    lib.new_context()
+    for fn, *args in draws[0].state:
+        getattr(lib.dll, fn)(*args)
+    vb = lib.vertex_buffer(mesh[0], 32); ib = lib.index_buffer(mesh[1])
+    prog = lib.program("gouraud", S.GOURAUD_VARYINGS, 12)
+    fbs = [lib.framebuffer(size, size) for _ in range(n_frames)]
+    arr = (C.POINTER(H.SRPFramebuffer) * n_frames)(*[f.ptr for f in fbs])
+    uni = np.frombuffer(b"".join(d.uniform for d in draws), dtype=np.uint8).copy()
+    stride = len(draws[0].uniform)
+    prog.set_uniform(draws[0].uniform)
+    lib.dll.srpB200SetSyncMode(H.SRP_B200_SYNC_EXPLICIT)
+    call = lambda: lib.dll.srpB200DrawBatch(ib, vb, arr, n_frames, C.byref(prog.sp), uni.ctypes.data, stride,
+                                            H.SRP_PRIM_TRIANGLES, 0, len(mesh[1]), 1)
+    call(); lib.dll.srpB200Finish()
+    lib.dll.srpB200ResetStats(); lib.dll.srpB200SetProfiling(1); lib.stage_times()
+    stream = torch.cuda.ExternalStream(lib.dll.srpB200Stream())
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    with torch.cuda.stream(stream):
+        for a, b in ev:
+            a.record(stream); call(); b.record(stream)
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    st = lib.stage_times(); lib.dll.srpB200SetProfiling(0)
+    stats = lib.stats()
+    lib.dll.srpB200SetSyncMode(H.SRP_B200_SYNC_DRAW)
+    for f in fbs:
+        f.free()
+    return {"scene": f"cfg5 batch: {n_frames} teapot frames {size}x{size} in one srpB200DrawBatch ({mesh[2]})",
+            "ms_per_batch": ms, "frames_per_s": n_frames / ms * 1e3, "stage_ms_per_batch": {k: st[k] / steps for k in ("geometry_ms", "binning_ms", "tiles_ms")},
+            "frags_emitted_per_frame": stats["fragsEmitted"] / steps / n_frames, "gfrag_per_s": stats["fragsEmitted"] / steps / ms / 1e6,
+            "framebuffer_bytes_per_frame": size * size * 9, "hbm_gbs_framebuffer_only": n_frames * size * size * 9 / ms / 1e6}
+
+
+def main():
+    lib = H.load_product()
+    out = {"version": lib.dll.srpB200Version().decode(), "results": []}
+    for make in (S.cfg1_textured_cube, S.cfg2_teapot, lambda: S.cfg2_teapot(3840, 2160), S.cfg3_shell,
+                 lambda: S.cfg3_shell(radius=1.2), S.cfg4_subpixel, lambda: S.cfg5_frame(0)):
+        r = time_scene(lib, make())
+        print(json.dumps(r)); out["results"].append(r)
+    r = time_batch(lib)
+    print(json.dumps(r)); out["results"].append(r)
+    Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
+    (ROOT / "gpurun_out" / "bench_all.json").write_text(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

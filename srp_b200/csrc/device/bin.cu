@@ -119,6 +119,7 @@ srpdBinScanKernel(const __grid_constant__ SrpdBinArgs a)
 		{
 			atomicAdd(&a.stats->overflow, 1ull);
 			atomicExch(a.abortFlag, 1u);
+			a.needed[1] = total;
 		}
 	}
 }

@@ -25,11 +25,11 @@
  * 16-byte loads.
  *
  *   word   TRIANGLE                         LINE                    POINT
- *   0-2    lambda at (minX+.5, minY+.5)     x0, y0, xInc            minBP.x, minBP.y, maxBP.x
+ *   0-2    lambda at (minX+.5, minY+.5)     x, y (segment), xInc    minBP.x, minBP.y, maxBP.x
  *   3      minX | maxX<<16                  yInc                    maxBP.y
- *   4-6    dlambda/dx                       tInc, steps, z0*iw0     minX, maxX, minY  (inclusive ints)
+ *   4-6    dlambda/dx                       tInc, count, z0*iw0     minX, maxX, minY  (inclusive ints)
  *   7      minY | maxY<<16                  z1*iw1                  maxY
- *   8-10   dlambda/dy                       iw0, iw1, -             ndc z, ndc w (=1), -
+ *   8-10   dlambda/dy                       iw0, iw1, t (segment)   ndc z, ndc w (=1), -
  *   11     flags: bit0-2 edge TL, bit3 frontFacing
  *   12-14  z_i * iw_i                       -                       -
  *   15     primitive id (all kinds)
@@ -349,55 +349,87 @@ SRP_HD bool srpdSmallTriangleCoversAnyPixel(const SrpdTriSetup& s)
  * rasterizeLine is hoisted here).  Both endpoints are clip-space positions. */
 struct SrpdLineSetup
 {
-	uint32_t w[SRPD_REC_HEADER_WORDS];
-	float invW[2];
-	uint16_t minX, minY, maxX, maxY;   /* conservative pixel bbox for binning, half-open */
+	float x0, y0, xInc, yInc, tInc;
+	int steps;                         /* the DDA emits steps + 1 fragments */
+	float zw[2], invW[2];
 };
 
 SRP_HD void srpdSetupLine(const SrpdState& st, const SrpdPos clip[2], SrpdLineSetup& out)
 {
 	SrpdPos v[2] = { clip[0], clip[1] };
-	float iw[2];
-	iw[0] = srpdPerspectiveDivide(v[0]);
-	iw[1] = srpdPerspectiveDivide(v[1]);
-	float x0, y0, x1, y1;
-	srpdNdcToScreen(st, v[0], x0, y0);
+	out.invW[0] = srpdPerspectiveDivide(v[0]);
+	out.invW[1] = srpdPerspectiveDivide(v[1]);
+	float x1, y1;
+	srpdNdcToScreen(st, v[0], out.x0, out.y0);
 	srpdNdcToScreen(st, v[1], x1, y1);
 
-	float dx = SRP_FSUB(x1, x0), dy = SRP_FSUB(y1, y0);
+	const float dx = SRP_FSUB(x1, out.x0), dy = SRP_FSUB(y1, out.y0);
 	int steps = (int) ceil(fmax(fabs((double) dx), fabs((double) dy)));
 	if (steps == 0)
 		steps = 1;
-	float xInc = SRP_FDIV(dx, (float) steps);
-	float yInc = SRP_FDIV(dy, (float) steps);
-	float tInc = (float) SRP_DDIV(1.0, (double) steps);
+	out.steps = steps;
+	out.xInc = SRP_FDIV(dx, (float) steps);
+	out.yInc = SRP_FDIV(dy, (float) steps);
+	out.tInc = (float) SRP_DDIV(1.0, (double) steps);
+	out.zw[0] = SRP_FMUL(v[0].z, out.invW[0]);
+	out.zw[1] = SRP_FMUL(v[1].z, out.invW[1]);
+}
 
-	memset(out.w, 0, sizeof(out.w));
-	out.w[0] = srpdF2U(x0); out.w[1] = srpdF2U(y0); out.w[2] = srpdF2U(xInc); out.w[3] = srpdF2U(yInc);
-	out.w[4] = srpdF2U(tInc); out.w[5] = (uint32_t) steps;
-	out.w[6] = srpdF2U(SRP_FMUL(v[0].z, iw[0])); out.w[7] = srpdF2U(SRP_FMUL(v[1].z, iw[1]));
-	out.w[8] = srpdF2U(iw[0]); out.w[9] = srpdF2U(iw[1]);
-	out.invW[0] = iw[0]; out.invW[1] = iw[1];
+/* round half away from zero of a float (C `round` on the promoted double, line.c:58-59);
+ * exact because d + 0.5 is exact for a float-valued double of this magnitude */
+SRP_HD int srpdRoundToInt(float v)
+{
+	const double d = (double) v;
+	return (int) trunc(d + copysign(0.5, d));
+}
 
-	/* Conservative bbox of every pixel the DDA can touch: the accumulated x/y stay
-	 * within a fraction of a pixel of the segment; +-2 px of slack.  A fragment whose
-	 * px reaches `width` (or goes negative) lands on the neighbouring row through the
-	 * reference's unchecked y*W+x indexing, so such a line is
-	 * binned over the full width and one more row either side. */
-	float lox = x0 < x1 ? x0 : x1, hix = x0 < x1 ? x1 : x0;
-	float loy = y0 < y1 ? y0 : y1, hiy = y0 < y1 ? y1 : y0;
-	long long bx0 = (long long) floor((double) lox) - 2, bx1 = (long long) ceil((double) hix) + 3;
-	long long by0 = (long long) floor((double) loy) - 2, by1 = (long long) ceil((double) hiy) + 3;
-	if (bx0 < 0 || bx1 > st.width)
+/* A line is stored as SEGMENTS of up to SRPD_LINE_SEG consecutive DDA fragments so that a
+ * tile never has to replay more than a segment of the chain: the geometry kernel walks the
+ * whole chain once (serial float additions, line.c:72-74) and records, per segment, the
+ * chain state (x, y, t) at its first fragment and the exact bounding box of the pixels its
+ * fragments land on -- including fragments whose x == width wraps them onto the next row
+ * through the reference's unchecked y*W + x index; fragments whose index
+ * falls outside the planes are not representable and are dropped.
+ *
+ * LINE record words: 0 x, 1 y at the segment's first fragment, 2 xInc, 3 yInc, 4 tInc,
+ * 5 fragment count, 6 z0*iw0, 7 z1*iw1, 8 iw0, 9 iw1, 10 t at the first fragment, 15 id. */
+#define SRPD_LINE_SEG 16
+
+struct SrpdLineSegment
+{
+	uint32_t w[SRPD_REC_HEADER_WORDS];
+	uint16_t minX, minY, maxX, maxY;   /* half-open pixel bbox of the fragments inside the planes */
+	bool any;
+};
+
+/* advances (x, y, t) over `n` fragments and fills `seg` */
+SRP_HD void srpdLineSegment(const SrpdState& st, const SrpdLineSetup& ln, float& x, float& y, float& t, int n, SrpdLineSegment& seg)
+{
+	for (int k = 0; k < SRPD_REC_HEADER_WORDS; k++)
+		seg.w[k] = 0;
+	seg.w[0] = srpdF2U(x); seg.w[1] = srpdF2U(y); seg.w[2] = srpdF2U(ln.xInc); seg.w[3] = srpdF2U(ln.yInc);
+	seg.w[4] = srpdF2U(ln.tInc); seg.w[5] = (uint32_t) n;
+	seg.w[6] = srpdF2U(ln.zw[0]); seg.w[7] = srpdF2U(ln.zw[1]);
+	seg.w[8] = srpdF2U(ln.invW[0]); seg.w[9] = srpdF2U(ln.invW[1]);
+	seg.w[10] = srpdF2U(t);
+	long long x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
+	const long long W = st.width, total = (long long) st.width * st.height;
+	for (int k = 0; k < n; k++)
 	{
-		bx0 = 0; bx1 = st.width; by0 -= 1; by1 += 1;
+		const long long idx = (long long) srpdRoundToInt(y) * W + srpdRoundToInt(x);
+		if (idx >= 0 && idx < total)
+		{
+			const long long px = idx % W, py = idx / W;
+			x0 = px < x0 ? px : x0; x1 = px > x1 ? px : x1;
+			y0 = py < y0 ? py : y0; y1 = py > y1 ? py : y1;
+		}
+		x = SRP_FADD(x, ln.xInc);
+		y = SRP_FADD(y, ln.yInc);
+		t = SRP_FADD(t, ln.tInc);
 	}
-	if (by0 < 0) by0 = 0;
-	if (by1 > st.height) by1 = st.height;
-	if (bx0 < 0) bx0 = 0;
-	if (bx1 > st.width) bx1 = st.width;
-	if (by1 < by0) by1 = by0;
-	out.minX = (uint16_t) bx0; out.maxX = (uint16_t) bx1; out.minY = (uint16_t) by0; out.maxY = (uint16_t) by1;
+	seg.any = x1 >= 0;
+	seg.minX = (uint16_t) (seg.any ? x0 : 0); seg.maxX = (uint16_t) (seg.any ? x1 + 1 : 0);
+	seg.minY = (uint16_t) (seg.any ? y0 : 0); seg.maxY = (uint16_t) (seg.any ? y1 + 1 : 0);
 }
 
 /* ---------------------------------------------------------------------------------

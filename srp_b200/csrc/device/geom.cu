@@ -230,13 +230,23 @@ __device__ void emitTriangle(Emitter& em, const SrpdState& st, const SrpdPos p[3
 template <bool WRITE>
 __device__ void emitLine(Emitter& em, const SrpdState& st, const SrpdPos p[2], const unsigned char* const vary[2])
 {
-	SrpdLineSetup s;
-	srpdSetupLine(st, p, s);
-	unsigned char* blobs = beginRecord<WRITE>(em, s.w, s.minX, s.minY, s.maxX, s.maxY);
-	if (WRITE && blobs)
-		for (int i = 0; i < 2; i++)
-			storeBlob(st, vary[i], s.invW[i], true, blobs + i * st.slotSize);
-	em.nStore++;
+	SrpdLineSetup ln;
+	srpdSetupLine(st, p, ln);
+	float x = ln.x0, y = ln.y0, t = 0.f;
+	const int total = ln.steps + 1;
+	for (int i = 0; i < total; i += SRPD_LINE_SEG)
+	{
+		SrpdLineSegment seg;
+		const int n = total - i < SRPD_LINE_SEG ? total - i : SRPD_LINE_SEG;
+		srpdLineSegment(st, ln, x, y, t, n, seg);
+		if (!seg.any)
+			continue;
+		unsigned char* blobs = beginRecord<WRITE>(em, seg.w, seg.minX, seg.minY, seg.maxX, seg.maxY);
+		if (WRITE && blobs)
+			for (int k = 0; k < 2; k++)
+				storeBlob(st, vary[k], ln.invW[k], true, blobs + k * st.slotSize);
+		em.nStore++;
+	}
 	em.nEmit++;
 }
 
@@ -572,6 +582,8 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 				const uint32_t e = sPrefix[0] + totE, st2 = sPrefix[1] + totS;
 				a.frameCounts[2 * frame + 0] = e;
 				a.frameCounts[2 * frame + 1] = st2 < a.recCapacity ? st2 : a.recCapacity;
+				if (st2 > a.recCapacity)
+					atomicMax(&a.needed[0], st2);
 				atomicAdd(&a.stats->primsIn, (unsigned long long) d.nInputPrims);
 				atomicAdd(&a.stats->primsEmitted, (unsigned long long) e);
 				atomicAdd(&a.stats->primsStored, (unsigned long long) st2);

@@ -31,6 +31,10 @@ constexpr int SRPD_STATS_SLOTS = 1024;   /* SrpdStats[slots]: counters are sprea
 constexpr int SRPD_BIN_THREADS = 256;
 constexpr int SRPD_BIN_CHUNK = 2048;     /* records per coarse-binning CTA                  */
 
+/* Per-draw zero-filled header in front of the scan state: word 0 batch ticket, 1 abort flag,
+ * 2 tile work counter, 3 records a frame needed (max over frames), 4 coarse-list entries needed */
+constexpr int SRPD_DRAW_HEADER_BYTES = 32;
+
 /* Decoupled look-back word: [63:62] status, [61:31] emitted ids, [30:0] stored records */
 constexpr unsigned long long SRPD_SCAN_AGG = 1ull << 62;
 constexpr unsigned long long SRPD_SCAN_PREFIX = 2ull << 62;
@@ -49,6 +53,7 @@ struct SrpdGeomArgs
 	uint32_t* ticket;                 /* zeroed per draw                                 */
 	uint32_t* abortFlag;              /* zeroed per draw; set when a scratch pool overflows: the
 	                                     tile kernel then leaves the framebuffer untouched  */
+	uint32_t* needed;                 /* [0] records needed per frame (max), [1] coarse-list entries needed */
 	uint32_t batchesPerFrame;
 	uint32_t* frameCounts;            /* [nFrames][2]: ids emitted, records stored       */
 	uint32_t* occupancy;              /* [nFrames][occWordsPerFrame], zeroed per draw: tiles touched by a stored record */
@@ -68,6 +73,7 @@ struct SrpdBinArgs
 	uint32_t* listIds;                /* [listCapacity] record indices, id order per supertile */
 	uint32_t listCapacity;
 	uint32_t* abortFlag;
+	uint32_t* needed;
 	SrpdStats* stats;
 };
 

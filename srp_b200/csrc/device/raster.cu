@@ -257,16 +257,11 @@ __device__ __forceinline__ void visitTriangle(
 	                depth, recW, recW, (flags & 8u) != 0, q3.w, rec + SRPD_REC_HEADER_BYTES, wgt);
 }
 
-/* round half away from zero of a float-valued double; exact because x + 0.5 is exact */
-__device__ __forceinline__ int roundToInt(float v)
-{
-	const double d = (double) v;
-	return (int) trunc(d + copysign(0.5, d));
-}
-
-/* rasterizeLine for one pixel, reference line.c:34-77: every lane replays the whole DDA
- * chain and keeps the fragments that land on its own linear index y*W + x -- including
- * the ones the reference's unchecked indexing wraps to the next row (App. B-1). */
+/* rasterizeLine for one pixel, reference line.c:34-77: every lane replays the DDA chain of
+ * the record's segment (<= SRPD_LINE_SEG fragments, starting from the chain state the
+ * geometry kernel recorded) and keeps the fragments that land on its own linear index
+ * y*W + x -- including the ones the reference's unchecked indexing wraps to the next row
+ * (App. B-1). */
 __device__ __forceinline__ void visitLine(
 	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, Pixel& px, FragCounters& cnt,
 	int x, int y, bool valid)
@@ -276,15 +271,15 @@ __device__ __forceinline__ void visitLine(
 	float fx = __uint_as_float(q0.x), fy = __uint_as_float(q0.y);
 	const float xInc = __uint_as_float(q0.z), yInc = __uint_as_float(q0.w);
 	const float tInc = __uint_as_float(q1.x);
-	const int steps = (int) q1.y;
+	const int count = (int) q1.y;
 	const float zw0 = __uint_as_float(q1.z), zw1 = __uint_as_float(q1.w);
 	const float iw0 = __uint_as_float(q2.x), iw1 = __uint_as_float(q2.y);
+	float t = __uint_as_float(q2.z);
 	const long long W = a.d.st.width;
 	const long long mine = valid ? (long long) y * W + x : -1;
-	float t = 0.f;
-	for (int i = 0; i <= steps; i++)
+	for (int i = 0; i < count; i++)
 	{
-		const int ipx = roundToInt(fx), ipy = roundToInt(fy);
+		const int ipx = srpdRoundToInt(fx), ipy = srpdRoundToInt(fy);
 		if ((long long) ipy * W + ipx == mine)
 		{
 			const float w0 = __fsub_rn(1.0f, t);

@@ -34,6 +34,7 @@ struct Runtime
 	std::string lastError;
 	Pool records, bboxes, scan, frameCounts, chunkCounts, superOffsets, listIds, uniforms, frames;
 	int smCount = 148;
+	uint64_t recFloor = 0, listFloor = 0;  /* minimum pool capacities, raised by srpcuTakeOverflow() */
 	SrpdStats* stats = nullptr;            /* device, SRPD_STATS_SLOTS slots */
 	SrpdStats* statsHost = nullptr;        /* pinned */
 	unsigned long long launches = 0, h2d = 0, d2h = 0;
@@ -50,7 +51,7 @@ struct Runtime
 
 Runtime g;
 int gRequestedDevice = -1;
-int gWorstCasePools = 0;
+
 
 bool fail(const char* what, cudaError_t e)
 {
@@ -111,7 +112,7 @@ int envInt(const char* name, int fallback)
 extern "C" {
 
 void srpcuSetDevice(int device) { gRequestedDevice = device; }
-void srpcuSetWorstCasePools(int on) { gWorstCasePools = on; }
+
 const char* srpcuLastError(void) { return g.lastError.c_str(); }
 void* srpcuStream(void) { return srpcuInit() == 0 ? (void*) g.stream : nullptr; }
 int srpcuTileWidth(void) { return SRPD_TILE_W; }
@@ -301,9 +302,12 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	const uint32_t recStride = srpdRecordStride(st, nVerts);
 	const uint64_t worst = (uint64_t) d.nInputPrims * d.maxOutPerInput;
 	uint64_t cap = (d.maxOutPerInput == 1) ? worst : (uint64_t) d.nInputPrims * 2 + 4096;
-	if (d.st.polygonMode != SRP_POLYGON_MODE_FILL && d.maxOutPerInput > 1)
+	if (d.kind == SRPD_KIND_LINE)          /* lines are stored as 16-fragment segments */
+		cap = (uint64_t) d.nInputPrims * (d.st.polygonMode == SRP_POLYGON_MODE_LINE ? 12 : 4) + 65536;
+	else if (d.st.polygonMode != SRP_POLYGON_MODE_FILL && d.maxOutPerInput > 1)
 		cap = (uint64_t) d.nInputPrims * 4 + 4096;
-	if (gWorstCasePools || getenv("SRP_B200_WORST_CASE_POOLS") || cap > worst) cap = worst;
+	if (cap < g.recFloor) cap = g.recFloor;     /* raised after an overflow to what that draw needed */
+	if (getenv("SRP_B200_WORST_CASE_POOLS") || cap > worst) cap = worst;
 	if (cap > 0x7FFFFFF0ull) cap = 0x7FFFFFF0ull;
 	const uint32_t recCapacity = (uint32_t) cap;
 	const uint32_t batchesPerFrame = (d.nInputPrims + SRPD_GEOM_THREADS - 1) / SRPD_GEOM_THREADS;
@@ -315,7 +319,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	const uint32_t tilesY = (st.height + SRPD_TILE_H - 1) / SRPD_TILE_H;
 	const uint32_t occWords = (tilesX * tilesY + 31) / 32;
 	const size_t scanStateBytes = sizeof(unsigned long long) * (size_t) batchesPerFrame * nFrames;
-	const size_t scanBytes = 16 + scanStateBytes + sizeof(uint32_t) * (size_t) occWords * nFrames;
+	const size_t scanBytes = SRPD_DRAW_HEADER_BYTES + scanStateBytes + sizeof(uint32_t) * (size_t) occWords * nFrames;
 	if (!grow(g.scan, scanBytes)) return 1;
 	if (!grow(g.frameCounts, sizeof(uint32_t) * 2 * nFrames)) return 1;
 	CU(cudaMemsetAsync(g.scan.ptr, 0, scanBytes, g.stream));
@@ -332,10 +336,11 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ga.recStride = recStride;
 	ga.ticket = (uint32_t*) g.scan.ptr;
 	ga.abortFlag = (uint32_t*) g.scan.ptr + 1;
-	ga.scanState = (unsigned long long*) ((unsigned char*) g.scan.ptr + 16);
+	ga.needed = (uint32_t*) g.scan.ptr + 3;
+	ga.scanState = (unsigned long long*) ((unsigned char*) g.scan.ptr + SRPD_DRAW_HEADER_BYTES);
 	ga.batchesPerFrame = batchesPerFrame;
 	ga.frameCounts = (uint32_t*) g.frameCounts.ptr;
-	ga.occupancy = (uint32_t*) ((unsigned char*) g.scan.ptr + 16 + scanStateBytes);
+	ga.occupancy = (uint32_t*) ((unsigned char*) g.scan.ptr + SRPD_DRAW_HEADER_BYTES + scanStateBytes);
 	ga.occWordsPerFrame = occWords;
 	ga.tilesX = tilesX;
 	ga.tilesY = tilesY;
@@ -386,7 +391,8 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		ba.superX = superX;
 		ba.superY = superY;
 		uint64_t listCap = (uint64_t) recCapacity * 2 + (uint64_t) nSuper * 64 + 65536;
-		if (gWorstCasePools || getenv("SRP_B200_WORST_CASE_POOLS")) listCap = (uint64_t) recCapacity * nSuper;
+		if (listCap < g.listFloor) listCap = g.listFloor;
+		if (getenv("SRP_B200_WORST_CASE_POOLS")) listCap = (uint64_t) recCapacity * nSuper;
 		if (listCap > 0x7FFFFFF0ull) listCap = 0x7FFFFFF0ull;
 		ba.listCapacity = (uint32_t) listCap;
 		if (!grow(g.chunkCounts, sizeof(uint32_t) * (size_t) ba.nChunksMax * nSuper)) return 1;
@@ -396,6 +402,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		ba.superOffsets = (uint32_t*) g.superOffsets.ptr;
 		ba.listIds = (uint32_t*) g.listIds.ptr;
 		ba.abortFlag = ga.abortFlag;
+		ba.needed = ga.needed;
 		ba.stats = g.stats;
 		srpdLaunchBin(ba, g.stream);
 		g.launches += 3;
@@ -443,7 +450,9 @@ void srpcuGetStats(SrpdStats* out, unsigned long long* launches, unsigned long l
 	}
 }
 
-/* Number of scratch-pool overflows since the previous call (synchronises; 8-byte copy).
+/* 1 if a scratch pool overflowed since the previous call (synchronises; small copies).  The
+ * kernels record what the overflowing draw would have needed (records per frame, coarse-list
+ * entries); the pool floors are raised to that, so repeating the draw succeeds.
  * Only slot 0 of the counter array is used for overflow accounting. */
 int srpcuTakeOverflow(void)
 {
@@ -455,6 +464,13 @@ int srpcuTakeOverflow(void)
 	const unsigned long long now = g.statsHost[0].overflow;
 	const int fresh = now > seen;
 	seen = now;
+	if (fresh && g.scan.ptr)
+	{
+		uint32_t needed[2] = { 0, 0 };
+		cudaMemcpy(needed, (uint32_t*) g.scan.ptr + 3, sizeof needed, cudaMemcpyDeviceToHost);
+		if (needed[0]) g.recFloor = (uint64_t) needed[0] + needed[0] / 8 + 1024;
+		if (needed[1]) g.listFloor = (uint64_t) needed[1] + needed[1] / 8 + 1024;
+	}
 	return fresh;
 }
 

@@ -41,10 +41,10 @@ int srpcuClearPlanes(uint32_t* color, float* depth, size_t nPixels);
 int srpcuDraw(const SrpdDraw* d, const SrpdFrame* frames,
               const void* uniforms, size_t uniformBytes, size_t uniformStride);
 
-/* 1 if a scratch pool overflowed since the previous call (the affected draw was
- * incomplete); the host then repeats the draw with worst-case pools. */
+/* 1 if a scratch pool overflowed since the previous call (the affected draw left the
+ * framebuffer untouched); the pools' minimum sizes have then been raised to what that draw
+ * needed, so the host simply repeats it. */
 int srpcuTakeOverflow(void);
-void srpcuSetWorstCasePools(int on);
 
 void srpcuSetProfiling(int on);
 unsigned long long srpcuCollectStageTimes(double outMs[3]);

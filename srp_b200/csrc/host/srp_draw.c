@@ -239,16 +239,21 @@ static bool buildDraw(
 	d->startIndex = startIndex;
 	d->count = count;
 	d->nInputPrims = (uint32_t) nPrims;
+	/* worst-case records per input primitive: a clipped triangle fans into <= 7; a line is
+	 * stored as segments of 16 DDA fragments and has <= max(W, H) + 1 of them */
+	const uint32_t maxDim = (uint32_t) (fb->width > fb->height ? fb->width : fb->height);
+	const uint32_t segmentsPerLine = (maxDim + 1) / 16 + 2;
 	if (isTriangle)
 	{
 		d->kind = st->polygonMode == SRP_POLYGON_MODE_FILL ? SRPD_KIND_TRIANGLE
 		        : st->polygonMode == SRP_POLYGON_MODE_LINE ? SRPD_KIND_LINE : SRPD_KIND_POINT;
-		d->maxOutPerInput = st->polygonMode == SRP_POLYGON_MODE_FILL ? 7 : 21;
+		d->maxOutPerInput = st->polygonMode == SRP_POLYGON_MODE_FILL ? 7
+		                  : st->polygonMode == SRP_POLYGON_MODE_LINE ? 21 * segmentsPerLine : 21;
 	}
 	else
 	{
 		d->kind = isLine ? SRPD_KIND_LINE : SRPD_KIND_POINT;
-		d->maxOutPerInput = 1;
+		d->maxOutPerInput = isLine ? segmentsPerLine : 1;
 	}
 	const size_t th = (size_t) srpcuTileHeight();
 	const size_t tilesY = (fb->height + th - 1) / th;
@@ -290,7 +295,7 @@ static void submit(
 	if (ok && buildDraw(&d, ib, vb, fbs[0], sp, primitive, startIndex, count, &prog))
 	{
 		d.nFrames = (uint32_t) nFrames;
-		for (int attempt = 0; attempt < 2; attempt++)
+		for (int attempt = 0; attempt < 3; attempt++)
 		{
 			for (size_t f = 0; f < nFrames; f++)
 			{
@@ -313,16 +318,16 @@ static void submit(
 				srpFramebufferAfterDraw(impls, nFrames, d.st.stencilEnabled);
 				break;
 			}
-			/* A scratch pool was too small for this draw (heavy clipping / huge primitives).
-			 * The kernels raised the draw's abort flag, so the tile kernel left the
-			 * framebuffer (and a pending clear) untouched: repeat once with worst-case pools. */
-			if (attempt == 1)
+			/* A scratch pool was too small for this draw (heavy clipping / long lines).  The
+			 * kernels raised the draw's abort flag, so the tile kernel left the framebuffer
+			 * (and a pending clear) untouched, and recorded what the draw needs; the pools'
+			 * floors are now at that size: repeat. */
+			if (attempt == 2)
 			{
-				srpFatalMessage("srpDraw", "scratch pools overflowed even at worst-case size; draw is incomplete");
+				srpFatalMessage("srpDraw", "scratch pools overflowed repeatedly; draw is incomplete");
 				srpFramebufferAfterDraw(impls, nFrames, d.st.stencilEnabled);
 				break;
 			}
-			srpcuSetWorstCasePools(1);
 		}
 	}
 	free(frames);

@@ -5,7 +5,8 @@
  * while still visiting them in primitive-id order.  Records are already stored in id
  * order by the geometry kernel, so "in order" means "in increasing record index".
  *
- * Bins are supertiles of 8x8 tiles (256x128 px).  Three passes over the 8-byte bounding
+ * Bins are supertiles of 2^k x 2^k tiles (k = 3: 256x128 px, down to k = 1 for dense
+ * sub-pixel geometry; chosen per draw).  Three passes over the 8-byte bounding
  * boxes (HBM-bound; the records themselves are not touched):
  *   count : one CTA per chunk of 2048 records counts, per supertile, how many of the
  *           chunk's records overlap it            -> chunkCounts[chunk][supertile]
@@ -24,12 +25,12 @@
 namespace {
 
 /* inclusive supertile rectangle of a pixel bbox: sx0 | sy0<<8 | sx1<<16 | sy1<<24 */
-__device__ __forceinline__ uint32_t superRect(uint2 bb, uint32_t superX, uint32_t superY)
+__device__ __forceinline__ uint32_t superRect(uint2 bb, uint32_t superX, uint32_t superY, uint32_t superShift)
 {
 	const uint32_t x0 = bb.x & 0xFFFFu, y0 = bb.x >> 16, x1 = bb.y & 0xFFFFu, y1 = bb.y >> 16;
 	if (x1 <= x0 || y1 <= y0)
 		return 0x00000101u;   /* empty: sx0 = 1 > sx1 = 0 */
-	constexpr uint32_t SW = SRPD_TILE_W * SRPD_SUPER_W, SH = SRPD_TILE_H * SRPD_SUPER_H;
+	const uint32_t SW = (uint32_t) SRPD_TILE_W << superShift, SH = (uint32_t) SRPD_TILE_H << superShift;
 	uint32_t sx0 = x0 / SW, sy0 = y0 / SH, sx1 = (x1 - 1) / SW, sy1 = (y1 - 1) / SH;
 	if (sx1 >= superX) sx1 = superX - 1;
 	if (sy1 >= superY) sy1 = superY - 1;
@@ -54,7 +55,7 @@ srpdBinCountKernel(const __grid_constant__ SrpdBinArgs a)
 		const uint32_t r = first + o;
 		if (r >= nStored)
 			break;
-		const uint32_t rect = superRect(a.bboxes[r], a.superX, a.superY);
+		const uint32_t rect = superRect(a.bboxes[r], a.superX, a.superY, a.superShift);
 		if (rectEmpty(rect))
 			continue;
 		for (uint32_t sy = (rect >> 8) & 0xFFu; sy <= (rect >> 24); sy++)
@@ -66,33 +67,58 @@ srpdBinCountKernel(const __grid_constant__ SrpdBinArgs a)
 		a.chunkCounts[(size_t) blockIdx.x * nSuper + s] = sCount[s];
 }
 
-__global__ void __launch_bounds__(1024)
-srpdBinScanKernel(const __grid_constant__ SrpdBinArgs a)
+/* Scan pass 1: thread = supertile column; exclusive scan over the chunks (independent,
+ * coalesced loads -- only the running sum is serial), total per supertile. */
+__global__ void __launch_bounds__(128)
+srpdBinScanColumnsKernel(const __grid_constant__ SrpdBinArgs a)
 {
-	/* single CTA; thread s owns supertile column s (coalesced across s) */
-	__shared__ uint32_t sTotals[1024];
-	__shared__ uint32_t sCarry;
 	const uint32_t nSuper = a.superX * a.superY;
 	const uint32_t nStored = a.frameCounts[1];
 	const uint32_t nChunks = (nStored + SRPD_BIN_CHUNK - 1) / SRPD_BIN_CHUNK;
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= nSuper)
+		return;
+	uint32_t run = 0;
+	uint32_t c = 0;
+	for (; c + 8 <= nChunks; c += 8)
+	{
+		uint32_t n[8];
+		#pragma unroll
+		for (int u = 0; u < 8; u++)
+			n[u] = a.chunkCounts[(size_t) (c + u) * nSuper + s];
+		#pragma unroll
+		for (int u = 0; u < 8; u++)
+		{
+			a.chunkCounts[(size_t) (c + u) * nSuper + s] = run;
+			run += n[u];
+		}
+	}
+	for (; c < nChunks; c++)
+	{
+		const size_t at = (size_t) c * nSuper + s;
+		const uint32_t n = a.chunkCounts[at];
+		a.chunkCounts[at] = run;
+		run += n;
+	}
+	a.superTotals[s] = run;
+}
+
+/* Scan pass 2: one CTA, exclusive scan of the supertile totals -> superOffsets */
+__global__ void __launch_bounds__(1024)
+srpdBinScanKernel(const __grid_constant__ SrpdBinArgs a)
+{
+	__shared__ uint32_t sTotals[1024];
+	__shared__ uint32_t sCarry;
+	const uint32_t nSuper = a.superX * a.superY;
 	if (threadIdx.x == 0)
 		sCarry = 0;
 	__syncthreads();
 	for (uint32_t s0 = 0; s0 < nSuper; s0 += 1024)
 	{
 		const uint32_t s = s0 + threadIdx.x;
-		uint32_t run = 0;
-		if (s < nSuper)
-			for (uint32_t c = 0; c < nChunks; c++)
-			{
-				const size_t at = (size_t) c * nSuper + s;
-				const uint32_t n = a.chunkCounts[at];
-				a.chunkCounts[at] = run;
-				run += n;
-			}
+		const uint32_t run = s < nSuper ? a.superTotals[s] : 0;
 		sTotals[threadIdx.x] = run;
 		__syncthreads();
-		/* exclusive scan of the 1024 totals (Hillis-Steele in shared memory) */
 		uint32_t v = run;
 		for (uint32_t o = 1; o < 1024; o <<= 1)
 		{
@@ -159,7 +185,7 @@ srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 	for (int r = 0; r < ROUNDS; r++)
 	{
 		const uint32_t rec = warpFirst + r * 32 + lane;
-		rect[r] = rec < nStored ? superRect(a.bboxes[rec], a.superX, a.superY) : 0x00000101u;
+		rect[r] = rec < nStored ? superRect(a.bboxes[rec], a.superX, a.superY, a.superShift) : 0x00000101u;
 	}
 	__syncthreads();
 	#pragma unroll
@@ -231,15 +257,23 @@ void srpdLaunchBin(const SrpdBinArgs& a, cudaStream_t stream)
 {
 	const uint32_t nSuper = a.superX * a.superY;
 	srpdBinCountKernel<<<a.nChunksMax, SRPD_BIN_THREADS, nSuper * sizeof(uint32_t), stream>>>(a);
+	srpdBinScanColumnsKernel<<<(nSuper + 127) / 128, 128, 0, stream>>>(a);
 	srpdBinScanKernel<<<1, 1024, 0, stream>>>(a);
 	/* as many warps per chunk as the cursor matrix allows in shared memory */
 	const size_t budget = 160 * 1024;
-	if (2 * 8 * (size_t) nSuper * sizeof(uint32_t) <= budget)
+	if (2 * 8 * (size_t) nSuper * sizeof(uint32_t) <= budget / 2)
 	{
 		const size_t bytes = 2 * 8 * (size_t) nSuper * sizeof(uint32_t);
 		static bool configured8 = false;
 		if (!configured8) { cudaFuncSetAttribute(srpdBinFillKernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget); configured8 = true; }
 		srpdBinFillKernel<8><<<a.nChunksMax, 8 * 32, bytes, stream>>>(a);
+	}
+	else if (2 * 4 * (size_t) nSuper * sizeof(uint32_t) <= budget)
+	{
+		const size_t bytes = 2 * 4 * (size_t) nSuper * sizeof(uint32_t);
+		static bool configured4 = false;
+		if (!configured4) { cudaFuncSetAttribute(srpdBinFillKernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget); configured4 = true; }
+		srpdBinFillKernel<4><<<a.nChunksMax, 4 * 32, bytes, stream>>>(a);
 	}
 	else
 	{
@@ -248,5 +282,5 @@ void srpdLaunchBin(const SrpdBinArgs& a, cudaStream_t stream)
 		if (!configured2) { cudaFuncSetAttribute(srpdBinFillKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget); configured2 = true; }
 		srpdBinFillKernel<2><<<a.nChunksMax, 2 * 32, bytes, stream>>>(a);
 	}
-	gBinLaunches += 3;
+	gBinLaunches += 4;
 }

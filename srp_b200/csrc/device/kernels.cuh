@@ -17,8 +17,10 @@ constexpr int SRPD_BLK_W = 8;            /* pixels owned by one warp: 8 x 4     
 constexpr int SRPD_BLK_H = 4;
 constexpr int SRPD_TILE_THREADS = SRPD_TILE_W * SRPD_TILE_H;       /* one thread per pixel */
 constexpr int SRPD_TILE_WARPS = SRPD_TILE_THREADS / 32;
-constexpr int SRPD_SUPER_W = 8;          /* tiles per supertile (coarse bin), x            */
-constexpr int SRPD_SUPER_H = 8;          /* tiles per supertile, y                         */
+/* coarse bins ("supertiles") are 2^k x 2^k tiles with k = superShift chosen per draw from the
+ * expected record density: 8x8 tiles (256x128 px) for ordinary meshes down to 2x2 for
+ * millions of sub-pixel primitives, so that a tile never filters more than ~1-2 k candidates */
+constexpr int SRPD_SUPER_SHIFT_MAX = 3;
 
 constexpr int SRPD_GEOM_THREADS = 256;   /* input primitives per geometry batch            */
 constexpr int SRPD_GEOM_MAX_VERTS = 3 * SRPD_GEOM_THREADS;
@@ -68,6 +70,8 @@ struct SrpdBinArgs
 	const uint32_t* frameCounts;      /* [0][1] = number of stored records               */
 	uint32_t nChunksMax;              /* grid size of the chunk kernels                  */
 	uint32_t superX, superY;          /* supertile grid                                  */
+	uint32_t superShift;              /* supertile = (1 << superShift)^2 tiles           */
+	uint32_t* superTotals;            /* [nSuper] entries per supertile (scan pass 1 -> 2)*/
 	uint32_t* chunkCounts;            /* [nChunksMax][nSuper]                            */
 	uint32_t* superOffsets;           /* [nSuper + 1]                                    */
 	uint32_t* listIds;                /* [listCapacity] record indices, id order per supertile */
@@ -90,6 +94,7 @@ struct SrpdTileArgs
 	const uint32_t* superOffsets;     /* nullptr: direct path, every tile scans all records */
 	const uint32_t* listIds;
 	uint32_t superX;
+	uint32_t superShift;
 	uint32_t tilesX, tilesY;
 	const uint32_t* abortFlag;
 	const uint32_t* occupancy;        /* [nFrames][occWordsPerFrame] bit per tile: some record's box touches it */

@@ -355,7 +355,7 @@ __device__ __forceinline__ void processTile(
 	const uint32_t* ids = nullptr;
 	if (a.superOffsets)
 	{
-		const uint32_t s = (uint32_t) (tileY / SRPD_SUPER_H) * a.superX + (uint32_t) (tileX / SRPD_SUPER_W);
+		const uint32_t s = ((uint32_t) tileY >> a.superShift) * a.superX + ((uint32_t) tileX >> a.superShift);
 		begin = a.superOffsets[s];
 		end = a.superOffsets[s + 1];
 		ids = a.listIds;

@@ -32,7 +32,7 @@ struct Runtime
 	int device = -1;
 	cudaStream_t stream = nullptr;
 	std::string lastError;
-	Pool records, bboxes, scan, frameCounts, chunkCounts, superOffsets, listIds, uniforms, frames;
+	Pool records, bboxes, scan, frameCounts, chunkCounts, superOffsets, superTotals, listIds, uniforms, frames;
 	int smCount = 148;
 	uint64_t recFloor = 0, listFloor = 0;  /* minimum pool capacities, raised by srpcuTakeOverflow() */
 	SrpdStats* stats = nullptr;            /* device, SRPD_STATS_SLOTS slots */
@@ -121,8 +121,8 @@ int srpcuTileHeight(void) { return SRPD_TILE_H; }
 const char* srpcuVersion(void)
 {
 	static char buf[128];
-	snprintf(buf, sizeof buf, "srp-b200 sm_100a tile %dx%d supertile %dx%d geom-batch %d",
-	         SRPD_TILE_W, SRPD_TILE_H, SRPD_SUPER_W, SRPD_SUPER_H, SRPD_GEOM_THREADS);
+	snprintf(buf, sizeof buf, "srp-b200 sm_100a tile %dx%d block %dx%d geom-batch %d line-seg %d",
+	         SRPD_TILE_W, SRPD_TILE_H, SRPD_BLK_W, SRPD_BLK_H, SRPD_GEOM_THREADS, SRPD_LINE_SEG);
 	return buf;
 }
 
@@ -350,8 +350,25 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	CU(cudaGetLastError());
 	mark();
 
-	const uint32_t superX = (tilesX + SRPD_SUPER_W - 1) / SRPD_SUPER_W;
-	const uint32_t superY = (tilesY + SRPD_SUPER_H - 1) / SRPD_SUPER_H;
+	/* supertile size from the expected record density: aim at <= ~1.5 k candidates per tile */
+	uint32_t superShift = SRPD_SUPER_SHIFT_MAX;
+	const uint64_t expected = recCapacity < d.nInputPrims ? recCapacity : d.nInputPrims;
+	while (superShift > 1)
+	{
+		const uint64_t sx = (tilesX + (1u << superShift) - 1) >> superShift, sy = (tilesY + (1u << superShift) - 1) >> superShift;
+		if (expected / (sx * sy) <= 1536)
+			break;
+		const uint64_t nx = (tilesX + (1u << (superShift - 1)) - 1) >> (superShift - 1);
+		const uint64_t ny = (tilesY + (1u << (superShift - 1)) - 1) >> (superShift - 1);
+		if (nx > 256 || ny > 256 || nx * ny > 8192)
+			break;                       /* the 8-bit supertile coordinates / shared-memory cursors would not fit */
+		superShift--;
+	}
+	if (const char* e = getenv("SRP_B200_SUPER_SHIFT")) superShift = (uint32_t) atoi(e);
+	if (superShift < 1) superShift = 1;
+	if (superShift > SRPD_SUPER_SHIFT_MAX) superShift = SRPD_SUPER_SHIFT_MAX;
+	const uint32_t superX = (tilesX + (1u << superShift) - 1) >> superShift;
+	const uint32_t superY = (tilesY + (1u << superShift) - 1) >> superShift;
 	const uint32_t nSuper = superX * superY;
 
 	bool binned = nFrames == 1 && recCapacity > g.binThreshold && nSuper > 1 && nSuper <= 8192
@@ -370,6 +387,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ta.recStride = recStride;
 	ta.frameCounts = ga.frameCounts;
 	ta.superX = superX;
+	ta.superShift = superShift;
 	ta.tilesX = tilesX;
 	ta.tilesY = tilesY;
 	ta.abortFlag = ga.abortFlag;
@@ -390,6 +408,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		ba.nChunksMax = (recCapacity + SRPD_BIN_CHUNK - 1) / SRPD_BIN_CHUNK;
 		ba.superX = superX;
 		ba.superY = superY;
+		ba.superShift = superShift;
 		uint64_t listCap = (uint64_t) recCapacity * 2 + (uint64_t) nSuper * 64 + 65536;
 		if (listCap < g.listFloor) listCap = g.listFloor;
 		if (getenv("SRP_B200_WORST_CASE_POOLS")) listCap = (uint64_t) recCapacity * nSuper;
@@ -397,15 +416,17 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		ba.listCapacity = (uint32_t) listCap;
 		if (!grow(g.chunkCounts, sizeof(uint32_t) * (size_t) ba.nChunksMax * nSuper)) return 1;
 		if (!grow(g.superOffsets, sizeof(uint32_t) * (nSuper + 1))) return 1;
+		if (!grow(g.superTotals, sizeof(uint32_t) * nSuper)) return 1;
 		if (!grow(g.listIds, sizeof(uint32_t) * (size_t) ba.listCapacity)) return 1;
 		ba.chunkCounts = (uint32_t*) g.chunkCounts.ptr;
 		ba.superOffsets = (uint32_t*) g.superOffsets.ptr;
+		ba.superTotals = (uint32_t*) g.superTotals.ptr;
 		ba.listIds = (uint32_t*) g.listIds.ptr;
 		ba.abortFlag = ga.abortFlag;
 		ba.needed = ga.needed;
 		ba.stats = g.stats;
 		srpdLaunchBin(ba, g.stream);
-		g.launches += 3;
+		g.launches += 4;
 		CU(cudaGetLastError());
 		ta.superOffsets = ba.superOffsets;
 		ta.listIds = ba.listIds;

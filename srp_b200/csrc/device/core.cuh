@@ -34,7 +34,7 @@
  *   12-14  z_i * iw_i                       -                       -
  *   15     primitive id (all kinds)
  *   16-18  iw_i (1 / clip w)                -                       -
- *   19     -
+ *   19     1 + offset into the barycentric checkpoint table (large triangles), 0 = none
  * For PERSPECTIVE float/double attributes the blobs hold a_i * iw_i (the first product
  * of the reference's `a_i * invW[i] * weights[i]`, interpolation.c:72), everything else
  * is stored verbatim. */

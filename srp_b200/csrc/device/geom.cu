@@ -133,6 +133,7 @@ struct Emitter
 	uint32_t* occupancy;        /* frame base */
 	uint32_t idBase, storeBase; /* global bases of this input primitive (valid when writing) */
 	uint32_t nEmit, nStore;
+	uint32_t frame;
 	bool overflow;
 };
 
@@ -218,6 +219,30 @@ __device__ void emitTriangle(Emitter& em, const SrpdState& st, const SrpdPos p[3
 		stored = false;
 	if (stored)
 	{
+		if (WRITE)
+		{
+			/* Large triangle: reserve a checkpoint table (rows x tile columns) and queue it for
+			 * the checkpoint pre-pass, so that no tile has to replay more than a tile's width of
+			 * its barycentric chain.  If the table or the queue is full the triangle simply has
+			 * no checkpoints and the tile kernel replays from the corner (slow, still exact). */
+			const uint32_t rows = (uint32_t) (s.maxY - s.minY), width = (uint32_t) (s.maxX - s.minX);
+			if (rows > SRPD_LARGE_EXTENT || width > SRPD_LARGE_EXTENT)
+			{
+				const uint32_t cols = (uint32_t) (s.maxX - 1) / SRPD_TILE_W - (uint32_t) s.minX / SRPD_TILE_W + 1;
+				const uint32_t entries = rows * cols;
+				const uint32_t slot = em.storeBase + em.nStore;
+				const uint32_t off = atomicAdd(em.a->ckptCursor, entries);
+				if (off + entries <= em.a->ckptCapacity && slot < em.a->recCapacity)
+				{
+					const uint32_t q = atomicAdd(em.a->largeCount, 1u);
+					if (q < em.a->largeCapacity)
+					{
+						em.a->largeList[q] = make_uint2(em.frame, slot);
+						s.w[19] = off + 1;
+					}
+				}
+			}
+		}
 		unsigned char* blobs = beginRecord<WRITE>(em, s.w, s.minX, s.minY, s.maxX, s.maxY);
 		if (WRITE && blobs)
 			for (int i = 0; i < 3; i++)
@@ -518,6 +543,7 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	em.bboxes = a.bboxes + (size_t) frame * a.recCapacity;
 	em.occupancy = a.occupancy + (size_t) frame * a.occWordsPerFrame;
 	em.idBase = 0; em.storeBase = 0; em.nEmit = 0; em.nStore = 0; em.overflow = false;
+	em.frame = frame;
 	if (active)
 		processPrimitive<false>(em, d, nv, p, vary);
 	const uint32_t myEmit = em.nEmit, myStore = em.nStore;

@@ -34,7 +34,8 @@ constexpr int SRPD_BIN_THREADS = 256;
 constexpr int SRPD_BIN_CHUNK = 2048;     /* records per coarse-binning CTA                  */
 
 /* Per-draw zero-filled header in front of the scan state: word 0 batch ticket, 1 abort flag,
- * 2 tile work counter, 3 records a frame needed (max over frames), 4 coarse-list entries needed */
+ * 2 tile work counter, 3 records a frame needed (max over frames), 4 coarse-list entries needed,
+ * 5 checkpoint-table cursor (entries), 6 number of large triangles */
 constexpr int SRPD_DRAW_HEADER_BYTES = 32;
 
 /* Decoupled look-back word: [63:62] status, [61:31] emitted ids, [30:0] stored records */
@@ -61,8 +62,29 @@ struct SrpdGeomArgs
 	uint32_t* occupancy;              /* [nFrames][occWordsPerFrame], zeroed per draw: tiles touched by a stored record */
 	uint32_t occWordsPerFrame;
 	uint32_t tilesX, tilesY;
+	/* large triangles: barycentric checkpoints (checkpoint.cu) */
+	uint32_t* ckptCursor;             /* header word 5: entries handed out               */
+	uint32_t* largeCount;             /* header word 6                                   */
+	uint2* largeList;                 /* [largeCapacity] {frame, record}                 */
+	uint32_t largeCapacity;
+	uint32_t ckptCapacity;            /* entries (3 floats each) in the checkpoint table */
 	SrpdStats* stats;
 };
+
+/* Barycentric checkpoints of large triangles: for every pixel row of the bounding box and
+ * every tile column it spans, lambda at the first covered pixel of that column.  Entry
+ * (row, col) of a triangle lives at ckptTable[3 * (offset + row * cols + col)]. */
+constexpr int SRPD_LARGE_EXTENT = 96;    /* a triangle is "large" when its box exceeds this in x or y */
+struct SrpdCkptArgs
+{
+	const unsigned char* records;
+	uint32_t recCapacity, recStride;
+	const uint32_t* largeCount;
+	const uint2* largeList;
+	uint32_t largeCapacity;
+	float* ckptTable;
+};
+void srpdLaunchCheckpoints(const SrpdCkptArgs& a, cudaStream_t stream);
 
 struct SrpdBinArgs
 {
@@ -101,6 +123,7 @@ struct SrpdTileArgs
 	uint32_t occWordsPerFrame;
 	uint32_t* workCounter;            /* zeroed per draw: next work item of the persistent tile kernel */
 	uint32_t tilesPerItem;            /* consecutive tiles of one frame per work item */
+	const float* ckptTable;           /* barycentric checkpoints of large triangles     */
 	uint32_t smCount;
 	SrpdStats* stats;
 };

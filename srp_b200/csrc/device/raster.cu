@@ -165,7 +165,7 @@ __device__ __forceinline__ void emitFragment(
  * rows, then right to the block's first column (clamped to the bounding box).  The twelve
  * row-start values go to shared memory; a pixel then only adds its <= 7 remaining x steps.
  * The sequence of additions each pixel's value goes through is unchanged => bit-exact. */
-__device__ __forceinline__ void prepareTriangle(const unsigned char* rec, int bx0, int by0, float* out)
+__device__ __forceinline__ void prepareTriangle(const unsigned char* rec, const float* ckptTable, int bx0, int by0, float* out)
 {
 	const uint4* h = (const uint4*) rec;
 	const uint4 q0 = __ldg(h + 0), q1 = __ldg(h + 1), q2 = __ldg(h + 2);
@@ -173,6 +173,43 @@ __device__ __forceinline__ void prepareTriangle(const unsigned char* rec, int bx
 	float l0 = __uint_as_float(q0.x), l1 = __uint_as_float(q0.y), l2 = __uint_as_float(q0.z);
 	const float dy0 = __uint_as_float(q2.x), dy1 = __uint_as_float(q2.y), dy2 = __uint_as_float(q2.z);
 	const float dx0 = __uint_as_float(q1.x), dx1 = __uint_as_float(q1.y), dx2 = __uint_as_float(q1.z);
+	const uint32_t ckpt = __ldg((const uint32_t*) rec + 19);
+	if (ckpt)
+	{
+		/* large triangle: start from the checkpoints of (row, this tile's column), written by
+		 * srpdCheckpointKernel with the reference's own sequence of additions */
+		const int maxX = (int) (q0.w >> 16), maxY = (int) (q1.w >> 16);
+		const int col0 = minX / SRPD_TILE_W;
+		const int cols = (maxX - 1) / SRPD_TILE_W - col0 + 1;
+		const int col = bx0 / SRPD_TILE_W - col0;
+		const int tileX0 = (bx0 / SRPD_TILE_W) * SRPD_TILE_W;
+		const int nx = bx0 - (tileX0 > minX ? tileX0 : minX);      /* steps from the checkpoint to the block's first column */
+		float r[SRPD_BLK_H][3];
+		#pragma unroll
+		for (int k = 0; k < SRPD_BLK_H; k++)
+		{
+			const int row = by0 + k - minY;
+			r[k][0] = 0.f; r[k][1] = 0.f; r[k][2] = 0.f;
+			if (row >= 0 && row < maxY - minY)
+			{
+				const float* e = ckptTable + 3 * ((size_t) (ckpt - 1) + (size_t) row * cols + col);
+				r[k][0] = __ldg(e + 0); r[k][1] = __ldg(e + 1); r[k][2] = __ldg(e + 2);
+			}
+		}
+		for (int i = 0; i < nx; i++)
+		{
+			#pragma unroll
+			for (int k = 0; k < SRPD_BLK_H; k++)
+			{
+				r[k][0] = __fadd_rn(r[k][0], dx0); r[k][1] = __fadd_rn(r[k][1], dx1); r[k][2] = __fadd_rn(r[k][2], dx2);
+			}
+		}
+		float4* o = (float4*) out;
+		o[0] = make_float4(r[0][0], r[0][1], r[0][2], r[1][0]);
+		o[1] = make_float4(r[1][1], r[1][2], r[2][0], r[2][1]);
+		o[2] = make_float4(r[2][2], r[3][0], r[3][1], r[3][2]);
+		return;
+	}
 	const int sy = by0 - minY;                 /* chain steps down to the block's first row (may be < 0) */
 	const int n0 = sy > 0 ? sy : 0;
 	int i = 0;
@@ -443,7 +480,7 @@ __device__ __forceinline__ void processTile(
 			{
 				float* prep = sPrep + (size_t) warp * 32 * SRPD_BLK_H * 3;
 				if (mine)
-					prepareTriangle(records + (size_t) sIds[j] * a.recStride, bx0, by0, prep + lane * SRPD_BLK_H * 3);
+					prepareTriangle(records + (size_t) sIds[j] * a.recStride, a.ckptTable, bx0, by0, prep + lane * SRPD_BLK_H * 3);
 				__syncwarp();
 			}
 			while (m)

@@ -33,6 +33,7 @@ struct Runtime
 	cudaStream_t stream = nullptr;
 	std::string lastError;
 	Pool records, bboxes, scan, frameCounts, chunkCounts, superOffsets, superTotals, listIds, uniforms, frames;
+	Pool ckptTable, largeList;
 	int smCount = 148;
 	uint64_t recFloor = 0, listFloor = 0;  /* minimum pool capacities, raised by srpcuTakeOverflow() */
 	SrpdStats* stats = nullptr;            /* device, SRPD_STATS_SLOTS slots */
@@ -344,10 +345,40 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ga.occWordsPerFrame = occWords;
 	ga.tilesX = tilesX;
 	ga.tilesY = tilesY;
+	/* checkpoint table for large triangles: room for 64 framebuffer-sized triangles */
+	const uint32_t largeCapacity = 65536;
+	uint64_t ckptEntries = 0;
+	if (d.kind == SRPD_KIND_TRIANGLE && (st.width > SRPD_LARGE_EXTENT || st.height > SRPD_LARGE_EXTENT))
+	{
+		ckptEntries = (uint64_t) (tilesX + 1) * st.height * 64;
+		if (ckptEntries > (1ull << 27)) ckptEntries = 1ull << 27;     /* 1.5 GiB of float3 at most */
+		if (!grow(g.ckptTable, ckptEntries * 3 * sizeof(float))) return 1;
+		if (!grow(g.largeList, sizeof(uint2) * largeCapacity)) return 1;
+	}
+	ga.ckptCursor = (uint32_t*) g.scan.ptr + 5;
+	ga.largeCount = (uint32_t*) g.scan.ptr + 6;
+	ga.largeList = (uint2*) g.largeList.ptr;
+	ga.largeCapacity = ckptEntries ? largeCapacity : 0;
+	ga.ckptCapacity = (uint32_t) ckptEntries;
 	ga.stats = g.stats;
 	srpdLaunchGeom(ga, g.stream);
 	g.launches++;
 	CU(cudaGetLastError());
+	if (ckptEntries)
+	{
+		SrpdCkptArgs ca;
+		memset(&ca, 0, sizeof ca);
+		ca.records = ga.records;
+		ca.recCapacity = recCapacity;
+		ca.recStride = recStride;
+		ca.largeCount = ga.largeCount;
+		ca.largeList = ga.largeList;
+		ca.largeCapacity = largeCapacity;
+		ca.ckptTable = (float*) g.ckptTable.ptr;
+		srpdLaunchCheckpoints(ca, g.stream);
+		g.launches++;
+		CU(cudaGetLastError());
+	}
 	mark();
 
 	/* supertile size from the expected record density: aim at <= ~1.5 k candidates per tile */
@@ -394,6 +425,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ta.occupancy = ga.occupancy;
 	ta.occWordsPerFrame = occWords;
 	ta.workCounter = (uint32_t*) g.scan.ptr + 2;
+	ta.ckptTable = (const float*) g.ckptTable.ptr;
 	ta.smCount = (uint32_t) g.smCount;
 	ta.stats = g.stats;
 	if (ta.d.tileRow1 > tilesY) ta.d.tileRow1 = tilesY;

@@ -262,6 +262,17 @@ def all_scenes() -> dict:
                clear_before=True),
         S.Draw("solid", H.SRP_PRIM_LINE_LOOP, tris[:17], 24, uniform=_xf() + np.array([0.2, 0.3, 1, 0.5], f32).tobytes())]))
 
+    # ---- large triangles: the barycentric-checkpoint path (boxes far wider than a tile) ----
+    quad = np.array([[-1, -1, 0.2, 1, 0, 0], [1, -1, 0.2, 0, 1, 0], [1, 1, -0.3, 0, 0, 1],
+                     [-1, -1, 0.2, 1, 0, 0], [1, 1, -0.3, 0, 0, 1], [-1, 1, 0.1, 1, 1, 0],
+                     [-0.95, 0.9, 0.5, 1, 1, 1], [0.1, -0.97, -0.5, 0.2, 0.2, 0.2], [0.93, 0.55, 0.4, 0, 1, 1],
+                     [-2.5, -0.3, 0.0, 1, 0, 1], [2.5, -0.2, 0.0, 0, 1, 0], [0.0, 3.0, 0.0, 0, 0, 1]], f32)
+    add(S.Scene("large_triangles_700x500", 700, 500, [
+        vcolor(quad, state=[("srpDepthTest", True)]),
+        vcolor(quad, uniform=_persp_xf(S.rotate(0.5, 0.9, 1.3), cam=(0, 0, -1.6), near=0.5, far=10), mode=H.SRP_INTERPOLATION_MODE_AFFINE),
+        S.Draw("primid", H.SRP_PRIM_TRIANGLES, quad, 24, uniform=_xf(S.rotate(0, 0, 2.2)),
+               state=[("srpDepthCompareOp", H.SRP_COMPARE_GEQUAL), ("srpRasterCullFace", H.SRP_FACE_BACK)])]))
+
     # ---- a mid-size mesh that takes the binned path (thousands of primitives) ----
     mverts, midx = grid_mesh(70, 50, z_fn=lambda x, y: 0.4 * np.sin(3 * x + y) * np.cos(2 * y - x))
     add(S.Scene("binned_mesh_640x360", 640, 360, [

@@ -3,6 +3,7 @@
 markdown summary kept under profiles/.   usage: ncu_summary.py REPORT.ncu-rep LAUNCHES.csv OUT.md [title]"""
 import collections
 import csv
+import io
 import subprocess
 import sys
 
@@ -43,7 +44,7 @@ def main():
         share = f"{100 * sum(v) / total:.1f} %" if "srpd" in k else "-"
         lines.append(f"| `{k}` | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {share} |")
     # ---- per-kernel metrics
-    raw = list(csv.reader(ncu("-i", rep, "--page", "raw", "--csv").splitlines()))
+    raw = list(csv.reader(io.StringIO(ncu("-i", rep, "--page", "raw", "--csv"))))
     hdr, units = raw[0], raw[1]
     idx = {h: i for i, h in enumerate(hdr)}
     lines += ["", "## `ncu --set full` of one frame's kernels", ""]
@@ -56,7 +57,7 @@ def main():
         lines.append("")
     # ---- hottest source lines of the two big kernels
     for kern in ("srpdTileKernel", "srpdGeomKernel"):
-        src = list(csv.reader(ncu("-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "--kernel-name", f"regex:{kern}").splitlines()))
+        src = list(csv.reader(io.StringIO(ncu("-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "--kernel-name", f"regex:{kern}"))))
         cur, items = None, []
         for r in src:
             if len(r) >= 2 and r[0] == "File Path":

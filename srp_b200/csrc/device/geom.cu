@@ -561,9 +561,8 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	}
 	if (warp == 0)
 	{
-		/* Decoupled look-back by one warp: lane l inspects predecessor (batch - 1 - l); the
-		 * window slides back 32 batches at a time until a batch that already knows its
-		 * inclusive prefix is found.  Batch 0 of every frame publishes a prefix at once, so
+		/* Decoupled look-back by one warp, 256 predecessors per step; the window slides back
+		 * until a batch that already knows its inclusive prefix is found.  Batch 0 of every frame publishes a prefix at once, so
 		 * the walk never leaves the frame. */
 		const unsigned long long agg = ((unsigned long long) totE << 31) | (unsigned long long) totS;
 		volatile unsigned long long* state = a.scanState;
@@ -573,28 +572,46 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 			state[batch] = (b == 0 ? SRPD_SCAN_PREFIX : SRPD_SCAN_AGG) | agg;
 		if (b != 0)
 		{
+			/* window of 256 predecessors per step: lane l inspects the 8 batches
+			 * [window - 8l - 7, window - 8l], nearest first (8 independent loads in flight) */
 			long long window = (long long) batch - 1;
 			for (;;)
 			{
-				const long long j = window - lane;
-				unsigned long long sv = SRPD_SCAN_PREFIX;            /* before the frame: prefix 0 */
-				if (j >= (long long) frameFirst)
-					sv = state[j];
-				const unsigned flag = (unsigned) (sv >> 62);
-				const uint32_t notReady = __ballot_sync(0xFFFFFFFFu, flag == 0);
-				const uint32_t isPrefix = __ballot_sync(0xFFFFFFFFu, flag == 2);
-				const int p = isPrefix ? __ffs(isPrefix) - 1 : 32;    /* nearest lane that holds a prefix */
+				unsigned long long sum = 0;
+				bool ready = true, hasPrefix = false;
+				#pragma unroll
+				for (int k = 0; k < 8; k++)
+				{
+					const long long j = window - 8 * lane - k;
+					unsigned long long sv = SRPD_SCAN_PREFIX;            /* before the frame: prefix 0 */
+					if (j >= (long long) frameFirst)
+						sv = state[j];
+					const unsigned flag = (unsigned) (sv >> 62);
+					if (!hasPrefix)                                       /* entries beyond this lane's nearest prefix do not count */
+					{
+						if (flag == 0)
+							ready = false;
+						else
+						{
+							sum += sv & SRPD_SCAN_VALUE_MASK;
+							hasPrefix = flag == 2;
+						}
+					}
+				}
+				const uint32_t isPrefix = __ballot_sync(0xFFFFFFFFu, hasPrefix);
+				const uint32_t notReady = __ballot_sync(0xFFFFFFFFu, !ready);
+				const int p = isPrefix ? __ffs(isPrefix) - 1 : 32;    /* nearest lane whose group holds a prefix */
 				const uint32_t need = p >= 31 ? 0xFFFFFFFFu : ((1u << (p + 1)) - 1u);
 				if (notReady & need)
 					continue;                                          /* a needed predecessor has not published yet */
-				unsigned long long v = (lane <= p) ? (sv & SRPD_SCAN_VALUE_MASK) : 0ull;
+				unsigned long long v = (lane <= p) ? sum : 0ull;
 				#pragma unroll
 				for (int o = 16; o > 0; o >>= 1)
 					v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
 				prefix += v;
 				if (p < 32)
 					break;
-				window -= 32;
+				window -= 256;
 			}
 			if (lane == 0)
 				state[batch] = SRPD_SCAN_PREFIX | (prefix + agg);

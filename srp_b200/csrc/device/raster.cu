@@ -250,20 +250,83 @@ __device__ __forceinline__ void prepareTriangle(const unsigned char* rec, const 
 	o[2] = make_float4(r[2][2], r[3][0], r[3][1], r[3][2]);
 }
 
-/* rasterizeTriangle for one pixel, reference triangle.c:73-111; `rowStart` = the prepared
- * row-start barycentrics of this triangle for the warp's block (prepareTriangle) */
-__device__ __forceinline__ void visitTriangle(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, const float* rowStart,
-	Pixel& px, FragCounters& cnt, int x, int y, int bx0, int ly, bool valid)
+/* Per-pixel fragment queue.  Coverage of a triangle is decided for the 32 pixels of a
+ * block at once, but typically only a handful of them are covered, so shading right away
+ * would run the (long) fragment stage with most lanes idle.  Instead a covered pixel pushes
+ * (barycentrics, record) into a 4-deep queue of its own, in primitive order; the queues are
+ * drained together -- entry 0 of every lane, then entry 1, ... -- so that the fragment
+ * stage runs with most lanes busy, each on its OWN next fragment.  Per pixel the order of
+ * fragments is unchanged, which is all the reference's semantics depend on. */
+constexpr int SRPD_FRAG_QUEUE = 4;
+struct FragQueue
 {
+	float l0[SRPD_FRAG_QUEUE], l1[SRPD_FRAG_QUEUE], l2[SRPD_FRAG_QUEUE];
+	uint32_t rec[SRPD_FRAG_QUEUE];
+	int n;
+};
+
+__device__ __forceinline__ void pushFragment(FragQueue& q, float l0, float l1, float l2, uint32_t rec)
+{
+	#pragma unroll
+	for (int i = 0; i < SRPD_FRAG_QUEUE; i++)
+		if (q.n == i)
+		{
+			q.l0[i] = l0; q.l1[i] = l1; q.l2[i] = l2; q.rec[i] = rec;
+		}
+	q.n++;
+}
+
+/* fragment stage of one queued triangle fragment: depth / 1/w interpolation
+ * (interpolateDepthAndWTriangle, interpolation.c:34-47) and emitFragment */
+__device__ __forceinline__ void shadeTriangleFragment(
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, uint32_t recIndex,
+	float l0, float l1, float l2, Pixel& px, FragCounters& cnt, int x, int y)
+{
+	const unsigned char* rec = records + (size_t) recIndex * a.recStride;
+	const uint4* h = (const uint4*) rec;
+	const uint4 q3 = __ldg(h + 3), q4 = __ldg(h + 4);
+	const uint32_t flags = __ldg((const uint32_t*) rec + 11);
+	const float wgt[3] = { l0, l1, l2 };
+	const float iwSum = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(q4.x), l0), __fmul_rn(__uint_as_float(q4.y), l1)),
+	                              __fmul_rn(__uint_as_float(q4.z), l2));
+	const float recW = __fdiv_rn(1.0f, iwSum);
+	const float depth = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(q3.x), l0), __fmul_rn(__uint_as_float(q3.y), l1)),
+	                              __fmul_rn(__uint_as_float(q3.z), l2));
+	emitFragment<3>(a.d.st, fr, px, cnt, x, y, (float) ((double) x + 0.5), (float) ((double) y + 0.5),
+	                depth, recW, recW, (flags & 8u) != 0, q3.w, rec + SRPD_REC_HEADER_BYTES, wgt);
+}
+
+/* drain the queues of the warp: level by level, all lanes that still have an entry */
+__device__ __forceinline__ void drainFragments(
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, FragQueue& q,
+	Pixel& px, FragCounters& cnt, int x, int y)
+{
+	#pragma unroll
+	for (int i = 0; i < SRPD_FRAG_QUEUE; i++)
+	{
+		if (!__any_sync(0xFFFFFFFFu, q.n > i))
+			break;
+		if (q.n > i)
+			shadeTriangleFragment(a, fr, records, q.rec[i], q.l0[i], q.l1[i], q.l2[i], px, cnt, x, y);
+	}
+	q.n = 0;
+}
+
+/* coverage of one triangle for one pixel, reference triangle.c:73-111; `rowStart` = the
+ * prepared row-start barycentrics of this triangle for the warp's block (prepareTriangle).
+ * Covered pixels queue a fragment; the warp drains the queues when one of them is full. */
+__device__ __forceinline__ void visitTriangle(
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, uint32_t recIndex, const float* rowStart,
+	FragQueue& q, Pixel& px, FragCounters& cnt, int x, int y, int bx0, int ly, bool valid)
+{
+	const unsigned char* rec = records + (size_t) recIndex * a.recStride;
 	const uint4* h = (const uint4*) rec;
 	const uint4 q0 = __ldg(h + 0), q1 = __ldg(h + 1);
 	const int minX = (int) (q0.w & 0xFFFFu), maxX = (int) (q0.w >> 16);
 	const int minY = (int) (q1.w & 0xFFFFu), maxY = (int) (q1.w >> 16);
-	if (!valid || x < minX || x >= maxX || y < minY || y >= maxY)
-		return;
-	float l0 = rowStart[ly * 3 + 0], l1 = rowStart[ly * 3 + 1], l2 = rowStart[ly * 3 + 2];
+	if (valid && x >= minX && x < maxX && y >= minY && y < maxY)
 	{
+		float l0 = rowStart[ly * 3 + 0], l1 = rowStart[ly * 3 + 1], l2 = rowStart[ly * 3 + 2];
 		const float dx0 = __uint_as_float(q1.x), dx1 = __uint_as_float(q1.y), dx2 = __uint_as_float(q1.z);
 		const int nx = x - (bx0 > minX ? bx0 : minX);      /* 0..7 remaining steps */
 		#pragma unroll
@@ -272,26 +335,16 @@ __device__ __forceinline__ void visitTriangle(
 			{
 				l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
 			}
+		/* top-left rule: lambda > 0 || (|lambda| <= 1e-9 && edgeTL), triangle.c:82-87 */
+		const uint32_t flags = __ldg((const uint32_t*) rec + 11);
+		const bool in0 = (l0 > 0.f) || (srpdRoughlyZero(l0) && (flags & 1u));
+		const bool in1 = (l1 > 0.f) || (srpdRoughlyZero(l1) && (flags & 2u));
+		const bool in2 = (l2 > 0.f) || (srpdRoughlyZero(l2) && (flags & 4u));
+		if (in0 && in1 && in2)
+			pushFragment(q, l0, l1, l2, recIndex);
 	}
-	/* top-left rule: lambda > 0 || (|lambda| <= 1e-9 && edgeTL), triangle.c:82-87 */
-	const uint4 q2 = __ldg(h + 2);
-	const uint32_t flags = q2.w;
-	const bool in0 = (l0 > 0.f) || (srpdRoughlyZero(l0) && (flags & 1u));
-	const bool in1 = (l1 > 0.f) || (srpdRoughlyZero(l1) && (flags & 2u));
-	const bool in2 = (l2 > 0.f) || (srpdRoughlyZero(l2) && (flags & 4u));
-	if (!(in0 && in1 && in2))
-		return;
-
-	const uint4 q3 = __ldg(h + 3), q4 = __ldg(h + 4);
-	const float wgt[3] = { l0, l1, l2 };
-	/* interpolateDepthAndWTriangle, interpolation.c:34-47 */
-	const float iwSum = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(q4.x), l0), __fmul_rn(__uint_as_float(q4.y), l1)),
-	                              __fmul_rn(__uint_as_float(q4.z), l2));
-	const float recW = __fdiv_rn(1.0f, iwSum);
-	const float depth = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(q3.x), l0), __fmul_rn(__uint_as_float(q3.y), l1)),
-	                              __fmul_rn(__uint_as_float(q3.z), l2));
-	emitFragment<3>(a.d.st, fr, px, cnt, x, y, (float) ((double) x + 0.5), (float) ((double) y + 0.5),
-	                depth, recW, recW, (flags & 8u) != 0, q3.w, rec + SRPD_REC_HEADER_BYTES, wgt);
+	if (__any_sync(0xFFFFFFFFu, q.n == SRPD_FRAG_QUEUE))
+		drainFragments(a, fr, records, q, px, cnt, x, y);
 }
 
 /* rasterizeLine for one pixel, reference line.c:34-77: every lane replays the DDA chain of
@@ -427,6 +480,8 @@ __device__ __forceinline__ void processTile(
 	if (tid == 0)
 		*sDirty = 0u;
 	__syncthreads();
+	FragQueue fq;
+	fq.n = 0;
 
 	for (uint32_t c = begin; c < end; c += SRPD_TILE_THREADS)
 	{
@@ -489,7 +544,7 @@ __device__ __forceinline__ void processTile(
 				m &= m - 1;
 				const unsigned char* rec = records + (size_t) sIds[j0 + bit] * a.recStride;
 				if (KIND == SRPD_KIND_TRIANGLE)
-					visitTriangle(a, fr, rec, sPrep + ((size_t) warp * 32 + bit) * SRPD_BLK_H * 3, px, cnt,
+					visitTriangle(a, fr, records, sIds[j0 + bit], sPrep + ((size_t) warp * 32 + bit) * SRPD_BLK_H * 3, fq, px, cnt,
 					              x, y, bx0, lane / SRPD_BLK_W, valid);
 				else if (KIND == SRPD_KIND_LINE)
 					visitLine(a, fr, rec, px, cnt, x, y, valid);
@@ -498,6 +553,8 @@ __device__ __forceinline__ void processTile(
 			}
 			__syncwarp();      /* the next step overwrites this warp's prepared values */
 		}
+		if (KIND == SRPD_KIND_TRIANGLE)      /* sIds is about to be refilled: finish what refers to it */
+			drainFragments(a, fr, records, fq, px, cnt, x, y);
 		__syncthreads();
 	}
 

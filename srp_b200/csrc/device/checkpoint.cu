@@ -59,5 +59,5 @@ srpdCheckpointKernel(const __grid_constant__ SrpdCkptArgs a)
 
 void srpdLaunchCheckpoints(const SrpdCkptArgs& a, cudaStream_t stream)
 {
-	srpdCheckpointKernel<<<1024, 128, 0, stream>>>(a);
+	srpdCheckpointKernel<<<296, 128, 0, stream>>>(a);
 }

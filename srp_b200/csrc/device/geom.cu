@@ -38,6 +38,15 @@ struct ClipVert
 	alignas(8) unsigned char vary[SRPD_MAX_VARYING_BYTES];
 };
 
+/* result of the count phase kept for the write phase (unclipped filled triangles only), so
+ * that the common case runs its setup -- nine IEEE divisions and the f64 islands -- once */
+struct FastTriangle
+{
+	bool valid;      /* the count phase went through the fast path */
+	bool stored;
+	SrpdTriSetup s;
+};
+
 __device__ __forceinline__ uint32_t fetchIndex(const SrpdDraw& d, uint64_t streamIndex)
 {
 	if (d.ib == nullptr)
@@ -87,41 +96,6 @@ __device__ __forceinline__ uint32_t hashInsert(uint32_t* keys, uint32_t key)
 			return h;
 		h = (h + 1) & (SRPD_HASH_SLOTS - 1);
 	}
-}
-
-/* Sutherland-Hodgman against one plane, reference clipping.c:199-242 (note it emits
- * `next`, so the polygon's starting vertex rotates from plane to plane). */
-__device__ int clipAgainstPlane(const SrpdState& st, const ClipVert* in, int n, int plane, ClipVert* out)
-{
-	int o = 0;
-	for (int i = 0; i < n; i++)
-	{
-		const ClipVert& cur = in[i];
-		const ClipVert& nxt = in[(i + 1) % n];
-		const float da = srpdPlaneDistance(cur.p, plane);
-		const float db = srpdPlaneDistance(nxt.p, plane);
-		const bool ci = da >= 0, ni = db >= 0;
-		if (ci && ni)
-		{
-			if (o < SRPD_CLIP_MAX_VERTS) out[o++] = nxt;
-		}
-		else if (ci || ni)
-		{
-			const float diff = SRP_FSUB(da, db);
-			if (srpdRoughlyZero(diff))
-				continue;
-			const float t = SRP_FDIV(da, diff);
-			if (o < SRPD_CLIP_MAX_VERTS)
-			{
-				out[o].p = srpdBlendPos(cur.p, nxt.p, t);
-				srpdBlendVaryings(st, cur.vary, nxt.vary, SRP_FSUB(1.0f, t), t, out[o].vary);
-				o++;
-			}
-			if (!ci && ni)
-				if (o < SRPD_CLIP_MAX_VERTS) out[o++] = nxt;
-		}
-	}
-	return o;
 }
 
 /* Where a thread's outputs go.  WRITE = false: count only. */
@@ -205,18 +179,22 @@ __device__ __forceinline__ unsigned char* beginRecord(Emitter& em, const uint32_
 	return rec + SRPD_REC_HEADER_BYTES;
 }
 
-template <bool WRITE>
-__device__ void emitTriangle(Emitter& em, const SrpdState& st, const SrpdPos p[3], const unsigned char* const vary[3])
+/* setup + the exact zero-coverage test; returns false if the triangle is culled (no id) */
+__device__ __forceinline__ bool setupAndClassify(const SrpdState& st, const SrpdPos p[3], SrpdTriSetup& s, bool& stored)
 {
-	SrpdTriSetup s;
-	bool stored;
 	if (!srpdSetupTriangle(st, p, s, stored))
-		return;
+		return false;
 	/* A triangle whose bounding box is a few pixels (sub-pixel geometry, cfg4) usually covers
 	 * no pixel centre at all.  Walking the reference's own chain over the box here decides
 	 * that exactly; such a triangle keeps its primitive id but needs no record. */
 	if (stored && srpdTriangleIsSmall(s) && !srpdSmallTriangleCoversAnyPixel(s))
 		stored = false;
+	return true;
+}
+
+template <bool WRITE>
+__device__ void writeTriangle(Emitter& em, const SrpdState& st, SrpdTriSetup& s, bool stored, const unsigned char* const vary[3])
+{
 	if (stored)
 	{
 		if (WRITE)
@@ -250,6 +228,15 @@ __device__ void emitTriangle(Emitter& em, const SrpdState& st, const SrpdPos p[3
 		em.nStore++;
 	}
 	em.nEmit++;
+}
+
+template <bool WRITE>
+__device__ void emitTriangle(Emitter& em, const SrpdState& st, const SrpdPos p[3], const unsigned char* const vary[3])
+{
+	SrpdTriSetup s;
+	bool stored;
+	if (setupAndClassify(st, p, s, stored))
+		writeTriangle<WRITE>(em, st, s, stored, vary);
 }
 
 template <bool WRITE>
@@ -308,7 +295,16 @@ __device__ void emitPolygonModeTriangle(Emitter& em, const SrpdState& st, const 
 			emitPoint<WRITE>(em, st, p[j], vary[j]);
 }
 
-/* clipTriangle + expansion, reference clipping.c:68-119 */
+/* clipTriangle + expansion, reference clipping.c:68-119 and :199-258.
+ * Sutherland-Hodgman over the six planes in the reference's order (L, R, B, T, N, F) with its
+ * emission rule -- for every edge (current, next): both inside -> emit next; crossing -> emit
+ * the intersection, and next too when entering -- so the polygon's first vertex rotates from
+ * plane to plane exactly as in the reference (that decides the fan and the provoking vertex).
+ * Vertices live in a small pool (the 3 originals stay in the shared-memory cache, only the
+ * intersections get local storage) and the polygon is an index list, so a plane that cuts
+ * nothing costs a rotation of <= 9 bytes instead of copying vertices. */
+constexpr int SRPD_CLIP_NEW_VERTS = 12;    /* at most two intersections per plane */
+
 template <bool WRITE>
 __device__ void processTriangle(Emitter& em, const SrpdState& st, const SrpdPos p[3], const unsigned char* const vary[3])
 {
@@ -321,26 +317,66 @@ __device__ void processTriangle(Emitter& em, const SrpdState& st, const SrpdPos 
 	if ((c0 & c1 & c2) != 0)
 		return;
 
-	ClipVert bufA[SRPD_CLIP_MAX_VERTS], bufB[SRPD_CLIP_MAX_VERTS];
-	ClipVert* src = bufA;
-	ClipVert* dst = bufB;
+	SrpdPos pos[3 + SRPD_CLIP_NEW_VERTS];
+	const unsigned char* vp[3 + SRPD_CLIP_NEW_VERTS];
+	alignas(8) unsigned char fresh[SRPD_CLIP_NEW_VERTS][SRPD_MAX_VARYING_BYTES];
+	uint8_t polyA[SRPD_CLIP_MAX_VERTS], polyB[SRPD_CLIP_MAX_VERTS];
 	for (int i = 0; i < 3; i++)
 	{
-		src[i].p = p[i];
-		copyBlobWords(vary[i], src[i].vary, st.slotSize);
+		pos[i] = p[i]; vp[i] = vary[i]; polyA[i] = (uint8_t) i;
 	}
-	int n = 3;
+	uint8_t* src = polyA;
+	uint8_t* dst = polyB;
+	int n = 3, nPool = 3;
 	for (int plane = 0; plane < 6; plane++)
 	{
-		n = clipAgainstPlane(st, src, n, plane, dst);
+		float dist[SRPD_CLIP_MAX_VERTS];
+		bool allInside = true;
+		for (int i = 0; i < n; i++)
+		{
+			dist[i] = srpdPlaneDistance(pos[src[i]], plane);
+			allInside = allInside && dist[i] >= 0;
+		}
+		int o = 0;
+		if (allInside)
+			for (int i = 0; i < n; i++)          /* every edge emits `next`: a rotation by one */
+				dst[o++] = src[(i + 1) % n];
+		else
+			for (int i = 0; i < n; i++)
+			{
+				const int k = (i + 1) % n;
+				const float da = dist[i], db = dist[k];
+				const bool ci = da >= 0, ni = db >= 0;
+				if (ci && ni)
+				{
+					if (o < SRPD_CLIP_MAX_VERTS) dst[o++] = src[k];
+				}
+				else if (ci || ni)
+				{
+					const float diff = SRP_FSUB(da, db);
+					if (srpdRoughlyZero(diff))
+						continue;
+					const float t = SRP_FDIV(da, diff);
+					if (o < SRPD_CLIP_MAX_VERTS && nPool < 3 + SRPD_CLIP_NEW_VERTS)
+					{
+						pos[nPool] = srpdBlendPos(pos[src[i]], pos[src[k]], t);
+						srpdBlendVaryings(st, vp[src[i]], vp[src[k]], SRP_FSUB(1.0f, t), t, fresh[nPool - 3]);
+						vp[nPool] = fresh[nPool - 3];
+						dst[o++] = (uint8_t) nPool++;
+					}
+					if (!ci && ni)
+						if (o < SRPD_CLIP_MAX_VERTS) dst[o++] = src[k];
+				}
+			}
+		n = o;
 		if (n == 0)
 			return;
-		ClipVert* t = src; src = dst; dst = t;
+		uint8_t* t = src; src = dst; dst = t;
 	}
 	for (int i = 1; i + 1 < n; i++)   /* fan (0, i, i+1) */
 	{
-		const SrpdPos tp[3] = { src[0].p, src[i].p, src[i + 1].p };
-		const unsigned char* const tv[3] = { src[0].vary, src[i].vary, src[i + 1].vary };
+		const SrpdPos tp[3] = { pos[src[0]], pos[src[i]], pos[src[i + 1]] };
+		const unsigned char* const tv[3] = { vp[src[0]], vp[src[i]], vp[src[i + 1]] };
 		emitPolygonModeTriangle<WRITE>(em, st, tp, tv);
 	}
 }
@@ -544,8 +580,24 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	em.occupancy = a.occupancy + (size_t) frame * a.occWordsPerFrame;
 	em.idBase = 0; em.storeBase = 0; em.nEmit = 0; em.nStore = 0; em.overflow = false;
 	em.frame = frame;
+	FastTriangle fast;
+	fast.valid = false; fast.stored = false;
 	if (active)
-		processPrimitive<false>(em, d, nv, p, vary);
+	{
+		if (nv == 3 && st.polygonMode == SRP_POLYGON_MODE_FILL
+		    && (srpdClipCode(p[0]) | srpdClipCode(p[1]) | srpdClipCode(p[2])) == 0)
+		{
+			/* unclipped filled triangle: set up once, remember the result for the write phase */
+			fast.valid = true;
+			if (setupAndClassify(st, p, fast.s, fast.stored))
+			{
+				em.nEmit = 1;
+				em.nStore = fast.stored ? 1 : 0;
+			}
+		}
+		else
+			processPrimitive<false>(em, d, nv, p, vary);
+	}
 	const uint32_t myEmit = em.nEmit, myStore = em.nStore;
 
 	/* 4. CTA scan + decoupled look-back over the frame's batches */
@@ -641,7 +693,10 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 		em.idBase = sPrefix[0] + baseE + incE - myEmit;
 		em.storeBase = sPrefix[1] + baseS + incS - myStore;
 		em.nEmit = 0; em.nStore = 0;
-		processPrimitive<true>(em, d, nv, p, vary);
+		if (fast.valid)
+			writeTriangle<true>(em, st, fast.s, fast.stored, vary);
+		else
+			processPrimitive<true>(em, d, nv, p, vary);
 		if (em.overflow)
 		{
 			atomicAdd(&a.stats->overflow, 1ull);

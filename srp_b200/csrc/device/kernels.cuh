@@ -36,7 +36,8 @@ constexpr int SRPD_BIN_CHUNK = 2048;     /* records per coarse-binning CTA      
 /* Per-draw zero-filled header in front of the scan state: word 0 batch ticket, 1 abort flag,
  * 2 tile work counter, 3 records a frame needed (max over frames), 4 coarse-list entries needed,
  * 5 checkpoint-table cursor (entries), 6 number of large triangles */
-constexpr int SRPD_DRAW_HEADER_BYTES = 32;
+constexpr int SRPD_DRAW_HEADER_BYTES = 64;   /* words 8..15: tile work counters of up to 8 bands */
+constexpr int SRPD_MAX_BANDS = 8;
 
 /* Decoupled look-back word: [63:62] status, [61:31] emitted ids, [30:0] stored records */
 constexpr unsigned long long SRPD_SCAN_AGG = 1ull << 62;

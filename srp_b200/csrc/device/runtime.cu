@@ -31,6 +31,12 @@ struct Runtime
 	bool failed = false;
 	int device = -1;
 	cudaStream_t stream = nullptr;
+	cudaStream_t copyStream = nullptr;     /* band-wise downloads overlapping the tile kernel */
+	cudaEvent_t bandEvents[SRPD_MAX_BANDS] = {};
+	cudaEvent_t copyDone = nullptr;
+	SrpcuMirror mirror = { nullptr, nullptr, nullptr };
+	int* mirrorDone = nullptr;
+	bool copyPending = false;
 	std::string lastError;
 	Pool records, bboxes, scan, frameCounts, chunkCounts, superOffsets, superTotals, listIds, uniforms, frames;
 	Pool ckptTable, largeList;
@@ -160,6 +166,10 @@ int srpcuInit(void)
 	g.device = dev;
 	g.smCount = prop.multiProcessorCount;
 	CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&g.copyStream, cudaStreamNonBlocking));
+	for (int i = 0; i < SRPD_MAX_BANDS; i++)
+		CU(cudaEventCreateWithFlags(&g.bandEvents[i], cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&g.copyDone, cudaEventDisableTiming));
 	CU(cudaMalloc(&g.stats, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
 	CU(cudaMemset(g.stats, 0, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
 	CU(cudaMallocHost(&g.statsHost, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
@@ -234,9 +244,21 @@ int srpcuDownload(void* dstHost, const void* srcDevice, size_t bytes)
 	g.d2h += bytes;
 	return 0;
 }
+void srpcuSetMirrorForNextDraw(const SrpcuMirror* mirror, int* done)
+{
+	g.mirror = mirror ? *mirror : SrpcuMirror{ nullptr, nullptr, nullptr };
+	g.mirrorDone = done;
+	if (done) *done = 0;
+}
+
 int srpcuSynchronize(void)
 {
 	if (!g.ready) return 0;
+	if (g.copyPending)
+	{
+		CU(cudaStreamSynchronize(g.copyStream));
+		g.copyPending = false;
+	}
 	CU(cudaStreamSynchronize(g.stream));
 	CU(cudaGetLastError());
 	return 0;
@@ -474,10 +496,57 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		while (per < 32 && tiles / (per * 2) >= target) per *= 2;
 		ta.tilesPerItem = per;
 	}
+	/* one-shot mirror request: rasterise in bands and download each band while the next one
+	 * is being rasterised (only worth it for big frames; small ones keep the single launch) */
+	const SrpcuMirror mirror = g.mirror;
+	int* mirrorDone = g.mirrorDone;
+	g.mirror = SrpcuMirror{ nullptr, nullptr, nullptr };
+	g.mirrorDone = nullptr;
+	const uint32_t rows = ta.d.tileRow1 - ta.d.tileRow0;
+	uint32_t nBands = 1;
+	if (mirror.color && nFrames == 1 && ta.d.tileRow0 == 0 && ta.d.tileRow1 == tilesY
+	    && (uint64_t) st.width * st.height >= (1u << 20) && !getenv("SRP_B200_NO_BANDS"))
+		nBands = rows >= 64 ? 4 : 1;
 	mark();
-	srpdLaunchTiles(ta, g.stream);
-	g.launches++;
-	CU(cudaGetLastError());
+	if (nBands == 1)
+	{
+		srpdLaunchTiles(ta, g.stream);
+		g.launches++;
+		CU(cudaGetLastError());
+	}
+	else
+	{
+		const size_t W = (size_t) st.width;
+		for (uint32_t b = 0; b < nBands; b++)
+		{
+			SrpdTileArgs band = ta;
+			band.d.tileRow0 = rows * b / nBands;
+			band.d.tileRow1 = rows * (b + 1) / nBands;
+			band.workCounter = (uint32_t*) g.scan.ptr + 8 + b;
+			srpdLaunchTiles(band, g.stream);
+			g.launches++;
+			CU(cudaGetLastError());
+			CU(cudaEventRecord(g.bandEvents[b], g.stream));
+			CU(cudaStreamWaitEvent(g.copyStream, g.bandEvents[b], 0));
+			const size_t y0 = (size_t) band.d.tileRow0 * SRPD_TILE_H;
+			size_t y1 = (size_t) band.d.tileRow1 * SRPD_TILE_H;
+			if (y1 > (size_t) st.height) y1 = (size_t) st.height;
+			const size_t first = y0 * W, count = (y1 - y0) * W;
+			CU(cudaMemcpyAsync((uint32_t*) mirror.color + first, frame0.color + first, count * 4, cudaMemcpyDeviceToHost, g.copyStream));
+			CU(cudaMemcpyAsync((float*) mirror.depth + first, frame0.depth + first, count * 4, cudaMemcpyDeviceToHost, g.copyStream));
+			g.d2h += count * 8;
+			if (mirror.stencil)
+			{
+				CU(cudaMemcpyAsync((uint8_t*) mirror.stencil + first, frame0.stencil + first, count, cudaMemcpyDeviceToHost, g.copyStream));
+				g.d2h += count;
+			}
+		}
+		/* later work on the main stream (the next draw) must not overtake the downloads */
+		CU(cudaEventRecord(g.copyDone, g.copyStream));
+		CU(cudaStreamWaitEvent(g.stream, g.copyDone, 0));
+		g.copyPending = true;
+		if (mirrorDone) *mirrorDone = 1;
+	}
 	mark();
 	return 0;
 }

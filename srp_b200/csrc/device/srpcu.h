@@ -41,6 +41,16 @@ int srpcuClearPlanes(uint32_t* color, float* depth, size_t nPixels);
 int srpcuDraw(const SrpdDraw* d, const SrpdFrame* frames,
               const void* uniforms, size_t uniformBytes, size_t uniformStride);
 
+/* Host mirror to refresh as part of the NEXT single-frame srpcuDraw (one-shot; cleared by that
+ * draw).  When set, the tile kernel runs in horizontal bands and each band's rows are copied
+ * to the host on a second stream while the next band is rasterised; srpcuSynchronize() then
+ * waits for both.  Returns through *done whether the draw took care of the download. */
+typedef struct SrpcuMirror
+{
+	void* color; void* depth; void* stencil;   /* pinned host planes; stencil may be NULL (not needed) */
+} SrpcuMirror;
+void srpcuSetMirrorForNextDraw(const SrpcuMirror* mirror, int* done);
+
 /* 1 if a scratch pool overflowed since the previous call (the affected draw left the
  * framebuffer untouched); the pools' minimum sizes have then been raised to what that draw
  * needed, so the host simply repeats it. */

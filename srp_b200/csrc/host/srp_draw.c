@@ -307,6 +307,15 @@ static void submit(
 				frames[f].pad = 0;
 			}
 			const size_t ubytes = uniforms ? prog->uniformSize : 0;
+			/* default policy: the draw itself may refresh the host mirror band by band, overlapping
+			 * the copies with rasterisation (it reports back whether it did) */
+			int mirrored = 0;
+			if (nFrames == 1 && srpB200GetSyncMode() == SRP_B200_SYNC_DRAW)
+			{
+				const bool wantStencil = impls[0]->stencilTouched || d.st.stencilEnabled;
+				SrpcuMirror m = { impls[0]->pub.color, impls[0]->pub.depth, wantStencil ? impls[0]->pub.stencil : NULL };
+				srpcuSetMirrorForNextDraw(&m, &mirrored);
+			}
 			if (srpcuDraw(&d, frames, uniforms, ubytes, uniformStride))
 			{
 				srpFatalMessage("srpDraw", "%s", srpcuLastError());
@@ -315,7 +324,7 @@ static void submit(
 			gDraws++;
 			if (srpB200GetSyncMode() != SRP_B200_SYNC_DRAW || !srpcuTakeOverflow())
 			{
-				srpFramebufferAfterDraw(impls, nFrames, d.st.stencilEnabled);
+				srpFramebufferAfterDraw(impls, nFrames, d.st.stencilEnabled, mirrored != 0);
 				break;
 			}
 			/* A scratch pool was too small for this draw (heavy clipping / long lines).  The
@@ -325,7 +334,7 @@ static void submit(
 			if (attempt == 2)
 			{
 				srpFatalMessage("srpDraw", "scratch pools overflowed repeatedly; draw is incomplete");
-				srpFramebufferAfterDraw(impls, nFrames, d.st.stencilEnabled);
+				srpFramebufferAfterDraw(impls, nFrames, d.st.stencilEnabled, false);
 				break;
 			}
 		}

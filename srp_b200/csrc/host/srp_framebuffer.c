@@ -159,7 +159,7 @@ void srpB200Finish(void)
 }
 
 /* called by the draw entry points once the draw's kernels are enqueued */
-void srpFramebufferAfterDraw(SRPFramebufferImpl* const* fbs, size_t n, bool stencilEnabled)
+void srpFramebufferAfterDraw(SRPFramebufferImpl* const* fbs, size_t n, bool stencilEnabled, bool alreadyMirrored)
 {
 	for (size_t i = 0; i < n; i++)
 	{
@@ -170,8 +170,15 @@ void srpFramebufferAfterDraw(SRPFramebufferImpl* const* fbs, size_t n, bool sten
 	}
 	if (gSyncMode != SRP_B200_SYNC_DRAW)
 		return;
-	for (size_t i = 0; i < n; i++)
-		enqueueDownload(fbs[i]);
+	if (alreadyMirrored)
+	{
+		/* the draw copied its bands to the host itself (runtime.cu); only bookkeeping is left */
+		fbs[0]->stencilTouched = false;
+		fbs[0]->mirrorStale = false;
+	}
+	else
+		for (size_t i = 0; i < n; i++)
+			enqueueDownload(fbs[i]);
 	if (srpcuSynchronize())
 		srpFatalMessage("srpDraw", "%s", srpcuLastError());
 }

@@ -72,7 +72,7 @@ const SRPProgramEntry* srpLookupProgram(SRPVertexShaderFunc vs, SRPFragmentShade
 
 /* framebuffer helpers (srp_framebuffer.c) */
 SRPFramebufferImpl* srpFramebufferImpl(const SRPFramebuffer* fb);
-void srpFramebufferAfterDraw(SRPFramebufferImpl* const* fbs, size_t n, bool stencilEnabled);
+void srpFramebufferAfterDraw(SRPFramebufferImpl* const* fbs, size_t n, bool stencilEnabled, bool alreadyMirrored);
 
 /* PNG loader (srp_png.c): returns malloc'ed RGB8 or NULL (+ reason) */
 uint8_t* srpLoadPngRgb(const char* path, int* width, int* height, const char** reason);

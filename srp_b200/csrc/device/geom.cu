@@ -19,12 +19,14 @@
  *      Liang-Barsky (lines) clipping on the rare path, polygon-mode expansion, setup,
  *      face / degenerate culling -- first only counting how many primitive ids the input
  *      primitive consumes and how many records it stores;
- *   4. order-preserving compaction: CTA exclusive scan of both counts + a decoupled
- *      look-back across the batches of the frame (batches are handed out by an atomic
- *      ticket so a predecessor is always resident) gives every input primitive the
- *      reference's serial `primitiveID++` base (primitive_assembly.c:64,90-91) and its
- *      record slot;
- *   5. the primitives are set up again and their records written in id order.
+ *   4. CTA exclusive scan of both counts; the batch reserves a contiguous range of record
+ *      slots from the frame's bump allocator and publishes its totals;
+ *   5. records are written (unclipped triangles from the set-up kept in step 3, clipped
+ *      ones are clipped again) with batch-local primitive ids.
+ * Two small kernels then restore the reference's serial order (primitive_assembly.c:64,90-91:
+ * `primitiveID++` over emitted primitives): srpdBatchScanKernel prefix-sums the batch totals
+ * in batch order, srpdRecordOrderKernel adds the id prefix to every record and builds the
+ * id-ordered view (ordered bounding boxes + permutation) that binning and tiles consume.
  *
  * HBM traffic per input triangle: 3 indices + (amortised) its vertices in, one record
  * (80 B header + 3 blobs) + one 8-byte bbox out. */
@@ -471,7 +473,6 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	float4*   vpos      = (float4*) (smem + 6 * SRPD_HASH_SLOTS + 4 * SRPD_GEOM_MAX_VERTS);
 	unsigned char* vvary = (unsigned char*) (vpos + SRPD_GEOM_MAX_VERTS);
 
-	__shared__ uint32_t sBatch;
 	__shared__ uint32_t sWarpSum[2][SRPD_GEOM_THREADS / 32];
 	__shared__ uint32_t sNUniq;
 	__shared__ uint32_t sPrefix[2];
@@ -480,13 +481,10 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	const SrpdState& st = d.st;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-	/* batches are handed out in order so that look-back predecessors are always scheduled */
-	if (tid == 0)
-		sBatch = atomicAdd(a.ticket, 1u);
 	for (int i = tid; i < SRPD_HASH_SLOTS; i += SRPD_GEOM_THREADS)
 		hashKey[i] = SRPD_HASH_EMPTY;
 	__syncthreads();
-	const uint32_t batch = sBatch;
+	const uint32_t batch = blockIdx.x;
 	const uint32_t frame = batch / a.batchesPerFrame;
 	const uint32_t b = batch - frame * a.batchesPerFrame;
 	const SrpdFrame fr = a.frames ? a.frames[frame] : a.frame0;
@@ -611,79 +609,17 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 		if (w < warp) { baseE += sWarpSum[0][w]; baseS += sWarpSum[1][w]; }
 		totE += sWarpSum[0][w]; totS += sWarpSum[1][w];
 	}
-	if (warp == 0)
+	if (tid == 0)
 	{
-		/* Decoupled look-back by one warp, 256 predecessors per step; the window slides back
-		 * until a batch that already knows its inclusive prefix is found.  Batch 0 of every frame publishes a prefix at once, so
-		 * the walk never leaves the frame. */
-		const unsigned long long agg = ((unsigned long long) totE << 31) | (unsigned long long) totS;
-		volatile unsigned long long* state = a.scanState;
-		const uint32_t frameFirst = frame * a.batchesPerFrame;
-		unsigned long long prefix = 0;
-		if (lane == 0)
-			state[batch] = (b == 0 ? SRPD_SCAN_PREFIX : SRPD_SCAN_AGG) | agg;
-		if (b != 0)
-		{
-			/* window of 256 predecessors per step: lane l inspects the 8 batches
-			 * [window - 8l - 7, window - 8l], nearest first (8 independent loads in flight) */
-			long long window = (long long) batch - 1;
-			for (;;)
-			{
-				unsigned long long sum = 0;
-				bool ready = true, hasPrefix = false;
-				#pragma unroll
-				for (int k = 0; k < 8; k++)
-				{
-					const long long j = window - 8 * lane - k;
-					unsigned long long sv = SRPD_SCAN_PREFIX;            /* before the frame: prefix 0 */
-					if (j >= (long long) frameFirst)
-						sv = state[j];
-					const unsigned flag = (unsigned) (sv >> 62);
-					if (!hasPrefix)                                       /* entries beyond this lane's nearest prefix do not count */
-					{
-						if (flag == 0)
-							ready = false;
-						else
-						{
-							sum += sv & SRPD_SCAN_VALUE_MASK;
-							hasPrefix = flag == 2;
-						}
-					}
-				}
-				const uint32_t isPrefix = __ballot_sync(0xFFFFFFFFu, hasPrefix);
-				const uint32_t notReady = __ballot_sync(0xFFFFFFFFu, !ready);
-				const int p = isPrefix ? __ffs(isPrefix) - 1 : 32;    /* nearest lane whose group holds a prefix */
-				const uint32_t need = p >= 31 ? 0xFFFFFFFFu : ((1u << (p + 1)) - 1u);
-				if (notReady & need)
-					continue;                                          /* a needed predecessor has not published yet */
-				unsigned long long v = (lane <= p) ? sum : 0ull;
-				#pragma unroll
-				for (int o = 16; o > 0; o >>= 1)
-					v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-				prefix += v;
-				if (p < 32)
-					break;
-				window -= 256;
-			}
-			if (lane == 0)
-				state[batch] = SRPD_SCAN_PREFIX | (prefix + agg);
-		}
-		if (lane == 0)
-		{
-			sPrefix[0] = (uint32_t) (prefix >> 31);
-			sPrefix[1] = (uint32_t) (prefix & 0x7FFFFFFFull);
-			if (b == a.batchesPerFrame - 1)
-			{
-				const uint32_t e = sPrefix[0] + totE, st2 = sPrefix[1] + totS;
-				a.frameCounts[2 * frame + 0] = e;
-				a.frameCounts[2 * frame + 1] = st2 < a.recCapacity ? st2 : a.recCapacity;
-				if (st2 > a.recCapacity)
-					atomicMax(&a.needed[0], st2);
-				atomicAdd(&a.stats->primsIn, (unsigned long long) d.nInputPrims);
-				atomicAdd(&a.stats->primsEmitted, (unsigned long long) e);
-				atomicAdd(&a.stats->primsStored, (unsigned long long) st2);
-			}
-		}
+		/* No CTA ever waits for another one: the batch takes a contiguous range of record slots
+		 * from the frame's bump allocator (arrival order) and leaves its counts behind; the
+		 * batch-order prefix sums and the id-ordered view of the records are built afterwards
+		 * (srpdBatchScanKernel, srpdRecordOrderKernel).  An in-kernel chained scan made every
+		 * resident CTA wait for the slowest batch in flight (clip-heavy batches: a convoy). */
+		const uint32_t physBase = totS ? atomicAdd(&a.frameBump[frame], totS) : 0u;
+		a.batchInfo[batch] = make_uint4(physBase, totE, totS, 0u);
+		sPrefix[0] = 0u;
+		sPrefix[1] = physBase;
 	}
 	__syncthreads();
 
@@ -705,6 +641,84 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	}
 }
 
+/* Exclusive prefix sums of (ids, records) over the batches of a frame, in batch order.
+ * One CTA per frame. */
+__global__ void __launch_bounds__(1024)
+srpdBatchScanKernel(const __grid_constant__ SrpdGeomArgs a)
+{
+	__shared__ uint32_t sE[1024], sS[1024];
+	__shared__ uint32_t sCarry[2];
+	const uint32_t frame = blockIdx.x;
+	const uint32_t first = frame * a.batchesPerFrame;
+	if (threadIdx.x == 0) { sCarry[0] = 0; sCarry[1] = 0; }
+	__syncthreads();
+	for (uint32_t b0 = 0; b0 < a.batchesPerFrame; b0 += 1024)
+	{
+		const uint32_t b = b0 + threadIdx.x;
+		uint32_t e = 0, s = 0;
+		if (b < a.batchesPerFrame)
+		{
+			const uint4 info = a.batchInfo[first + b];
+			e = info.y; s = info.z;
+		}
+		sE[threadIdx.x] = e; sS[threadIdx.x] = s;
+		__syncthreads();
+		uint32_t ve = e, vs = s;
+		for (uint32_t o = 1; o < 1024; o <<= 1)
+		{
+			const uint32_t ae = threadIdx.x >= o ? sE[threadIdx.x - o] : 0;
+			const uint32_t as = threadIdx.x >= o ? sS[threadIdx.x - o] : 0;
+			__syncthreads();
+			ve += ae; vs += as;
+			sE[threadIdx.x] = ve; sS[threadIdx.x] = vs;
+			__syncthreads();
+		}
+		const uint32_t ce = sCarry[0], cs = sCarry[1];
+		if (b < a.batchesPerFrame)
+			a.batchPrefix[first + b] = make_uint2(ce + ve - e, cs + vs - s);
+		__syncthreads();
+		if (threadIdx.x == 1023) { sCarry[0] = ce + ve; sCarry[1] = cs + vs; }
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+	{
+		const uint32_t e = sCarry[0], s = sCarry[1];
+		a.frameCounts[2 * frame + 0] = e;
+		a.frameCounts[2 * frame + 1] = s < a.recCapacity ? s : a.recCapacity;
+		if (s > a.recCapacity)
+			atomicMax(&a.needed[0], s);
+		atomicAdd(&a.stats->primsIn, (unsigned long long) a.d.nInputPrims);
+		atomicAdd(&a.stats->primsEmitted, (unsigned long long) e);
+		atomicAdd(&a.stats->primsStored, (unsigned long long) s);
+	}
+}
+
+/* The id-ordered view: one warp per batch adds the batch's id prefix to its records and
+ * writes, at the records' positions in primitive order, their bounding boxes and physical
+ * slots.  Binning and the tile kernel only ever walk this view. */
+__global__ void __launch_bounds__(256)
+srpdRecordOrderKernel(const __grid_constant__ SrpdGeomArgs a)
+{
+	const uint32_t batch = blockIdx.x * 8 + (threadIdx.x >> 5);
+	const uint32_t lane = threadIdx.x & 31;
+	if (batch >= a.batchesPerFrame * a.d.nFrames)
+		return;
+	const uint32_t frame = batch / a.batchesPerFrame;
+	const uint4 info = a.batchInfo[batch];
+	const uint2 prefix = a.batchPrefix[batch];
+	const size_t base = (size_t) frame * a.recCapacity;
+	for (uint32_t j = lane; j < info.z; j += 32)
+	{
+		const uint32_t phys = info.x + j, ord = prefix.y + j;
+		if (phys >= a.recCapacity || ord >= a.recCapacity)
+			break;
+		a.bboxesOrdered[base + ord] = a.bboxes[base + phys];
+		a.perm[base + ord] = phys;
+		uint32_t* id = (uint32_t*) (a.records + (base + phys) * a.recStride) + 15;
+		*id += prefix.x;
+	}
+}
+
 static int gGeomLaunches = 0;
 int srpdGeomLaunchCount(void) { return gGeomLaunches; }
 
@@ -720,5 +734,7 @@ void srpdLaunchGeom(const SrpdGeomArgs& a, cudaStream_t stream)
 	}
 	const unsigned grid = a.batchesPerFrame * a.d.nFrames;
 	srpdGeomKernel<<<grid, SRPD_GEOM_THREADS, smemBytes, stream>>>(a);
-	gGeomLaunches++;
+	srpdBatchScanKernel<<<a.d.nFrames, 1024, 0, stream>>>(a);
+	srpdRecordOrderKernel<<<(grid + 7) / 8, 256, 0, stream>>>(a);
+	gGeomLaunches += 3;
 }

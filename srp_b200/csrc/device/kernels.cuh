@@ -39,10 +39,6 @@ constexpr int SRPD_BIN_CHUNK = 2048;     /* records per coarse-binning CTA      
 constexpr int SRPD_DRAW_HEADER_BYTES = 64;   /* words 8..15: tile work counters of up to 8 bands */
 constexpr int SRPD_MAX_BANDS = 8;
 
-/* Decoupled look-back word: [63:62] status, [61:31] emitted ids, [30:0] stored records */
-constexpr unsigned long long SRPD_SCAN_AGG = 1ull << 62;
-constexpr unsigned long long SRPD_SCAN_PREFIX = 2ull << 62;
-constexpr unsigned long long SRPD_SCAN_VALUE_MASK = (1ull << 62) - 1;
 
 struct SrpdGeomArgs
 {
@@ -53,8 +49,11 @@ struct SrpdGeomArgs
 	uint2* bboxes;                    /* [nFrames][recCapacity] x0|y0<<16, x1|y1<<16 (half-open, pixels) */
 	uint32_t recCapacity;
 	uint32_t recStride;
-	unsigned long long* scanState;    /* [nFrames * batchesPerFrame], zeroed per draw    */
-	uint32_t* ticket;                 /* zeroed per draw                                 */
+	uint2* bboxesOrdered;             /* the same boxes at their position in primitive order */
+	uint32_t* perm;                   /* [nFrames][recCapacity] position in primitive order -> record slot */
+	uint32_t* frameBump;              /* [nFrames], zeroed per draw: record slots handed out */
+	uint4* batchInfo;                 /* [nFrames * batchesPerFrame] {first slot, ids, records, -} */
+	uint2* batchPrefix;               /* [nFrames * batchesPerFrame] exclusive {ids, records} in batch order */
 	uint32_t* abortFlag;              /* zeroed per draw; set when a scratch pool overflows: the
 	                                     tile kernel then leaves the framebuffer untouched  */
 	uint32_t* needed;                 /* [0] records needed per frame (max), [1] coarse-list entries needed */
@@ -110,7 +109,8 @@ struct SrpdTileArgs
 	SrpdFrame frame0;
 	const SrpdFrame* frames;
 	const unsigned char* records;
-	const uint2* bboxes;
+	const uint2* bboxes;              /* in primitive order */
+	const uint32_t* perm;             /* position in primitive order -> record slot */
 	uint32_t recCapacity;
 	uint32_t recStride;
 	const uint32_t* frameCounts;

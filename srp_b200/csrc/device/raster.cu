@@ -455,6 +455,7 @@ __device__ __forceinline__ void processTile(
 
 	const unsigned char* records = a.records + (size_t) frame * a.recCapacity * a.recStride;
 	const uint2* bboxes = a.bboxes + (size_t) frame * a.recCapacity;
+	const uint32_t* perm = a.perm + (size_t) frame * a.recCapacity;
 
 	/* pixel ownership: warp w -> 8x4 block (w % 4, w / 4); lane -> (lane % 8, lane / 8) */
 	const int tx0 = tileX * SRPD_TILE_W, ty0 = tileY * SRPD_TILE_H;
@@ -492,7 +493,7 @@ __device__ __forceinline__ void processTile(
 		uint2 bb = make_uint2(0u, 0u);
 		if (i < end)
 		{
-			rid = ids ? ids[i] : i;
+			rid = ids ? ids[i] : i;          /* position in primitive order */
 			bb = bboxes[rid];
 			const int x0 = (int) (bb.x & 0xFFFFu), y0 = (int) (bb.x >> 16);
 			const int x1 = (int) (bb.y & 0xFFFFu), y1 = (int) (bb.y >> 16);
@@ -513,7 +514,7 @@ __device__ __forceinline__ void processTile(
 		if (hit)
 		{
 			const uint32_t pos = base + __popc(ballot & ((1u << lane) - 1u));
-			sIds[pos] = rid;
+			sIds[pos] = perm[rid];           /* record slot */
 			sBox[pos] = bb;
 		}
 		__syncthreads();

@@ -39,7 +39,7 @@ struct Runtime
 	bool copyPending = false;
 	std::string lastError;
 	Pool records, bboxes, scan, frameCounts, chunkCounts, superOffsets, superTotals, listIds, uniforms, frames;
-	Pool ckptTable, largeList;
+	Pool ckptTable, largeList, bboxesOrdered, perm, batchInfo, batchPrefix;
 	int smCount = 148;
 	uint64_t recFloor = 0, listFloor = 0;  /* minimum pool capacities, raised by srpcuTakeOverflow() */
 	SrpdStats* stats = nullptr;            /* device, SRPD_STATS_SLOTS slots */
@@ -337,11 +337,11 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 
 	if (!grow(g.records, (size_t) recCapacity * recStride * nFrames)) return 1;
 	if (!grow(g.bboxes, (size_t) recCapacity * sizeof(uint2) * nFrames)) return 1;
-	/* one zero-filled block per draw: [ticket, abort flag, tile work counter, pad] [scan state] [tile occupancy bitmap] */
+	/* one zero-filled block per draw: [header] [per-frame record bump allocators] [tile occupancy bitmap] */
 	const uint32_t tilesX = (st.width + SRPD_TILE_W - 1) / SRPD_TILE_W;
 	const uint32_t tilesY = (st.height + SRPD_TILE_H - 1) / SRPD_TILE_H;
 	const uint32_t occWords = (tilesX * tilesY + 31) / 32;
-	const size_t scanStateBytes = sizeof(unsigned long long) * (size_t) batchesPerFrame * nFrames;
+	const size_t scanStateBytes = (sizeof(uint32_t) * (size_t) nFrames + 7) & ~(size_t) 7;
 	const size_t scanBytes = SRPD_DRAW_HEADER_BYTES + scanStateBytes + sizeof(uint32_t) * (size_t) occWords * nFrames;
 	if (!grow(g.scan, scanBytes)) return 1;
 	if (!grow(g.frameCounts, sizeof(uint32_t) * 2 * nFrames)) return 1;
@@ -357,10 +357,17 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ga.bboxes = (uint2*) g.bboxes.ptr;
 	ga.recCapacity = recCapacity;
 	ga.recStride = recStride;
-	ga.ticket = (uint32_t*) g.scan.ptr;
 	ga.abortFlag = (uint32_t*) g.scan.ptr + 1;
 	ga.needed = (uint32_t*) g.scan.ptr + 3;
-	ga.scanState = (unsigned long long*) ((unsigned char*) g.scan.ptr + SRPD_DRAW_HEADER_BYTES);
+	ga.frameBump = (uint32_t*) ((unsigned char*) g.scan.ptr + SRPD_DRAW_HEADER_BYTES);
+	if (!grow(g.bboxesOrdered, (size_t) recCapacity * sizeof(uint2) * nFrames)) return 1;
+	if (!grow(g.perm, (size_t) recCapacity * sizeof(uint32_t) * nFrames)) return 1;
+	if (!grow(g.batchInfo, sizeof(uint4) * (size_t) batchesPerFrame * nFrames)) return 1;
+	if (!grow(g.batchPrefix, sizeof(uint2) * (size_t) batchesPerFrame * nFrames)) return 1;
+	ga.bboxesOrdered = (uint2*) g.bboxesOrdered.ptr;
+	ga.perm = (uint32_t*) g.perm.ptr;
+	ga.batchInfo = (uint4*) g.batchInfo.ptr;
+	ga.batchPrefix = (uint2*) g.batchPrefix.ptr;
 	ga.batchesPerFrame = batchesPerFrame;
 	ga.frameCounts = (uint32_t*) g.frameCounts.ptr;
 	ga.occupancy = (uint32_t*) ((unsigned char*) g.scan.ptr + SRPD_DRAW_HEADER_BYTES + scanStateBytes);
@@ -384,7 +391,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ga.ckptCapacity = (uint32_t) ckptEntries;
 	ga.stats = g.stats;
 	srpdLaunchGeom(ga, g.stream);
-	g.launches++;
+	g.launches += 3;
 	CU(cudaGetLastError());
 	if (ckptEntries)
 	{
@@ -435,7 +442,8 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ta.frame0 = frame0;
 	ta.frames = framesDev;
 	ta.records = ga.records;
-	ta.bboxes = ga.bboxes;
+	ta.bboxes = ga.bboxesOrdered;
+	ta.perm = ga.perm;
 	ta.recCapacity = recCapacity;
 	ta.recStride = recStride;
 	ta.frameCounts = ga.frameCounts;
@@ -457,7 +465,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	{
 		SrpdBinArgs ba;
 		memset(&ba, 0, sizeof ba);
-		ba.bboxes = ga.bboxes;
+		ba.bboxes = ga.bboxesOrdered;
 		ba.frameCounts = ga.frameCounts;
 		ba.nChunksMax = (recCapacity + SRPD_BIN_CHUNK - 1) / SRPD_BIN_CHUNK;
 		ba.superX = superX;

@@ -130,6 +130,21 @@ SRP_HD bool srpdTypeIsDouble(uint8_t type) { return type == SRP_DOUBLE; }
 SRP_HD void srpdBlendVaryings(const SrpdState& st, const unsigned char* a, const unsigned char* b,
                               float w0, float w1, unsigned char* out)
 {
+	if (st.allFloat)
+	{
+		/* all-float, 4-byte aligned layout: every float is blended (FLAT ones too, App. B-15) */
+		const float* fa = (const float*) a;
+		const float* fb = (const float*) b;
+		float* fo = (float*) out;
+		for (int e = 0; e < st.nFloats; e++)
+		{
+			float v = 0.f;
+			v = SRP_FADD(v, SRP_FMUL(fa[e], w0));
+			v = SRP_FADD(v, SRP_FMUL(fb[e], w1));
+			fo[e] = v;
+		}
+		return;
+	}
 	for (int ai = 0; ai < st.nVaryings; ai++)
 	{
 		const SrpdVarying& at = st.varyings[ai];

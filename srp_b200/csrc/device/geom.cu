@@ -124,6 +124,18 @@ __device__ __forceinline__ void copyBlobWords(const unsigned char* src, unsigned
 
 __device__ void storeBlob(const SrpdState& st, const unsigned char* src, float invW, bool persp, unsigned char* dst)
 {
+	if (st.allFloat)
+	{
+		/* all-float layout: one pass over the floats, PERSPECTIVE ones pre-multiplied by 1/w */
+		const float* s = (const float*) src;
+		float* d = (float*) dst;
+		uint32_t modes = st.floatModes;
+		for (int e = 0; e < st.nFloats; e++, modes >>= 2)
+			d[e] = (persp && (modes & 3u) == SRP_INTERPOLATION_MODE_PERSPECTIVE) ? SRP_FMUL(s[e], invW) : s[e];
+		for (int e = st.nFloats; e < st.slotSize / 4; e++)
+			d[e] = s[e];
+		return;
+	}
 	copyBlobWords(src, dst, st.slotSize);
 	if (!persp)
 		return;

@@ -109,6 +109,20 @@ def build_library(jobs: int = 8) -> Path:
     return so
 
 
+def build_variant(name: str, defines: list[str], jobs: int = 8) -> Path:
+    """development aid: libsrp_b200_<name>.so built with extra -D flags (kernel tuning
+    experiments; select it with SRP_B200_LIBRARY=<path> when loading)"""
+    obj = BUILD / f"obj_{name}"
+    with ThreadPoolExecutor(jobs) as pool:
+        dev = [pool.submit(_compile_device, s, obj / "device" / (s.stem + ".o"), defines) for s in DEVICE_SOURCES]
+        dev.append(pool.submit(_compile_device, CSRC / "programs" / "builtin_device.cu", obj / "programs" / "builtin_device.o", defines))
+        dev = [t.result() for t in dev]
+    host = [OBJ / "host" / (s.stem + ".o") for s in HOST_SOURCES] + [OBJ / "programs" / "builtin_host.o"]
+    so = LIBDIR / f"libsrp_b200_{name}.so"
+    _run([NVCC, "-shared", *DLINK_FLAGS, "-Xlinker", "-Bsymbolic", *dev, *host, "-o", so, "-lz"])
+    return so
+
+
 def build_oracle() -> bool:
     """the unmodified reference -> oracle/_ref (needs /root/reference; skipped elsewhere)"""
     if not (REFERENCE / "src").is_dir():

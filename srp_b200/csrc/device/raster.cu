@@ -253,11 +253,14 @@ __device__ __forceinline__ void prepareTriangle(const unsigned char* rec, const 
 /* Per-pixel fragment queue.  Coverage of a triangle is decided for the 32 pixels of a
  * block at once, but typically only a handful of them are covered, so shading right away
  * would run the (long) fragment stage with most lanes idle.  Instead a covered pixel pushes
- * (barycentrics, record) into a 4-deep queue of its own, in primitive order; the queues are
+ * (barycentrics, record) into a small queue of its own (2 entries: deeper queues cost registers and measured slower), in primitive order; the queues are
  * drained together -- entry 0 of every lane, then entry 1, ... -- so that the fragment
  * stage runs with most lanes busy, each on its OWN next fragment.  Per pixel the order of
  * fragments is unchanged, which is all the reference's semantics depend on. */
-constexpr int SRPD_FRAG_QUEUE = 4;
+#ifndef SRPD_FRAG_QUEUE_DEPTH
+#define SRPD_FRAG_QUEUE_DEPTH 2
+#endif
+constexpr int SRPD_FRAG_QUEUE = SRPD_FRAG_QUEUE_DEPTH;
 struct FragQueue
 {
 	float l0[SRPD_FRAG_QUEUE], l1[SRPD_FRAG_QUEUE], l2[SRPD_FRAG_QUEUE];

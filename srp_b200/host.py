@@ -313,6 +313,10 @@ _loaded: dict[str, SrpLibrary] = {}
 def load_product() -> SrpLibrary:
     """The CUDA library.  Raises if it has not been built -- there is no fallback."""
     if "product" not in _loaded:
+        so = Path(os.environ.get("SRP_B200_LIBRARY", PRODUCT_SO))   # tuning experiments may point at a variant build
+        if so != PRODUCT_SO:
+            _loaded["product"] = SrpLibrary(so, is_product=True)
+            return _loaded["product"]
         if not PRODUCT_SO.exists():
             raise RuntimeError(
                 f"{PRODUCT_SO} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "

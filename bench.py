@@ -284,12 +284,30 @@ def main():
     e2e_s = time.perf_counter() - t0
     barrier()
     st2 = lib.stats()
+    # two friendlier variants of the same step, reported next to the headline e2e figure:
+    # (a) the mesh stays resident (real srp programs upload once and change only the uniform),
+    # (b) additionally only the colour plane is mirrored (what the reference's own programs read)
+    def timed(fn):
+        for _ in range(W):
+            fn()
+        barrier()
+        t = time.perf_counter()
+        for _ in range(K):
+            fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        barrier()
+        return dt
+    e2e_static_s = timed(prep.draw_all)
+    lib.dll.srpB200SetMirrorPlanes(1)
+    e2e_color_s = timed(prep.draw_all)
+    lib.dll.srpB200SetMirrorPlanes(7)
     checksum = int(np.ctypeslib.as_array(prep.fb.ptr.contents.color, shape=(scene.width * scene.height,))[::4099].sum())
 
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, e2e_s * 1e3, e2e_static_s * 1e3, e2e_color_s * 1e3], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s = float(t[0]), float(t[1]) / 1e3
+        dev_ms, e2e_s, e2e_static_s, e2e_color_s = float(t[0]), float(t[1]) / 1e3, float(t[2]) / 1e3, float(t[3]) / 1e3
 
     if rank == 0:
         peaks = {}
@@ -323,7 +341,11 @@ def main():
                          "frame": {"algorithmic_bytes": alg, "achieved": frame_gbs, "frac": frame_gbs / hbm}},
             "e2e": {"value": world * K / e2e_s, "unit": "frames/s",
                     "h2d_bytes_per_step": st2["h2dBytes"] // K, "d2h_bytes_per_step": st2["d2hBytes"] // K,
-                    "ms_per_step": 1e3 * e2e_s / K, "result_checksum": checksum},
+                    "ms_per_step": 1e3 * e2e_s / K, "result_checksum": checksum,
+                    "what": "per step: srpVertexBufferCopyData + srpIndexBufferCopyData from pinned host memory, srpFramebufferClear, "
+                            "srpDrawIndexBuffer returning with colour + depth mirrored on the host",
+                    "variants": {"mesh_resident_frames_per_s": world * K / e2e_static_s,
+                                 "mesh_resident_color_only_frames_per_s": world * K / e2e_color_s}},
             "gpu_launches": launches,
             "clocks": clocks,
             "version": lib.dll.srpB200Version().decode(),

@@ -40,6 +40,12 @@ int srpB200RegisterProgram(SRPVertexShaderFunc hostVS, SRPFragmentShaderFunc hos
 typedef enum { SRP_B200_SYNC_DRAW = 0, SRP_B200_SYNC_EXPLICIT = 1 } SRPB200SyncMode;
 void srpB200SetSyncMode(SRPB200SyncMode mode);
 SRPB200SyncMode srpB200GetSyncMode(void);
+/* Which planes the automatic refresh of the host mirror covers (default: all three).  A
+ * program that only ever reads fb->color (like the reference's examples and tests) can drop
+ * depth and stencil and halve the PCIe traffic of every draw; explicit downloads still bring
+ * everything. */
+enum { SRP_B200_MIRROR_COLOR = 1, SRP_B200_MIRROR_DEPTH = 2, SRP_B200_MIRROR_STENCIL = 4, SRP_B200_MIRROR_ALL = 7 };
+void srpB200SetMirrorPlanes(int planeMask);
 void srpB200Finish(void);                                   /* wait for all enqueued work */
 void srpB200FramebufferDownload(const SRPFramebuffer* fb);  /* device planes -> host mirror (synchronous) */
 void srpB200FramebufferUpload(const SRPFramebuffer* fb);    /* host mirror -> device planes */

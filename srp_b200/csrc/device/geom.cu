@@ -475,7 +475,7 @@ __device__ __forceinline__ uint32_t warpInclusiveScan(uint32_t v, int lane)
 
 /* 4 CTAs/SM (64 registers): a CTA spends part of its life waiting in the look-back, which
  * the other resident CTAs hide */
-__global__ void __launch_bounds__(SRPD_GEOM_THREADS, 4)
+__global__ void __launch_bounds__(SRPD_GEOM_THREADS, SRPD_GEOM_CTAS_PER_SM)
 srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem[];

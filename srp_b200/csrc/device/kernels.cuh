@@ -11,8 +11,17 @@ extern "C" __device__ void srpB200DeviceVS(int programId, SRPVertexShaderIn* in,
 extern "C" __device__ void srpB200DeviceFS(int programId, SRPFragmentShaderIn* in, SRPFragmentShaderOut* out);
 
 /* ---- launch geometry -------------------------------------------------------------- */
+#ifndef SRPD_TILE_H_PX
+#define SRPD_TILE_H_PX 16
+#endif
+#ifndef SRPD_TILE_CTAS_PER_SM
+#define SRPD_TILE_CTAS_PER_SM 2
+#endif
+#ifndef SRPD_GEOM_CTAS_PER_SM
+#define SRPD_GEOM_CTAS_PER_SM 4
+#endif
 constexpr int SRPD_TILE_W = 32;          /* pixels; one 128-byte colour row per tile row   */
-constexpr int SRPD_TILE_H = 16;
+constexpr int SRPD_TILE_H = SRPD_TILE_H_PX;
 constexpr int SRPD_BLK_W = 8;            /* pixels owned by one warp: 8 x 4                */
 constexpr int SRPD_BLK_H = 4;
 constexpr int SRPD_TILE_THREADS = SRPD_TILE_W * SRPD_TILE_H;       /* one thread per pixel */

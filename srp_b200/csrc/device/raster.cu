@@ -610,7 +610,7 @@ __device__ __forceinline__ void clearTile(const SrpdState& st, const SrpdFrame& 
  * missing minimum makes the linker's code generator cap the kernel at 64 registers and
  * spill).  Triangles and points fit two 512-thread CTAs per SM; the line walker does not. */
 template <int KIND>
-__global__ void __launch_bounds__(SRPD_TILE_THREADS, KIND == SRPD_KIND_LINE ? 1 : 2)
+__global__ void __launch_bounds__(SRPD_TILE_THREADS, KIND == SRPD_KIND_LINE ? SRPD_TILE_CTAS_PER_SM / 2 : SRPD_TILE_CTAS_PER_SM)
 srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 {
 	__shared__ __align__(16) uint32_t sIds[SRPD_TILE_THREADS];     /* reused as the colour staging tile */
@@ -717,7 +717,7 @@ void srpdLaunchTiles(const SrpdTileArgs& a, cudaStream_t stream)
 	/* persistent grid: resident CTAs per SM x SM count (no more CTAs than work items) */
 	const uint32_t tilesPerFrame = a.tilesX * rows;
 	const uint64_t nItems = (uint64_t) ((tilesPerFrame + a.tilesPerItem - 1) / a.tilesPerItem) * a.d.nFrames;
-	const uint32_t perSm = a.d.kind == SRPD_KIND_LINE ? 1u : 2u;
+	const uint32_t perSm = a.d.kind == SRPD_KIND_LINE ? SRPD_TILE_CTAS_PER_SM / 2 : SRPD_TILE_CTAS_PER_SM;
 	uint64_t grid = (uint64_t) a.smCount * perSm;
 	if (grid > nItems) grid = nItems;
 	if (grid == 0) return;

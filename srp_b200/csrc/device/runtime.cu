@@ -499,7 +499,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		 * one atomic per tile when a batch has millions of mostly empty tiles */
 		const uint32_t rows = ta.d.tileRow1 - ta.d.tileRow0;
 		const uint64_t tiles = (uint64_t) tilesX * rows * nFrames;
-		const uint64_t target = (uint64_t) g.smCount * 2 * 32;
+		const uint64_t target = (uint64_t) g.smCount * SRPD_TILE_CTAS_PER_SM * 32;
 		uint32_t per = 1;
 		while (per < 32 && tiles / (per * 2) >= target) per *= 2;
 		ta.tilesPerItem = per;
@@ -512,7 +512,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	g.mirrorDone = nullptr;
 	const uint32_t rows = ta.d.tileRow1 - ta.d.tileRow0;
 	uint32_t nBands = 1;
-	if (mirror.color && nFrames == 1 && ta.d.tileRow0 == 0 && ta.d.tileRow1 == tilesY
+	if ((mirror.color || mirror.depth) && nFrames == 1 && ta.d.tileRow0 == 0 && ta.d.tileRow1 == tilesY
 	    && (uint64_t) st.width * st.height >= (1u << 20) && !getenv("SRP_B200_NO_BANDS"))
 		nBands = rows >= 64 ? 4 : 1;
 	mark();
@@ -540,9 +540,16 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 			size_t y1 = (size_t) band.d.tileRow1 * SRPD_TILE_H;
 			if (y1 > (size_t) st.height) y1 = (size_t) st.height;
 			const size_t first = y0 * W, count = (y1 - y0) * W;
-			CU(cudaMemcpyAsync((uint32_t*) mirror.color + first, frame0.color + first, count * 4, cudaMemcpyDeviceToHost, g.copyStream));
-			CU(cudaMemcpyAsync((float*) mirror.depth + first, frame0.depth + first, count * 4, cudaMemcpyDeviceToHost, g.copyStream));
-			g.d2h += count * 8;
+			if (mirror.color)
+			{
+				CU(cudaMemcpyAsync((uint32_t*) mirror.color + first, frame0.color + first, count * 4, cudaMemcpyDeviceToHost, g.copyStream));
+				g.d2h += count * 4;
+			}
+			if (mirror.depth)
+			{
+				CU(cudaMemcpyAsync((float*) mirror.depth + first, frame0.depth + first, count * 4, cudaMemcpyDeviceToHost, g.copyStream));
+				g.d2h += count * 4;
+			}
 			if (mirror.stencil)
 			{
 				CU(cudaMemcpyAsync((uint8_t*) mirror.stencil + first, frame0.stencil + first, count, cudaMemcpyDeviceToHost, g.copyStream));

@@ -312,8 +312,11 @@ static void submit(
 			int mirrored = 0;
 			if (nFrames == 1 && srpB200GetSyncMode() == SRP_B200_SYNC_DRAW)
 			{
-				const bool wantStencil = impls[0]->stencilTouched || d.st.stencilEnabled;
-				SrpcuMirror m = { impls[0]->pub.color, impls[0]->pub.depth, wantStencil ? impls[0]->pub.stencil : NULL };
+				const int planes = srpMirrorPlanes();
+				const bool wantStencil = (planes & SRP_B200_MIRROR_STENCIL) && (impls[0]->stencilTouched || d.st.stencilEnabled);
+				SrpcuMirror m = { (planes & SRP_B200_MIRROR_COLOR) ? impls[0]->pub.color : NULL,
+				                  (planes & SRP_B200_MIRROR_DEPTH) ? impls[0]->pub.depth : NULL,
+				                  wantStencil ? impls[0]->pub.stencil : NULL };
 				srpcuSetMirrorForNextDraw(&m, &mirrored);
 			}
 			if (srpcuDraw(&d, frames, uniforms, ubytes, uniformStride))

@@ -15,6 +15,10 @@
 #include "srp_internal.h"
 
 static SRPB200SyncMode gSyncMode = SRP_B200_SYNC_DRAW;
+static int gMirrorPlanes = SRP_B200_MIRROR_ALL;
+
+void srpB200SetMirrorPlanes(int planeMask) { gMirrorPlanes = planeMask & SRP_B200_MIRROR_ALL; }
+int srpMirrorPlanes(void) { return gMirrorPlanes; }
 
 void srpB200SetSyncMode(SRPB200SyncMode mode) { gSyncMode = mode; }
 SRPB200SyncMode srpB200GetSyncMode(void) { return gSyncMode; }
@@ -115,18 +119,22 @@ static void materializeClear(SRPFramebufferImpl* fb)
 	fb->clearPending = false;
 }
 
-static void enqueueDownload(SRPFramebufferImpl* fb)
+static void enqueueDownload(SRPFramebufferImpl* fb, int planes)
 {
 	materializeClear(fb);
 	const size_t n = fb->pub.size;
-	int err = srpcuDownload(fb->pub.color, fb->dColor, n * sizeof(uint32_t));
-	err |= srpcuDownload(fb->pub.depth, fb->dDepth, n * sizeof(float));
-	if (fb->stencilTouched)
+	int err = 0;
+	if (planes & SRP_B200_MIRROR_COLOR)
+		err |= srpcuDownload(fb->pub.color, fb->dColor, n * sizeof(uint32_t));
+	if (planes & SRP_B200_MIRROR_DEPTH)
+		err |= srpcuDownload(fb->pub.depth, fb->dDepth, n * sizeof(float));
+	if ((planes & SRP_B200_MIRROR_STENCIL) && fb->stencilTouched)
 		err |= srpcuDownload(fb->pub.stencil, fb->dStencil, n * sizeof(uint8_t));
 	if (err)
 		srpFatalMessage("srpB200FramebufferDownload", "%s", srpcuLastError());
-	fb->stencilTouched = false;
-	fb->mirrorStale = false;
+	if (planes & SRP_B200_MIRROR_STENCIL)
+		fb->stencilTouched = false;
+	fb->mirrorStale = planes != SRP_B200_MIRROR_ALL;
 }
 
 void srpB200FramebufferDownload(const SRPFramebuffer* pub)
@@ -134,7 +142,7 @@ void srpB200FramebufferDownload(const SRPFramebuffer* pub)
 	SRPFramebufferImpl* fb = srpFramebufferImpl(pub);
 	if (!fb) return;
 	fb->stencilTouched = true;      /* explicit request: bring everything */
-	enqueueDownload(fb);
+	enqueueDownload(fb, SRP_B200_MIRROR_ALL);
 	if (srpcuSynchronize())
 		srpFatalMessage(__func__, "%s", srpcuLastError());
 }
@@ -173,12 +181,13 @@ void srpFramebufferAfterDraw(SRPFramebufferImpl* const* fbs, size_t n, bool sten
 	if (alreadyMirrored)
 	{
 		/* the draw copied its bands to the host itself (runtime.cu); only bookkeeping is left */
-		fbs[0]->stencilTouched = false;
-		fbs[0]->mirrorStale = false;
+		if (gMirrorPlanes & SRP_B200_MIRROR_STENCIL)
+			fbs[0]->stencilTouched = false;
+		fbs[0]->mirrorStale = gMirrorPlanes != SRP_B200_MIRROR_ALL;
 	}
 	else
 		for (size_t i = 0; i < n; i++)
-			enqueueDownload(fbs[i]);
+			enqueueDownload(fbs[i], gMirrorPlanes);
 	if (srpcuSynchronize())
 		srpFatalMessage("srpDraw", "%s", srpcuLastError());
 }

@@ -74,6 +74,8 @@ const SRPProgramEntry* srpLookupProgram(SRPVertexShaderFunc vs, SRPFragmentShade
 SRPFramebufferImpl* srpFramebufferImpl(const SRPFramebuffer* fb);
 void srpFramebufferAfterDraw(SRPFramebufferImpl* const* fbs, size_t n, bool stencilEnabled, bool alreadyMirrored);
 
+int srpMirrorPlanes(void);
+
 /* PNG loader (srp_png.c): returns malloc'ed RGB8 or NULL (+ reason) */
 uint8_t* srpLoadPngRgb(const char* path, int* width, int* height, const char** reason);
 

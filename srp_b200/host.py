@@ -211,6 +211,7 @@ class SrpLibrary:
             "srpB200RegisterProgram": (i32, [vp, vp, i32, sz]),
             "srpB200SetSyncMode": (None, [i32]), "srpB200GetSyncMode": (i32, []),
             "srpB200Finish": (None, []),
+            "srpB200SetMirrorPlanes": (None, [i32]),
             "srpB200FramebufferDownload": (None, [C.POINTER(SRPFramebuffer)]),
             "srpB200FramebufferUpload": (None, [C.POINTER(SRPFramebuffer)]),
             "srpB200NewFramebufferOnDevice": (C.POINTER(SRPFramebuffer), [sz, sz, vp, vp, vp]),

@@ -90,7 +90,7 @@ __device__ __forceinline__ void resolveTopology(const SrpdDraw& d, uint32_t k, u
 
 __device__ __forceinline__ uint32_t hashInsert(uint32_t* keys, uint32_t key)
 {
-	uint32_t h = (key * 2654435761u) >> 22;
+	uint32_t h = (key * 2654435761u) >> SRPD_HASH_SHIFT;
 	for (;;)
 	{
 		const uint32_t prev = atomicCAS(&keys[h], SRPD_HASH_EMPTY, key);

@@ -31,9 +31,13 @@ constexpr int SRPD_TILE_WARPS = SRPD_TILE_THREADS / 32;
  * millions of sub-pixel primitives, so that a tile never filters more than ~1-2 k candidates */
 constexpr int SRPD_SUPER_SHIFT_MAX = 3;
 
-constexpr int SRPD_GEOM_THREADS = 256;   /* input primitives per geometry batch            */
+#ifndef SRPD_GEOM_BATCH
+#define SRPD_GEOM_BATCH 256
+#endif
+constexpr int SRPD_GEOM_THREADS = SRPD_GEOM_BATCH;   /* input primitives per geometry batch (128, 256 or 512) */
 constexpr int SRPD_GEOM_MAX_VERTS = 3 * SRPD_GEOM_THREADS;
-constexpr int SRPD_HASH_SLOTS = 1024;    /* post-VS cache: open-addressing table in smem   */
+constexpr int SRPD_HASH_SLOTS = 4 * SRPD_GEOM_THREADS;   /* post-VS cache: open-addressing table in smem, load <= 3/4 */
+constexpr int SRPD_HASH_SHIFT = SRPD_GEOM_THREADS == 128 ? 23 : (SRPD_GEOM_THREADS == 256 ? 22 : 21);
 constexpr uint32_t SRPD_HASH_EMPTY = 0xFFFFFFFFu;
 constexpr int SRPD_CLIP_MAX_VERTS = 10;  /* a triangle against 6 planes has <= 9 vertices  */
 

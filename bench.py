@@ -326,6 +326,11 @@ def main():
                      "tiles_ms": alg["framebuffer"] + alg["texture"]}[dom]
         achieved = dom_bytes / (per[dom] / 1e3) / 1e9 if per[dom] > 0 else 0.0
         frame_gbs = alg["total"] * (value / world) / 1e9
+        traffic = None
+        tr = ROOT / "profiles" / "r01_cfg3_ncu_summary_traffic.json"
+        dom_kernel = {"geometry_ms": "srpdGeomKernel", "binning_ms": "srpdBinFillKernel", "tiles_ms": "srpdTileKernel"}[dom]
+        if tr.exists() and args.workload == "cfg3":
+            traffic = json.loads(tr.read_text())["kernels"].get(dom_kernel, {}).get("dram_bytes")
         line = {
             "metric": f"frames_per_s_{args.workload}", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
@@ -336,7 +341,8 @@ def main():
             "input_triangles_per_s": world * (count // 3) * K / (dev_ms / 1e3),
             "stage_ms_per_frame": per,
             "roofline": {"bound": "hbm", "kernel": {"geometry_ms": "srpdGeomKernel", "binning_ms": "srpdBin*Kernel", "tiles_ms": "srpdTileKernel"}[dom],
-                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                         "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+                         "traffic_source": "profiles/r01_cfg3_ncu_summary_traffic.json (ncu --set full, one full-frame launch; the 126 MB L2 absorbs most of the plane writes within the launch)" if traffic else None,
                          "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_src,
                          "frame": {"algorithmic_bytes": alg, "achieved": frame_gbs, "frac": frame_gbs / hbm}},
             "e2e": {"value": world * K / e2e_s, "unit": "frames/s",

@@ -74,6 +74,22 @@ def main():
         for i in sorted(items, reverse=True)[:18]:
             lines.append(f"{100 * i[0] / ti:5.1f}% inst {100 * i[1] / ts:5.1f}% stall  {i[2]}:{i[3]}  {i[4]}")
         lines += ["```", ""]
+    # per-kernel DRAM traffic of one launch, for bench.py's roofline.traffic
+    import json
+    def to_bytes(v, unit):
+        f = float(v.replace(",", ""))
+        return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+    traffic = {}
+    for r in raw[2:]:
+        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0]
+        if name in traffic:
+            continue
+        rd = to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]])
+        wr = to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
+        traffic[name] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "dram_bytes": rd + wr,
+                         "duration_us": float(r[idx["gpu__time_duration.sum"]].replace(",", ""))}
+    json.dump({"source": rep.split("/")[-1], "note": "one launch each, ncu --set full --clock-control none (cold cache, serialised)",
+               "kernels": traffic}, open(out.replace(".md", "_traffic.json"), "w"), indent=1)
     open(out, "w").write("\n".join(lines) + "\n")
     print("wrote", out)
 

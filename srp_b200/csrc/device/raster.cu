@@ -157,135 +157,126 @@ __device__ __forceinline__ void emitFragment(
 	}
 }
 
-/* Barycentric chain, part 1 (one LANE per TRIANGLE): the reference reaches pixel (x, y) of a
- * triangle by (y - minY) float additions of dlambda/dy from the value at the bounding-box
- * corner, then (x - minX) additions of dlambda/dx (triangle.c:102-109).  All 32 pixels of a
- * warp's 8x4 block share most of that chain, so before a warp visits the up-to-32 triangles
- * of a list step, lane k walks triangle k's chain once: down to each of the block's four
- * rows, then right to the block's first column (clamped to the bounding box).  The twelve
- * row-start values go to shared memory; a pixel then only adds its <= 7 remaining x steps.
- * The sequence of additions each pixel's value goes through is unchanged => bit-exact. */
-__device__ __forceinline__ void prepareTriangle(const unsigned char* rec, const float* ckptTable, int bx0, int by0, float* out)
+/* Triangle coverage, one LANE per (TRIANGLE, BLOCK ROW).
+ *
+ * The reference reaches pixel (x, y) of a triangle by (y - minY) float additions of
+ * dlambda/dy from the value at the bounding-box corner, then (x - minX) additions of
+ * dlambda/dx (triangle.c:102-109).  The 8 pixels of a block row share that chain up to the
+ * row's first pixel, and only a handful of the (up to 32) triangles of a list step touch a
+ * warp's 8x4 block, so coverage is not decided by the pixel threads (most of which would
+ * only find out that they are outside) but by "row lanes": lane 4*k + r takes row r of the
+ * k-th touching triangle, walks the chain down to its row and right to the first column
+ * (from the box corner, or from the (row, tile column) checkpoint of a large triangle),
+ * tests the row's <= 8 pixels with the top-left rule and leaves
+ *   - the row's 8 coverage bits (combined by shuffles into the triangle's 32-bit block mask),
+ *   - lambda at the first column, for the pixel threads to resume from.
+ * The pixel threads then transpose the masks (bit t of `cov` = triangle t covers my pixel)
+ * and shade their own covered triangles in primitive order, resuming the chain with their
+ * <= 7 remaining x steps: every value goes through exactly the reference's sequence of
+ * additions => bit-exact. */
+struct RowStart { float l0, l1, l2; int xs; };         /* lambda at column xs of the row        */
+struct TriStep  { float dx0, dx1, dx2; uint32_t mask; };/* dlambda/dx and the block coverage mask */
+
+__device__ __forceinline__ uint32_t coverTriangleRow(
+	const unsigned char* rec, const float* ckptTable, int bx0, int y, RowStart* rowOut, TriStep* stepOut, bool first)
 {
 	const uint4* h = (const uint4*) rec;
 	const uint4 q0 = __ldg(h + 0), q1 = __ldg(h + 1), q2 = __ldg(h + 2);
-	const int minX = (int) (q0.w & 0xFFFFu), minY = (int) (q1.w & 0xFFFFu);
-	float l0 = __uint_as_float(q0.x), l1 = __uint_as_float(q0.y), l2 = __uint_as_float(q0.z);
-	const float dy0 = __uint_as_float(q2.x), dy1 = __uint_as_float(q2.y), dy2 = __uint_as_float(q2.z);
+	const int minX = (int) (q0.w & 0xFFFFu), maxX = (int) (q0.w >> 16);
+	const int minY = (int) (q1.w & 0xFFFFu), maxY = (int) (q1.w >> 16);
 	const float dx0 = __uint_as_float(q1.x), dx1 = __uint_as_float(q1.y), dx2 = __uint_as_float(q1.z);
+	if (first)
+	{
+		stepOut->dx0 = dx0; stepOut->dx1 = dx1; stepOut->dx2 = dx2;
+	}
+	const int xs = bx0 > minX ? bx0 : minX;
+	const int xe = bx0 + SRPD_BLK_W < maxX ? bx0 + SRPD_BLK_W : maxX;
+	if (y < minY || y >= maxY || xs >= xe)
+		return 0u;
+	float l0, l1, l2;
+	int nx;
 	const uint32_t ckpt = __ldg((const uint32_t*) rec + 19);
 	if (ckpt)
 	{
-		/* large triangle: start from the checkpoints of (row, this tile's column), written by
+		/* large triangle: resume from the checkpoint of (row, this tile's column), written by
 		 * srpdCheckpointKernel with the reference's own sequence of additions */
-		const int maxX = (int) (q0.w >> 16), maxY = (int) (q1.w >> 16);
 		const int col0 = minX / SRPD_TILE_W;
 		const int cols = (maxX - 1) / SRPD_TILE_W - col0 + 1;
-		const int col = bx0 / SRPD_TILE_W - col0;
 		const int tileX0 = (bx0 / SRPD_TILE_W) * SRPD_TILE_W;
-		const int nx = bx0 - (tileX0 > minX ? tileX0 : minX);      /* steps from the checkpoint to the block's first column */
-		float r[SRPD_BLK_H][3];
-		#pragma unroll
-		for (int k = 0; k < SRPD_BLK_H; k++)
-		{
-			const int row = by0 + k - minY;
-			r[k][0] = 0.f; r[k][1] = 0.f; r[k][2] = 0.f;
-			if (row >= 0 && row < maxY - minY)
-			{
-				const float* e = ckptTable + 3 * ((size_t) (ckpt - 1) + (size_t) row * cols + col);
-				r[k][0] = __ldg(e + 0); r[k][1] = __ldg(e + 1); r[k][2] = __ldg(e + 2);
-			}
-		}
-		for (int i = 0; i < nx; i++)
+		const float* e = ckptTable + 3 * ((size_t) (ckpt - 1) + (size_t) (y - minY) * cols + (bx0 / SRPD_TILE_W - col0));
+		l0 = __ldg(e + 0); l1 = __ldg(e + 1); l2 = __ldg(e + 2);
+		nx = xs - (tileX0 > minX ? tileX0 : minX);
+	}
+	else
+	{
+		l0 = __uint_as_float(q0.x); l1 = __uint_as_float(q0.y); l2 = __uint_as_float(q0.z);
+		const float dy0 = __uint_as_float(q2.x), dy1 = __uint_as_float(q2.y), dy2 = __uint_as_float(q2.z);
+		const int ny = y - minY;
+		int i = 0;
+		for (; i + 4 <= ny; i += 4)
 		{
 			#pragma unroll
-			for (int k = 0; k < SRPD_BLK_H; k++)
+			for (int u = 0; u < 4; u++)
 			{
-				r[k][0] = __fadd_rn(r[k][0], dx0); r[k][1] = __fadd_rn(r[k][1], dx1); r[k][2] = __fadd_rn(r[k][2], dx2);
+				l0 = __fadd_rn(l0, dy0); l1 = __fadd_rn(l1, dy1); l2 = __fadd_rn(l2, dy2);
 			}
 		}
-		float4* o = (float4*) out;
-		o[0] = make_float4(r[0][0], r[0][1], r[0][2], r[1][0]);
-		o[1] = make_float4(r[1][1], r[1][2], r[2][0], r[2][1]);
-		o[2] = make_float4(r[2][2], r[3][0], r[3][1], r[3][2]);
-		return;
-	}
-	const int sy = by0 - minY;                 /* chain steps down to the block's first row (may be < 0) */
-	const int n0 = sy > 0 ? sy : 0;
-	int i = 0;
-	for (; i + 4 <= n0; i += 4)
-	{
-		#pragma unroll
-		for (int u = 0; u < 4; u++)
+		for (; i < ny; i++)
 		{
 			l0 = __fadd_rn(l0, dy0); l1 = __fadd_rn(l1, dy1); l2 = __fadd_rn(l2, dy2);
 		}
+		nx = xs - minX;
 	}
-	for (; i < n0; i++)
 	{
-		l0 = __fadd_rn(l0, dy0); l1 = __fadd_rn(l1, dy1); l2 = __fadd_rn(l2, dy2);
+		int i = 0;
+		for (; i + 4 <= nx; i += 4)
+		{
+			#pragma unroll
+			for (int u = 0; u < 4; u++)
+			{
+				l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
+			}
+		}
+		for (; i < nx; i++)
+		{
+			l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
+		}
 	}
-	float r[SRPD_BLK_H][3];
+	rowOut->l0 = l0; rowOut->l1 = l1; rowOut->l2 = l2; rowOut->xs = xs;
+	/* the row's pixels, top-left rule: lambda > 0 || (|lambda| <= 1e-9 && edgeTL), triangle.c:82-87 */
+	const uint32_t flags = q2.w;
+	const int n = xe - xs;
+	uint32_t bits = 0u;
 	#pragma unroll
-	for (int k = 0; k < SRPD_BLK_H; k++)
+	for (int i = 0; i < SRPD_BLK_W; i++)
 	{
-		r[k][0] = l0; r[k][1] = l1; r[k][2] = l2;
-		if (sy + k >= 0)                       /* rows above the bounding box do not advance the chain */
+		if (i < n)
 		{
-			l0 = __fadd_rn(l0, dy0); l1 = __fadd_rn(l1, dy1); l2 = __fadd_rn(l2, dy2);
+			const bool in0 = (l0 > 0.f) || (srpdRoughlyZero(l0) && (flags & 1u));
+			const bool in1 = (l1 > 0.f) || (srpdRoughlyZero(l1) && (flags & 2u));
+			const bool in2 = (l2 > 0.f) || (srpdRoughlyZero(l2) && (flags & 4u));
+			if (in0 && in1 && in2)
+				bits |= 1u << i;
+			l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
 		}
 	}
-	const int nx = bx0 > minX ? bx0 - minX : 0;   /* steps right to the block's first column */
-	for (i = 0; i < nx; i++)
-	{
-		#pragma unroll
-		for (int k = 0; k < SRPD_BLK_H; k++)
-		{
-			r[k][0] = __fadd_rn(r[k][0], dx0); r[k][1] = __fadd_rn(r[k][1], dx1); r[k][2] = __fadd_rn(r[k][2], dx2);
-		}
-	}
-	float4* o = (float4*) out;
-	o[0] = make_float4(r[0][0], r[0][1], r[0][2], r[1][0]);
-	o[1] = make_float4(r[1][1], r[1][2], r[2][0], r[2][1]);
-	o[2] = make_float4(r[2][2], r[3][0], r[3][1], r[3][2]);
+	return bits << (xs - bx0);
 }
 
-/* Per-pixel fragment queue.  Coverage of a triangle is decided for the 32 pixels of a
- * block at once, but typically only a handful of them are covered, so shading right away
- * would run the (long) fragment stage with most lanes idle.  Instead a covered pixel pushes
- * (barycentrics, record) into a small queue of its own (2 entries: deeper queues cost registers and measured slower), in primitive order; the queues are
- * drained together -- entry 0 of every lane, then entry 1, ... -- so that the fragment
- * stage runs with most lanes busy, each on its OWN next fragment.  Per pixel the order of
- * fragments is unchanged, which is all the reference's semantics depend on. */
-#ifndef SRPD_FRAG_QUEUE_DEPTH
-#define SRPD_FRAG_QUEUE_DEPTH 2
-#endif
-constexpr int SRPD_FRAG_QUEUE = SRPD_FRAG_QUEUE_DEPTH;
-struct FragQueue
-{
-	float l0[SRPD_FRAG_QUEUE], l1[SRPD_FRAG_QUEUE], l2[SRPD_FRAG_QUEUE];
-	uint32_t rec[SRPD_FRAG_QUEUE];
-	int n;
-};
-
-__device__ __forceinline__ void pushFragment(FragQueue& q, float l0, float l1, float l2, uint32_t rec)
-{
-	#pragma unroll
-	for (int i = 0; i < SRPD_FRAG_QUEUE; i++)
-		if (q.n == i)
-		{
-			q.l0[i] = l0; q.l1[i] = l1; q.l2[i] = l2; q.rec[i] = rec;
-		}
-	q.n++;
-}
-
-/* fragment stage of one queued triangle fragment: depth / 1/w interpolation
- * (interpolateDepthAndWTriangle, interpolation.c:34-47) and emitFragment */
+/* fragment stage of one covered pixel of a triangle: the pixel's remaining x steps, depth /
+ * 1/w interpolation (interpolateDepthAndWTriangle, interpolation.c:34-47) and emitFragment */
 __device__ __forceinline__ void shadeTriangleFragment(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, uint32_t recIndex,
-	float l0, float l1, float l2, Pixel& px, FragCounters& cnt, int x, int y)
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, const RowStart& rs, const TriStep& ts,
+	Pixel& px, FragCounters& cnt, int x, int y)
 {
-	const unsigned char* rec = records + (size_t) recIndex * a.recStride;
+	float l0 = rs.l0, l1 = rs.l1, l2 = rs.l2;
+	const int nx = x - rs.xs;      /* 0..7 */
+	#pragma unroll
+	for (int i = 0; i < SRPD_BLK_W - 1; i++)
+		if (i < nx)
+		{
+			l0 = __fadd_rn(l0, ts.dx0); l1 = __fadd_rn(l1, ts.dx1); l2 = __fadd_rn(l2, ts.dx2);
+		}
 	const uint4* h = (const uint4*) rec;
 	const uint4 q3 = __ldg(h + 3), q4 = __ldg(h + 4);
 	const uint32_t flags = __ldg((const uint32_t*) rec + 11);
@@ -299,55 +290,53 @@ __device__ __forceinline__ void shadeTriangleFragment(
 	                depth, recW, recW, (flags & 8u) != 0, q3.w, rec + SRPD_REC_HEADER_BYTES, wgt);
 }
 
-/* drain the queues of the warp: level by level, all lanes that still have an entry */
-__device__ __forceinline__ void drainFragments(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, FragQueue& q,
-	Pixel& px, FragCounters& cnt, int x, int y)
+/* One list step of a warp: `m` = which of the 32 entries sIds[j0 ..] touch the warp's block.
+ * Row lanes decide coverage (8 triangles x 4 rows per round), pixel threads shade. */
+__device__ __forceinline__ void visitTriangles(
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, const uint32_t* stepIds, uint32_t m,
+	RowStart* sRow, TriStep* sStep, Pixel& px, FragCounters& cnt, int x, int y, int bx0, int by0, int lane)
 {
-	#pragma unroll
-	for (int i = 0; i < SRPD_FRAG_QUEUE; i++)
+	const int row = lane & (SRPD_BLK_H - 1), k = lane >> 2;
+	for (uint32_t rem = m; rem; )
 	{
-		if (!__any_sync(0xFFFFFFFFu, q.n > i))
-			break;
-		if (q.n > i)
-			shadeTriangleFragment(a, fr, records, q.rec[i], q.l0[i], q.l1[i], q.l2[i], px, cnt, x, y);
-	}
-	q.n = 0;
-}
-
-/* coverage of one triangle for one pixel, reference triangle.c:73-111; `rowStart` = the
- * prepared row-start barycentrics of this triangle for the warp's block (prepareTriangle).
- * Covered pixels queue a fragment; the warp drains the queues when one of them is full. */
-__device__ __forceinline__ void visitTriangle(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, uint32_t recIndex, const float* rowStart,
-	FragQueue& q, Pixel& px, FragCounters& cnt, int x, int y, int bx0, int ly, bool valid)
-{
-	const unsigned char* rec = records + (size_t) recIndex * a.recStride;
-	const uint4* h = (const uint4*) rec;
-	const uint4 q0 = __ldg(h + 0), q1 = __ldg(h + 1);
-	const int minX = (int) (q0.w & 0xFFFFu), maxX = (int) (q0.w >> 16);
-	const int minY = (int) (q1.w & 0xFFFFu), maxY = (int) (q1.w >> 16);
-	if (valid && x >= minX && x < maxX && y >= minY && y < maxY)
-	{
-		float l0 = rowStart[ly * 3 + 0], l1 = rowStart[ly * 3 + 1], l2 = rowStart[ly * 3 + 2];
-		const float dx0 = __uint_as_float(q1.x), dx1 = __uint_as_float(q1.y), dx2 = __uint_as_float(q1.z);
-		const int nx = x - (bx0 > minX ? bx0 : minX);      /* 0..7 remaining steps */
+		uint32_t r = rem;
 		#pragma unroll
-		for (int i = 0; i < SRPD_BLK_W - 1; i++)
-			if (i < nx)
-			{
-				l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
-			}
-		/* top-left rule: lambda > 0 || (|lambda| <= 1e-9 && edgeTL), triangle.c:82-87 */
-		const uint32_t flags = __ldg((const uint32_t*) rec + 11);
-		const bool in0 = (l0 > 0.f) || (srpdRoughlyZero(l0) && (flags & 1u));
-		const bool in1 = (l1 > 0.f) || (srpdRoughlyZero(l1) && (flags & 2u));
-		const bool in2 = (l2 > 0.f) || (srpdRoughlyZero(l2) && (flags & 4u));
-		if (in0 && in1 && in2)
-			pushFragment(q, l0, l1, l2, recIndex);
+		for (int i = 0; i < 7; i++)
+		{
+			if (i < k) r &= r - 1u;
+			rem &= rem - 1u;
+		}
+		rem &= rem - 1u;
+		const int slot = r ? __ffs(r) - 1 : -1;
+		uint32_t bits = 0u;
+		if (slot >= 0)
+			bits = coverTriangleRow(records + (size_t) stepIds[slot] * a.recStride, a.ckptTable, bx0, by0 + row,
+			                        sRow + slot * SRPD_BLK_H + row, sStep + slot, row == 0) << (row * SRPD_BLK_W);
+		bits |= __shfl_xor_sync(0xFFFFFFFFu, bits, 1);
+		bits |= __shfl_xor_sync(0xFFFFFFFFu, bits, 2);
+		if (slot >= 0 && row == 0)
+			sStep[slot].mask = bits;
 	}
-	if (__any_sync(0xFFFFFFFFu, q.n == SRPD_FRAG_QUEUE))
-		drainFragments(a, fr, records, q, px, cnt, x, y);
+	__syncwarp();
+	/* transpose: bit t of cov <=> entry t of the step covers my pixel */
+	uint32_t cov = 0u;
+	for (uint32_t mm = m; mm; mm &= mm - 1u)
+	{
+		const int t = __ffs(mm) - 1;
+		cov |= ((sStep[t].mask >> lane) & 1u) << t;
+	}
+	const int ly = lane / SRPD_BLK_W;
+	while (__any_sync(0xFFFFFFFFu, cov != 0u))
+	{
+		if (cov)
+		{
+			const int t = __ffs(cov) - 1;
+			cov &= cov - 1u;
+			shadeTriangleFragment(a, fr, records + (size_t) stepIds[t] * a.recStride, sRow[t * SRPD_BLK_H + ly], sStep[t],
+			                      px, cnt, x, y);
+		}
+	}
+	__syncwarp();      /* the next step overwrites this warp's row starts and masks */
 }
 
 /* rasterizeLine for one pixel, reference line.c:34-77: every lane replays the DDA chain of
@@ -438,7 +427,7 @@ __device__ __forceinline__ void storePlane(const T* staged, T* plane, int W, int
 template <int KIND>
 __device__ __forceinline__ void processTile(
 	const SrpdTileArgs& a, const SrpdFrame& fr, uint32_t frame, int tileX, int tileY,
-	uint32_t* sIds, uint2* sBox, uint32_t* sWarpCnt, uint32_t* sDirty, float* sPrep, FragCounters& cnt)
+	uint32_t* sIds, uint2* sBox, uint32_t* sWarpCnt, uint32_t* sDirty, RowStart* sRow, TriStep* sStep, FragCounters& cnt)
 {
 	const SrpdState& st = a.d.st;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -484,8 +473,6 @@ __device__ __forceinline__ void processTile(
 	if (tid == 0)
 		*sDirty = 0u;
 	__syncthreads();
-	FragQueue fq;
-	fq.n = 0;
 
 	for (uint32_t c = begin; c < end; c += SRPD_TILE_THREADS)
 	{
@@ -535,30 +522,24 @@ __device__ __forceinline__ void processTile(
 				mine = x0 < bx0 + SRPD_BLK_W && x1 > bx0 && y0 < by0 + SRPD_BLK_H && y1 > by0;
 			}
 			uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
-			if (KIND == SRPD_KIND_TRIANGLE && m)
+			if (KIND == SRPD_KIND_TRIANGLE)
 			{
-				float* prep = sPrep + (size_t) warp * 32 * SRPD_BLK_H * 3;
-				if (mine)
-					prepareTriangle(records + (size_t) sIds[j] * a.recStride, a.ckptTable, bx0, by0, prep + lane * SRPD_BLK_H * 3);
-				__syncwarp();
+				if (m)
+					visitTriangles(a, fr, records, sIds + j0, m, sRow + (size_t) warp * 32 * SRPD_BLK_H, sStep + (size_t) warp * 32,
+					               px, cnt, x, y, bx0, by0, lane);
+				continue;
 			}
 			while (m)
 			{
 				const int bit = __ffs(m) - 1;
 				m &= m - 1;
 				const unsigned char* rec = records + (size_t) sIds[j0 + bit] * a.recStride;
-				if (KIND == SRPD_KIND_TRIANGLE)
-					visitTriangle(a, fr, records, sIds[j0 + bit], sPrep + ((size_t) warp * 32 + bit) * SRPD_BLK_H * 3, fq, px, cnt,
-					              x, y, bx0, lane / SRPD_BLK_W, valid);
-				else if (KIND == SRPD_KIND_LINE)
+				if (KIND == SRPD_KIND_LINE)
 					visitLine(a, fr, rec, px, cnt, x, y, valid);
 				else
 					visitPoint(a, fr, rec, px, cnt, x, y, valid);
 			}
-			__syncwarp();      /* the next step overwrites this warp's prepared values */
 		}
-		if (KIND == SRPD_KIND_TRIANGLE)      /* sIds is about to be refilled: finish what refers to it */
-			drainFragments(a, fr, records, fq, px, cnt, x, y);
 		__syncthreads();
 	}
 
@@ -618,8 +599,9 @@ srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 	__shared__ uint32_t sWarpCnt[SRPD_TILE_WARPS];
 	__shared__ uint32_t sDirty;
 	__shared__ uint32_t sItem[2];
-	/* per warp: row-start barycentrics of the (up to) 32 triangles of the current list step */
-	__shared__ __align__(16) float sPrep[KIND == SRPD_KIND_TRIANGLE ? SRPD_TILE_WARPS * 32 * SRPD_BLK_H * 3 : 4];
+	/* per warp: row starts and dlambda/dx + coverage masks of the (up to) 32 triangles of the current list step */
+	__shared__ __align__(16) RowStart sRow[KIND == SRPD_KIND_TRIANGLE ? SRPD_TILE_WARPS * 32 * SRPD_BLK_H : 1];
+	__shared__ __align__(16) TriStep sStep[KIND == SRPD_KIND_TRIANGLE ? SRPD_TILE_WARPS * 32 : 1];
 
 	if (*a.abortFlag)      /* a scratch pool overflowed: the host repeats the draw with larger pools */
 		return;
@@ -654,7 +636,7 @@ srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 			const uint32_t tileIndex = (uint32_t) tileY * a.tilesX + (uint32_t) tileX;
 			const bool occupied = (occ[tileIndex >> 5] >> (tileIndex & 31u)) & 1u;
 			if (occupied)
-				processTile<KIND>(a, fr, frame, tileX, tileY, sIds, sBox, sWarpCnt, &sDirty, sPrep, cnt);
+				processTile<KIND>(a, fr, frame, tileX, tileY, sIds, sBox, sWarpCnt, &sDirty, sRow, sStep, cnt);
 			else if (fr.clearPending)
 				clearTile(a.d.st, fr, tileX, tileY);
 		}

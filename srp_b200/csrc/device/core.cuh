@@ -548,9 +548,9 @@ SRP_HD uint8_t srpdStencilWrite(uint8_t current, uint8_t val, uint8_t writeMask)
 SRP_HD uint32_t srpdPackChannel(float c)
 {
 	float v = SRP_FMUL(c, 255.0f);
-	/* v < 0 -> 0, v > 255 -> 255, else truncate; NaN is UB in the reference (unpinned): 0 here */
-	const uint32_t t = (uint32_t) (int) v & 0xFFu;
-	return (v < 0) ? 0u : ((v > 255) ? 255u : t);
+	/* v < 0 -> 0, v > 255 -> 255, else truncate; NaN is UB in the reference (unpinned): 0 here
+	 * (fmaxf returns its non-NaN argument) */
+	return (uint32_t) (int) fminf(fmaxf(v, 0.0f), 255.0f);
 }
 SRP_HD uint32_t srpdColorPack(const float c[4])
 {

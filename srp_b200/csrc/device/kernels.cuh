@@ -137,6 +137,7 @@ struct SrpdTileArgs
 	uint32_t occWordsPerFrame;
 	uint32_t* workCounter;            /* zeroed per draw: next work item of the persistent tile kernel */
 	uint32_t tilesPerItem;            /* consecutive tiles of one frame per work item */
+	uint64_t tilesXInv;               /* floor(2^40 / tilesX) + 1, filled by srpdLaunchTiles */
 	const float* ckptTable;           /* barycentric checkpoints of large triangles     */
 	uint32_t smCount;
 	SrpdStats* stats;

@@ -51,15 +51,14 @@ __device__ __forceinline__ void emitFragment(
 	const unsigned char* blobs, const float* wgt)
 {
 	cnt.emitted++;
-	if (!srpdScissor(st, sx, sy))
+	if (st.scissorEnabled && !srpdScissor(st, sx, sy))
 		return;
 
-	const SrpdStencilFace& sf = frontFacing ? st.stencilFront : st.stencilBack;
 	const float storedDepth = px.depth;
-	const uint8_t storedStencil = (uint8_t) px.stencil;
-
 	if (st.stencilEnabled)
 	{
+		const SrpdStencilFace& sf = frontFacing ? st.stencilFront : st.stencilBack;
+		const uint8_t storedStencil = (uint8_t) px.stencil;
 		if (!srpdCompareU8(sf.func, (uint8_t) (sf.ref & sf.mask), (uint8_t) (storedStencil & sf.mask)))
 		{
 			px.stencil = srpdStencilWrite(storedStencil, srpdStencilOp(sf.sfailOp, storedStencil, sf.ref), sf.writeMask);
@@ -71,6 +70,8 @@ __device__ __forceinline__ void emitFragment(
 	{
 		if (st.stencilEnabled)
 		{
+			const SrpdStencilFace& sf = frontFacing ? st.stencilFront : st.stencilBack;
+			const uint8_t storedStencil = (uint8_t) px.stencil;
 			px.stencil = srpdStencilWrite(storedStencil, srpdStencilOp(sf.dfailOp, storedStencil, sf.ref), sf.writeMask);
 			px.dirty |= 4u;
 		}
@@ -86,27 +87,31 @@ __device__ __forceinline__ void emitFragment(
 	else if (st.allFloat)
 	{
 		/* all attributes are floats: the blob is an array of st.nFloats floats, two bits of
-		 * interpolation mode each; same operation order as srpdInterpolate (interpolation.c:63-83) */
-		const int slotWords = st.slotSize / 4;
-		const float* b = (const float*) blobs;
-		const int prov = st.provokingFirst ? 0 : NV - 1;
+		 * interpolation mode each; same operation order as srpdInterpolate (interpolation.c:63-83).
+		 * Blobs are 8-byte aligned and slotSize is a multiple of 8: two floats per load. */
+		const int slotPairs = st.slotSize / 8;
+		const float2* b = (const float2*) blobs;
 		uint32_t modes = st.floatModes;
-		for (int e = 0; e < st.nFloats; e++, modes >>= 2)
+		for (int e = 0; e < st.nFloats; e += 2, modes >>= 4)
 		{
-			const uint32_t m = modes & 3u;
-			float v;
-			if (m == SRP_INTERPOLATION_MODE_FLAT)
-				v = __ldg(b + prov * slotWords + e);
-			else
+			float2 in[NV];
+			#pragma unroll
+			for (int i = 0; i < NV; i++)
+				in[i] = __ldg(b + i * slotPairs + (e >> 1));
+			float vx = 0.f, vy = 0.f;
+			#pragma unroll
+			for (int i = 0; i < NV; i++)
 			{
-				v = 0.f;
-				#pragma unroll
-				for (int i = 0; i < NV; i++)
-					v = __fadd_rn(v, __fmul_rn(__ldg(b + i * slotWords + e), wgt[i]));
-				if (m == SRP_INTERPOLATION_MODE_PERSPECTIVE)
-					v = __fmul_rn(v, rec);
+				vx = __fadd_rn(vx, __fmul_rn(in[i].x, wgt[i]));
+				vy = __fadd_rn(vy, __fmul_rn(in[i].y, wgt[i]));
 			}
-			((float*) interpolated)[e] = v;
+			const uint32_t mx = modes & 3u, my = (modes >> 2) & 3u;
+			if (mx == SRP_INTERPOLATION_MODE_PERSPECTIVE) vx = __fmul_rn(vx, rec);
+			if (my == SRP_INTERPOLATION_MODE_PERSPECTIVE) vy = __fmul_rn(vy, rec);
+			const float2 pv = st.provokingFirst ? in[0] : in[NV - 1];
+			if (mx == SRP_INTERPOLATION_MODE_FLAT) vx = pv.x;
+			if (my == SRP_INTERPOLATION_MODE_FLAT) vy = pv.y;
+			((float2*) interpolated)[e >> 1] = make_float2(vx, vy);
 		}
 	}
 	else
@@ -137,6 +142,8 @@ __device__ __forceinline__ void emitFragment(
 		{
 			if (st.stencilEnabled)
 			{
+				const SrpdStencilFace& sf = frontFacing ? st.stencilFront : st.stencilBack;
+				const uint8_t storedStencil = (uint8_t) px.stencil;
 				px.stencil = srpdStencilWrite(storedStencil, srpdStencilOp(sf.dfailOp, storedStencil, sf.ref), sf.writeMask);
 				px.dirty |= 4u;
 			}
@@ -145,6 +152,8 @@ __device__ __forceinline__ void emitFragment(
 	}
 	if (st.stencilEnabled)
 	{
+		const SrpdStencilFace& sf = frontFacing ? st.stencilFront : st.stencilBack;
+		const uint8_t storedStencil = (uint8_t) px.stencil;
 		px.stencil = srpdStencilWrite(storedStencil, srpdStencilOp(sf.passOp, storedStencil, sf.ref), sf.writeMask);
 		px.dirty |= 4u;
 	}
@@ -174,11 +183,28 @@ __device__ __forceinline__ void emitFragment(
  * and shade their own covered triangles in primitive order, resuming the chain with their
  * <= 7 remaining x steps: every value goes through exactly the reference's sequence of
  * additions => bit-exact. */
-struct RowStart { float l0, l1, l2; int xs; };         /* lambda at column xs of the row        */
-struct TriStep  { float dx0, dx1, dx2; uint32_t mask; };/* dlambda/dx and the block coverage mask */
+struct RowStart { float l0, l1, l2; int xs; };          /* lambda at column xs of the row          */
+struct TriStep  { float dx0, dx1, dx2; uint32_t rec; };  /* dlambda/dx and the record slot          */
+
+/* per-warp scratch of one list step (shared memory) */
+struct WarpStep
+{
+	RowStart row[32 * SRPD_BLK_H];       /* [compact triangle][block row]                          */
+	TriStep  tri[32];                    /* [compact triangle]                                     */
+	uint8_t  bits[SRPD_BLK_H * 32];      /* [block row][compact triangle]: the row's 8 coverage bits */
+};
+
+/* top-left rule as ONE comparison per edge: the reference accepts lambda when
+ * lambda > 0 || (|lambda| <= 1e-9 && edgeTL) (triangle.c:82-87).  With F = the largest float
+ * <= 1e-9 (srpdRoughlyZero) that is lambda > 0 for a non-TL edge and lambda >= -F, i.e.
+ * lambda > nextbelow(-F), for a TL edge; NaN fails both forms. */
+__device__ __forceinline__ float coverageThreshold(bool topLeft)
+{
+	return topLeft ? __uint_as_float(0xB0897060u) : 0.0f;      /* 0xB089705F = -F; one ulp further from zero */
+}
 
 __device__ __forceinline__ uint32_t coverTriangleRow(
-	const unsigned char* rec, const float* ckptTable, int bx0, int y, RowStart* rowOut, TriStep* stepOut, bool first)
+	const unsigned char* rec, const float* ckptTable, int bx0, int y, RowStart* rowOut, TriStep* triOut, bool first)
 {
 	const uint4* h = (const uint4*) rec;
 	const uint4 q0 = __ldg(h + 0), q1 = __ldg(h + 1), q2 = __ldg(h + 2);
@@ -187,11 +213,11 @@ __device__ __forceinline__ uint32_t coverTriangleRow(
 	const float dx0 = __uint_as_float(q1.x), dx1 = __uint_as_float(q1.y), dx2 = __uint_as_float(q1.z);
 	if (first)
 	{
-		stepOut->dx0 = dx0; stepOut->dx1 = dx1; stepOut->dx2 = dx2;
+		triOut->dx0 = dx0; triOut->dx1 = dx1; triOut->dx2 = dx2;
 	}
-	const int xs = bx0 > minX ? bx0 : minX;
-	const int xe = bx0 + SRPD_BLK_W < maxX ? bx0 + SRPD_BLK_W : maxX;
-	if (y < minY || y >= maxY || xs >= xe)
+	const int xs = max(bx0, minX);
+	const int n = min(bx0 + SRPD_BLK_W, maxX) - xs;
+	if (y < minY || y >= maxY || n <= 0)
 		return 0u;
 	float l0, l1, l2;
 	int nx;
@@ -205,15 +231,14 @@ __device__ __forceinline__ uint32_t coverTriangleRow(
 		const int tileX0 = (bx0 / SRPD_TILE_W) * SRPD_TILE_W;
 		const float* e = ckptTable + 3 * ((size_t) (ckpt - 1) + (size_t) (y - minY) * cols + (bx0 / SRPD_TILE_W - col0));
 		l0 = __ldg(e + 0); l1 = __ldg(e + 1); l2 = __ldg(e + 2);
-		nx = xs - (tileX0 > minX ? tileX0 : minX);
+		nx = xs - max(tileX0, minX);
 	}
 	else
 	{
 		l0 = __uint_as_float(q0.x); l1 = __uint_as_float(q0.y); l2 = __uint_as_float(q0.z);
 		const float dy0 = __uint_as_float(q2.x), dy1 = __uint_as_float(q2.y), dy2 = __uint_as_float(q2.z);
-		const int ny = y - minY;
-		int i = 0;
-		for (; i + 4 <= ny; i += 4)
+		int ny = y - minY;
+		for (; ny >= 4; ny -= 4)
 		{
 			#pragma unroll
 			for (int u = 0; u < 4; u++)
@@ -221,52 +246,50 @@ __device__ __forceinline__ uint32_t coverTriangleRow(
 				l0 = __fadd_rn(l0, dy0); l1 = __fadd_rn(l1, dy1); l2 = __fadd_rn(l2, dy2);
 			}
 		}
-		for (; i < ny; i++)
-		{
-			l0 = __fadd_rn(l0, dy0); l1 = __fadd_rn(l1, dy1); l2 = __fadd_rn(l2, dy2);
-		}
+		#pragma unroll
+		for (int u = 0; u < 3; u++)
+			if (u < ny)
+			{
+				l0 = __fadd_rn(l0, dy0); l1 = __fadd_rn(l1, dy1); l2 = __fadd_rn(l2, dy2);
+			}
 		nx = xs - minX;
 	}
+	for (; nx >= 4; nx -= 4)
 	{
-		int i = 0;
-		for (; i + 4 <= nx; i += 4)
-		{
-			#pragma unroll
-			for (int u = 0; u < 4; u++)
-			{
-				l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
-			}
-		}
-		for (; i < nx; i++)
+		#pragma unroll
+		for (int u = 0; u < 4; u++)
 		{
 			l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
 		}
 	}
+	#pragma unroll
+	for (int u = 0; u < 3; u++)
+		if (u < nx)
+		{
+			l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
+		}
 	rowOut->l0 = l0; rowOut->l1 = l1; rowOut->l2 = l2; rowOut->xs = xs;
-	/* the row's pixels, top-left rule: lambda > 0 || (|lambda| <= 1e-9 && edgeTL), triangle.c:82-87 */
+	/* the row's pixels; values past the row's last pixel are computed but masked off */
 	const uint32_t flags = q2.w;
-	const int n = xe - xs;
+	const float t0 = coverageThreshold(flags & 1u), t1 = coverageThreshold(flags & 2u), t2 = coverageThreshold(flags & 4u);
 	uint32_t bits = 0u;
 	#pragma unroll
 	for (int i = 0; i < SRPD_BLK_W; i++)
 	{
-		if (i < n)
+		if (l0 > t0 && l1 > t1 && l2 > t2)
+			bits |= 1u << i;
+		if (i + 1 < SRPD_BLK_W)
 		{
-			const bool in0 = (l0 > 0.f) || (srpdRoughlyZero(l0) && (flags & 1u));
-			const bool in1 = (l1 > 0.f) || (srpdRoughlyZero(l1) && (flags & 2u));
-			const bool in2 = (l2 > 0.f) || (srpdRoughlyZero(l2) && (flags & 4u));
-			if (in0 && in1 && in2)
-				bits |= 1u << i;
 			l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
 		}
 	}
-	return bits << (xs - bx0);
+	return (bits & ((1u << n) - 1u)) << (xs - bx0);
 }
 
 /* fragment stage of one covered pixel of a triangle: the pixel's remaining x steps, depth /
  * 1/w interpolation (interpolateDepthAndWTriangle, interpolation.c:34-47) and emitFragment */
 __device__ __forceinline__ void shadeTriangleFragment(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, const RowStart& rs, const TriStep& ts,
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, const RowStart& rs, const TriStep& ts,
 	Pixel& px, FragCounters& cnt, int x, int y)
 {
 	float l0 = rs.l0, l1 = rs.l1, l2 = rs.l2;
@@ -277,6 +300,7 @@ __device__ __forceinline__ void shadeTriangleFragment(
 		{
 			l0 = __fadd_rn(l0, ts.dx0); l1 = __fadd_rn(l1, ts.dx1); l2 = __fadd_rn(l2, ts.dx2);
 		}
+	const unsigned char* rec = records + (size_t) ts.rec * a.recStride;
 	const uint4* h = (const uint4*) rec;
 	const uint4 q3 = __ldg(h + 3), q4 = __ldg(h + 4);
 	const uint32_t flags = __ldg((const uint32_t*) rec + 11);
@@ -290,53 +314,53 @@ __device__ __forceinline__ void shadeTriangleFragment(
 	                depth, recW, recW, (flags & 8u) != 0, q3.w, rec + SRPD_REC_HEADER_BYTES, wgt);
 }
 
-/* One list step of a warp: `m` = which of the 32 entries sIds[j0 ..] touch the warp's block.
- * Row lanes decide coverage (8 triangles x 4 rows per round), pixel threads shade. */
+/* One list step of a warp.  `mine` = this lane's list entry (record slot `recSlot`) touches the
+ * warp's block.  The touching entries are compacted in order (t = 0 .. n-1); row lanes decide
+ * coverage, 8 triangles x 4 rows per round; pixel threads gather the bits of their pixel --
+ * bit t of `cov` <=> triangle t covers my pixel -- and shade them in order. */
 __device__ __forceinline__ void visitTriangles(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, const uint32_t* stepIds, uint32_t m,
-	RowStart* sRow, TriStep* sStep, Pixel& px, FragCounters& cnt, int x, int y, int bx0, int by0, int lane)
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, bool mine, uint32_t recSlot,
+	WarpStep& ws, Pixel& px, FragCounters& cnt, int x, int y, int bx0, int by0, int lane)
 {
-	const int row = lane & (SRPD_BLK_H - 1), k = lane >> 2;
-	for (uint32_t rem = m; rem; )
+	const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
+	if (m == 0u)
+		return;
+	const int n = __popc(m);
+	if (mine)
+		ws.tri[__popc(m & ((1u << lane) - 1u))].rec = recSlot;
+	__syncwarp();
+	const int row = lane & (SRPD_BLK_H - 1);
+	for (int t = lane >> 2; t < n; t += 8)
 	{
-		uint32_t r = rem;
-		#pragma unroll
-		for (int i = 0; i < 7; i++)
-		{
-			if (i < k) r &= r - 1u;
-			rem &= rem - 1u;
-		}
-		rem &= rem - 1u;
-		const int slot = r ? __ffs(r) - 1 : -1;
-		uint32_t bits = 0u;
-		if (slot >= 0)
-			bits = coverTriangleRow(records + (size_t) stepIds[slot] * a.recStride, a.ckptTable, bx0, by0 + row,
-			                        sRow + slot * SRPD_BLK_H + row, sStep + slot, row == 0) << (row * SRPD_BLK_W);
-		bits |= __shfl_xor_sync(0xFFFFFFFFu, bits, 1);
-		bits |= __shfl_xor_sync(0xFFFFFFFFu, bits, 2);
-		if (slot >= 0 && row == 0)
-			sStep[slot].mask = bits;
+		const uint32_t bits = coverTriangleRow(records + (size_t) ws.tri[t].rec * a.recStride, a.ckptTable, bx0, by0 + row,
+		                                       &ws.row[t * SRPD_BLK_H + row], &ws.tri[t], row == 0);
+		ws.bits[row * 32 + t] = (uint8_t) bits;
 	}
 	__syncwarp();
-	/* transpose: bit t of cov <=> entry t of the step covers my pixel */
+	/* gather: byte t of my row's 32 bytes holds the row's coverage of triangle t; bit (lane % 8)
+	 * of it is my pixel.  Four triangles per 32-bit word: isolate the bit in each byte, then
+	 * one multiply moves the four bits next to each other (no carries: all partial products
+	 * land on distinct bit positions). */
+	const int ly = lane / SRPD_BLK_W, lx = lane % SRPD_BLK_W;
 	uint32_t cov = 0u;
-	for (uint32_t mm = m; mm; mm &= mm - 1u)
+	const uint32_t* rowBits = (const uint32_t*) (ws.bits + ly * 32);
+	for (int w = 0; w * 4 < n; w++)
 	{
-		const int t = __ffs(mm) - 1;
-		cov |= ((sStep[t].mask >> lane) & 1u) << t;
+		const uint32_t four = (rowBits[w] >> lx) & 0x01010101u;
+		cov |= (((four * 0x00204081u) >> 21) & 0xFu) << (4 * w);
 	}
-	const int ly = lane / SRPD_BLK_W;
+	if (n < 32)
+		cov &= (1u << n) - 1u;         /* bytes of triangles beyond n are stale */
 	while (__any_sync(0xFFFFFFFFu, cov != 0u))
 	{
 		if (cov)
 		{
 			const int t = __ffs(cov) - 1;
 			cov &= cov - 1u;
-			shadeTriangleFragment(a, fr, records + (size_t) stepIds[t] * a.recStride, sRow[t * SRPD_BLK_H + ly], sStep[t],
-			                      px, cnt, x, y);
+			shadeTriangleFragment(a, fr, records, ws.row[t * SRPD_BLK_H + ly], ws.tri[t], px, cnt, x, y);
 		}
 	}
-	__syncwarp();      /* the next step overwrites this warp's row starts and masks */
+	__syncwarp();      /* the next step overwrites this warp's scratch */
 }
 
 /* rasterizeLine for one pixel, reference line.c:34-77: every lane replays the DDA chain of
@@ -423,11 +447,21 @@ __device__ __forceinline__ void storePlane(const T* staged, T* plane, int W, int
 
 } // namespace
 
+/* shared memory of the tile kernel (dynamic: with the per-warp step scratch it exceeds 48 KB) */
+struct TileShared
+{
+	uint32_t ids[SRPD_TILE_THREADS];     /* record slots of the tile's list chunk; reused as the colour staging tile */
+	uint2    box[SRPD_TILE_THREADS];     /* their boxes; reused as depth (+ stencil) staging */
+	uint32_t warpCnt[32];
+	uint32_t item[2];
+};
+template <int KIND> struct TileSharedK : TileShared {};
+template <> struct TileSharedK<SRPD_KIND_TRIANGLE> : TileShared { WarpStep step[SRPD_TILE_WARPS]; };
+
 /* One tile: filter the candidate list, visit the primitives in order, write the tile back. */
 template <int KIND>
 __device__ __forceinline__ void processTile(
-	const SrpdTileArgs& a, const SrpdFrame& fr, uint32_t frame, int tileX, int tileY,
-	uint32_t* sIds, uint2* sBox, uint32_t* sWarpCnt, uint32_t* sDirty, RowStart* sRow, TriStep* sStep, FragCounters& cnt)
+	const SrpdTileArgs& a, const SrpdFrame& fr, uint32_t frame, int tileX, int tileY, TileSharedK<KIND>& sm, FragCounters& cnt)
 {
 	const SrpdState& st = a.d.st;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -455,12 +489,12 @@ __device__ __forceinline__ void processTile(
 	const int by0 = ty0 + (warp / (SRPD_TILE_W / SRPD_BLK_W)) * SRPD_BLK_H;
 	const int x = bx0 + (lane % SRPD_BLK_W), y = by0 + (lane / SRPD_BLK_W);
 	const bool valid = x < st.width && y < st.height;
-	const size_t pixelIndex = (size_t) y * st.width + x;
 
 	Pixel px;
 	px.color = 0u; px.depth = -1.0f; px.stencil = 0u; px.dirty = 0u;
-	if (valid)
+	if (valid && (!fr.clearPending || st.stencilEnabled))
 	{
+		const size_t pixelIndex = (size_t) y * st.width + x;
 		if (!fr.clearPending)
 		{
 			px.color = fr.color[pixelIndex];
@@ -470,9 +504,6 @@ __device__ __forceinline__ void processTile(
 		if (st.stencilEnabled)
 			px.stencil = fr.stencil[pixelIndex];
 	}
-	if (tid == 0)
-		*sDirty = 0u;
-	__syncthreads();
 
 	for (uint32_t c = begin; c < end; c += SRPD_TILE_THREADS)
 	{
@@ -490,22 +521,18 @@ __device__ __forceinline__ void processTile(
 			hit = x0 < tx0 + SRPD_TILE_W && x1 > tx0 && y0 < ty0 + SRPD_TILE_H && y1 > ty0;
 		}
 		const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+		__syncthreads();                     /* the previous chunk's list (and warpCnt) is no longer read */
 		if (lane == 0)
-			sWarpCnt[warp] = __popc(ballot);
+			sm.warpCnt[warp] = __popc(ballot);
 		__syncthreads();
-		uint32_t base = 0, total = 0;
-		#pragma unroll
-		for (int w = 0; w < SRPD_TILE_WARPS; w++)
-		{
-			const uint32_t n = sWarpCnt[w];
-			if (w < warp) base += n;
-			total += n;
-		}
+		const uint32_t wc = lane < SRPD_TILE_WARPS ? sm.warpCnt[lane] : 0u;
+		const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, wc);
+		const uint32_t base = __reduce_add_sync(0xFFFFFFFFu, lane < warp ? wc : 0u);
 		if (hit)
 		{
 			const uint32_t pos = base + __popc(ballot & ((1u << lane) - 1u));
-			sIds[pos] = perm[rid];           /* record slot */
-			sBox[pos] = bb;
+			sm.ids[pos] = perm[rid];         /* record slot */
+			sm.box[pos] = bb;
 		}
 		__syncthreads();
 
@@ -514,58 +541,55 @@ __device__ __forceinline__ void processTile(
 		{
 			const uint32_t j = j0 + lane;
 			bool mine = false;
+			uint32_t slot = 0u;
 			if (j < total)
 			{
-				const uint2 b2 = sBox[j];
+				const uint2 b2 = sm.box[j];
 				const int x0 = (int) (b2.x & 0xFFFFu), y0 = (int) (b2.x >> 16);
 				const int x1 = (int) (b2.y & 0xFFFFu), y1 = (int) (b2.y >> 16);
 				mine = x0 < bx0 + SRPD_BLK_W && x1 > bx0 && y0 < by0 + SRPD_BLK_H && y1 > by0;
+				slot = sm.ids[j];
 			}
-			uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
-			if (KIND == SRPD_KIND_TRIANGLE)
+			if constexpr (KIND == SRPD_KIND_TRIANGLE)
+				visitTriangles(a, fr, records, mine, slot, sm.step[warp], px, cnt, x, y, bx0, by0, lane);
+			else
 			{
-				if (m)
-					visitTriangles(a, fr, records, sIds + j0, m, sRow + (size_t) warp * 32 * SRPD_BLK_H, sStep + (size_t) warp * 32,
-					               px, cnt, x, y, bx0, by0, lane);
-				continue;
-			}
-			while (m)
-			{
-				const int bit = __ffs(m) - 1;
-				m &= m - 1;
-				const unsigned char* rec = records + (size_t) sIds[j0 + bit] * a.recStride;
-				if (KIND == SRPD_KIND_LINE)
-					visitLine(a, fr, rec, px, cnt, x, y, valid);
-				else
-					visitPoint(a, fr, rec, px, cnt, x, y, valid);
+				uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
+				while (m)
+				{
+					const int bit = __ffs(m) - 1;
+					m &= m - 1;
+					const unsigned char* rec = records + (size_t) sm.ids[j0 + bit] * a.recStride;
+					if (KIND == SRPD_KIND_LINE)
+						visitLine(a, fr, rec, px, cnt, x, y, valid);
+					else
+						visitPoint(a, fr, rec, px, cnt, x, y, valid);
+				}
 			}
 		}
-		__syncthreads();
 	}
 
 	/* write-back: stage the tile in shared memory, leave as 16-byte vectors */
-	uint32_t dirty = px.dirty;
-	#pragma unroll
-	for (int o = 16; o > 0; o >>= 1)
-		dirty |= __shfl_xor_sync(0xFFFFFFFFu, dirty, o);
-	if (lane == 0 && dirty)
-		atomicOr(sDirty, dirty);
-	uint32_t* sColor = sIds;
-	float* sDepth = (float*) sBox;
+	const uint32_t warpDirty = __reduce_or_sync(0xFFFFFFFFu, px.dirty);
+	__syncthreads();                         /* every warp is done with the list */
+	if (lane == 0)
+		sm.warpCnt[warp] = warpDirty;
+	uint32_t* sColor = sm.ids;
+	float* sDepth = (float*) sm.box;
 	uint8_t* sStencil = (uint8_t*) (sDepth + SRPD_TILE_THREADS);
 	const int local = (y - ty0) * SRPD_TILE_W + (x - tx0);
 	sColor[local] = px.color;
 	sDepth[local] = px.depth;
 	sStencil[local] = (uint8_t) px.stencil;
 	__syncthreads();
-	const uint32_t tileDirty = *sDirty | (fr.clearPending ? 3u : 0u);
+	const uint32_t tileDirty = __reduce_or_sync(0xFFFFFFFFu, lane < SRPD_TILE_WARPS ? sm.warpCnt[lane] : 0u) | (fr.clearPending ? 3u : 0u);
 	if (tileDirty & 1u)
 		storePlane<uint32_t>(sColor, fr.color, st.width, st.height, tx0, ty0, tid);
 	if (tileDirty & 2u)
 		storePlane<float>(sDepth, fr.depth, st.width, st.height, tx0, ty0, tid);
 	if (tileDirty & 4u)
 		storePlane<uint8_t>(sStencil, fr.stencil, st.width, st.height, tx0, ty0, tid);
-	__syncthreads();      /* the staging arrays are reused by the next tile */
+	/* the next tile's first barrier comes before anything is written to the staging arrays */
 }
 
 /* A tile no primitive touches while a clear is pending: just write the clear values
@@ -590,18 +614,12 @@ __device__ __forceinline__ void clearTile(const SrpdState& st, const SrpdFrame& 
  * Register budget: both launch-bound arguments are given explicitly (under device LTO a
  * missing minimum makes the linker's code generator cap the kernel at 64 registers and
  * spill).  Triangles and points fit two 512-thread CTAs per SM; the line walker does not. */
-template <int KIND>
+template <int KIND, bool BATCH>
 __global__ void __launch_bounds__(SRPD_TILE_THREADS, KIND == SRPD_KIND_LINE ? SRPD_TILE_CTAS_PER_SM / 2 : SRPD_TILE_CTAS_PER_SM)
 srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 {
-	__shared__ __align__(16) uint32_t sIds[SRPD_TILE_THREADS];     /* reused as the colour staging tile */
-	__shared__ __align__(16) uint2 sBox[SRPD_TILE_THREADS];        /* reused as depth (+ stencil) staging */
-	__shared__ uint32_t sWarpCnt[SRPD_TILE_WARPS];
-	__shared__ uint32_t sDirty;
-	__shared__ uint32_t sItem[2];
-	/* per warp: row starts and dlambda/dx + coverage masks of the (up to) 32 triangles of the current list step */
-	__shared__ __align__(16) RowStart sRow[KIND == SRPD_KIND_TRIANGLE ? SRPD_TILE_WARPS * 32 * SRPD_BLK_H : 1];
-	__shared__ __align__(16) TriStep sStep[KIND == SRPD_KIND_TRIANGLE ? SRPD_TILE_WARPS * 32 : 1];
+	extern __shared__ __align__(16) unsigned char srpdTileSmem[];
+	TileSharedK<KIND>& sm = *reinterpret_cast<TileSharedK<KIND>*>(srpdTileSmem);
 
 	if (*a.abortFlag)      /* a scratch pool overflowed: the host repeats the draw with larger pools */
 		return;
@@ -615,44 +633,55 @@ srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 	cnt.emitted = 0; cnt.shaded = 0;
 
 	if (tid == 0)
-		sItem[0] = atomicAdd(a.workCounter, 1u);
+		sm.item[0] = atomicAdd(a.workCounter, 1u);
 	__syncthreads();
 	for (uint32_t it = 0;; it++)
 	{
-		const uint32_t item = sItem[it & 1];
+		const uint32_t item = sm.item[it & 1];
 		if (item >= nItems)
 			break;
 		if (tid == 0)      /* fetch the next item while this one is processed */
-			sItem[(it + 1) & 1] = atomicAdd(a.workCounter, 1u);
-		const uint32_t frame = item / itemsPerFrame;
-		const uint32_t first = (item - frame * itemsPerFrame) * a.tilesPerItem;
+			sm.item[(it + 1) & 1] = atomicAdd(a.workCounter, 1u);
+		/* BATCH: many frames, bindings in a device array; otherwise the one frame of the argument block */
+		uint32_t frame = 0u, inFrame = item;
+		if (BATCH)
+		{
+			frame = item / itemsPerFrame;
+			inFrame = item - frame * itemsPerFrame;
+		}
+		const uint32_t first = inFrame * a.tilesPerItem;
 		const uint32_t last = min(first + a.tilesPerItem, tilesPerFrame);
-		const SrpdFrame fr = a.frames ? a.frames[frame] : a.frame0;
+		SrpdFrame frCopy;
+		if (BATCH)
+			frCopy = a.frames[frame];
+		const SrpdFrame& fr = BATCH ? frCopy : a.frame0;
 		const uint32_t* occ = a.occupancy + (size_t) frame * a.occWordsPerFrame;
+		/* first / tilesX by multiplication: tilesXInv = floor(2^40 / tilesX) + 1 is exact while
+		 * first * tilesX < 2^40 (tiles per frame < 2^23, tilesX <= 2^11) */
+		uint32_t rowInBand = (uint32_t) (((uint64_t) first * a.tilesXInv) >> 40);
+		int tileX = (int) (first - rowInBand * a.tilesX);
+		int tileY = (int) (a.d.tileRow0 + rowInBand);
 		for (uint32_t t = first; t < last; t++)
 		{
-			const int tileX = (int) (t % a.tilesX);
-			const int tileY = (int) (a.d.tileRow0 + t / a.tilesX);
 			const uint32_t tileIndex = (uint32_t) tileY * a.tilesX + (uint32_t) tileX;
 			const bool occupied = (occ[tileIndex >> 5] >> (tileIndex & 31u)) & 1u;
 			if (occupied)
-				processTile<KIND>(a, fr, frame, tileX, tileY, sIds, sBox, sWarpCnt, &sDirty, sRow, sStep, cnt);
+				processTile<KIND>(a, fr, frame, tileX, tileY, sm, cnt);
 			else if (fr.clearPending)
 				clearTile(a.d.st, fr, tileX, tileY);
+			if (++tileX == (int) a.tilesX)
+			{
+				tileX = 0;
+				tileY++;
+			}
 		}
-		__syncthreads();   /* sItem[(it + 1) & 1] is visible; sItem[it & 1] may be overwritten next round */
+		__syncthreads();   /* item[(it + 1) & 1] is visible; item[it & 1] may be overwritten next round */
 	}
 
 	/* counters: warp reduction, then one atomic per warp into one of the slots, so the atomics
 	 * of a frame do not serialise on one L2 address */
 	{
-		uint32_t e = cnt.emitted, s = cnt.shaded;
-		#pragma unroll
-		for (int o = 16; o > 0; o >>= 1)
-		{
-			e += __shfl_xor_sync(0xFFFFFFFFu, e, o);
-			s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-		}
+		const uint32_t e = __reduce_add_sync(0xFFFFFFFFu, cnt.emitted), s = __reduce_add_sync(0xFFFFFFFFu, cnt.shaded);
 		if (lane == 0 && e)
 		{
 			SrpdStats* slot = a.stats + ((blockIdx.x * SRPD_TILE_WARPS + warp) & (SRPD_STATS_SLOTS - 1));
@@ -691,11 +720,34 @@ void srpdLaunchClear(uint32_t* color, float* depth, size_t nPixels, cudaStream_t
 	srpdClearKernel<<<grid, 256, 0, stream>>>((uint4*) color, (uint4*) depth, nVec, color + nVec * 4, depth + nVec * 4, nTail);
 }
 
-void srpdLaunchTiles(const SrpdTileArgs& a, cudaStream_t stream)
+template <int KIND, bool BATCH>
+static void launchTileKernelB(const SrpdTileArgs& a, unsigned grid, cudaStream_t stream)
 {
+	static bool configured = false;
+	const int bytes = (int) sizeof(TileSharedK<KIND>);
+	if (!configured)
+	{
+		cudaFuncSetAttribute(srpdTileKernel<KIND, BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+		configured = true;
+	}
+	srpdTileKernel<KIND, BATCH><<<grid, SRPD_TILE_THREADS, bytes, stream>>>(a);
+}
+template <int KIND>
+static void launchTileKernel(const SrpdTileArgs& a, unsigned grid, cudaStream_t stream)
+{
+	if (a.frames)
+		launchTileKernelB<KIND, true>(a, grid, stream);
+	else
+		launchTileKernelB<KIND, false>(a, grid, stream);
+}
+
+void srpdLaunchTiles(const SrpdTileArgs& a0, cudaStream_t stream)
+{
+	SrpdTileArgs a = a0;
 	const uint32_t rows = a.d.tileRow1 - a.d.tileRow0;
 	if (rows == 0 || a.tilesX == 0)
 		return;
+	a.tilesXInv = (1ull << 40) / a.tilesX + 1ull;
 	/* persistent grid: resident CTAs per SM x SM count (no more CTAs than work items) */
 	const uint32_t tilesPerFrame = a.tilesX * rows;
 	const uint64_t nItems = (uint64_t) ((tilesPerFrame + a.tilesPerItem - 1) / a.tilesPerItem) * a.d.nFrames;
@@ -704,9 +756,9 @@ void srpdLaunchTiles(const SrpdTileArgs& a, cudaStream_t stream)
 	if (grid > nItems) grid = nItems;
 	if (grid == 0) return;
 	if (a.d.kind == SRPD_KIND_TRIANGLE)
-		srpdTileKernel<SRPD_KIND_TRIANGLE><<<(unsigned) grid, SRPD_TILE_THREADS, 0, stream>>>(a);
+		launchTileKernel<SRPD_KIND_TRIANGLE>(a, (unsigned) grid, stream);
 	else if (a.d.kind == SRPD_KIND_LINE)
-		srpdTileKernel<SRPD_KIND_LINE><<<(unsigned) grid, SRPD_TILE_THREADS, 0, stream>>>(a);
+		launchTileKernel<SRPD_KIND_LINE>(a, (unsigned) grid, stream);
 	else
-		srpdTileKernel<SRPD_KIND_POINT><<<(unsigned) grid, SRPD_TILE_THREADS, 0, stream>>>(a);
+		launchTileKernel<SRPD_KIND_POINT>(a, (unsigned) grid, stream);
 }

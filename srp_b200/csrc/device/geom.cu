@@ -207,7 +207,7 @@ __device__ __forceinline__ bool setupAndClassify(const SrpdState& st, const Srpd
 }
 
 template <bool WRITE>
-__device__ void writeTriangle(Emitter& em, const SrpdState& st, SrpdTriSetup& s, bool stored, const unsigned char* const vary[3])
+__device__ __forceinline__ void writeTriangle(Emitter& em, const SrpdState& st, SrpdTriSetup& s, bool stored, const unsigned char* const vary[3])
 {
 	if (stored)
 	{
@@ -245,7 +245,7 @@ __device__ void writeTriangle(Emitter& em, const SrpdState& st, SrpdTriSetup& s,
 }
 
 template <bool WRITE>
-__device__ void emitTriangle(Emitter& em, const SrpdState& st, const SrpdPos p[3], const unsigned char* const vary[3])
+__device__ __noinline__ void emitTriangle(Emitter& em, const SrpdState& st, const SrpdPos p[3], const unsigned char* const vary[3])
 {
 	SrpdTriSetup s;
 	bool stored;
@@ -254,7 +254,7 @@ __device__ void emitTriangle(Emitter& em, const SrpdState& st, const SrpdPos p[3
 }
 
 template <bool WRITE>
-__device__ void emitLine(Emitter& em, const SrpdState& st, const SrpdPos p[2], const unsigned char* const vary[2])
+__device__ __noinline__ void emitLine(Emitter& em, const SrpdState& st, const SrpdPos p[2], const unsigned char* const vary[2])
 {
 	SrpdLineSetup ln;
 	srpdSetupLine(st, p, ln);
@@ -277,7 +277,7 @@ __device__ void emitLine(Emitter& em, const SrpdState& st, const SrpdPos p[2], c
 }
 
 template <bool WRITE>
-__device__ void emitPoint(Emitter& em, const SrpdState& st, const SrpdPos& p, const unsigned char* vary)
+__device__ __noinline__ void emitPoint(Emitter& em, const SrpdState& st, const SrpdPos& p, const unsigned char* vary)
 {
 	SrpdPointSetup s;
 	if (srpdSetupPoint(st, p, s))
@@ -448,8 +448,12 @@ __device__ void processLine(Emitter& em, const SrpdState& st, const SrpdPos p[2]
 	emitLine<WRITE>(em, st, cp, cvc);
 }
 
+/* Everything but the unclipped filled triangle goes through here.  Deliberately NOT inlined
+ * (nor are the emit* helpers): inlined into the kernel at every call site the front-end grew to
+ * 38 k instructions and, with the warps of an SM in different stages, stalled on instruction
+ * fetch a third of the time; as functions the common path is a few thousand instructions. */
 template <bool WRITE>
-__device__ __forceinline__ void processPrimitive(Emitter& em, const SrpdDraw& d, int nv,
+__device__ __noinline__ void processPrimitive(Emitter& em, const SrpdDraw& d, int nv,
                                                  const SrpdPos p[3], const unsigned char* const vary[3])
 {
 	if (nv == 3)
@@ -473,37 +477,64 @@ __device__ __forceinline__ uint32_t warpInclusiveScan(uint32_t v, int lane)
 
 } // namespace
 
-/* 4 CTAs/SM (64 registers): a CTA spends part of its life waiting in the look-back, which
- * the other resident CTAs hide */
+/* per-warp shared memory: the post-VS cache of one batch */
+struct GeomWarpShared
+{
+	uint32_t hashKey[SRPD_HASH_SLOTS];       /* open-addressing table of the batch's vertex indices   */
+	uint8_t  hashDense[SRPD_HASH_SLOTS];     /* table slot -> dense number of the distinct index      */
+	uint32_t uniq[SRPD_GEOM_MAX_VERTS];      /* dense number -> vertex index                          */
+	float4   vpos[SRPD_GEOM_MAX_VERTS];      /* clip-space positions (VS output)                      */
+};                                           /* followed by SRPD_GEOM_MAX_VERTS varyings blobs         */
+
+/* One WARP = one batch of SRPD_GEOM_PRIMS consecutive input primitives; the warps of a CTA are
+ * independent of each other (no CTA barrier anywhere), so a warp that sits in a long-latency
+ * step -- vertex fetch, the rare clipping path, the bump-allocator atomic -- never holds up the
+ * other seven: the SM always has warps in different stages to issue from. */
 __global__ void __launch_bounds__(SRPD_GEOM_THREADS, SRPD_GEOM_CTAS_PER_SM)
 srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
-	uint32_t* hashKey   = (uint32_t*) smem;                                   /* 4096 B */
-	uint16_t* hashDense = (uint16_t*) (smem + 4 * SRPD_HASH_SLOTS);           /* 2048 B */
-	uint32_t* uniq      = (uint32_t*) (smem + 6 * SRPD_HASH_SLOTS);           /* 3072 B */
-	float4*   vpos      = (float4*) (smem + 6 * SRPD_HASH_SLOTS + 4 * SRPD_GEOM_MAX_VERTS);
-	unsigned char* vvary = (unsigned char*) (vpos + SRPD_GEOM_MAX_VERTS);
-
-	__shared__ uint32_t sWarpSum[2][SRPD_GEOM_THREADS / 32];
-	__shared__ uint32_t sNUniq;
-	__shared__ uint32_t sPrefix[2];
-
 	const SrpdDraw& d = a.d;
 	const SrpdState& st = d.st;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-	for (int i = tid; i < SRPD_HASH_SLOTS; i += SRPD_GEOM_THREADS)
-		hashKey[i] = SRPD_HASH_EMPTY;
-	__syncthreads();
-	const uint32_t batch = blockIdx.x;
+	const size_t warpBytes = sizeof(GeomWarpShared) + (size_t) SRPD_GEOM_MAX_VERTS * st.slotSize;
+	GeomWarpShared& ws = *reinterpret_cast<GeomWarpShared*>(smem + warp * warpBytes);
+	unsigned char* vvary = reinterpret_cast<unsigned char*>(&ws + 1);
+	const uint32_t nBatches = a.batchesPerFrame * d.nFrames;
+	const int nv = (d.topology >= SRPD_TOPO_TRIANGLES) ? 3 : (d.topology == SRPD_TOPO_POINTS ? 1 : 2);
+
+	/* persistent warps: each pulls runs of SRPD_GEOM_GRAB consecutive batches from a counter */
+	uint32_t next = 0u;
+#if SRPD_GEOM_PERSISTENT
+	if (lane == 0)
+		next = atomicAdd(a.batchCounter, (uint32_t) SRPD_GEOM_GRAB);
+#else
+	next = (blockIdx.x * SRPD_GEOM_WARPS + warp) * SRPD_GEOM_GRAB;
+#endif
+	for (;;)
+	{
+	const uint32_t batch0 = __shfl_sync(0xFFFFFFFFu, next, 0);
+	if (batch0 >= nBatches)
+		break;
+#if SRPD_GEOM_PERSISTENT
+	if (lane == 0)      /* the next run is requested now and looked at after this one is done */
+		next = atomicAdd(a.batchCounter, (uint32_t) SRPD_GEOM_GRAB);
+#else
+	next = 0xFFFFFFFFu;
+#endif
+	for (uint32_t batch = batch0; batch < min(batch0 + SRPD_GEOM_GRAB, nBatches); batch++)
+	{
+	__syncwarp();      /* the previous batch no longer reads the cache */
+	#pragma unroll
+	for (int i = 0; i < SRPD_HASH_SLOTS / 32; i++)
+		ws.hashKey[lane + 32 * i] = SRPD_HASH_EMPTY;
 	const uint32_t frame = batch / a.batchesPerFrame;
 	const uint32_t b = batch - frame * a.batchesPerFrame;
-	const SrpdFrame fr = a.frames ? a.frames[frame] : a.frame0;
+	const void* uniform = a.frames ? a.frames[frame].uniform : a.frame0.uniform;
 
-	const uint32_t k = b * SRPD_GEOM_THREADS + tid;
-	const bool active = k < d.nInputPrims;
-	const int nv = (d.topology >= SRPD_TOPO_TRIANGLES) ? 3 : (d.topology == SRPD_TOPO_POINTS ? 1 : 2);
+	const uint32_t k = b * SRPD_GEOM_PRIMS + lane;
+	const bool active = lane < SRPD_GEOM_PRIMS && k < d.nInputPrims;
 
 	/* 1. topology + typed index fetch */
 	uint32_t vi[3] = { 0, 0, 0 };
@@ -515,6 +546,7 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 		for (int i = 0; i < nv; i++)
 			vi[i] = fetchIndex(d, s[i]);
 	}
+	__syncwarp();
 
 	/* 2. post-VS cache: de-duplicate the batch's indices, shade each distinct one once.
 	 * Points bypass the cache like the reference (primitive_assembly.c:239-240). */
@@ -523,63 +555,63 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	{
 		if (active)
 			for (int i = 0; i < nv; i++)
-				slot[i] = hashInsert(hashKey, vi[i]);
-		__syncthreads();
-		/* number the occupied slots: thread t owns slots 4t..4t+3 */
+				slot[i] = hashInsert(ws.hashKey, vi[i]);
+		__syncwarp();
+		/* number the occupied slots: lane l owns slots 4l..4l+3 */
+		constexpr int PER = SRPD_HASH_SLOTS / 32;
+		uint32_t keys[PER];
 		uint32_t occ = 0;
-		for (int i = 0; i < SRPD_HASH_SLOTS / SRPD_GEOM_THREADS; i++)
-			occ += hashKey[tid * (SRPD_HASH_SLOTS / SRPD_GEOM_THREADS) + i] != SRPD_HASH_EMPTY;
-		const uint32_t inc = warpInclusiveScan(occ, lane);
-		if (lane == 31) sWarpSum[0][warp] = inc;
-		__syncthreads();
-		uint32_t base = 0;
-		for (int w = 0; w < warp; w++) base += sWarpSum[0][w];
-		if (tid == SRPD_GEOM_THREADS - 1) sNUniq = base + inc;
-		uint32_t dense = base + inc - occ;
-		for (int i = 0; i < SRPD_HASH_SLOTS / SRPD_GEOM_THREADS; i++)
+		#pragma unroll
+		for (int i = 0; i < PER; i++)
 		{
-			const int h = tid * (SRPD_HASH_SLOTS / SRPD_GEOM_THREADS) + i;
-			if (hashKey[h] != SRPD_HASH_EMPTY)
+			keys[i] = ws.hashKey[lane * PER + i];
+			occ += keys[i] != SRPD_HASH_EMPTY;
+		}
+		const uint32_t inc = warpInclusiveScan(occ, lane);
+		nUniq = __shfl_sync(0xFFFFFFFFu, inc, 31);
+		uint32_t dense = inc - occ;
+		#pragma unroll
+		for (int i = 0; i < PER; i++)
+			if (keys[i] != SRPD_HASH_EMPTY)
 			{
-				hashDense[h] = (uint16_t) dense;
-				uniq[dense] = hashKey[h];
+				ws.hashDense[lane * PER + i] = (uint8_t) dense;
+				ws.uniq[dense] = keys[i];
 				dense++;
 			}
-		}
-		__syncthreads();
-		nUniq = sNUniq;
+		__syncwarp();
 		for (int i = 0; i < nv; i++)
-			slot[i] = hashDense[slot[i]];
+			slot[i] = ws.hashDense[slot[i]];
 	}
 	else
 	{
-		nUniq = min((uint32_t) SRPD_GEOM_THREADS, d.nInputPrims - b * SRPD_GEOM_THREADS);
-		if (active) uniq[tid] = vi[0];
-		slot[0] = tid;
-		__syncthreads();
+		const uint32_t first = b * SRPD_GEOM_PRIMS;
+		nUniq = min((uint32_t) SRPD_GEOM_PRIMS, d.nInputPrims - first);
+		if (active) ws.uniq[lane] = vi[0];
+		slot[0] = lane;
+		__syncwarp();
 	}
 
-	for (uint32_t u = tid; u < nUniq; u += SRPD_GEOM_THREADS)
+	for (uint32_t u = lane; u < nUniq; u += 32)
 	{
-		const uint32_t vertexIndex = uniq[u];
+		const uint32_t vertexIndex = ws.uniq[u];
 		SRPVertexShaderIn in;
-		in.uniform = (SRPUniform*) fr.uniform;
+		in.uniform = (SRPUniform*) uniform;
 		in.vertex = (SRPVertex*) (d.vb + (size_t) vertexIndex * d.vbStride);
 		in.vertexID = vertexIndex;
 		SRPVertexShaderOut out;
 		out.clipPosition[0] = 0.f; out.clipPosition[1] = 0.f; out.clipPosition[2] = 0.f; out.clipPosition[3] = 0.f;
 		out.varyings = (SRPVarying*) (vvary + (size_t) u * st.slotSize);
 		srpB200DeviceVS(st.programId, &in, &out);
-		vpos[u] = make_float4(out.clipPosition[0], out.clipPosition[1], out.clipPosition[2], out.clipPosition[3]);
+		ws.vpos[u] = make_float4(out.clipPosition[0], out.clipPosition[1], out.clipPosition[2], out.clipPosition[3]);
 	}
-	__syncthreads();
+	__syncwarp();
 
 	/* 3. count */
 	SrpdPos p[3];
 	const unsigned char* vary[3];
 	for (int i = 0; i < 3; i++)
 	{
-		const float4 q = vpos[active && i < nv ? slot[i] : 0];
+		const float4 q = ws.vpos[active && i < nv ? slot[i] : 0];
 		p[i].x = q.x; p[i].y = q.y; p[i].z = q.z; p[i].w = q.w;
 		vary[i] = vvary + (size_t) (active && i < nv ? slot[i] : 0) * st.slotSize;
 	}
@@ -606,102 +638,122 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 			}
 		}
 		else
-			processPrimitive<false>(em, d, nv, p, vary);
+		{
+			Emitter slow = em;      /* its address escapes into the out-of-line path; `em` stays in registers */
+			processPrimitive<false>(slow, d, nv, p, vary);
+			em.nEmit = slow.nEmit; em.nStore = slow.nStore;
+		}
 	}
 	const uint32_t myEmit = em.nEmit, myStore = em.nStore;
 
-	/* 4. CTA scan + decoupled look-back over the frame's batches */
+	/* 4. warp scan of both counts.  No warp ever waits for another one: the batch takes a
+	 * contiguous range of record slots from the frame's bump allocator (arrival order) and leaves
+	 * its counts behind; the batch-order prefix sums and the id-ordered view of the records are
+	 * built afterwards (srpdBatchScanKernel, srpdRecordOrderKernel). */
 	const uint32_t incE = warpInclusiveScan(myEmit, lane);
 	const uint32_t incS = warpInclusiveScan(myStore, lane);
-	if (lane == 31) { sWarpSum[0][warp] = incE; sWarpSum[1][warp] = incS; }
-	__syncthreads();
-	uint32_t baseE = 0, baseS = 0, totE = 0, totS = 0;
-	for (int w = 0; w < SRPD_GEOM_THREADS / 32; w++)
+	const uint32_t totE = __shfl_sync(0xFFFFFFFFu, incE, 31), totS = __shfl_sync(0xFFFFFFFFu, incS, 31);
+	uint32_t physBase = 0u;
+	if (lane == 0)
 	{
-		if (w < warp) { baseE += sWarpSum[0][w]; baseS += sWarpSum[1][w]; }
-		totE += sWarpSum[0][w]; totS += sWarpSum[1][w];
-	}
-	if (tid == 0)
-	{
-		/* No CTA ever waits for another one: the batch takes a contiguous range of record slots
-		 * from the frame's bump allocator (arrival order) and leaves its counts behind; the
-		 * batch-order prefix sums and the id-ordered view of the records are built afterwards
-		 * (srpdBatchScanKernel, srpdRecordOrderKernel).  An in-kernel chained scan made every
-		 * resident CTA wait for the slowest batch in flight (clip-heavy batches: a convoy). */
-		const uint32_t physBase = totS ? atomicAdd(&a.frameBump[frame], totS) : 0u;
+		physBase = totS ? atomicAdd(&a.frameBump[frame], totS) : 0u;
 		a.batchInfo[batch] = make_uint4(physBase, totE, totS, 0u);
-		sPrefix[0] = 0u;
-		sPrefix[1] = physBase;
+		/* totals of the scan chunk this batch belongs to (srpdBatchScanKernel adds up the chunks before its own) */
+		uint2* cs = a.chunkSums + (size_t) frame * a.chunksPerFrame + b / SRPD_SCAN_CHUNK;
+		if (totE) atomicAdd(&cs->x, totE);
+		if (totS) atomicAdd(&cs->y, totS);
 	}
-	__syncthreads();
+	if (totS == 0u)
+		continue;
+	physBase = __shfl_sync(0xFFFFFFFFu, physBase, 0);
 
-	/* 5. write, in id order */
+	/* 5. write, in id order (batch-local ids) */
 	if (active && myStore > 0)
 	{
-		em.idBase = sPrefix[0] + baseE + incE - myEmit;
-		em.storeBase = sPrefix[1] + baseS + incS - myStore;
+		em.idBase = incE - myEmit;
+		em.storeBase = physBase + incS - myStore;
 		em.nEmit = 0; em.nStore = 0;
 		if (fast.valid)
 			writeTriangle<true>(em, st, fast.s, fast.stored, vary);
 		else
-			processPrimitive<true>(em, d, nv, p, vary);
+		{
+			Emitter slow = em;
+			processPrimitive<true>(slow, d, nv, p, vary);
+			em.overflow = slow.overflow;
+		}
 		if (em.overflow)
 		{
 			atomicAdd(&a.stats->overflow, 1ull);
 			atomicExch(a.abortFlag, 1u);
 		}
 	}
+	}   /* batch */
+	}   /* grab */
 }
 
-/* Exclusive prefix sums of (ids, records) over the batches of a frame, in batch order.
- * One CTA per frame. */
-__global__ void __launch_bounds__(1024)
+/* Exclusive prefix sums of (ids, records) over the batches of a frame, in batch order: this is
+ * the reference's serial `primitiveID++`.  One CTA per chunk of SRPD_SCAN_CHUNK batches; the
+ * geometry warps have already accumulated every chunk's totals, so a CTA adds up the chunks in
+ * front of its own and scans its own batches (4 per thread, warp-shuffle scans). */
+__global__ void __launch_bounds__(SRPD_SCAN_CHUNK / 4)
 srpdBatchScanKernel(const __grid_constant__ SrpdGeomArgs a)
 {
-	__shared__ uint32_t sE[1024], sS[1024];
-	__shared__ uint32_t sCarry[2];
-	const uint32_t frame = blockIdx.x;
+	constexpr int WARPS = SRPD_SCAN_CHUNK / 4 / 32;
+	__shared__ uint32_t sWarpE[WARPS], sWarpS[WARPS];
+	__shared__ uint32_t sBase[2];
+	const uint32_t frame = blockIdx.x / a.chunksPerFrame, chunk = blockIdx.x - frame * a.chunksPerFrame;
 	const uint32_t first = frame * a.batchesPerFrame;
-	if (threadIdx.x == 0) { sCarry[0] = 0; sCarry[1] = 0; }
-	__syncthreads();
-	for (uint32_t b0 = 0; b0 < a.batchesPerFrame; b0 += 1024)
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint2* cs = a.chunkSums + (size_t) frame * a.chunksPerFrame;
+	if (warp == 0)
 	{
-		const uint32_t b = b0 + threadIdx.x;
-		uint32_t e = 0, s = 0;
-		if (b < a.batchesPerFrame)
+		uint32_t pe = 0, ps = 0;
+		for (uint32_t c = lane; c < chunk; c += 32)
 		{
-			const uint4 info = a.batchInfo[first + b];
-			e = info.y; s = info.z;
+			const uint2 v = cs[c];
+			pe += v.x; ps += v.y;
 		}
-		sE[threadIdx.x] = e; sS[threadIdx.x] = s;
-		__syncthreads();
-		uint32_t ve = e, vs = s;
-		for (uint32_t o = 1; o < 1024; o <<= 1)
-		{
-			const uint32_t ae = threadIdx.x >= o ? sE[threadIdx.x - o] : 0;
-			const uint32_t as = threadIdx.x >= o ? sS[threadIdx.x - o] : 0;
-			__syncthreads();
-			ve += ae; vs += as;
-			sE[threadIdx.x] = ve; sS[threadIdx.x] = vs;
-			__syncthreads();
-		}
-		const uint32_t ce = sCarry[0], cs = sCarry[1];
-		if (b < a.batchesPerFrame)
-			a.batchPrefix[first + b] = make_uint2(ce + ve - e, cs + vs - s);
-		__syncthreads();
-		if (threadIdx.x == 1023) { sCarry[0] = ce + ve; sCarry[1] = cs + vs; }
-		__syncthreads();
+		pe = __reduce_add_sync(0xFFFFFFFFu, pe);
+		ps = __reduce_add_sync(0xFFFFFFFFu, ps);
+		if (lane == 0) { sBase[0] = pe; sBase[1] = ps; }
 	}
-	if (threadIdx.x == 0)
+	const uint32_t b = chunk * SRPD_SCAN_CHUNK + threadIdx.x * 4;
+	uint32_t e[4], s[4];
+	uint32_t sumE = 0, sumS = 0;
+	#pragma unroll
+	for (int i = 0; i < 4; i++)
 	{
-		const uint32_t e = sCarry[0], s = sCarry[1];
-		a.frameCounts[2 * frame + 0] = e;
-		a.frameCounts[2 * frame + 1] = s < a.recCapacity ? s : a.recCapacity;
-		if (s > a.recCapacity)
-			atomicMax(&a.needed[0], s);
+		e[i] = 0; s[i] = 0;
+		if (b + i < a.batchesPerFrame)
+		{
+			const uint4 info = a.batchInfo[first + b + i];
+			e[i] = info.y; s[i] = info.z;
+		}
+		sumE += e[i]; sumS += s[i];
+	}
+	const uint32_t incE = warpInclusiveScan(sumE, lane), incS = warpInclusiveScan(sumS, lane);
+	if (lane == 31) { sWarpE[warp] = incE; sWarpS[warp] = incS; }
+	__syncthreads();
+	uint32_t baseE = sBase[0], baseS = sBase[1];
+	for (int w = 0; w < warp; w++) { baseE += sWarpE[w]; baseS += sWarpS[w]; }
+	uint32_t pe = baseE + incE - sumE, ps = baseS + incS - sumS;
+	#pragma unroll
+	for (int i = 0; i < 4; i++)
+	{
+		if (b + i < a.batchesPerFrame)
+			a.batchPrefix[first + b + i] = make_uint2(pe, ps);
+		pe += e[i]; ps += s[i];
+	}
+	if (chunk == a.chunksPerFrame - 1 && threadIdx.x == SRPD_SCAN_CHUNK / 4 - 1)
+	{
+		/* the frame's totals (the last thread of the last chunk has seen everything) */
+		a.frameCounts[2 * frame + 0] = pe;
+		a.frameCounts[2 * frame + 1] = ps < a.recCapacity ? ps : a.recCapacity;
+		if (ps > a.recCapacity)
+			atomicMax(&a.needed[0], ps);
 		atomicAdd(&a.stats->primsIn, (unsigned long long) a.d.nInputPrims);
-		atomicAdd(&a.stats->primsEmitted, (unsigned long long) e);
-		atomicAdd(&a.stats->primsStored, (unsigned long long) s);
+		atomicAdd(&a.stats->primsEmitted, (unsigned long long) pe);
+		atomicAdd(&a.stats->primsStored, (unsigned long long) ps);
 	}
 }
 
@@ -736,17 +788,20 @@ int srpdGeomLaunchCount(void) { return gGeomLaunches; }
 
 void srpdLaunchGeom(const SrpdGeomArgs& a, cudaStream_t stream)
 {
-	const size_t smemBytes = 6 * SRPD_HASH_SLOTS + 4 * SRPD_GEOM_MAX_VERTS
-		+ (size_t) SRPD_GEOM_MAX_VERTS * (16 + a.d.st.slotSize);
+	const size_t smemBytes = (size_t) SRPD_GEOM_WARPS * (sizeof(GeomWarpShared) + (size_t) SRPD_GEOM_MAX_VERTS * a.d.st.slotSize);
 	static bool configured = false;
 	if (!configured)
 	{
 		cudaFuncSetAttribute(srpdGeomKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 		configured = true;
 	}
-	const unsigned grid = a.batchesPerFrame * a.d.nFrames;
+	const unsigned batches = a.batchesPerFrame * a.d.nFrames;
+	unsigned grid = (batches + SRPD_GEOM_WARPS * SRPD_GEOM_GRAB - 1) / (SRPD_GEOM_WARPS * SRPD_GEOM_GRAB);
+#if SRPD_GEOM_PERSISTENT
+	if (grid > (unsigned) a.smCount * SRPD_GEOM_CTAS_PER_SM) grid = (unsigned) a.smCount * SRPD_GEOM_CTAS_PER_SM;
+#endif
 	srpdGeomKernel<<<grid, SRPD_GEOM_THREADS, smemBytes, stream>>>(a);
-	srpdBatchScanKernel<<<a.d.nFrames, 1024, 0, stream>>>(a);
-	srpdRecordOrderKernel<<<(grid + 7) / 8, 256, 0, stream>>>(a);
+	srpdBatchScanKernel<<<a.d.nFrames * a.chunksPerFrame, SRPD_SCAN_CHUNK / 4, 0, stream>>>(a);
+	srpdRecordOrderKernel<<<(batches + 7) / 8, 256, 0, stream>>>(a);
 	gGeomLaunches += 3;
 }

@@ -17,9 +17,6 @@ extern "C" __device__ void srpB200DeviceFS(int programId, SRPFragmentShaderIn* i
 #ifndef SRPD_TILE_CTAS_PER_SM
 #define SRPD_TILE_CTAS_PER_SM 2
 #endif
-#ifndef SRPD_GEOM_CTAS_PER_SM
-#define SRPD_GEOM_CTAS_PER_SM 4
-#endif
 constexpr int SRPD_TILE_W = 32;          /* pixels; one 128-byte colour row per tile row   */
 constexpr int SRPD_TILE_H = SRPD_TILE_H_PX;
 constexpr int SRPD_BLK_W = 8;            /* pixels owned by one warp: 8 x 4                */
@@ -31,13 +28,36 @@ constexpr int SRPD_TILE_WARPS = SRPD_TILE_THREADS / 32;
  * millions of sub-pixel primitives, so that a tile never filters more than ~1-2 k candidates */
 constexpr int SRPD_SUPER_SHIFT_MAX = 3;
 
-#ifndef SRPD_GEOM_BATCH
-#define SRPD_GEOM_BATCH 256
+/* geometry: one WARP per batch of SRPD_GEOM_PRIMS consecutive input primitives.  30 rather than
+ * 32: a batch of 2n triangles of a regular grid or strip references n + 2 .. 2n + 2 distinct
+ * vertices, so 30 keeps the distinct vertices of such a batch within one 32-lane pass of the
+ * vertex shader (a 33rd vertex would cost a second, almost empty pass) */
+#ifndef SRPD_GEOM_WARP_PRIMS
+#define SRPD_GEOM_WARP_PRIMS 30
 #endif
-constexpr int SRPD_GEOM_THREADS = SRPD_GEOM_BATCH;   /* input primitives per geometry batch (128, 256 or 512) */
-constexpr int SRPD_GEOM_MAX_VERTS = 3 * SRPD_GEOM_THREADS;
-constexpr int SRPD_HASH_SLOTS = 4 * SRPD_GEOM_THREADS;   /* post-VS cache: open-addressing table in smem, load <= 3/4 */
-constexpr int SRPD_HASH_SHIFT = SRPD_GEOM_THREADS == 128 ? 23 : (SRPD_GEOM_THREADS == 256 ? 22 : 21);
+constexpr int SRPD_GEOM_PRIMS = SRPD_GEOM_WARP_PRIMS;
+#ifndef SRPD_GEOM_WARPS_PER_CTA
+#define SRPD_GEOM_WARPS_PER_CTA 4
+#endif
+constexpr int SRPD_GEOM_WARPS = SRPD_GEOM_WARPS_PER_CTA;
+#ifndef SRPD_GEOM_CTAS_PER_SM
+#define SRPD_GEOM_CTAS_PER_SM (32 / SRPD_GEOM_WARPS_PER_CTA)
+#endif
+/* 0: one batch per warp and small CTAs (the hardware refills a CTA slot as soon as its warps are
+ * done); 1: persistent warps pulling batches from a counter -- measured slower on cfg3 (the
+ * same-address counter atomics queue up behind the bump-allocator ones) */
+#ifndef SRPD_GEOM_PERSISTENT
+#define SRPD_GEOM_PERSISTENT 0
+#endif
+constexpr int SRPD_SCAN_CHUNK = 1024;    /* batches per CTA of the batch-order scan */
+#ifndef SRPD_GEOM_GRAB_BATCHES
+#define SRPD_GEOM_GRAB_BATCHES 1
+#endif
+constexpr int SRPD_GEOM_GRAB = SRPD_GEOM_GRAB_BATCHES;         /* consecutive batches a warp takes per visit to the work counter */
+constexpr int SRPD_GEOM_THREADS = 32 * SRPD_GEOM_WARPS;
+constexpr int SRPD_GEOM_MAX_VERTS = 3 * 32;
+constexpr int SRPD_HASH_SLOTS = 128;     /* post-VS cache: open-addressing table in smem, load <= 3/4 */
+constexpr int SRPD_HASH_SHIFT = 25;
 constexpr uint32_t SRPD_HASH_EMPTY = 0xFFFFFFFFu;
 constexpr int SRPD_CLIP_MAX_VERTS = 10;  /* a triangle against 6 planes has <= 9 vertices  */
 
@@ -65,12 +85,16 @@ struct SrpdGeomArgs
 	uint2* bboxesOrdered;             /* the same boxes at their position in primitive order */
 	uint32_t* perm;                   /* [nFrames][recCapacity] position in primitive order -> record slot */
 	uint32_t* frameBump;              /* [nFrames], zeroed per draw: record slots handed out */
+	uint32_t* batchCounter;           /* header word 0, zeroed per draw: next batch of the persistent geometry warps */
+	uint32_t smCount;
 	uint4* batchInfo;                 /* [nFrames * batchesPerFrame] {first slot, ids, records, -} */
 	uint2* batchPrefix;               /* [nFrames * batchesPerFrame] exclusive {ids, records} in batch order */
 	uint32_t* abortFlag;              /* zeroed per draw; set when a scratch pool overflows: the
 	                                     tile kernel then leaves the framebuffer untouched  */
 	uint32_t* needed;                 /* [0] records needed per frame (max), [1] coarse-list entries needed */
 	uint32_t batchesPerFrame;
+	uint32_t chunksPerFrame;          /* ceil(batchesPerFrame / SRPD_SCAN_CHUNK) */
+	uint2* chunkSums;                 /* [nFrames][chunksPerFrame] {ids, records}, zeroed per draw */
 	uint32_t* frameCounts;            /* [nFrames][2]: ids emitted, records stored       */
 	uint32_t* occupancy;              /* [nFrames][occWordsPerFrame], zeroed per draw: tiles touched by a stored record */
 	uint32_t occWordsPerFrame;

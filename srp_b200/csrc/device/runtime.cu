@@ -129,7 +129,7 @@ const char* srpcuVersion(void)
 {
 	static char buf[128];
 	snprintf(buf, sizeof buf, "srp-b200 sm_100a tile %dx%d block %dx%d geom-batch %d line-seg %d",
-	         SRPD_TILE_W, SRPD_TILE_H, SRPD_BLK_W, SRPD_BLK_H, SRPD_GEOM_THREADS, SRPD_LINE_SEG);
+	         SRPD_TILE_W, SRPD_TILE_H, SRPD_BLK_W, SRPD_BLK_H, SRPD_GEOM_PRIMS, SRPD_LINE_SEG);
 	return buf;
 }
 
@@ -333,7 +333,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	if (getenv("SRP_B200_WORST_CASE_POOLS") || cap > worst) cap = worst;
 	if (cap > 0x7FFFFFF0ull) cap = 0x7FFFFFF0ull;
 	const uint32_t recCapacity = (uint32_t) cap;
-	const uint32_t batchesPerFrame = (d.nInputPrims + SRPD_GEOM_THREADS - 1) / SRPD_GEOM_THREADS;
+	const uint32_t batchesPerFrame = (d.nInputPrims + SRPD_GEOM_PRIMS - 1) / SRPD_GEOM_PRIMS;
 
 	if (!grow(g.records, (size_t) recCapacity * recStride * nFrames)) return 1;
 	if (!grow(g.bboxes, (size_t) recCapacity * sizeof(uint2) * nFrames)) return 1;
@@ -342,7 +342,9 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	const uint32_t tilesY = (st.height + SRPD_TILE_H - 1) / SRPD_TILE_H;
 	const uint32_t occWords = (tilesX * tilesY + 31) / 32;
 	const size_t scanStateBytes = (sizeof(uint32_t) * (size_t) nFrames + 7) & ~(size_t) 7;
-	const size_t scanBytes = SRPD_DRAW_HEADER_BYTES + scanStateBytes + sizeof(uint32_t) * (size_t) occWords * nFrames;
+	const uint32_t chunksPerFrame = (batchesPerFrame + SRPD_SCAN_CHUNK - 1) / SRPD_SCAN_CHUNK;
+	const size_t occBytes = (sizeof(uint32_t) * (size_t) occWords * nFrames + 7) & ~(size_t) 7;
+	const size_t scanBytes = SRPD_DRAW_HEADER_BYTES + scanStateBytes + occBytes + sizeof(uint2) * (size_t) chunksPerFrame * nFrames;
 	if (!grow(g.scan, scanBytes)) return 1;
 	if (!grow(g.frameCounts, sizeof(uint32_t) * 2 * nFrames)) return 1;
 	CU(cudaMemsetAsync(g.scan.ptr, 0, scanBytes, g.stream));
@@ -357,6 +359,8 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ga.bboxes = (uint2*) g.bboxes.ptr;
 	ga.recCapacity = recCapacity;
 	ga.recStride = recStride;
+	ga.batchCounter = (uint32_t*) g.scan.ptr + 0;
+	ga.smCount = (uint32_t) g.smCount;
 	ga.abortFlag = (uint32_t*) g.scan.ptr + 1;
 	ga.needed = (uint32_t*) g.scan.ptr + 3;
 	ga.frameBump = (uint32_t*) ((unsigned char*) g.scan.ptr + SRPD_DRAW_HEADER_BYTES);
@@ -369,6 +373,8 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ga.batchInfo = (uint4*) g.batchInfo.ptr;
 	ga.batchPrefix = (uint2*) g.batchPrefix.ptr;
 	ga.batchesPerFrame = batchesPerFrame;
+	ga.chunksPerFrame = chunksPerFrame;
+	ga.chunkSums = (uint2*) ((unsigned char*) g.scan.ptr + SRPD_DRAW_HEADER_BYTES + scanStateBytes + occBytes);
 	ga.frameCounts = (uint32_t*) g.frameCounts.ptr;
 	ga.occupancy = (uint32_t*) ((unsigned char*) g.scan.ptr + SRPD_DRAW_HEADER_BYTES + scanStateBytes);
 	ga.occWordsPerFrame = occWords;

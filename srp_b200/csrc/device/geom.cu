@@ -185,7 +185,7 @@ __device__ __forceinline__ unsigned char* beginRecord(Emitter& em, const uint32_
 			{
 				const uint32_t lo = w == (b0 >> 5) ? (b0 & 31u) : 0u, hi = w == (b1 >> 5) ? (b1 & 31u) : 31u;
 				const uint32_t mask = (hi == 31u ? 0xFFFFFFFFu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
-				if ((em.occupancy[w] & mask) != mask)
+				if ((em.occupancy[w] & mask) != mask)      /* (measured: the pre-check beats unconditional reductions) */
 					atomicOr(&em.occupancy[w], mask);
 			}
 		}

@@ -11,17 +11,23 @@ extern "C" __device__ void srpB200DeviceVS(int programId, SRPVertexShaderIn* in,
 extern "C" __device__ void srpB200DeviceFS(int programId, SRPFragmentShaderIn* in, SRPFragmentShaderOut* out);
 
 /* ---- launch geometry -------------------------------------------------------------- */
+/* pixels per thread of the tile kernel (1 or 2): a thread owns rows ly and ly + 4 of its column */
+#ifndef SRPD_PX_PER_THREAD
+#define SRPD_PX_PER_THREAD 2
+#endif
 #ifndef SRPD_TILE_H_PX
-#define SRPD_TILE_H_PX 16
+#define SRPD_TILE_H_PX (16 * SRPD_PX_PER_THREAD)
 #endif
 #ifndef SRPD_TILE_CTAS_PER_SM
 #define SRPD_TILE_CTAS_PER_SM 2
 #endif
 constexpr int SRPD_TILE_W = 32;          /* pixels; one 128-byte colour row per tile row   */
 constexpr int SRPD_TILE_H = SRPD_TILE_H_PX;
-constexpr int SRPD_BLK_W = 8;            /* pixels owned by one warp: 8 x 4                */
-constexpr int SRPD_BLK_H = 4;
-constexpr int SRPD_TILE_THREADS = SRPD_TILE_W * SRPD_TILE_H;       /* one thread per pixel */
+constexpr int SRPD_BLK_W = 8;            /* pixels owned by one warp: 8 x (4 * pixels per thread) */
+constexpr int SRPD_PX = SRPD_PX_PER_THREAD;
+static_assert(SRPD_PX == 1 || SRPD_PX == 2, "a thread owns one or two pixels");
+constexpr int SRPD_BLK_H = 4 * SRPD_PX;
+constexpr int SRPD_TILE_THREADS = SRPD_TILE_W * SRPD_TILE_H / SRPD_PX;
 constexpr int SRPD_TILE_WARPS = SRPD_TILE_THREADS / 32;
 /* coarse bins ("supertiles") are 2^k x 2^k tiles with k = superShift chosen per draw from the
  * expected record density: 8x8 tiles (256x128 px) for ordinary meshes down to 2x2 for

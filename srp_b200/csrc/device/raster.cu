@@ -183,6 +183,35 @@ __device__ __forceinline__ void emitFragment(
  * and shade their own covered triangles in primitive order, resuming the chain with their
  * <= 7 remaining x steps: every value goes through exactly the reference's sequence of
  * additions => bit-exact. */
+/* A thread owns SRPD_PX pixels of its column (rows ly and ly + 4 of the warp's block).  Their
+ * state lives in small arrays that are only ever indexed by compile-time constants, so they
+ * stay in registers; a run-time choice between them goes through selects (getSel / setSel),
+ * which lets the long fragment stage exist once in the code instead of once per pixel. */
+template <typename T>
+__device__ __forceinline__ T getSel(const T (&v)[SRPD_PX], int h)
+{
+	T r = v[0];
+	#pragma unroll
+	for (int i = 1; i < SRPD_PX; i++)
+		if (h == i) r = v[i];
+	return r;
+}
+template <typename T>
+__device__ __forceinline__ void setSel(T (&v)[SRPD_PX], int h, const T& x)
+{
+	#pragma unroll
+	for (int i = 0; i < SRPD_PX; i++)
+		if (h == i) v[i] = x;
+}
+__device__ __forceinline__ int pickPending(const uint32_t (&cov)[SRPD_PX])
+{
+	int h = 0;
+	#pragma unroll
+	for (int i = SRPD_PX - 1; i > 0; i--)
+		if (cov[i] != 0u && cov[0] == 0u) h = i;
+	return h;
+}
+
 struct RowStart { float l0, l1, l2; int xs; };          /* lambda at column xs of the row          */
 struct TriStep  { float dx0, dx1, dx2; uint32_t rec; };  /* dlambda/dx and the record slot          */
 
@@ -191,7 +220,7 @@ struct WarpStep
 {
 	RowStart row[32 * SRPD_BLK_H];       /* [compact triangle][block row]                          */
 	TriStep  tri[32];                    /* [compact triangle]                                     */
-	uint8_t  bits[SRPD_BLK_H * 32];      /* [block row][compact triangle]: the row's 8 coverage bits */
+	alignas(16) uint8_t bits[SRPD_BLK_H * 32];   /* [block row][compact triangle]: the row's 8 coverage bits */
 };
 
 /* top-left rule as ONE comparison per edge: the reference accepts lambda when
@@ -320,7 +349,7 @@ __device__ __forceinline__ void shadeTriangleFragment(
  * bit t of `cov` <=> triangle t covers my pixel -- and shade them in order. */
 __device__ __forceinline__ void visitTriangles(
 	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, bool mine, uint32_t recSlot,
-	WarpStep& ws, Pixel& px, FragCounters& cnt, int x, int y, int bx0, int by0, int lane)
+	WarpStep& ws, Pixel (&px)[SRPD_PX], FragCounters& cnt, int x, int y0, int bx0, int by0, int lane)
 {
 	const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
 	if (m == 0u)
@@ -329,35 +358,52 @@ __device__ __forceinline__ void visitTriangles(
 	if (mine)
 		ws.tri[__popc(m & ((1u << lane) - 1u))].rec = recSlot;
 	__syncwarp();
+	constexpr int PER_ROUND = 32 / SRPD_BLK_H;      /* triangles per round of row lanes */
 	const int row = lane & (SRPD_BLK_H - 1);
-	for (int t = lane >> 2; t < n; t += 8)
+	for (int t = lane / SRPD_BLK_H; t < n; t += PER_ROUND)
 	{
 		const uint32_t bits = coverTriangleRow(records + (size_t) ws.tri[t].rec * a.recStride, a.ckptTable, bx0, by0 + row,
 		                                       &ws.row[t * SRPD_BLK_H + row], &ws.tri[t], row == 0);
 		ws.bits[row * 32 + t] = (uint8_t) bits;
 	}
 	__syncwarp();
-	/* gather: byte t of my row's 32 bytes holds the row's coverage of triangle t; bit (lane % 8)
+	/* gather: byte t of a row's 32 bytes holds the row's coverage of triangle t; bit (lane % 8)
 	 * of it is my pixel.  Four triangles per 32-bit word: isolate the bit in each byte, then
 	 * one multiply moves the four bits next to each other (no carries: all partial products
 	 * land on distinct bit positions). */
 	const int ly = lane / SRPD_BLK_W, lx = lane % SRPD_BLK_W;
-	uint32_t cov = 0u;
-	const uint32_t* rowBits = (const uint32_t*) (ws.bits + ly * 32);
-	for (int w = 0; w * 4 < n; w++)
+	uint32_t cov[SRPD_PX];
+	#pragma unroll
+	for (int h = 0; h < SRPD_PX; h++)
 	{
-		const uint32_t four = (rowBits[w] >> lx) & 0x01010101u;
-		cov |= (((four * 0x00204081u) >> 21) & 0xFu) << (4 * w);
-	}
-	if (n < 32)
-		cov &= (1u << n) - 1u;         /* bytes of triangles beyond n are stale */
-	while (__any_sync(0xFFFFFFFFu, cov != 0u))
-	{
-		if (cov)
+		cov[h] = 0u;
+		const uint32_t* rowBits = (const uint32_t*) (ws.bits + (ly + 4 * h) * 32);
+		for (int w = 0; w * 4 < n; w++)
 		{
-			const int t = __ffs(cov) - 1;
-			cov &= cov - 1u;
-			shadeTriangleFragment(a, fr, records, ws.row[t * SRPD_BLK_H + ly], ws.tri[t], px, cnt, x, y);
+			const uint32_t four = (rowBits[w] >> lx) & 0x01010101u;
+			cov[h] |= (((four * 0x00204081u) >> 21) & 0xFu) << (4 * w);
+		}
+		if (n < 32)
+			cov[h] &= (1u << n) - 1u;      /* bytes of triangles beyond n are stale */
+	}
+	/* shade: every lane works through the covering triangles of its own pixel(s), in order */
+	for (;;)
+	{
+		uint32_t any = cov[0];
+		#pragma unroll
+		for (int h = 1; h < SRPD_PX; h++)
+			any |= cov[h];
+		if (!__any_sync(0xFFFFFFFFu, any != 0u))
+			break;
+		if (any)
+		{
+			const int h = pickPending(cov);
+			const uint32_t c = getSel(cov, h);
+			const int t = __ffs(c) - 1;
+			setSel(cov, h, c & (c - 1u));
+			Pixel cur = getSel(px, h);
+			shadeTriangleFragment(a, fr, records, ws.row[t * SRPD_BLK_H + ly + 4 * h], ws.tri[t], cur, cnt, x, y0 + 4 * h);
+			setSel(px, h, cur);
 		}
 	}
 	__syncwarp();      /* the next step overwrites this warp's scratch */
@@ -369,8 +415,8 @@ __device__ __forceinline__ void visitTriangles(
  * y*W + x -- including the ones the reference's unchecked indexing wraps to the next row
  * (App. B-1). */
 __device__ __forceinline__ void visitLine(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, Pixel& px, FragCounters& cnt,
-	int x, int y, bool valid)
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, Pixel (&px)[SRPD_PX], FragCounters& cnt,
+	int x, int y0, const bool (&valid)[SRPD_PX])
 {
 	const uint4* h = (const uint4*) rec;
 	const uint4 q0 = __ldg(h + 0), q1 = __ldg(h + 1), q2 = __ldg(h + 2), q3 = __ldg(h + 3);
@@ -382,19 +428,29 @@ __device__ __forceinline__ void visitLine(
 	const float iw0 = __uint_as_float(q2.x), iw1 = __uint_as_float(q2.y);
 	float t = __uint_as_float(q2.z);
 	const long long W = a.d.st.width;
-	const long long mine = valid ? (long long) y * W + x : -1;
+	long long mine[SRPD_PX];
+	#pragma unroll
+	for (int k = 0; k < SRPD_PX; k++)
+		mine[k] = valid[k] ? (long long) (y0 + 4 * k) * W + x : -1;
 	for (int i = 0; i < count; i++)
 	{
 		const int ipx = srpdRoundToInt(fx), ipy = srpdRoundToInt(fy);
-		if ((long long) ipy * W + ipx == mine)
+		const long long idx = (long long) ipy * W + ipx;
+		int which = -1;
+		#pragma unroll
+		for (int k = 0; k < SRPD_PX; k++)
+			if (idx == mine[k]) which = k;
+		if (which >= 0)
 		{
 			const float w0 = __fsub_rn(1.0f, t);
 			const float wgt[2] = { w0, t };
 			/* interpolateDepthAndWLine, interpolation.c:49-60 */
 			const float recW = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(iw0, w0), __fmul_rn(iw1, t)));
 			const float depth = __fadd_rn(__fmul_rn(zw0, w0), __fmul_rn(zw1, t));
-			emitFragment<2>(a.d.st, fr, px, cnt, ipx, ipy, (float) ((double) ipx + 0.5), (float) ((double) ipy + 0.5),
+			Pixel cur = getSel(px, which);
+			emitFragment<2>(a.d.st, fr, cur, cnt, ipx, ipy, (float) ((double) ipx + 0.5), (float) ((double) ipy + 0.5),
 			                depth, recW, recW, true, q3.w, rec + SRPD_REC_HEADER_BYTES, wgt);
+			setSel(px, which, cur);
 		}
 		fx = __fadd_rn(fx, xInc);
 		fy = __fadd_rn(fy, yInc);
@@ -402,22 +458,34 @@ __device__ __forceinline__ void visitLine(
 	}
 }
 
-/* rasterizePoint for one pixel, reference point.c:32-74 */
+/* rasterizePoint for the thread's pixels, reference point.c:32-74 */
 __device__ __forceinline__ void visitPoint(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, Pixel& px, FragCounters& cnt,
-	int x, int y, bool valid)
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, Pixel (&px)[SRPD_PX], FragCounters& cnt,
+	int x, int y0, const bool (&valid)[SRPD_PX])
 {
 	const uint4* h = (const uint4*) rec;
 	const uint4 q1 = __ldg(h + 1);
-	if (!valid || x < (int) q1.x || x > (int) q1.y || y < (int) q1.z || y > (int) q1.w)
+	if (x < (int) q1.x || x > (int) q1.y)
 		return;
 	const uint4 q0 = __ldg(h + 0);
-	const float pcx = (float) ((double) x + 0.5), pcy = (float) ((double) y + 0.5);
-	if (pcx < __uint_as_float(q0.x) || pcx >= __uint_as_float(q0.z) || pcy < __uint_as_float(q0.y) || pcy >= __uint_as_float(q0.w))
+	const float pcx = (float) ((double) x + 0.5);
+	if (pcx < __uint_as_float(q0.x) || pcx >= __uint_as_float(q0.z))
 		return;
-	const uint4 q2 = __ldg(h + 2), q3 = __ldg(h + 3);
-	emitFragment<1>(a.d.st, fr, px, cnt, x, y, pcx, pcy, __uint_as_float(q2.x), 0.f, __uint_as_float(q2.y),
-	                true, q3.w, rec + SRPD_REC_HEADER_BYTES, nullptr);
+	#pragma unroll 1
+	for (int k = 0; k < SRPD_PX; k++)
+	{
+		const int y = y0 + 4 * k;
+		if (!getSel(valid, k) || y < (int) q1.z || y > (int) q1.w)
+			continue;
+		const float pcy = (float) ((double) y + 0.5);
+		if (pcy < __uint_as_float(q0.y) || pcy >= __uint_as_float(q0.w))
+			continue;
+		const uint4 q2 = __ldg(h + 2), q3 = __ldg(h + 3);
+		Pixel cur = getSel(px, k);
+		emitFragment<1>(a.d.st, fr, cur, cnt, x, y, pcx, pcy, __uint_as_float(q2.x), 0.f, __uint_as_float(q2.y),
+		                true, q3.w, rec + SRPD_REC_HEADER_BYTES, nullptr);
+		setSel(px, k, cur);
+	}
 }
 
 /* Tile plane -> framebuffer: threads cooperatively emit 16-byte stores from the staged
@@ -450,9 +518,12 @@ __device__ __forceinline__ void storePlane(const T* staged, T* plane, int W, int
 /* shared memory of the tile kernel (dynamic: with the per-warp step scratch it exceeds 48 KB) */
 struct TileShared
 {
-	uint32_t ids[SRPD_TILE_THREADS];     /* record slots of the tile's list chunk; reused as the colour staging tile */
-	uint2    box[SRPD_TILE_THREADS];     /* their boxes; reused as depth (+ stencil) staging */
-	uint32_t warpCnt[32];
+	uint32_t ids[SRPD_TILE_THREADS];     /* record slots of the tile's list chunk */
+	uint2    box[SRPD_TILE_THREADS];     /* their boxes */
+	alignas(16) uint32_t color[SRPD_TILE_W * SRPD_TILE_H];    /* write-back staging of the three planes */
+	alignas(16) float    depth[SRPD_TILE_W * SRPD_TILE_H];
+	alignas(16) uint8_t  stencil[SRPD_TILE_W * SRPD_TILE_H];
+	uint32_t warpCnt[64];               /* [0, warps): filter counters; [warps, 2 warps): dirty flags */
 	uint32_t item[2];
 };
 template <int KIND> struct TileSharedK : TileShared {};
@@ -483,26 +554,33 @@ __device__ __forceinline__ void processTile(
 	const uint2* bboxes = a.bboxes + (size_t) frame * a.recCapacity;
 	const uint32_t* perm = a.perm + (size_t) frame * a.recCapacity;
 
-	/* pixel ownership: warp w -> 8x4 block (w % 4, w / 4); lane -> (lane % 8, lane / 8) */
+	/* pixel ownership: warp w -> block (w % 4, w / 4) of 8 x SRPD_BLK_H pixels;
+	 * lane -> column lane % 8, rows lane / 8 (+ 4 for the thread's second pixel) */
 	const int tx0 = tileX * SRPD_TILE_W, ty0 = tileY * SRPD_TILE_H;
 	const int bx0 = tx0 + (warp % (SRPD_TILE_W / SRPD_BLK_W)) * SRPD_BLK_W;
 	const int by0 = ty0 + (warp / (SRPD_TILE_W / SRPD_BLK_W)) * SRPD_BLK_H;
-	const int x = bx0 + (lane % SRPD_BLK_W), y = by0 + (lane / SRPD_BLK_W);
-	const bool valid = x < st.width && y < st.height;
+	const int x = bx0 + (lane % SRPD_BLK_W), y0 = by0 + (lane / SRPD_BLK_W);
 
-	Pixel px;
-	px.color = 0u; px.depth = -1.0f; px.stencil = 0u; px.dirty = 0u;
-	if (valid && (!fr.clearPending || st.stencilEnabled))
+	Pixel px[SRPD_PX];
+	bool valid[SRPD_PX];
+	#pragma unroll
+	for (int k = 0; k < SRPD_PX; k++)
 	{
-		const size_t pixelIndex = (size_t) y * st.width + x;
-		if (!fr.clearPending)
+		const int y = y0 + 4 * k;
+		valid[k] = x < st.width && y < st.height;
+		px[k].color = 0u; px[k].depth = -1.0f; px[k].stencil = 0u; px[k].dirty = 0u;
+		if (valid[k] && (!fr.clearPending || st.stencilEnabled))
 		{
-			px.color = fr.color[pixelIndex];
-			if (st.depthTest)
-				px.depth = fr.depth[pixelIndex];
+			const size_t pixelIndex = (size_t) y * st.width + x;
+			if (!fr.clearPending)
+			{
+				px[k].color = fr.color[pixelIndex];
+				if (st.depthTest)
+					px[k].depth = fr.depth[pixelIndex];
+			}
+			if (st.stencilEnabled)
+				px[k].stencil = fr.stencil[pixelIndex];
 		}
-		if (st.stencilEnabled)
-			px.stencil = fr.stencil[pixelIndex];
 	}
 
 	for (uint32_t c = begin; c < end; c += SRPD_TILE_THREADS)
@@ -516,9 +594,9 @@ __device__ __forceinline__ void processTile(
 		{
 			rid = ids ? ids[i] : i;          /* position in primitive order */
 			bb = bboxes[rid];
-			const int x0 = (int) (bb.x & 0xFFFFu), y0 = (int) (bb.x >> 16);
-			const int x1 = (int) (bb.y & 0xFFFFu), y1 = (int) (bb.y >> 16);
-			hit = x0 < tx0 + SRPD_TILE_W && x1 > tx0 && y0 < ty0 + SRPD_TILE_H && y1 > ty0;
+			const int x0 = (int) (bb.x & 0xFFFFu), y0b = (int) (bb.x >> 16);
+			const int x1 = (int) (bb.y & 0xFFFFu), y1b = (int) (bb.y >> 16);
+			hit = x0 < tx0 + SRPD_TILE_W && x1 > tx0 && y0b < ty0 + SRPD_TILE_H && y1b > ty0;
 		}
 		const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
 		__syncthreads();                     /* the previous chunk's list (and warpCnt) is no longer read */
@@ -536,7 +614,7 @@ __device__ __forceinline__ void processTile(
 		}
 		__syncthreads();
 
-		/* warp: visit, in order, the entries that touch this warp's 8x4 block */
+		/* warp: visit, in order, the entries that touch this warp's block */
 		for (uint32_t j0 = 0; j0 < total; j0 += 32)
 		{
 			const uint32_t j = j0 + lane;
@@ -545,13 +623,13 @@ __device__ __forceinline__ void processTile(
 			if (j < total)
 			{
 				const uint2 b2 = sm.box[j];
-				const int x0 = (int) (b2.x & 0xFFFFu), y0 = (int) (b2.x >> 16);
-				const int x1 = (int) (b2.y & 0xFFFFu), y1 = (int) (b2.y >> 16);
-				mine = x0 < bx0 + SRPD_BLK_W && x1 > bx0 && y0 < by0 + SRPD_BLK_H && y1 > by0;
+				const int x0 = (int) (b2.x & 0xFFFFu), y0b = (int) (b2.x >> 16);
+				const int x1 = (int) (b2.y & 0xFFFFu), y1b = (int) (b2.y >> 16);
+				mine = x0 < bx0 + SRPD_BLK_W && x1 > bx0 && y0b < by0 + SRPD_BLK_H && y1b > by0;
 				slot = sm.ids[j];
 			}
 			if constexpr (KIND == SRPD_KIND_TRIANGLE)
-				visitTriangles(a, fr, records, mine, slot, sm.step[warp], px, cnt, x, y, bx0, by0, lane);
+				visitTriangles(a, fr, records, mine, slot, sm.step[warp], px, cnt, x, y0, bx0, by0, lane);
 			else
 			{
 				uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
@@ -561,35 +639,38 @@ __device__ __forceinline__ void processTile(
 					m &= m - 1;
 					const unsigned char* rec = records + (size_t) sm.ids[j0 + bit] * a.recStride;
 					if (KIND == SRPD_KIND_LINE)
-						visitLine(a, fr, rec, px, cnt, x, y, valid);
+						visitLine(a, fr, rec, px, cnt, x, y0, valid);
 					else
-						visitPoint(a, fr, rec, px, cnt, x, y, valid);
+						visitPoint(a, fr, rec, px, cnt, x, y0, valid);
 				}
 			}
 		}
 	}
 
 	/* write-back: stage the tile in shared memory, leave as 16-byte vectors */
-	const uint32_t warpDirty = __reduce_or_sync(0xFFFFFFFFu, px.dirty);
-	__syncthreads();                         /* every warp is done with the list */
+	uint32_t dirty = 0u;
+	#pragma unroll
+	for (int k = 0; k < SRPD_PX; k++)
+	{
+		dirty |= px[k].dirty;
+		const int local = (y0 + 4 * k - ty0) * SRPD_TILE_W + (x - tx0);
+		sm.color[local] = px[k].color;
+		sm.depth[local] = px[k].depth;
+		sm.stencil[local] = (uint8_t) px[k].stencil;
+	}
+	const uint32_t warpDirty = __reduce_or_sync(0xFFFFFFFFu, dirty);
 	if (lane == 0)
-		sm.warpCnt[warp] = warpDirty;
-	uint32_t* sColor = sm.ids;
-	float* sDepth = (float*) sm.box;
-	uint8_t* sStencil = (uint8_t*) (sDepth + SRPD_TILE_THREADS);
-	const int local = (y - ty0) * SRPD_TILE_W + (x - tx0);
-	sColor[local] = px.color;
-	sDepth[local] = px.depth;
-	sStencil[local] = (uint8_t) px.stencil;
+		sm.warpCnt[SRPD_TILE_WARPS + warp] = warpDirty;      /* upper half: not the filter's counters */
 	__syncthreads();
-	const uint32_t tileDirty = __reduce_or_sync(0xFFFFFFFFu, lane < SRPD_TILE_WARPS ? sm.warpCnt[lane] : 0u) | (fr.clearPending ? 3u : 0u);
+	const uint32_t tileDirty = __reduce_or_sync(0xFFFFFFFFu, lane < SRPD_TILE_WARPS ? sm.warpCnt[SRPD_TILE_WARPS + lane] : 0u)
+	                           | (fr.clearPending ? 3u : 0u);
 	if (tileDirty & 1u)
-		storePlane<uint32_t>(sColor, fr.color, st.width, st.height, tx0, ty0, tid);
+		storePlane<uint32_t>(sm.color, fr.color, st.width, st.height, tx0, ty0, tid);
 	if (tileDirty & 2u)
-		storePlane<float>(sDepth, fr.depth, st.width, st.height, tx0, ty0, tid);
+		storePlane<float>(sm.depth, fr.depth, st.width, st.height, tx0, ty0, tid);
 	if (tileDirty & 4u)
-		storePlane<uint8_t>(sStencil, fr.stencil, st.width, st.height, tx0, ty0, tid);
-	/* the next tile's first barrier comes before anything is written to the staging arrays */
+		storePlane<uint8_t>(sm.stencil, fr.stencil, st.width, st.height, tx0, ty0, tid);
+	__syncthreads();      /* the staging planes and the dirty words are rewritten by the next tile */
 }
 
 /* A tile no primitive touches while a clear is pending: just write the clear values
@@ -597,12 +678,16 @@ __device__ __forceinline__ void processTile(
 __device__ __forceinline__ void clearTile(const SrpdState& st, const SrpdFrame& fr, int tileX, int tileY)
 {
 	const int x = tileX * SRPD_TILE_W + (threadIdx.x % SRPD_TILE_W);
-	const int y = tileY * SRPD_TILE_H + (threadIdx.x / SRPD_TILE_W);
-	if (x < st.width && y < st.height)
+	#pragma unroll
+	for (int k = 0; k < SRPD_PX; k++)
 	{
-		const size_t i = (size_t) y * st.width + x;
-		fr.color[i] = 0u;
-		fr.depth[i] = -1.0f;
+		const int y = tileY * SRPD_TILE_H + (threadIdx.x / SRPD_TILE_W) + k * (SRPD_TILE_H / SRPD_PX);
+		if (x < st.width && y < st.height)
+		{
+			const size_t i = (size_t) y * st.width + x;
+			fr.color[i] = 0u;
+			fr.depth[i] = -1.0f;
+		}
 	}
 }
 

@@ -508,6 +508,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		const uint64_t target = (uint64_t) g.smCount * SRPD_TILE_CTAS_PER_SM * 32;
 		uint32_t per = 1;
 		while (per < 32 && tiles / (per * 2) >= target) per *= 2;
+		if (const char* e = getenv("SRP_B200_TILES_PER_ITEM")) per = (uint32_t) atoi(e) > 0 ? (uint32_t) atoi(e) : per;
 		ta.tilesPerItem = per;
 	}
 	/* one-shot mirror request: rasterise in bands and download each band while the next one

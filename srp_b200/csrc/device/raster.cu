@@ -43,19 +43,26 @@ struct FragCounters { uint32_t emitted, shaded; };
 /* emitFragment, reference src/raster/fragment.c:63-125.  `sx, sy` are the (unwrapped)
  * integer fragment coordinates the scissor test sees; interpolation of the varyings is
  * deferred until the early tests have passed (it is pure). */
-template <int NV>
+/* SIMPLE (compile-time): no scissor, no stencil, the shader does not write depth and all
+ * varyings are floats -- the state almost every draw has; the tests on the draw state then
+ * disappear from the fragment stage instead of being evaluated per fragment. */
+template <int NV, bool SIMPLE>
 __device__ __forceinline__ void emitFragment(
 	const SrpdState& st, const SrpdFrame& fr, Pixel& px, FragCounters& cnt,
 	int sx, int sy, float fragX, float fragY, float depth, float rec, float fragW,
 	bool frontFacing, uint32_t primitiveID,
 	const unsigned char* blobs, const float* wgt)
 {
+	const bool scissorEnabled = SIMPLE ? false : (bool) st.scissorEnabled;
+	const bool stencilEnabled = SIMPLE ? false : (bool) st.stencilEnabled;
+	const bool earlyDepth = SIMPLE ? true : (bool) st.earlyDepth;
+	const bool allFloat = SIMPLE ? true : (bool) st.allFloat;
 	cnt.emitted++;
-	if (st.scissorEnabled && !srpdScissor(st, sx, sy))
+	if (scissorEnabled && !srpdScissor(st, sx, sy))
 		return;
 
 	const float storedDepth = px.depth;
-	if (st.stencilEnabled)
+	if (stencilEnabled)
 	{
 		const SrpdStencilFace& sf = frontFacing ? st.stencilFront : st.stencilBack;
 		const uint8_t storedStencil = (uint8_t) px.stencil;
@@ -66,9 +73,9 @@ __device__ __forceinline__ void emitFragment(
 			return;
 		}
 	}
-	if (st.earlyDepth && st.depthTest && !srpdCompare(st.depthOp, depth, storedDepth))
+	if (earlyDepth && st.depthTest && !srpdCompare(st.depthOp, depth, storedDepth))
 	{
-		if (st.stencilEnabled)
+		if (stencilEnabled)
 		{
 			const SrpdStencilFace& sf = frontFacing ? st.stencilFront : st.stencilBack;
 			const uint8_t storedStencil = (uint8_t) px.stencil;
@@ -84,7 +91,7 @@ __device__ __forceinline__ void emitFragment(
 		for (int k = 0; k < st.slotSize / 4; k++)
 			((uint32_t*) interpolated)[k] = __ldg((const uint32_t*) blobs + k);
 	}
-	else if (st.allFloat)
+	else if (allFloat)
 	{
 		/* all attributes are floats: the blob is an array of st.nFloats floats, two bits of
 		 * interpolation mode each; same operation order as srpdInterpolate (interpolation.c:63-83).
@@ -134,13 +141,13 @@ __device__ __forceinline__ void emitFragment(
 	srpB200DeviceFS(st.programId, &in, &out);
 	cnt.shaded++;
 
-	if (!st.earlyDepth)
+	if (!earlyDepth)
 	{
 		if (!isnan(out.fragDepth))
 			depth = out.fragDepth;
 		if (st.depthTest && !srpdCompare(st.depthOp, depth, storedDepth))
 		{
-			if (st.stencilEnabled)
+			if (stencilEnabled)
 			{
 				const SrpdStencilFace& sf = frontFacing ? st.stencilFront : st.stencilBack;
 				const uint8_t storedStencil = (uint8_t) px.stencil;
@@ -150,7 +157,7 @@ __device__ __forceinline__ void emitFragment(
 			return;
 		}
 	}
-	if (st.stencilEnabled)
+	if (stencilEnabled)
 	{
 		const SrpdStencilFace& sf = frontFacing ? st.stencilFront : st.stencilBack;
 		const uint8_t storedStencil = (uint8_t) px.stencil;
@@ -183,6 +190,17 @@ __device__ __forceinline__ void emitFragment(
  * and shade their own covered triangles in primitive order, resuming the chain with their
  * <= 7 remaining x steps: every value goes through exactly the reference's sequence of
  * additions => bit-exact. */
+__device__ __forceinline__ uint32_t warpInclusiveScan(uint32_t v, int lane)
+{
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, v, o);
+		if (lane >= o) v += n;
+	}
+	return v;
+}
+
 /* A thread owns SRPD_PX pixels of its column (rows ly and ly + 4 of the warp's block).  Their
  * state lives in small arrays that are only ever indexed by compile-time constants, so they
  * stay in registers; a run-time choice between them goes through selects (getSel / setSel),
@@ -221,6 +239,7 @@ struct WarpStep
 	RowStart row[32 * SRPD_BLK_H];       /* [compact triangle][block row]                          */
 	TriStep  tri[32];                    /* [compact triangle]                                     */
 	alignas(16) uint8_t bits[SRPD_BLK_H * 32];   /* [block row][compact triangle]: the row's 8 coverage bits */
+	uint8_t  pair[SRPD_BLK_H * 32];      /* work list of the row lanes: triangle * SRPD_BLK_H + row   */
 };
 
 /* top-left rule as ONE comparison per edge: the reference accepts lambda when
@@ -233,17 +252,14 @@ __device__ __forceinline__ float coverageThreshold(bool topLeft)
 }
 
 __device__ __forceinline__ uint32_t coverTriangleRow(
-	const unsigned char* rec, const float* ckptTable, int bx0, int y, RowStart* rowOut, TriStep* triOut, bool first)
+	const unsigned char* rec, const float* ckptTable, int bx0, int y, RowStart* rowOut, TriStep* triOut)
 {
 	const uint4* h = (const uint4*) rec;
 	const uint4 q0 = __ldg(h + 0), q1 = __ldg(h + 1), q2 = __ldg(h + 2);
 	const int minX = (int) (q0.w & 0xFFFFu), maxX = (int) (q0.w >> 16);
 	const int minY = (int) (q1.w & 0xFFFFu), maxY = (int) (q1.w >> 16);
 	const float dx0 = __uint_as_float(q1.x), dx1 = __uint_as_float(q1.y), dx2 = __uint_as_float(q1.z);
-	if (first)
-	{
-		triOut->dx0 = dx0; triOut->dx1 = dx1; triOut->dx2 = dx2;
-	}
+	triOut->dx0 = dx0; triOut->dx1 = dx1; triOut->dx2 = dx2;      /* (every row lane of the triangle writes the same values) */
 	const int xs = max(bx0, minX);
 	const int n = min(bx0 + SRPD_BLK_W, maxX) - xs;
 	if (y < minY || y >= maxY || n <= 0)
@@ -317,6 +333,7 @@ __device__ __forceinline__ uint32_t coverTriangleRow(
 
 /* fragment stage of one covered pixel of a triangle: the pixel's remaining x steps, depth /
  * 1/w interpolation (interpolateDepthAndWTriangle, interpolation.c:34-47) and emitFragment */
+template <bool SIMPLE>
 __device__ __forceinline__ void shadeTriangleFragment(
 	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, const RowStart& rs, const TriStep& ts,
 	Pixel& px, FragCounters& cnt, int x, int y)
@@ -339,7 +356,7 @@ __device__ __forceinline__ void shadeTriangleFragment(
 	const float recW = __fdiv_rn(1.0f, iwSum);
 	const float depth = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(q3.x), l0), __fmul_rn(__uint_as_float(q3.y), l1)),
 	                              __fmul_rn(__uint_as_float(q3.z), l2));
-	emitFragment<3>(a.d.st, fr, px, cnt, x, y, (float) ((double) x + 0.5), (float) ((double) y + 0.5),
+	emitFragment<3, SIMPLE>(a.d.st, fr, px, cnt, x, y, (float) ((double) x + 0.5), (float) ((double) y + 0.5),
 	                depth, recW, recW, (flags & 8u) != 0, q3.w, rec + SRPD_REC_HEADER_BYTES, wgt);
 }
 
@@ -347,23 +364,37 @@ __device__ __forceinline__ void shadeTriangleFragment(
  * warp's block.  The touching entries are compacted in order (t = 0 .. n-1); row lanes decide
  * coverage, 8 triangles x 4 rows per round; pixel threads gather the bits of their pixel --
  * bit t of `cov` <=> triangle t covers my pixel -- and shade them in order. */
+template <bool SIMPLE>
 __device__ __forceinline__ void visitTriangles(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, bool mine, uint32_t recSlot,
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, bool mine, uint32_t recSlot, int rowLo, int rowCnt,
 	WarpStep& ws, Pixel (&px)[SRPD_PX], FragCounters& cnt, int x, int y0, int bx0, int by0, int lane)
 {
 	const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
 	if (m == 0u)
 		return;
 	const int n = __popc(m);
+	/* work list of (triangle, row) pairs: only the block rows inside a triangle's bounding box,
+	 * so the row lanes are (nearly) all busy whatever the triangles' heights */
+	const uint32_t inc = warpInclusiveScan(mine ? (uint32_t) rowCnt : 0u, lane);
+	const int nPairs = (int) __shfl_sync(0xFFFFFFFFu, inc, 31);
+	#pragma unroll
+	for (int i = 0; i < SRPD_BLK_H * 32 / 4 / 32; i++)
+		((uint32_t*) ws.bits)[lane + 32 * i] = 0u;
 	if (mine)
-		ws.tri[__popc(m & ((1u << lane) - 1u))].rec = recSlot;
-	__syncwarp();
-	constexpr int PER_ROUND = 32 / SRPD_BLK_H;      /* triangles per round of row lanes */
-	const int row = lane & (SRPD_BLK_H - 1);
-	for (int t = lane / SRPD_BLK_H; t < n; t += PER_ROUND)
 	{
+		const int t = __popc(m & ((1u << lane) - 1u));
+		ws.tri[t].rec = recSlot;
+		uint8_t* out = ws.pair + (inc - (uint32_t) rowCnt);
+		for (int r = 0; r < rowCnt; r++)
+			out[r] = (uint8_t) (t * SRPD_BLK_H + rowLo + r);
+	}
+	__syncwarp();
+	for (int q = lane; q < nPairs; q += 32)
+	{
+		const int pr = ws.pair[q];
+		const int t = pr / SRPD_BLK_H, row = pr % SRPD_BLK_H;
 		const uint32_t bits = coverTriangleRow(records + (size_t) ws.tri[t].rec * a.recStride, a.ckptTable, bx0, by0 + row,
-		                                       &ws.row[t * SRPD_BLK_H + row], &ws.tri[t], row == 0);
+		                                       &ws.row[pr], &ws.tri[t]);
 		ws.bits[row * 32 + t] = (uint8_t) bits;
 	}
 	__syncwarp();
@@ -402,7 +433,7 @@ __device__ __forceinline__ void visitTriangles(
 			const int t = __ffs(c) - 1;
 			setSel(cov, h, c & (c - 1u));
 			Pixel cur = getSel(px, h);
-			shadeTriangleFragment(a, fr, records, ws.row[t * SRPD_BLK_H + ly + 4 * h], ws.tri[t], cur, cnt, x, y0 + 4 * h);
+			shadeTriangleFragment<SIMPLE>(a, fr, records, ws.row[t * SRPD_BLK_H + ly + 4 * h], ws.tri[t], cur, cnt, x, y0 + 4 * h);
 			setSel(px, h, cur);
 		}
 	}
@@ -448,7 +479,7 @@ __device__ __forceinline__ void visitLine(
 			const float recW = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(iw0, w0), __fmul_rn(iw1, t)));
 			const float depth = __fadd_rn(__fmul_rn(zw0, w0), __fmul_rn(zw1, t));
 			Pixel cur = getSel(px, which);
-			emitFragment<2>(a.d.st, fr, cur, cnt, ipx, ipy, (float) ((double) ipx + 0.5), (float) ((double) ipy + 0.5),
+			emitFragment<2, false>(a.d.st, fr, cur, cnt, ipx, ipy, (float) ((double) ipx + 0.5), (float) ((double) ipy + 0.5),
 			                depth, recW, recW, true, q3.w, rec + SRPD_REC_HEADER_BYTES, wgt);
 			setSel(px, which, cur);
 		}
@@ -482,7 +513,7 @@ __device__ __forceinline__ void visitPoint(
 			continue;
 		const uint4 q2 = __ldg(h + 2), q3 = __ldg(h + 3);
 		Pixel cur = getSel(px, k);
-		emitFragment<1>(a.d.st, fr, cur, cnt, x, y, pcx, pcy, __uint_as_float(q2.x), 0.f, __uint_as_float(q2.y),
+		emitFragment<1, false>(a.d.st, fr, cur, cnt, x, y, pcx, pcy, __uint_as_float(q2.x), 0.f, __uint_as_float(q2.y),
 		                true, q3.w, rec + SRPD_REC_HEADER_BYTES, nullptr);
 		setSel(px, k, cur);
 	}
@@ -530,11 +561,12 @@ template <int KIND> struct TileSharedK : TileShared {};
 template <> struct TileSharedK<SRPD_KIND_TRIANGLE> : TileShared { WarpStep step[SRPD_TILE_WARPS]; };
 
 /* One tile: filter the candidate list, visit the primitives in order, write the tile back. */
-template <int KIND>
+template <int KIND, bool SIMPLE>
 __device__ __forceinline__ void processTile(
 	const SrpdTileArgs& a, const SrpdFrame& fr, uint32_t frame, int tileX, int tileY, TileSharedK<KIND>& sm, FragCounters& cnt)
 {
 	const SrpdState& st = a.d.st;
+	const bool stencilEnabled = SIMPLE ? false : (bool) st.stencilEnabled;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
 	/* candidate list of this tile */
@@ -569,7 +601,7 @@ __device__ __forceinline__ void processTile(
 		const int y = y0 + 4 * k;
 		valid[k] = x < st.width && y < st.height;
 		px[k].color = 0u; px[k].depth = -1.0f; px[k].stencil = 0u; px[k].dirty = 0u;
-		if (valid[k] && (!fr.clearPending || st.stencilEnabled))
+		if (valid[k] && (!fr.clearPending || stencilEnabled))
 		{
 			const size_t pixelIndex = (size_t) y * st.width + x;
 			if (!fr.clearPending)
@@ -578,7 +610,7 @@ __device__ __forceinline__ void processTile(
 				if (st.depthTest)
 					px[k].depth = fr.depth[pixelIndex];
 			}
-			if (st.stencilEnabled)
+			if (stencilEnabled)
 				px[k].stencil = fr.stencil[pixelIndex];
 		}
 	}
@@ -599,7 +631,10 @@ __device__ __forceinline__ void processTile(
 			hit = x0 < tx0 + SRPD_TILE_W && x1 > tx0 && y0b < ty0 + SRPD_TILE_H && y1b > ty0;
 		}
 		const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
-		__syncthreads();                     /* the previous chunk's list (and warpCnt) is no longer read */
+		/* (no barrier needed here: whoever gets this far has passed the previous chunk's second
+		 * barrier, which every warp reaches only after it has read that chunk's counters; and the
+		 * list itself is rewritten only after the next barrier, which every warp reaches only
+		 * after it has finished walking the previous list) */
 		if (lane == 0)
 			sm.warpCnt[warp] = __popc(ballot);
 		__syncthreads();
@@ -620,6 +655,7 @@ __device__ __forceinline__ void processTile(
 			const uint32_t j = j0 + lane;
 			bool mine = false;
 			uint32_t slot = 0u;
+			int rowLo = 0, rowCnt = 0;
 			if (j < total)
 			{
 				const uint2 b2 = sm.box[j];
@@ -627,9 +663,11 @@ __device__ __forceinline__ void processTile(
 				const int x1 = (int) (b2.y & 0xFFFFu), y1b = (int) (b2.y >> 16);
 				mine = x0 < bx0 + SRPD_BLK_W && x1 > bx0 && y0b < by0 + SRPD_BLK_H && y1b > by0;
 				slot = sm.ids[j];
+				rowLo = max(y0b, by0) - by0;
+				rowCnt = min(y1b, by0 + SRPD_BLK_H) - by0 - rowLo;
 			}
 			if constexpr (KIND == SRPD_KIND_TRIANGLE)
-				visitTriangles(a, fr, records, mine, slot, sm.step[warp], px, cnt, x, y0, bx0, by0, lane);
+				visitTriangles<SIMPLE>(a, fr, records, mine, slot, rowLo, rowCnt, sm.step[warp], px, cnt, x, y0, bx0, by0, lane);
 			else
 			{
 				uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
@@ -699,7 +737,7 @@ __device__ __forceinline__ void clearTile(const SrpdState& st, const SrpdFrame& 
  * Register budget: both launch-bound arguments are given explicitly (under device LTO a
  * missing minimum makes the linker's code generator cap the kernel at 64 registers and
  * spill).  Triangles and points fit two 512-thread CTAs per SM; the line walker does not. */
-template <int KIND, bool BATCH>
+template <int KIND, bool BATCH, bool SIMPLE>
 __global__ void __launch_bounds__(SRPD_TILE_THREADS, KIND == SRPD_KIND_LINE ? SRPD_TILE_CTAS_PER_SM / 2 : SRPD_TILE_CTAS_PER_SM)
 srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 {
@@ -751,7 +789,7 @@ srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 			const uint32_t tileIndex = (uint32_t) tileY * a.tilesX + (uint32_t) tileX;
 			const bool occupied = (occ[tileIndex >> 5] >> (tileIndex & 31u)) & 1u;
 			if (occupied)
-				processTile<KIND>(a, fr, frame, tileX, tileY, sm, cnt);
+				processTile<KIND, SIMPLE>(a, fr, frame, tileX, tileY, sm, cnt);
 			else if (fr.clearPending)
 				clearTile(a.d.st, fr, tileX, tileY);
 			if (++tileX == (int) a.tilesX)
@@ -805,25 +843,34 @@ void srpdLaunchClear(uint32_t* color, float* depth, size_t nPixels, cudaStream_t
 	srpdClearKernel<<<grid, 256, 0, stream>>>((uint4*) color, (uint4*) depth, nVec, color + nVec * 4, depth + nVec * 4, nTail);
 }
 
-template <int KIND, bool BATCH>
-static void launchTileKernelB(const SrpdTileArgs& a, unsigned grid, cudaStream_t stream)
+template <int KIND, bool BATCH, bool SIMPLE>
+static void launchTileKernelS(const SrpdTileArgs& a, unsigned grid, cudaStream_t stream)
 {
 	static bool configured = false;
 	const int bytes = (int) sizeof(TileSharedK<KIND>);
 	if (!configured)
 	{
-		cudaFuncSetAttribute(srpdTileKernel<KIND, BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+		cudaFuncSetAttribute(srpdTileKernel<KIND, BATCH, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 		configured = true;
 	}
-	srpdTileKernel<KIND, BATCH><<<grid, SRPD_TILE_THREADS, bytes, stream>>>(a);
+	srpdTileKernel<KIND, BATCH, SIMPLE><<<grid, SRPD_TILE_THREADS, bytes, stream>>>(a);
 }
 template <int KIND>
 static void launchTileKernel(const SrpdTileArgs& a, unsigned grid, cudaStream_t stream)
 {
-	if (a.frames)
-		launchTileKernelB<KIND, true>(a, grid, stream);
-	else
-		launchTileKernelB<KIND, false>(a, grid, stream);
+	const SrpdState& st = a.d.st;
+	const bool simple = KIND == SRPD_KIND_TRIANGLE && !st.scissorEnabled && !st.stencilEnabled && st.earlyDepth && st.allFloat;
+	if constexpr (KIND == SRPD_KIND_TRIANGLE)
+	{
+		if (simple)
+		{
+			if (a.frames) launchTileKernelS<KIND, true, true>(a, grid, stream);
+			else          launchTileKernelS<KIND, false, true>(a, grid, stream);
+			return;
+		}
+	}
+	if (a.frames) launchTileKernelS<KIND, true, false>(a, grid, stream);
+	else          launchTileKernelS<KIND, false, false>(a, grid, stream);
 }
 
 void srpdLaunchTiles(const SrpdTileArgs& a0, cudaStream_t stream)

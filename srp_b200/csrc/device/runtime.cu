@@ -422,7 +422,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	while (superShift > 1)
 	{
 		const uint64_t sx = (tilesX + (1u << superShift) - 1) >> superShift, sy = (tilesY + (1u << superShift) - 1) >> superShift;
-		if (expected / (sx * sy) <= 1536)
+		if (expected / (sx * sy) <= 2048)
 			break;
 		const uint64_t nx = (tilesX + (1u << (superShift - 1)) - 1) >> (superShift - 1);
 		const uint64_t ny = (tilesY + (1u << (superShift - 1)) - 1) >> (superShift - 1);

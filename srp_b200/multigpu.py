@@ -49,6 +49,33 @@ def gather_strips(strip: torch.Tensor, height: int, tile_h: int, dst: int = 0, g
     return torch.cat([p[: b - a] for p, (a, b) in zip(parts, rows)], 0)
 
 
+def gather_strips_inplace(planes, height: int, tile_h: int, dst: int = 0, group=None):
+    """In-place form of the gather: `planes` = full-frame [height, W] tensors (e.g. zero-copy
+    views of the framebuffer's device planes) of which this rank has rendered rows
+    [row0, row1).  Every other rank sends its rows of every plane straight into the same rows
+    of `dst`'s planes -- one batch of point-to-point transfers (ncclSend/ncclRecv over NVLink,
+    or gloo on CPU), no staging copies, no padding.  Returns the list of in-flight requests'
+    completion having been waited for; on `dst` the planes then hold the whole frame."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1:
+        return planes
+    rows = [strip_rows(height, tile_h, world, r) for r in range(world)]
+    ops = []
+    if rank == dst:
+        for r, (a, b) in enumerate(rows):
+            if r != dst and b > a:
+                ops += [dist.P2POp(dist.irecv, p[a:b], r, group) for p in planes]
+    else:
+        a, b = rows[rank]
+        if b > a:
+            ops += [dist.P2POp(dist.isend, p[a:b], dst, group) for p in planes]
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return planes
+
+
 def device_plane_tensor(lib, fb, which: int) -> torch.Tensor:
     """zero-copy torch view of a framebuffer's device plane (0 colour, 1 depth bits, 2 stencil)"""
     ptr = lib.dll.srpB200FramebufferDevicePlane(fb.ptr, which)

@@ -39,11 +39,19 @@ def _worker(rank, world, port, height, width, out):
         r0, r1 = M.strip_rows(height, 16, world, rank)
         mine = full[r0:r1].clone()                       # what this rank "rendered"
         got = M.gather_strips(mine, height, 16, dst=0)
+        # in-place form: every rank holds full-size planes of which only its own rows are valid
+        planes = []
+        for k in range(3):
+            pl = torch.full((height, width), -7, dtype=torch.int32)
+            pl[r0:r1] = full[r0:r1] + k
+            planes.append(pl)
+        M.gather_strips_inplace(planes, height, 16, dst=0)
+        inplace_ok = rank != 0 or all(bool(torch.equal(pl, full + k)) for k, pl in enumerate(planes))
         # frame-parallel bookkeeping: every rank reports which frames it owns
         frames = torch.zeros(37, dtype=torch.int32)
         frames[list(M.frame_partition(37, world, rank))] = 1
         dist.all_reduce(frames)
-        ok = bool((frames == 1).all())
+        ok = bool((frames == 1).all()) and inplace_ok
         if rank == 0:
             ok = ok and got is not None and bool(torch.equal(got, full))
         else:

@@ -49,8 +49,8 @@ def main():
 
     def step():
         prep.draw_all()
-        with torch.cuda.stream(stream):
-            return [M.gather_strips(p[r0:r1], scene.height, th, dst=0) for p in planes]
+        with torch.cuda.stream(stream):          # ordered after the draw on the library's stream
+            return M.gather_strips_inplace(planes, scene.height, th, dst=0)
 
     for _ in range(3):
         out = step()
@@ -61,6 +61,12 @@ def main():
         out = step()
     torch.cuda.synchronize(); dist.barrier()
     ms = (time.perf_counter() - t0) / K * 1e3
+    # one more frame from wiped planes, so that stale rows of the earlier full render cannot pass the check
+    with torch.cuda.stream(stream):
+        for p in planes:
+            p.zero_()
+    out = step()
+    torch.cuda.synchronize(); dist.barrier()
     if rank == 0:
         got = [o.cpu().numpy() for o in out]
         ok = all(np.array_equal(g.view(np.uint32) if g.dtype != np.uint8 else g, f) for g, f in zip(got, full))

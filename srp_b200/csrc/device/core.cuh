@@ -509,6 +509,18 @@ SRP_HD bool srpdCompare(uint8_t op, float a, float b)
 	}
 	return false;
 }
+/* The same comparison without a switch per fragment: the operator becomes a 4-bit set of
+ * accepted relations {a < b, a == b, a > b, unordered} (NOTEQUAL accepts unordered: `a != b`
+ * is true for NaN; an unknown operator accepts nothing, like the reference's default). */
+SRP_HD uint32_t srpdCompareMask(uint8_t op)
+{
+	return op < 8 ? (0xD26431F0u >> (4 * op)) & 0xFu : 0u;
+}
+SRP_HD bool srpdComparePass(uint32_t mask, float a, float b)
+{
+	const uint32_t rel = (a < b) ? 1u : ((a == b) ? 2u : ((a > b) ? 4u : 8u));
+	return (mask & rel) != 0u;
+}
 SRP_HD bool srpdCompareU8(uint8_t op, uint8_t a, uint8_t b)
 {
 	switch (op)
@@ -548,9 +560,15 @@ SRP_HD uint8_t srpdStencilWrite(uint8_t current, uint8_t val, uint8_t writeMask)
 SRP_HD uint32_t srpdPackChannel(float c)
 {
 	float v = SRP_FMUL(c, 255.0f);
-	/* v < 0 -> 0, v > 255 -> 255, else truncate; NaN is UB in the reference (unpinned): 0 here
-	 * (fmaxf returns its non-NaN argument) */
-	return (uint32_t) (int) fminf(fmaxf(v, 0.0f), 255.0f);
+	/* v < 0 -> 0, v > 255 -> 255, else truncate; NaN is UB in the reference (unpinned): 0 here */
+#ifdef __CUDA_ARCH__
+	/* a float -> u8 conversion does exactly that: truncation, clamped to [0, 255], NaN -> 0 */
+	uint32_t r;
+	asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+	return r;
+#else
+	return (uint32_t) (int) fminf(fmaxf(v, 0.0f), 255.0f);   /* fmaxf returns its non-NaN argument */
+#endif
 }
 SRP_HD uint32_t srpdColorPack(const float c[4])
 {

@@ -40,6 +40,37 @@ struct Pixel
 
 struct FragCounters { uint32_t emitted, shaded; };
 
+/* float varyings of one fragment, two per step; PAIRS > 0: compile-time trip count */
+template <int NV, int PAIRS>
+__device__ __forceinline__ void interpolateFloatPairs(
+	const SrpdState& st, const float2* b, int slotPairs, int pairs, const float* wgt, float rec, float2* out)
+{
+	uint32_t modes = st.floatModes;
+	const int n = PAIRS > 0 ? PAIRS : pairs;
+	#pragma unroll
+	for (int e = 0; e < n; e++, modes >>= 4)
+	{
+		float2 in[NV];
+		#pragma unroll
+		for (int i = 0; i < NV; i++)
+			in[i] = __ldg(b + i * slotPairs + e);
+		float vx = 0.f, vy = 0.f;
+		#pragma unroll
+		for (int i = 0; i < NV; i++)
+		{
+			vx = __fadd_rn(vx, __fmul_rn(in[i].x, wgt[i]));
+			vy = __fadd_rn(vy, __fmul_rn(in[i].y, wgt[i]));
+		}
+		const uint32_t mx = modes & 3u, my = (modes >> 2) & 3u;
+		if (mx == SRP_INTERPOLATION_MODE_PERSPECTIVE) vx = __fmul_rn(vx, rec);
+		if (my == SRP_INTERPOLATION_MODE_PERSPECTIVE) vy = __fmul_rn(vy, rec);
+		const float2 pv = st.provokingFirst ? in[0] : in[NV - 1];
+		if (mx == SRP_INTERPOLATION_MODE_FLAT) vx = pv.x;
+		if (my == SRP_INTERPOLATION_MODE_FLAT) vy = pv.y;
+		out[e] = make_float2(vx, vy);
+	}
+}
+
 /* emitFragment, reference src/raster/fragment.c:63-125.  `sx, sy` are the (unwrapped)
  * integer fragment coordinates the scissor test sees; interpolation of the varyings is
  * deferred until the early tests have passed (it is pure). */
@@ -73,7 +104,7 @@ __device__ __forceinline__ void emitFragment(
 			return;
 		}
 	}
-	if (earlyDepth && st.depthTest && !srpdCompare(st.depthOp, depth, storedDepth))
+	if (earlyDepth && st.depthTest && !srpdComparePass(srpdCompareMask(st.depthOp), depth, storedDepth))
 	{
 		if (stencilEnabled)
 		{
@@ -95,30 +126,18 @@ __device__ __forceinline__ void emitFragment(
 	{
 		/* all attributes are floats: the blob is an array of st.nFloats floats, two bits of
 		 * interpolation mode each; same operation order as srpdInterpolate (interpolation.c:63-83).
-		 * Blobs are 8-byte aligned and slotSize is a multiple of 8: two floats per load. */
-		const int slotPairs = st.slotSize / 8;
+		 * Blobs are 8-byte aligned and slotSize is a multiple of 8: two floats per load; the
+		 * usual sizes are unrolled so that the mode bits are decoded once per draw, not per fragment. */
 		const float2* b = (const float2*) blobs;
-		uint32_t modes = st.floatModes;
-		for (int e = 0; e < st.nFloats; e += 2, modes >>= 4)
+		float2* o = (float2*) interpolated;
+		const int pairs = (st.nFloats + 1) >> 1, slotPairs = st.slotSize / 8;
+		switch (pairs)
 		{
-			float2 in[NV];
-			#pragma unroll
-			for (int i = 0; i < NV; i++)
-				in[i] = __ldg(b + i * slotPairs + (e >> 1));
-			float vx = 0.f, vy = 0.f;
-			#pragma unroll
-			for (int i = 0; i < NV; i++)
-			{
-				vx = __fadd_rn(vx, __fmul_rn(in[i].x, wgt[i]));
-				vy = __fadd_rn(vy, __fmul_rn(in[i].y, wgt[i]));
-			}
-			const uint32_t mx = modes & 3u, my = (modes >> 2) & 3u;
-			if (mx == SRP_INTERPOLATION_MODE_PERSPECTIVE) vx = __fmul_rn(vx, rec);
-			if (my == SRP_INTERPOLATION_MODE_PERSPECTIVE) vy = __fmul_rn(vy, rec);
-			const float2 pv = st.provokingFirst ? in[0] : in[NV - 1];
-			if (mx == SRP_INTERPOLATION_MODE_FLAT) vx = pv.x;
-			if (my == SRP_INTERPOLATION_MODE_FLAT) vy = pv.y;
-			((float2*) interpolated)[e >> 1] = make_float2(vx, vy);
+			case 1:  interpolateFloatPairs<NV, 1>(st, b, slotPairs, 1, wgt, rec, o); break;
+			case 2:  interpolateFloatPairs<NV, 2>(st, b, slotPairs, 2, wgt, rec, o); break;
+			case 3:  interpolateFloatPairs<NV, 3>(st, b, slotPairs, 3, wgt, rec, o); break;
+			case 4:  interpolateFloatPairs<NV, 4>(st, b, slotPairs, 4, wgt, rec, o); break;
+			default: interpolateFloatPairs<NV, 0>(st, b, slotPairs, pairs, wgt, rec, o); break;
 		}
 	}
 	else
@@ -145,7 +164,7 @@ __device__ __forceinline__ void emitFragment(
 	{
 		if (!isnan(out.fragDepth))
 			depth = out.fragDepth;
-		if (st.depthTest && !srpdCompare(st.depthOp, depth, storedDepth))
+		if (st.depthTest && !srpdComparePass(srpdCompareMask(st.depthOp), depth, storedDepth))
 		{
 			if (stencilEnabled)
 			{
@@ -356,7 +375,8 @@ __device__ __forceinline__ void shadeTriangleFragment(
 	const float recW = __fdiv_rn(1.0f, iwSum);
 	const float depth = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(q3.x), l0), __fmul_rn(__uint_as_float(q3.y), l1)),
 	                              __fmul_rn(__uint_as_float(q3.z), l2));
-	emitFragment<3, SIMPLE>(a.d.st, fr, px, cnt, x, y, (float) ((double) x + 0.5), (float) ((double) y + 0.5),
+	/* pixel centre: (float) ((double) x + 0.5) is exact, and so is the float sum for these magnitudes */
+	emitFragment<3, SIMPLE>(a.d.st, fr, px, cnt, x, y, __fadd_rn((float) x, 0.5f), __fadd_rn((float) y, 0.5f),
 	                depth, recW, recW, (flags & 8u) != 0, q3.w, rec + SRPD_REC_HEADER_BYTES, wgt);
 }
 

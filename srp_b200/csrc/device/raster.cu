@@ -7,25 +7,27 @@
  *   pipeline/interpolation.c:34-163, core/color.c:14-23 (colorPack)
  * and srpFramebufferClear (core/framebuffer.c:57-62), which is fused in here.
  *
- * Ownership model: every thread owns ONE pixel of the tile for the whole draw and keeps
- * its colour / depth / stencil in registers; the tile's primitives are visited in
- * primitive-id order, so the reference's "later primitive wins" semantics (no blending,
- * depth EQUAL/ALWAYS, stencil counters) hold with no atomics.  A warp owns an 8x4 pixel
- * block.  Work distribution:
+ * Ownership model: every thread owns TWO pixels of the tile (same column, rows ly and ly + 4
+ * of its warp's 8x8 block) for the whole draw and keeps their colour / depth / stencil in
+ * registers; the tile's primitives are visited in primitive-id order, so the reference's
+ * "later primitive wins" semantics (no blending, depth EQUAL/ALWAYS, stencil counters) hold
+ * with no atomics.  Work distribution (CTA = 8 warps = one 32x16 tile):
  *   - the CTA scans its candidate list (all records of the frame, or the coarse bin of
- *     its supertile) 512 records at a time and compacts the ones whose bounding box
- *     touches the tile into shared memory with a ballot + warp-scan (order preserved);
- *   - each warp walks that list 32 entries per step, ballots "touches my 8x4 block" and
- *     visits only those, in order.
- * Exact arithmetic: a pixel's barycentrics are NOT evaluated in closed form; the thread
- * replays the reference's incremental chain -- (y - minY) float additions of dlambda/dy
- * from the value at the bounding-box corner, then (x - minX) additions of dlambda/dx
- * (triangle.c:102-109) -- which is what makes depth bit-exact.
- * Lines replay the DDA chain of line.c:56-76 the same way.
+ *     its supertile) one record per thread at a time and compacts the ones whose bounding
+ *     box touches the tile into shared memory with a ballot + warp reductions (order kept);
+ *   - each warp walks that list 32 entries per step and keeps those touching its block;
+ *   - triangles: "row lanes" -- one lane per (triangle, block row) -- walk the barycentric
+ *     chain to their row and decide the coverage of its 8 pixels; the pixel threads then
+ *     gather the bits of their own pixels and shade their covering triangles in order.
+ * Exact arithmetic: a pixel's barycentrics are NOT evaluated in closed form; the reference's
+ * incremental chain is replayed -- (y - minY) float additions of dlambda/dy from the value at
+ * the bounding-box corner, then (x - minX) additions of dlambda/dx (triangle.c:102-109) --
+ * which is what makes depth bit-exact.  Lines replay the DDA chain of
+ * line.c:56-76 the same way.
  *
- * Framebuffer traffic per tile: at most one read and one write of 9 B/px; with a
- * pending clear no read at all.  Stores go through shared memory and leave as 16-byte
- * vectors, one 128-byte row segment per 8 threads. */
+ * Framebuffer traffic per tile: at most one read and one write of 9 B/px; with a pending
+ * clear no read at all.  Stores leave straight from the registers, every warp store as four
+ * full 32-byte sectors (the eight lanes of a block row hold eight neighbouring pixels). */
 #include "kernels.cuh"
 
 namespace {
@@ -539,31 +541,6 @@ __device__ __forceinline__ void visitPoint(
 	}
 }
 
-/* Tile plane -> framebuffer: threads cooperatively emit 16-byte stores from the staged
- * tile (row-major TILE_W x TILE_H elements of T in shared memory). */
-template <typename T>
-__device__ __forceinline__ void storePlane(const T* staged, T* plane, int W, int H, int tx0, int ty0, int tid)
-{
-	constexpr int PER_VEC = 16 / (int) sizeof(T);
-	constexpr int VECS_PER_ROW = SRPD_TILE_W / PER_VEC;
-	constexpr int NVEC = VECS_PER_ROW * SRPD_TILE_H;
-	const bool vectorOk = (W % PER_VEC) == 0 && ((uintptr_t) plane % 16) == 0;
-	for (int v = tid; v < NVEC; v += SRPD_TILE_THREADS)
-	{
-		const int row = v / VECS_PER_ROW, cv = v % VECS_PER_ROW;
-		const int gy = ty0 + row, gx = tx0 + cv * PER_VEC;
-		if (gy >= H || gx >= W)
-			continue;
-		T* dst = plane + (size_t) gy * W + gx;
-		const T* src = staged + row * SRPD_TILE_W + cv * PER_VEC;
-		if (vectorOk && gx + PER_VEC <= W)
-			*(uint4*) dst = *(const uint4*) src;
-		else
-			for (int e = 0; e < PER_VEC && gx + e < W; e++)
-				dst[e] = src[e];
-	}
-}
-
 } // namespace
 
 /* shared memory of the tile kernel (dynamic: with the per-warp step scratch it exceeds 48 KB) */
@@ -571,10 +548,7 @@ struct TileShared
 {
 	uint32_t ids[SRPD_TILE_THREADS];     /* record slots of the tile's list chunk */
 	uint2    box[SRPD_TILE_THREADS];     /* their boxes */
-	alignas(16) uint32_t color[SRPD_TILE_W * SRPD_TILE_H];    /* write-back staging of the three planes */
-	alignas(16) float    depth[SRPD_TILE_W * SRPD_TILE_H];
-	alignas(16) uint8_t  stencil[SRPD_TILE_W * SRPD_TILE_H];
-	uint32_t warpCnt[64];               /* [0, warps): filter counters; [warps, 2 warps): dirty flags */
+	uint32_t warpCnt[32];
 	uint32_t item[2];
 };
 template <int KIND> struct TileSharedK : TileShared {};
@@ -705,30 +679,24 @@ __device__ __forceinline__ void processTile(
 		}
 	}
 
-	/* write-back: stage the tile in shared memory, leave as 16-byte vectors */
-	uint32_t dirty = 0u;
+	/* write-back, straight from the registers: the eight lanes of a block row hold eight
+	 * neighbouring pixels, so every store instruction of the warp leaves as four full 32-byte
+	 * sectors (one per row); no staging in shared memory and no barrier -- a warp that is done
+	 * with its block moves on to the next tile's list.  With a pending clear every pixel is
+	 * written (untouched ones with the clear values), otherwise only what a fragment changed. */
 	#pragma unroll
 	for (int k = 0; k < SRPD_PX; k++)
 	{
-		dirty |= px[k].dirty;
-		const int local = (y0 + 4 * k - ty0) * SRPD_TILE_W + (x - tx0);
-		sm.color[local] = px[k].color;
-		sm.depth[local] = px[k].depth;
-		sm.stencil[local] = (uint8_t) px[k].stencil;
+		if (!valid[k])
+			continue;
+		const size_t pixelIndex = (size_t) (y0 + 4 * k) * st.width + x;
+		if (fr.clearPending || (px[k].dirty & 1u))
+			fr.color[pixelIndex] = px[k].color;
+		if (fr.clearPending || (px[k].dirty & 2u))
+			fr.depth[pixelIndex] = px[k].depth;
+		if (px[k].dirty & 4u)
+			fr.stencil[pixelIndex] = (uint8_t) px[k].stencil;
 	}
-	const uint32_t warpDirty = __reduce_or_sync(0xFFFFFFFFu, dirty);
-	if (lane == 0)
-		sm.warpCnt[SRPD_TILE_WARPS + warp] = warpDirty;      /* upper half: not the filter's counters */
-	__syncthreads();
-	const uint32_t tileDirty = __reduce_or_sync(0xFFFFFFFFu, lane < SRPD_TILE_WARPS ? sm.warpCnt[SRPD_TILE_WARPS + lane] : 0u)
-	                           | (fr.clearPending ? 3u : 0u);
-	if (tileDirty & 1u)
-		storePlane<uint32_t>(sm.color, fr.color, st.width, st.height, tx0, ty0, tid);
-	if (tileDirty & 2u)
-		storePlane<float>(sm.depth, fr.depth, st.width, st.height, tx0, ty0, tid);
-	if (tileDirty & 4u)
-		storePlane<uint8_t>(sm.stencil, fr.stencil, st.width, st.height, tx0, ty0, tid);
-	__syncthreads();      /* the staging planes and the dirty words are rewritten by the next tile */
 }
 
 /* A tile no primitive touches while a clear is pending: just write the clear values

@@ -49,6 +49,16 @@ void srpB200SetMirrorPlanes(int planeMask);
 void srpB200Finish(void);                                   /* wait for all enqueued work */
 void srpB200FramebufferDownload(const SRPFramebuffer* fb);  /* device planes -> host mirror (synchronous) */
 void srpB200FramebufferUpload(const SRPFramebuffer* fb);    /* host mirror -> device planes */
+/* Pipelined frames under SRP_B200_SYNC_EXPLICIT (the per-draw wait of the
+ * reference's synchronous srpDraw*Buffer contract, examples/03_textured_cube.c:133-160, is what
+ * bounds a frame loop once rendering takes microseconds).  DownloadAsync enqueues the
+ * device->host copy of the planes selected by srpB200SetMirrorPlanes behind the draws issued
+ * so far and returns; Wait blocks until that framebuffer's mirror is complete.  A program that
+ * alternates between two framebuffers renders frame i+1 (uploads included) while frame i
+ * crosses PCIe; a draw into a framebuffer whose download is still in flight is ordered
+ * behind it, so results never tear. */
+void srpB200FramebufferDownloadAsync(const SRPFramebuffer* fb);
+void srpB200FramebufferWait(const SRPFramebuffer* fb);
 
 /* ---- device-resident objects -------------------------------------------------------
  * Framebuffer on caller-owned device memory (e.g. planes of a torch tensor that NCCL

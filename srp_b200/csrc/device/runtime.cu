@@ -34,6 +34,7 @@ struct Runtime
 	cudaStream_t copyStream = nullptr;     /* band-wise downloads overlapping the tile kernel */
 	cudaEvent_t bandEvents[SRPD_MAX_BANDS] = {};
 	cudaEvent_t copyDone = nullptr;
+	cudaEvent_t submitted = nullptr;       /* async downloads: "everything enqueued so far" on the submission stream */
 	SrpcuMirror mirror = { nullptr, nullptr, nullptr };
 	int* mirrorDone = nullptr;
 	bool copyPending = false;
@@ -170,6 +171,7 @@ int srpcuInit(void)
 	for (int i = 0; i < SRPD_MAX_BANDS; i++)
 		CU(cudaEventCreateWithFlags(&g.bandEvents[i], cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&g.copyDone, cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&g.submitted, cudaEventDisableTiming));
 	CU(cudaMalloc(&g.stats, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
 	CU(cudaMemset(g.stats, 0, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
 	CU(cudaMallocHost(&g.statsHost, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
@@ -249,6 +251,56 @@ void srpcuSetMirrorForNextDraw(const SrpcuMirror* mirror, int* done)
 	g.mirror = mirror ? *mirror : SrpcuMirror{ nullptr, nullptr, nullptr };
 	g.mirrorDone = done;
 	if (done) *done = 0;
+}
+
+void* srpcuNewEvent(void)
+{
+	if (srpcuInit()) return nullptr;
+	cudaEvent_t e = nullptr;
+	cudaError_t err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+	if (err != cudaSuccess) { fail("cudaEventCreate", err); return nullptr; }
+	return (void*) e;
+}
+void srpcuFreeEvent(void* event)
+{
+	if (event && g.ready) cudaEventDestroy((cudaEvent_t) event);
+}
+int srpcuDownloadPlanesAsync(const SrpcuMirror* host, const void* dColor, const void* dDepth, const void* dStencil,
+                             size_t nPixels, void* doneEvent)
+{
+	if (srpcuInit()) return 1;
+	CU(cudaEventRecord(g.submitted, g.stream));
+	CU(cudaStreamWaitEvent(g.copyStream, g.submitted, 0));
+	if (host->color)
+	{
+		CU(cudaMemcpyAsync(host->color, dColor, nPixels * 4, cudaMemcpyDeviceToHost, g.copyStream));
+		g.d2h += nPixels * 4;
+	}
+	if (host->depth)
+	{
+		CU(cudaMemcpyAsync(host->depth, dDepth, nPixels * 4, cudaMemcpyDeviceToHost, g.copyStream));
+		g.d2h += nPixels * 4;
+	}
+	if (host->stencil)
+	{
+		CU(cudaMemcpyAsync(host->stencil, dStencil, nPixels, cudaMemcpyDeviceToHost, g.copyStream));
+		g.d2h += nPixels;
+	}
+	CU(cudaEventRecord((cudaEvent_t) doneEvent, g.copyStream));
+	g.copyPending = true;
+	return 0;
+}
+int srpcuHostWaitEvent(void* event)
+{
+	if (!g.ready || !event) return 0;
+	CU(cudaEventSynchronize((cudaEvent_t) event));
+	return 0;
+}
+int srpcuStreamWaitEvent(void* event)
+{
+	if (!g.ready || !event) return 0;
+	CU(cudaStreamWaitEvent(g.stream, (cudaEvent_t) event, 0));
+	return 0;
 }
 
 int srpcuSynchronize(void)

@@ -51,6 +51,19 @@ typedef struct SrpcuMirror
 } SrpcuMirror;
 void srpcuSetMirrorForNextDraw(const SrpcuMirror* mirror, int* done);
 
+/* Asynchronous download (explicit synchronisation policy): the planes named in `host` are
+ * copied to the pinned host mirror on the copy stream once everything enqueued so far on the
+ * submission stream has finished; `doneEvent` (srpcuNewEvent) is recorded behind the copies.
+ * The submission stream is NOT held up: later draws into OTHER framebuffers overlap with the
+ * copies.  Before anything overwrites the source planes the caller makes the submission
+ * stream wait for the event (srpcuStreamWaitEvent); the host waits with srpcuHostWaitEvent. */
+void* srpcuNewEvent(void);
+void srpcuFreeEvent(void* event);
+int srpcuDownloadPlanesAsync(const SrpcuMirror* host, const void* dColor, const void* dDepth, const void* dStencil,
+                             size_t nPixels, void* doneEvent);
+int srpcuHostWaitEvent(void* event);
+int srpcuStreamWaitEvent(void* event);
+
 /* 1 if a scratch pool overflowed since the previous call (the affected draw left the
  * framebuffer untouched); the pools' minimum sizes have then been raised to what that draw
  * needed, so the host simply repeats it. */

@@ -286,6 +286,7 @@ static void submit(
 			ok = false;
 			break;
 		}
+		srpFramebufferBeforeWrite(impls[f]);
 		if (clearFirst)
 			srpFramebufferClear(fbs[f]);
 	}

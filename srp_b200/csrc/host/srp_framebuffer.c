@@ -81,6 +81,11 @@ void srpFreeFramebuffer(SRPFramebuffer* pub)
 {
 	SRPFramebufferImpl* fb = srpFramebufferImpl(pub);
 	if (!fb) return;
+	if (fb->downloadEvent)
+	{
+		srpcuHostWaitEvent(fb->downloadEvent);
+		srpcuFreeEvent(fb->downloadEvent);
+	}
 	if (fb->ownsDevicePlanes)
 	{
 		srpcuFree(fb->dColor);
@@ -114,6 +119,7 @@ static void materializeClear(SRPFramebufferImpl* fb)
 {
 	if (!fb->clearPending)
 		return;
+	srpFramebufferBeforeWrite(fb);
 	if (srpcuClearPlanes(fb->dColor, fb->dDepth, fb->pub.size))
 		srpFatalMessage("srpFramebufferClear", "%s", srpcuLastError());
 	fb->clearPending = false;
@@ -147,10 +153,59 @@ void srpB200FramebufferDownload(const SRPFramebuffer* pub)
 		srpFatalMessage(__func__, "%s", srpcuLastError());
 }
 
+/* Asynchronous counterpart of srpB200FramebufferDownload for the explicit policy: the planes
+ * selected by srpB200SetMirrorPlanes are copied on the copy stream as soon as the draws
+ * enqueued so far have finished, and the call returns at once.  Draws into OTHER framebuffers
+ * issued afterwards overlap with the copies (a program keeps two framebuffers and alternates);
+ * a draw into THIS framebuffer is ordered behind them.  srpB200FramebufferWait() blocks until
+ * the mirror is complete. */
+void srpB200FramebufferDownloadAsync(const SRPFramebuffer* pub)
+{
+	SRPFramebufferImpl* fb = srpFramebufferImpl(pub);
+	if (!fb) return;
+	if (!fb->downloadEvent)
+		fb->downloadEvent = srpcuNewEvent();
+	if (!fb->downloadEvent)
+	{
+		srpFatalMessage(__func__, "%s", srpcuLastError());
+		return;
+	}
+	materializeClear(fb);
+	const int planes = gMirrorPlanes;
+	const SrpcuMirror m = { (planes & SRP_B200_MIRROR_COLOR) ? fb->pub.color : NULL,
+	                        (planes & SRP_B200_MIRROR_DEPTH) ? fb->pub.depth : NULL,
+	                        ((planes & SRP_B200_MIRROR_STENCIL) && fb->stencilTouched) ? fb->pub.stencil : NULL };
+	if (srpcuDownloadPlanesAsync(&m, fb->dColor, fb->dDepth, fb->dStencil, fb->pub.size, fb->downloadEvent))
+	{
+		srpFatalMessage(__func__, "%s", srpcuLastError());
+		return;
+	}
+	if (planes & SRP_B200_MIRROR_STENCIL)
+		fb->stencilTouched = false;
+	fb->mirrorStale = planes != SRP_B200_MIRROR_ALL;
+	fb->downloadInFlight = true;
+}
+
+void srpB200FramebufferWait(const SRPFramebuffer* pub)
+{
+	SRPFramebufferImpl* fb = srpFramebufferImpl(pub);
+	if (!fb || !fb->downloadInFlight) return;
+	if (srpcuHostWaitEvent(fb->downloadEvent))
+		srpFatalMessage(__func__, "%s", srpcuLastError());
+	fb->downloadInFlight = false;
+}
+
+void srpFramebufferBeforeWrite(SRPFramebufferImpl* fb)
+{
+	if (fb->downloadInFlight && srpcuStreamWaitEvent(fb->downloadEvent))
+		srpFatalMessage("srpDraw", "%s", srpcuLastError());
+}
+
 void srpB200FramebufferUpload(const SRPFramebuffer* pub)
 {
 	SRPFramebufferImpl* fb = srpFramebufferImpl(pub);
 	if (!fb) return;
+	srpFramebufferBeforeWrite(fb);
 	const size_t n = fb->pub.size;
 	fb->clearPending = false;
 	int err = srpcuUpload(fb->dColor, fb->pub.color, n * sizeof(uint32_t));

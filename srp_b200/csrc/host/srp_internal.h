@@ -42,6 +42,8 @@ typedef struct SRPFramebufferImpl
 	bool clearPending;          /* srpFramebufferClear deferred into the next draw */
 	bool mirrorStale;           /* device planes changed since the last download   */
 	bool stencilTouched;        /* a stencil-enabled draw ran since the last download */
+	bool downloadInFlight;      /* srpB200FramebufferDownloadAsync not yet waited for */
+	void* downloadEvent;        /* recorded behind the asynchronous download's copies */
 } SRPFramebufferImpl;
 #define SRP_FB_MAGIC 0x53524246u   /* "SRBF" */
 
@@ -72,6 +74,9 @@ const SRPProgramEntry* srpLookupProgram(SRPVertexShaderFunc vs, SRPFragmentShade
 
 /* framebuffer helpers (srp_framebuffer.c) */
 SRPFramebufferImpl* srpFramebufferImpl(const SRPFramebuffer* fb);
+/* before anything on the submission stream overwrites the device planes: order it behind an
+ * asynchronous download that may still be reading them */
+void srpFramebufferBeforeWrite(SRPFramebufferImpl* fb);
 void srpFramebufferAfterDraw(SRPFramebufferImpl* const* fbs, size_t n, bool stencilEnabled, bool alreadyMirrored);
 
 int srpMirrorPlanes(void);

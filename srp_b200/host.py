@@ -214,6 +214,8 @@ class SrpLibrary:
             "srpB200SetMirrorPlanes": (None, [i32]),
             "srpB200FramebufferDownload": (None, [C.POINTER(SRPFramebuffer)]),
             "srpB200FramebufferUpload": (None, [C.POINTER(SRPFramebuffer)]),
+            "srpB200FramebufferDownloadAsync": (None, [C.POINTER(SRPFramebuffer)]),
+            "srpB200FramebufferWait": (None, [C.POINTER(SRPFramebuffer)]),
             "srpB200NewFramebufferOnDevice": (C.POINTER(SRPFramebuffer), [sz, sz, vp, vp, vp]),
             "srpB200FramebufferDevicePlane": (vp, [C.POINTER(SRPFramebuffer), i32]),
             "srpB200DrawBatch": (None, [vp, vp, C.POINTER(C.POINTER(SRPFramebuffer)), sz,

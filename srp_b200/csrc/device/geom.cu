@@ -237,8 +237,14 @@ __device__ __forceinline__ void writeTriangle(Emitter& em, const SrpdState& st, 
 		}
 		unsigned char* blobs = beginRecord<WRITE>(em, s.w, s.minX, s.minY, s.maxX, s.maxY);
 		if (WRITE && blobs)
-			for (int i = 0; i < 3; i++)
-				storeBlob(st, vary[s.order[i]], s.invW[i], true, blobs + i * st.slotSize);
+		{
+			/* the winding normalisation either keeps the order or swaps v1 and v2: selects, not a
+			 * run-time index (which would force `vary` -- and the caller's copy -- into local memory) */
+			const bool swapped = s.order[1] != 1;
+			storeBlob(st, vary[0], s.invW[0], true, blobs);
+			storeBlob(st, swapped ? vary[2] : vary[1], s.invW[1], true, blobs + st.slotSize);
+			storeBlob(st, swapped ? vary[1] : vary[2], s.invW[2], true, blobs + 2 * st.slotSize);
+		}
 		em.nStore++;
 	}
 	em.nEmit++;
@@ -490,6 +496,7 @@ struct GeomWarpShared
  * independent of each other (no CTA barrier anywhere), so a warp that sits in a long-latency
  * step -- vertex fetch, the rare clipping path, the bump-allocator atomic -- never holds up the
  * other seven: the SM always has warps in different stages to issue from. */
+template <bool BATCH>
 __global__ void __launch_bounds__(SRPD_GEOM_THREADS, SRPD_GEOM_CTAS_PER_SM)
 srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 {
@@ -531,7 +538,8 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 		ws.hashKey[lane + 32 * i] = SRPD_HASH_EMPTY;
 	const uint32_t frame = batch / a.batchesPerFrame;
 	const uint32_t b = batch - frame * a.batchesPerFrame;
-	const void* uniform = a.frames ? a.frames[frame].uniform : a.frame0.uniform;
+	/* single draw: the uniform block sits in the argument block (constant bank) */
+	const void* uniform = BATCH ? a.frames[frame].uniform : (const void*) a.uniformInline;
 
 	const uint32_t k = b * SRPD_GEOM_PRIMS + lane;
 	const bool active = lane < SRPD_GEOM_PRIMS && k < d.nInputPrims;
@@ -624,10 +632,20 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	em.frame = frame;
 	FastTriangle fast;
 	fast.valid = false; fast.stored = false;
-	if (active)
+	/* outcodes once, here: a primitive entirely outside one clip plane is rejected on the spot
+	 * (clipping.c:75-76,146-147 -- the usual fate of most of a mesh that surrounds the camera)
+	 * and only primitives that really cross a plane take the out-of-line path */
+	uint32_t codeOr = 0u, codeAnd = 0u;
+	if (nv >= 2)
 	{
-		if (nv == 3 && st.polygonMode == SRP_POLYGON_MODE_FILL
-		    && (srpdClipCode(p[0]) | srpdClipCode(p[1]) | srpdClipCode(p[2])) == 0)
+		const uint32_t c0 = srpdClipCode(p[0]), c1 = srpdClipCode(p[1]);
+		const uint32_t c2 = nv == 3 ? srpdClipCode(p[2]) : c1;
+		codeOr = c0 | c1 | c2;
+		codeAnd = c0 & c1 & c2;
+	}
+	if (active && codeAnd == 0u)
+	{
+		if (nv == 3 && st.polygonMode == SRP_POLYGON_MODE_FILL && codeOr == 0u)
 		{
 			/* unclipped filled triangle: set up once, remember the result for the write phase */
 			fast.valid = true;
@@ -639,8 +657,11 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 		}
 		else
 		{
-			Emitter slow = em;      /* its address escapes into the out-of-line path; `em` stays in registers */
-			processPrimitive<false>(slow, d, nv, p, vary);
+			/* copies whose addresses escape into the out-of-line path; `em`, `p` and `vary` stay in registers */
+			Emitter slow = em;
+			const SrpdPos sp[3] = { p[0], p[1], p[2] };
+			const unsigned char* const sv[3] = { vary[0], vary[1], vary[2] };
+			processPrimitive<false>(slow, d, nv, sp, sv);
 			em.nEmit = slow.nEmit; em.nStore = slow.nStore;
 		}
 	}
@@ -678,7 +699,9 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 		else
 		{
 			Emitter slow = em;
-			processPrimitive<true>(slow, d, nv, p, vary);
+			const SrpdPos sp[3] = { p[0], p[1], p[2] };
+			const unsigned char* const sv[3] = { vary[0], vary[1], vary[2] };
+			processPrimitive<true>(slow, d, nv, sp, sv);
 			em.overflow = slow.overflow;
 		}
 		if (em.overflow)
@@ -792,7 +815,8 @@ void srpdLaunchGeom(const SrpdGeomArgs& a, cudaStream_t stream)
 	static bool configured = false;
 	if (!configured)
 	{
-		cudaFuncSetAttribute(srpdGeomKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+		cudaFuncSetAttribute(srpdGeomKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+		cudaFuncSetAttribute(srpdGeomKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 		configured = true;
 	}
 	const unsigned batches = a.batchesPerFrame * a.d.nFrames;
@@ -800,7 +824,8 @@ void srpdLaunchGeom(const SrpdGeomArgs& a, cudaStream_t stream)
 #if SRPD_GEOM_PERSISTENT
 	if (grid > (unsigned) a.smCount * SRPD_GEOM_CTAS_PER_SM) grid = (unsigned) a.smCount * SRPD_GEOM_CTAS_PER_SM;
 #endif
-	srpdGeomKernel<<<grid, SRPD_GEOM_THREADS, smemBytes, stream>>>(a);
+	if (a.frames) srpdGeomKernel<true><<<grid, SRPD_GEOM_THREADS, smemBytes, stream>>>(a);
+	else          srpdGeomKernel<false><<<grid, SRPD_GEOM_THREADS, smemBytes, stream>>>(a);
 	srpdBatchScanKernel<<<a.d.nFrames * a.chunksPerFrame, SRPD_SCAN_CHUNK / 4, 0, stream>>>(a);
 	srpdRecordOrderKernel<<<(batches + 7) / 8, 256, 0, stream>>>(a);
 	gGeomLaunches += 3;

@@ -69,6 +69,12 @@ constexpr int SRPD_HASH_SHIFT = 25;
 constexpr uint32_t SRPD_HASH_EMPTY = 0xFFFFFFFFu;
 constexpr int SRPD_CLIP_MAX_VERTS = 10;  /* a triangle against 6 planes has <= 9 vertices  */
 
+/* A single-frame draw carries its uniform block inside the kernel argument block (constant
+ * bank): the shaders' uniform reads -- matrices, light parameters, texture pointers, the same
+ * for every thread -- then are constant-bank operands instead of generic loads.  Larger
+ * uniforms, NULL uniforms and batches go through the per-frame device bindings. */
+constexpr int SRPD_INLINE_UNIFORM_BYTES = 1024;
+
 constexpr int SRPD_STATS_SLOTS = 1024;   /* SrpdStats[slots]: counters are spread to avoid same-address atomics */
 
 constexpr int SRPD_BIN_THREADS = 256;
@@ -85,7 +91,8 @@ struct SrpdGeomArgs
 {
 	SrpdDraw d;
 	SrpdFrame frame0;                 /* used when frames == nullptr (single draw)       */
-	const SrpdFrame* frames;          /* device array [nFrames]                          */
+	const SrpdFrame* frames;          /* device array [nFrames]; nullptr: frame0 + uniformInline */
+	alignas(16) unsigned char uniformInline[SRPD_INLINE_UNIFORM_BYTES];
 	unsigned char* records;           /* [nFrames][recCapacity] records of recStride B   */
 	uint2* bboxes;                    /* [nFrames][recCapacity] x0|y0<<16, x1|y1<<16 (half-open, pixels) */
 	uint32_t recCapacity;
@@ -152,7 +159,8 @@ struct SrpdTileArgs
 {
 	SrpdDraw d;
 	SrpdFrame frame0;
-	const SrpdFrame* frames;
+	const SrpdFrame* frames;          /* nullptr: frame0 + uniformInline                 */
+	alignas(16) unsigned char uniformInline[SRPD_INLINE_UNIFORM_BYTES];
 	const unsigned char* records;
 	const uint2* bboxes;              /* in primitive order */
 	const uint32_t* perm;             /* position in primitive order -> record slot */

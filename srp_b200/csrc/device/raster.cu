@@ -765,7 +765,12 @@ srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 		SrpdFrame frCopy;
 		if (BATCH)
 			frCopy = a.frames[frame];
-		const SrpdFrame& fr = BATCH ? frCopy : a.frame0;
+		else
+		{
+			frCopy = a.frame0;
+			frCopy.uniform = a.uniformInline;      /* constant bank (kernels.cuh) */
+		}
+		const SrpdFrame& fr = frCopy;
 		const uint32_t* occ = a.occupancy + (size_t) frame * a.occWordsPerFrame;
 		/* first / tilesX by multiplication: tilesXInv = floor(2^40 / tilesX) + 1 is exact while
 		 * first * tilesX < 2^40 (tiles per frame < 2^23, tilesX <= 2^11) */

@@ -335,10 +335,13 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	if (nFrames == 0 || d.nInputPrims == 0)
 		return 0;
 
-	/* uniforms: one 256-byte aligned block per frame */
+	/* A single frame whose uniform fits travels inside the kernel argument blocks (constant
+	 * bank, kernels.cuh); everything else -- batches, large or NULL uniforms -- binds per-frame
+	 * device copies: one 256-byte aligned block per frame */
+	const bool inlineUniform = nFrames == 1 && uniforms && uniformBytes > 0 && uniformBytes <= (size_t) SRPD_INLINE_UNIFORM_BYTES;
 	const size_t ublock = (uniformBytes + 255) & ~(size_t) 255;
 	unsigned char* uniDev = nullptr;
-	if (uniforms && uniformBytes)
+	if (uniforms && uniformBytes && !inlineUniform)
 	{
 		if (!grow(g.uniforms, ublock * nFrames)) return 1;
 		uniDev = (unsigned char*) g.uniforms.ptr;
@@ -353,7 +356,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	SrpdFrame frame0 = framesHost[0];
 	frame0.uniform = uniDev;
 	const SrpdFrame* framesDev = nullptr;
-	if (nFrames > 1)
+	if (!inlineUniform)
 	{
 		if (!grow(g.frames, sizeof(SrpdFrame) * nFrames)) return 1;
 		SrpdFrame* tmp = (SrpdFrame*) malloc(sizeof(SrpdFrame) * nFrames);
@@ -407,6 +410,8 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ga.d = d;
 	ga.frame0 = frame0;
 	ga.frames = framesDev;
+	if (inlineUniform)
+		memcpy(ga.uniformInline, uniforms, uniformBytes);
 	ga.records = (unsigned char*) g.records.ptr;
 	ga.bboxes = (uint2*) g.bboxes.ptr;
 	ga.recCapacity = recCapacity;
@@ -499,6 +504,8 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ta.d = d;
 	ta.frame0 = frame0;
 	ta.frames = framesDev;
+	if (inlineUniform)
+		memcpy(ta.uniformInline, uniforms, uniformBytes);
 	ta.records = ga.records;
 	ta.bboxes = ga.bboxesOrdered;
 	ta.perm = ga.perm;

@@ -316,89 +316,200 @@ __device__ void emitPolygonModeTriangle(Emitter& em, const SrpdState& st, const 
 }
 
 /* clipTriangle + expansion, reference clipping.c:68-119 and :199-258.
+ *
  * Sutherland-Hodgman over the six planes in the reference's order (L, R, B, T, N, F) with its
  * emission rule -- for every edge (current, next): both inside -> emit next; crossing -> emit
  * the intersection, and next too when entering -- so the polygon's first vertex rotates from
  * plane to plane exactly as in the reference (that decides the fan and the provoking vertex).
- * Vertices live in a small pool (the 3 originals stay in the shared-memory cache, only the
- * intersections get local storage) and the polygon is an index list, so a plane that cuts
- * nothing costs a rotation of <= 9 bytes instead of copying vertices. */
+ *
+ * Few triangles cross a clip plane (cfg3: 2 k of a million), but the warps that own them decide
+ * when the kernel ends, so the clipped path is built for LATENCY:
+ *   - batches with such triangles are not processed where they are found: the main pass only
+ *     notes them down, and a second launch of this kernel -- one warp per CTA, more registers,
+ *     a private scratch area -- takes them all at once, so they run side by side from time zero
+ *     instead of trailing behind the last ordinary batches (srpdLaunchGeom);
+ *   - every clipped triangle of the batch gets a scratch slot in shared memory (vertex pool +
+ *     polygon index lists; the 3 originals are copied from the post-VS cache, intersections
+ *     are appended);
+ *   - the owner lanes clip side by side, one lane per triangle, entirely in that scratch (no
+ *     indexed local memory), keeping the edge's first endpoint and distance in registers;
+ *   - the fan triangles (0, i, i+1) of ALL clipped triangles of the batch are then spread over
+ *     the lanes -- 32 setups per pass through the polygon mode, whatever mix of triangles they
+ *     came from -- and their id / record counts are left in the slots;
+ *   - the slots stay allocated across the batch's scan, so the write phase only hands every
+ *     fan triangle its id / record base and emits it: nothing is clipped twice. */
 constexpr int SRPD_CLIP_NEW_VERTS = 12;    /* at most two intersections per plane */
+constexpr int SRPD_CLIP_POOL = 3 + SRPD_CLIP_NEW_VERTS;
+constexpr int SRPD_CLIP_SLOTS = 32;        /* scratch slots of a clipper warp: one per lane, every triangle of a batch may need one */
+constexpr int SRPD_CLIP_MAX_FANS = SRPD_CLIP_MAX_VERTS - 2;
 
-template <bool WRITE>
-__device__ void processTriangle(Emitter& em, const SrpdState& st, const SrpdPos p[3], const unsigned char* const vary[3])
+struct ClipSlot
 {
-	const uint32_t c0 = srpdClipCode(p[0]), c1 = srpdClipCode(p[1]), c2 = srpdClipCode(p[2]);
-	if ((c0 | c1 | c2) == 0)
-	{
-		emitPolygonModeTriangle<WRITE>(em, st, p, vary);
-		return;
-	}
-	if ((c0 & c1 & c2) != 0)
-		return;
+	float4 pos[SRPD_CLIP_POOL];                 /* clip-space positions of the pool vertices           */
+	uint32_t idBase, storeBase;                 /* the owner's bases (write phase)                     */
+	uint16_t cnt[SRPD_CLIP_MAX_FANS][2];        /* per fan triangle: primitive ids, records            */
+	uint8_t list[2][12];                        /* polygon (pool indices), ping-pong                   */
+	uint8_t origSlot[3];                        /* post-VS cache slots of the 3 original vertices      */
+	uint8_t n;                                  /* vertices of the clipped polygon                     */
+	uint8_t cur, pad[3];                        /* which list holds it                                 */
+};                                              /* followed by SRPD_CLIP_NEW_VERTS varyings blobs       */
 
-	SrpdPos pos[3 + SRPD_CLIP_NEW_VERTS];
-	const unsigned char* vp[3 + SRPD_CLIP_NEW_VERTS];
-	alignas(8) unsigned char fresh[SRPD_CLIP_NEW_VERTS][SRPD_MAX_VARYING_BYTES];
-	uint8_t polyA[SRPD_CLIP_MAX_VERTS], polyB[SRPD_CLIP_MAX_VERTS];
-	for (int i = 0; i < 3; i++)
+__host__ __device__ inline size_t clipSlotStride(int slotSize)
+{
+	size_t b = (sizeof(ClipSlot) + (size_t) SRPD_CLIP_NEW_VERTS * slotSize + 15) & ~(size_t) 15;
+	if (b % 128 == 0) b += 16;                  /* keep the slots of neighbouring lanes on different banks */
+	return b;
+}
+
+__device__ __forceinline__ const unsigned char* clipVary(const ClipSlot& sl, const unsigned char* fresh, const unsigned char* vvary, int slotSize, int v)
+{
+	return v < 3 ? vvary + (size_t) sl.origSlot[v] * slotSize : fresh + (size_t) (v - 3) * slotSize;
+}
+
+struct ClipResult { uint32_t nEmit, nStore; bool overflow; };
+enum { SRPD_CLIP_COUNT = 1, SRPD_CLIP_WRITE = 2 };
+
+/* The clipped triangles of a batch, owned by the lanes of chunkMask (the r-th owner uses slot r).
+ * mode: COUNT = clip + count the fan triangles (returns, in the owner lanes, the ids / records
+ * their triangle produces); WRITE = emit them from idBase / storeBase of their owner, from the
+ * slots the COUNT call left behind.  Called by all 32 lanes. */
+__device__ __noinline__ ClipResult clipChunk(
+	Emitter em, const SrpdState& st, int mode, unsigned char* slots, uint32_t chunkMask,
+	const float4* vpos, const unsigned char* vvary, uint32_t slot0, uint32_t slot1, uint32_t slot2,
+	uint32_t idBase, uint32_t storeBase)
+{
+	ClipResult res;
+	res.nEmit = 0u; res.nStore = 0u; res.overflow = false;
+	const int lane = threadIdx.x & 31;
+	const bool mine = (chunkMask >> lane) & 1u;
+	const size_t stride = clipSlotStride(st.slotSize);
+	const uint32_t mySlot = mine ? (uint32_t) __popc(chunkMask & ((1u << lane) - 1u)) : 0u;
+	ClipSlot& sl = *reinterpret_cast<ClipSlot*>(slots + (size_t) mySlot * stride);
+	unsigned char* fresh = reinterpret_cast<unsigned char*>(&sl + 1);
+
+	if ((mode & SRPD_CLIP_COUNT) && mine)
 	{
-		pos[i] = p[i]; vp[i] = vary[i]; polyA[i] = (uint8_t) i;
-	}
-	uint8_t* src = polyA;
-	uint8_t* dst = polyB;
-	int n = 3, nPool = 3;
-	for (int plane = 0; plane < 6; plane++)
-	{
-		float dist[SRPD_CLIP_MAX_VERTS];
-		bool allInside = true;
-		for (int i = 0; i < n; i++)
+		sl.pos[0] = vpos[slot0]; sl.pos[1] = vpos[slot1]; sl.pos[2] = vpos[slot2];
+		sl.origSlot[0] = (uint8_t) slot0; sl.origSlot[1] = (uint8_t) slot1; sl.origSlot[2] = (uint8_t) slot2;
+		sl.list[0][0] = 0; sl.list[0][1] = 1; sl.list[0][2] = 2;
+		int n = 3, nPool = 3, cur = 0;
+		for (int plane = 0; plane < 6 && n > 0; plane++)
 		{
-			dist[i] = srpdPlaneDistance(pos[src[i]], plane);
-			allInside = allInside && dist[i] >= 0;
-		}
-		int o = 0;
-		if (allInside)
-			for (int i = 0; i < n; i++)          /* every edge emits `next`: a rotation by one */
-				dst[o++] = src[(i + 1) % n];
-		else
+			const uint8_t* src = sl.list[cur];
+			uint8_t* dst = sl.list[cur ^ 1];
+			int o = 0;
+			int vi = src[0];
+			float4 qa = sl.pos[vi];
+			SrpdPos pa; pa.x = qa.x; pa.y = qa.y; pa.z = qa.z; pa.w = qa.w;
+			float da = srpdPlaneDistance(pa, plane);
 			for (int i = 0; i < n; i++)
 			{
-				const int k = (i + 1) % n;
-				const float da = dist[i], db = dist[k];
+				const int vk = src[i + 1 == n ? 0 : i + 1];
+				const float4 qb = sl.pos[vk];
+				SrpdPos pb; pb.x = qb.x; pb.y = qb.y; pb.z = qb.z; pb.w = qb.w;
+				const float db = srpdPlaneDistance(pb, plane);
 				const bool ci = da >= 0, ni = db >= 0;
 				if (ci && ni)
 				{
-					if (o < SRPD_CLIP_MAX_VERTS) dst[o++] = src[k];
+					if (o < SRPD_CLIP_MAX_VERTS) dst[o++] = (uint8_t) vk;
 				}
 				else if (ci || ni)
 				{
 					const float diff = SRP_FSUB(da, db);
-					if (srpdRoughlyZero(diff))
-						continue;
-					const float t = SRP_FDIV(da, diff);
-					if (o < SRPD_CLIP_MAX_VERTS && nPool < 3 + SRPD_CLIP_NEW_VERTS)
+					if (!srpdRoughlyZero(diff))              /* clipping.c:226: otherwise the edge is skipped */
 					{
-						pos[nPool] = srpdBlendPos(pos[src[i]], pos[src[k]], t);
-						srpdBlendVaryings(st, vp[src[i]], vp[src[k]], SRP_FSUB(1.0f, t), t, fresh[nPool - 3]);
-						vp[nPool] = fresh[nPool - 3];
-						dst[o++] = (uint8_t) nPool++;
+						const float t = SRP_FDIV(da, diff);
+						if (o < SRPD_CLIP_MAX_VERTS && nPool < SRPD_CLIP_POOL)
+						{
+							const SrpdPos np = srpdBlendPos(pa, pb, t);
+							sl.pos[nPool] = make_float4(np.x, np.y, np.z, np.w);
+							srpdBlendVaryings(st, clipVary(sl, fresh, vvary, st.slotSize, vi), clipVary(sl, fresh, vvary, st.slotSize, vk),
+							                  SRP_FSUB(1.0f, t), t, fresh + (size_t) (nPool - 3) * st.slotSize);
+							dst[o++] = (uint8_t) nPool++;
+						}
+						if (!ci && ni)
+							if (o < SRPD_CLIP_MAX_VERTS) dst[o++] = (uint8_t) vk;
 					}
-					if (!ci && ni)
-						if (o < SRPD_CLIP_MAX_VERTS) dst[o++] = src[k];
 				}
+				pa = pb; da = db; vi = vk;
 			}
-		n = o;
-		if (n == 0)
-			return;
-		uint8_t* t = src; src = dst; dst = t;
+			n = o;
+			cur ^= 1;
+		}
+		sl.n = (uint8_t) n;
+		sl.cur = (uint8_t) cur;
 	}
-	for (int i = 1; i + 1 < n; i++)   /* fan (0, i, i+1) */
+	if ((mode & SRPD_CLIP_WRITE) && mine)
 	{
-		const SrpdPos tp[3] = { pos[src[0]], pos[src[i]], pos[src[i + 1]] };
-		const unsigned char* const tv[3] = { vp[src[0]], vp[src[i]], vp[src[i + 1]] };
-		emitPolygonModeTriangle<WRITE>(em, st, tp, tv);
+		sl.idBase = idBase; sl.storeBase = storeBase;
 	}
+	__syncwarp();
+
+	/* fan (0, i, i+1), clipping.c:103-118, of all the chunk's triangles, spread over the lanes */
+	const uint32_t fans = mine ? (uint32_t) (sl.n > 2 ? sl.n - 2 : 0) : 0u;
+	uint32_t inc = fans;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+		if (lane >= o) inc += v;
+	}
+	const uint32_t nFans = __shfl_sync(0xFFFFFFFFu, inc, 31);
+	const uint32_t fanBase = inc - fans;
+	for (int pass = 0; pass < 2; pass++)
+	{
+		const bool writing = pass == 1;
+		if (!(mode & (writing ? SRPD_CLIP_WRITE : SRPD_CLIP_COUNT)))
+			continue;
+		for (uint32_t f0 = 0; f0 < nFans; f0 += 32)
+		{
+			const uint32_t f = f0 + lane;
+			const bool valid = f < nFans;
+			/* whose fan triangle is f?  the last owner whose base is <= f */
+			uint32_t oSlot = 0u, oBase = 0u;
+			for (uint32_t m = chunkMask; m != 0u; m &= m - 1u)
+			{
+				const int L = __ffs(m) - 1;
+				const uint32_t b = __shfl_sync(0xFFFFFFFFu, fanBase, L), sidx = __shfl_sync(0xFFFFFFFFu, mySlot, L);
+				const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, fans, L);
+				if (cnt != 0u && f >= b) { oSlot = sidx; oBase = b; }
+			}
+			if (!valid)
+				continue;
+			ClipSlot& os = *reinterpret_cast<ClipSlot*>(slots + (size_t) oSlot * stride);
+			const unsigned char* ofresh = reinterpret_cast<const unsigned char*>(&os + 1);
+			const int i = (int) (f - oBase);
+			SrpdPos tp[3];
+			const unsigned char* tv[3];
+			#pragma unroll
+			for (int k = 0; k < 3; k++)
+			{
+				const int v = os.list[os.cur][k == 0 ? 0 : i + k];
+				const float4 q = os.pos[v];
+				tp[k].x = q.x; tp[k].y = q.y; tp[k].z = q.z; tp[k].w = q.w;
+				tv[k] = clipVary(os, ofresh, vvary, st.slotSize, v);
+			}
+			em.idBase = 0; em.storeBase = 0; em.nEmit = 0; em.nStore = 0; em.overflow = false;
+			if (!writing)
+			{
+				emitPolygonModeTriangle<false>(em, st, tp, tv);
+				os.cnt[i][0] = (uint16_t) em.nEmit; os.cnt[i][1] = (uint16_t) em.nStore;
+			}
+			else if (os.cnt[i][1] != 0)
+			{
+				uint32_t preE = 0u, preS = 0u;
+				for (int j = 0; j < i; j++) { preE += os.cnt[j][0]; preS += os.cnt[j][1]; }
+				em.idBase = os.idBase + preE;
+				em.storeBase = os.storeBase + preS;
+				emitPolygonModeTriangle<true>(em, st, tp, tv);
+				if (em.overflow) res.overflow = true;
+			}
+		}
+		__syncwarp();
+	}
+	if (mine)
+		for (uint32_t j = 0; j < fans; j++) { res.nEmit += sl.cnt[j][0]; res.nStore += sl.cnt[j][1]; }
+	return res;
 }
 
 /* clipLine (Liang-Barsky) + setup, reference clipping.c:139-183 */
@@ -454,7 +565,7 @@ __device__ void processLine(Emitter& em, const SrpdState& st, const SrpdPos p[2]
 	emitLine<WRITE>(em, st, cp, cvc);
 }
 
-/* Everything but the unclipped filled triangle goes through here.  Deliberately NOT inlined
+/* Lines, points and unclipped triangles in polygon modes LINE / POINT go through here.  Deliberately NOT inlined
  * (nor are the emit* helpers): inlined into the kernel at every call site the front-end grew to
  * 38 k instructions and, with the warps of an SM in different stages, stalled on instruction
  * fetch a third of the time; as functions the common path is a few thousand instructions. */
@@ -462,8 +573,8 @@ template <bool WRITE>
 __device__ __noinline__ void processPrimitive(Emitter& em, const SrpdDraw& d, int nv,
                                                  const SrpdPos p[3], const unsigned char* const vary[3])
 {
-	if (nv == 3)
-		processTriangle<WRITE>(em, d.st, p, vary);
+	if (nv == 3)      /* unclipped, polygon mode LINE / POINT (clipped triangles: clipChunk) */
+		emitPolygonModeTriangle<WRITE>(em, d.st, p, vary);
 	else if (nv == 2)
 		processLine<WRITE>(em, d.st, p, vary);
 	else if (!srpdClipPoint(p[0]))
@@ -492,46 +603,50 @@ struct GeomWarpShared
 	float4   vpos[SRPD_GEOM_MAX_VERTS];      /* clip-space positions (VS output)                      */
 };                                           /* followed by SRPD_GEOM_MAX_VERTS varyings blobs         */
 
+/* per warp: the cache and its varyings blobs; a clipper warp adds the clip slots behind them */
+__host__ __device__ inline size_t geomWarpBytes(int slotSize)
+{
+	return (sizeof(GeomWarpShared) + (size_t) SRPD_GEOM_MAX_VERTS * slotSize + 15) & ~(size_t) 15;
+}
+__host__ __device__ inline size_t geomCtaBytes(int slotSize, bool clipper)
+{
+	return clipper ? geomWarpBytes(slotSize) + (size_t) SRPD_CLIP_SLOTS * clipSlotStride(slotSize)
+	               : (size_t) SRPD_GEOM_WARPS * geomWarpBytes(slotSize);
+}
+
 /* One WARP = one batch of SRPD_GEOM_PRIMS consecutive input primitives; the warps of a CTA are
  * independent of each other (no CTA barrier anywhere), so a warp that sits in a long-latency
  * step -- vertex fetch, the rare clipping path, the bump-allocator atomic -- never holds up the
  * other seven: the SM always has warps in different stages to issue from. */
-template <bool BATCH>
-__global__ void __launch_bounds__(SRPD_GEOM_THREADS, SRPD_GEOM_CTAS_PER_SM)
+/* CLIPPER = false: the main pass of a large draw, SRPD_GEOM_WARPS batches per CTA; a batch that
+ * contains a triangle crossing a clip plane is appended to the deferred list and left alone.
+ * CLIPPER = true: one warp per CTA with the clipper's scratch and a larger register budget;
+ * it processes either the deferred list of the main pass or, for small draws (where a second
+ * launch would cost more than it saves), every batch. */
+template <bool BATCH, bool CLIPPER>
+__global__ void __launch_bounds__(CLIPPER ? 32 : SRPD_GEOM_THREADS, CLIPPER ? 16 : SRPD_GEOM_CTAS_PER_SM)
 srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
 	const SrpdDraw& d = a.d;
 	const SrpdState& st = d.st;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	constexpr int WARPS = CLIPPER ? 1 : SRPD_GEOM_WARPS;
 
-	const size_t warpBytes = sizeof(GeomWarpShared) + (size_t) SRPD_GEOM_MAX_VERTS * st.slotSize;
+	const size_t warpBytes = geomWarpBytes(st.slotSize);
 	GeomWarpShared& ws = *reinterpret_cast<GeomWarpShared*>(smem + warp * warpBytes);
 	unsigned char* vvary = reinterpret_cast<unsigned char*>(&ws + 1);
+	unsigned char* clipSlots = smem + warpBytes;      /* CLIPPER only */
 	const uint32_t nBatches = a.batchesPerFrame * d.nFrames;
 	const int nv = (d.topology >= SRPD_TOPO_TRIANGLES) ? 3 : (d.topology == SRPD_TOPO_POINTS ? 1 : 2);
 
-	/* persistent warps: each pulls runs of SRPD_GEOM_GRAB consecutive batches from a counter */
-	uint32_t next = 0u;
-#if SRPD_GEOM_PERSISTENT
-	if (lane == 0)
-		next = atomicAdd(a.batchCounter, (uint32_t) SRPD_GEOM_GRAB);
-#else
-	next = (blockIdx.x * SRPD_GEOM_WARPS + warp) * SRPD_GEOM_GRAB;
-#endif
-	for (;;)
+	/* one batch per warp; a clipper working off the deferred list strides through it */
+	const bool fromList = CLIPPER && a.deferred;
+	const uint64_t limit = fromList ? (uint64_t) min(*a.deferCount, nBatches) : (uint64_t) nBatches;
+	const uint64_t stride = fromList ? (uint64_t) gridDim.x : (1ull << 40);
+	for (uint64_t it = (uint64_t) blockIdx.x * WARPS + warp; it < limit; it += stride)
 	{
-	const uint32_t batch0 = __shfl_sync(0xFFFFFFFFu, next, 0);
-	if (batch0 >= nBatches)
-		break;
-#if SRPD_GEOM_PERSISTENT
-	if (lane == 0)      /* the next run is requested now and looked at after this one is done */
-		next = atomicAdd(a.batchCounter, (uint32_t) SRPD_GEOM_GRAB);
-#else
-	next = 0xFFFFFFFFu;
-#endif
-	for (uint32_t batch = batch0; batch < min(batch0 + SRPD_GEOM_GRAB, nBatches); batch++)
-	{
+	const uint32_t batch = fromList ? a.deferList[it] : (uint32_t) it;
 	__syncwarp();      /* the previous batch no longer reads the cache */
 	#pragma unroll
 	for (int i = 0; i < SRPD_HASH_SLOTS / 32; i++)
@@ -643,9 +758,18 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 		codeOr = c0 | c1 | c2;
 		codeAnd = c0 & c1 & c2;
 	}
-	if (active && codeAnd == 0u)
+	const bool needsClip = active && nv == 3 && codeAnd == 0u && codeOr != 0u;
+	const uint32_t clipMask = __ballot_sync(0xFFFFFFFFu, needsClip);
+	if (!CLIPPER && clipMask != 0u)
 	{
-		if (nv == 3 && st.polygonMode == SRP_POLYGON_MODE_FILL && codeOr == 0u)
+		/* a triangle of this batch crosses a clip plane: the whole batch goes to the clipper pass */
+		if (lane == 0)
+			a.deferList[atomicAdd(a.deferCount, 1u)] = batch;
+		continue;
+	}
+	if (active && codeAnd == 0u && !needsClip)
+	{
+		if (nv == 3 && st.polygonMode == SRP_POLYGON_MODE_FILL)
 		{
 			/* unclipped filled triangle: set up once, remember the result for the write phase */
 			fast.valid = true;
@@ -663,6 +787,16 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 			const unsigned char* const sv[3] = { vary[0], vary[1], vary[2] };
 			processPrimitive<false>(slow, d, nv, sp, sv);
 			em.nEmit = slow.nEmit; em.nStore = slow.nStore;
+		}
+	}
+	/* triangles that cross a clip plane (clipChunk): clipped and counted now, in slots that stay
+	 * as they are until the batch has written its records */
+	if (CLIPPER && clipMask != 0u)
+	{
+		const ClipResult r = clipChunk(em, st, SRPD_CLIP_COUNT, clipSlots, clipMask, ws.vpos, vvary, slot[0], slot[1], slot[2], 0u, 0u);
+		if (needsClip)
+		{
+			em.nEmit = r.nEmit; em.nStore = r.nStore;
 		}
 	}
 	const uint32_t myEmit = em.nEmit, myStore = em.nStore;
@@ -689,10 +823,19 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	physBase = __shfl_sync(0xFFFFFFFFu, physBase, 0);
 
 	/* 5. write, in id order (batch-local ids) */
-	if (active && myStore > 0)
+	em.idBase = incE - myEmit;
+	em.storeBase = physBase + incS - myStore;
+	if (CLIPPER && clipMask != 0u)
 	{
-		em.idBase = incE - myEmit;
-		em.storeBase = physBase + incS - myStore;
+		const bool ovf = clipChunk(em, st, SRPD_CLIP_WRITE, clipSlots, clipMask, ws.vpos, vvary, slot[0], slot[1], slot[2], em.idBase, em.storeBase).overflow;
+		if (ovf)
+		{
+			atomicAdd(&a.stats->overflow, 1ull);
+			atomicExch(a.abortFlag, 1u);
+		}
+	}
+	if (active && myStore > 0 && !needsClip)
+	{
 		em.nEmit = 0; em.nStore = 0;
 		if (fast.valid)
 			writeTriangle<true>(em, st, fast.s, fast.stored, vary);
@@ -711,7 +854,6 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 		}
 	}
 	}   /* batch */
-	}   /* grab */
 }
 
 /* Exclusive prefix sums of (ids, records) over the batches of a frame, in batch order: this is
@@ -809,24 +951,49 @@ srpdRecordOrderKernel(const __grid_constant__ SrpdGeomArgs a)
 static int gGeomLaunches = 0;
 int srpdGeomLaunchCount(void) { return gGeomLaunches; }
 
-void srpdLaunchGeom(const SrpdGeomArgs& a, cudaStream_t stream)
+template <bool BATCH, bool CLIPPER>
+static void launchGeomKernel(const SrpdGeomArgs& a, unsigned grid, cudaStream_t stream)
 {
-	const size_t smemBytes = (size_t) SRPD_GEOM_WARPS * (sizeof(GeomWarpShared) + (size_t) SRPD_GEOM_MAX_VERTS * a.d.st.slotSize);
 	static bool configured = false;
 	if (!configured)
 	{
-		cudaFuncSetAttribute(srpdGeomKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-		cudaFuncSetAttribute(srpdGeomKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+		cudaFuncSetAttribute(srpdGeomKernel<BATCH, CLIPPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 		configured = true;
 	}
+	srpdGeomKernel<BATCH, CLIPPER><<<grid, CLIPPER ? 32 : SRPD_GEOM_THREADS, geomCtaBytes(a.d.st.slotSize, CLIPPER), stream>>>(a);
+}
+
+/* Small draws: one launch, every batch by a clipper warp.  Large draws: the main pass, then the
+ * clipper pass over the batches the main pass deferred (their number is only known on the device:
+ * the grid is sized for the machine and strides through the list).  Returns the launches made. */
+int srpdLaunchGeom(const SrpdGeomArgs& a0, cudaStream_t stream)
+{
+	SrpdGeomArgs a = a0;
 	const unsigned batches = a.batchesPerFrame * a.d.nFrames;
-	unsigned grid = (batches + SRPD_GEOM_WARPS * SRPD_GEOM_GRAB - 1) / (SRPD_GEOM_WARPS * SRPD_GEOM_GRAB);
-#if SRPD_GEOM_PERSISTENT
-	if (grid > (unsigned) a.smCount * SRPD_GEOM_CTAS_PER_SM) grid = (unsigned) a.smCount * SRPD_GEOM_CTAS_PER_SM;
-#endif
-	if (a.frames) srpdGeomKernel<true><<<grid, SRPD_GEOM_THREADS, smemBytes, stream>>>(a);
-	else          srpdGeomKernel<false><<<grid, SRPD_GEOM_THREADS, smemBytes, stream>>>(a);
+	int launches = 0;
+	if (batches <= SRPD_GEOM_SMALL_DRAW_BATCHES)
+	{
+		a.deferred = 0;
+		if (a.frames) launchGeomKernel<true, true>(a, batches, stream);
+		else          launchGeomKernel<false, true>(a, batches, stream);
+		launches = 1;
+	}
+	else
+	{
+		a.deferred = 0;
+		const unsigned grid = (batches + SRPD_GEOM_WARPS - 1) / SRPD_GEOM_WARPS;
+		if (a.frames) launchGeomKernel<true, false>(a, grid, stream);
+		else          launchGeomKernel<false, false>(a, grid, stream);
+		a.deferred = 1;
+		unsigned clipGrid = a.smCount * 16u;
+		if (clipGrid > batches) clipGrid = batches;
+		if (a.frames) launchGeomKernel<true, true>(a, clipGrid, stream);
+		else          launchGeomKernel<false, true>(a, clipGrid, stream);
+		launches = 2;
+	}
 	srpdBatchScanKernel<<<a.d.nFrames * a.chunksPerFrame, SRPD_SCAN_CHUNK / 4, 0, stream>>>(a);
 	srpdRecordOrderKernel<<<(batches + 7) / 8, 256, 0, stream>>>(a);
-	gGeomLaunches += 3;
+	launches += 2;
+	gGeomLaunches += launches;
+	return launches;
 }

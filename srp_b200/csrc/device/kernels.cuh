@@ -51,17 +51,9 @@ constexpr int SRPD_GEOM_WARPS = SRPD_GEOM_WARPS_PER_CTA;
 #ifndef SRPD_GEOM_CTAS_PER_SM
 #define SRPD_GEOM_CTAS_PER_SM (32 / SRPD_GEOM_WARPS_PER_CTA)
 #endif
-/* 0: one batch per warp and small CTAs (the hardware refills a CTA slot as soon as its warps are
- * done); 1: persistent warps pulling batches from a counter -- measured slower on cfg3 (the
- * same-address counter atomics queue up behind the bump-allocator ones) */
-#ifndef SRPD_GEOM_PERSISTENT
-#define SRPD_GEOM_PERSISTENT 0
-#endif
 constexpr int SRPD_SCAN_CHUNK = 1024;    /* batches per CTA of the batch-order scan */
-#ifndef SRPD_GEOM_GRAB_BATCHES
-#define SRPD_GEOM_GRAB_BATCHES 1
-#endif
-constexpr int SRPD_GEOM_GRAB = SRPD_GEOM_GRAB_BATCHES;         /* consecutive batches a warp takes per visit to the work counter */
+/* draws of at most this many batches run as one launch of clipper warps (geom.cu) */
+constexpr unsigned SRPD_GEOM_SMALL_DRAW_BATCHES = 512;
 constexpr int SRPD_GEOM_THREADS = 32 * SRPD_GEOM_WARPS;
 constexpr int SRPD_GEOM_MAX_VERTS = 3 * 32;
 constexpr int SRPD_HASH_SLOTS = 128;     /* post-VS cache: open-addressing table in smem, load <= 3/4 */
@@ -82,7 +74,7 @@ constexpr int SRPD_BIN_CHUNK = 2048;     /* records per coarse-binning CTA      
 
 /* Per-draw zero-filled header in front of the scan state: word 0 batch ticket, 1 abort flag,
  * 2 tile work counter, 3 records a frame needed (max over frames), 4 coarse-list entries needed,
- * 5 checkpoint-table cursor (entries), 6 number of large triangles */
+ * 5 checkpoint-table cursor (entries), 6 number of large triangles, 7 deferred batches */
 constexpr int SRPD_DRAW_HEADER_BYTES = 64;   /* words 8..15: tile work counters of up to 8 bands */
 constexpr int SRPD_MAX_BANDS = 8;
 
@@ -100,7 +92,9 @@ struct SrpdGeomArgs
 	uint2* bboxesOrdered;             /* the same boxes at their position in primitive order */
 	uint32_t* perm;                   /* [nFrames][recCapacity] position in primitive order -> record slot */
 	uint32_t* frameBump;              /* [nFrames], zeroed per draw: record slots handed out */
-	uint32_t* batchCounter;           /* header word 0, zeroed per draw: next batch of the persistent geometry warps */
+	uint32_t* deferCount;             /* header word 7, zeroed per draw: batches the main pass left to the clipper pass */
+	uint32_t* deferList;              /* [nFrames * batchesPerFrame] their indices              */
+	uint32_t deferred;                /* set by srpdLaunchGeom: this launch works off the list  */
 	uint32_t smCount;
 	uint4* batchInfo;                 /* [nFrames * batchesPerFrame] {first slot, ids, records, -} */
 	uint2* batchPrefix;               /* [nFrames * batchesPerFrame] exclusive {ids, records} in batch order */
@@ -184,7 +178,7 @@ struct SrpdTileArgs
 };
 
 /* launchers (defined next to their kernels) */
-void srpdLaunchGeom(const SrpdGeomArgs& a, cudaStream_t stream);
+int srpdLaunchGeom(const SrpdGeomArgs& a, cudaStream_t stream);
 void srpdLaunchBin(const SrpdBinArgs& a, cudaStream_t stream);
 void srpdLaunchTiles(const SrpdTileArgs& a, cudaStream_t stream);
 void srpdLaunchClear(uint32_t* color, float* depth, size_t nPixels, cudaStream_t stream);

@@ -40,7 +40,7 @@ struct Runtime
 	bool copyPending = false;
 	std::string lastError;
 	Pool records, bboxes, scan, frameCounts, chunkCounts, superOffsets, superTotals, listIds, uniforms, frames;
-	Pool ckptTable, largeList, bboxesOrdered, perm, batchInfo, batchPrefix;
+	Pool ckptTable, largeList, bboxesOrdered, perm, batchInfo, batchPrefix, deferList;
 	int smCount = 148;
 	uint64_t recFloor = 0, listFloor = 0;  /* minimum pool capacities, raised by srpcuTakeOverflow() */
 	SrpdStats* stats = nullptr;            /* device, SRPD_STATS_SLOTS slots */
@@ -416,7 +416,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ga.bboxes = (uint2*) g.bboxes.ptr;
 	ga.recCapacity = recCapacity;
 	ga.recStride = recStride;
-	ga.batchCounter = (uint32_t*) g.scan.ptr + 0;
+	ga.deferCount = (uint32_t*) g.scan.ptr + 7;
 	ga.smCount = (uint32_t) g.smCount;
 	ga.abortFlag = (uint32_t*) g.scan.ptr + 1;
 	ga.needed = (uint32_t*) g.scan.ptr + 3;
@@ -425,6 +425,8 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	if (!grow(g.perm, (size_t) recCapacity * sizeof(uint32_t) * nFrames)) return 1;
 	if (!grow(g.batchInfo, sizeof(uint4) * (size_t) batchesPerFrame * nFrames)) return 1;
 	if (!grow(g.batchPrefix, sizeof(uint2) * (size_t) batchesPerFrame * nFrames)) return 1;
+	if (!grow(g.deferList, sizeof(uint32_t) * (size_t) batchesPerFrame * nFrames)) return 1;
+	ga.deferList = (uint32_t*) g.deferList.ptr;
 	ga.bboxesOrdered = (uint2*) g.bboxesOrdered.ptr;
 	ga.perm = (uint32_t*) g.perm.ptr;
 	ga.batchInfo = (uint4*) g.batchInfo.ptr;
@@ -453,8 +455,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ga.largeCapacity = ckptEntries ? largeCapacity : 0;
 	ga.ckptCapacity = (uint32_t) ckptEntries;
 	ga.stats = g.stats;
-	srpdLaunchGeom(ga, g.stream);
-	g.launches += 3;
+	g.launches += (unsigned long long) srpdLaunchGeom(ga, g.stream);
 	CU(cudaGetLastError());
 	if (ckptEntries)
 	{

@@ -18,10 +18,11 @@ extern "C" __device__ void srpB200DeviceFS(int programId, SRPFragmentShaderIn* i
 #ifndef SRPD_TILE_H_PX
 #define SRPD_TILE_H_PX (8 * SRPD_PX_PER_THREAD)
 #endif
-/* 256-thread CTAs, four per SM: measured better than two of 512 (fewer warps wait at each of
- * the tile's barriers) and than eight of 128 */
+/* 256-thread CTAs, five per SM (47 registers): measured on cfg3 against three (78 registers,
+ * -11 %), four (62, -4 %); the kernel is bound by instruction issue and every extra resident
+ * warp fills issue slots.  Six do not fit the per-warp step scratch in shared memory. */
 #ifndef SRPD_TILE_CTAS_PER_SM
-#define SRPD_TILE_CTAS_PER_SM 4
+#define SRPD_TILE_CTAS_PER_SM 5
 #endif
 constexpr int SRPD_TILE_W = 32;          /* pixels; one 128-byte colour row per tile row   */
 constexpr int SRPD_TILE_H = SRPD_TILE_H_PX;

@@ -76,10 +76,33 @@ __device__ __forceinline__ void interpolateFloatPairs(
 /* emitFragment, reference src/raster/fragment.c:63-125.  `sx, sy` are the (unwrapped)
  * integer fragment coordinates the scissor test sees; interpolation of the varyings is
  * deferred until the early tests have passed (it is pure). */
-/* SIMPLE (compile-time): no scissor, no stencil, the shader does not write depth and all
+/* SIMPLE (compile-time) = 1: no scissor, no stencil, the shader does not write depth and all
  * varyings are floats -- the state almost every draw has; the tests on the draw state then
  * disappear from the fragment stage instead of being evaluated per fragment. */
-template <int NV, bool SIMPLE>
+/* SIMPLE = 2: additionally every varying is PERSPECTIVE (what Gouraud colours and texture
+ * coordinates are): the two mode bits per float are not decoded per fragment at all. */
+template <int NV, int PAIRS>
+__device__ __forceinline__ void interpolatePerspectivePairs(const float2* b, int slotPairs, const float* wgt, float rec, float2* out)
+{
+	#pragma unroll
+	for (int e = 0; e < PAIRS; e++)
+	{
+		float2 in[NV];
+		#pragma unroll
+		for (int i = 0; i < NV; i++)
+			in[i] = __ldg(b + i * slotPairs + e);
+		float vx = 0.f, vy = 0.f;
+		#pragma unroll
+		for (int i = 0; i < NV; i++)
+		{
+			vx = __fadd_rn(vx, __fmul_rn(in[i].x, wgt[i]));
+			vy = __fadd_rn(vy, __fmul_rn(in[i].y, wgt[i]));
+		}
+		out[e] = make_float2(__fmul_rn(vx, rec), __fmul_rn(vy, rec));
+	}
+}
+
+template <int NV, int SIMPLE>
 __device__ __forceinline__ void emitFragment(
 	const SrpdState& st, const SrpdFrame& fr, Pixel& px, FragCounters& cnt,
 	int sx, int sy, float fragX, float fragY, float depth, float rec, float fragW,
@@ -133,14 +156,23 @@ __device__ __forceinline__ void emitFragment(
 		const float2* b = (const float2*) blobs;
 		float2* o = (float2*) interpolated;
 		const int pairs = (st.nFloats + 1) >> 1, slotPairs = st.slotSize / 8;
-		switch (pairs)
-		{
-			case 1:  interpolateFloatPairs<NV, 1>(st, b, slotPairs, 1, wgt, rec, o); break;
-			case 2:  interpolateFloatPairs<NV, 2>(st, b, slotPairs, 2, wgt, rec, o); break;
-			case 3:  interpolateFloatPairs<NV, 3>(st, b, slotPairs, 3, wgt, rec, o); break;
-			case 4:  interpolateFloatPairs<NV, 4>(st, b, slotPairs, 4, wgt, rec, o); break;
-			default: interpolateFloatPairs<NV, 0>(st, b, slotPairs, pairs, wgt, rec, o); break;
-		}
+		if (SIMPLE == 2)
+			switch (pairs)      /* 1..4 (launchTileKernel) */
+			{
+				case 1:  interpolatePerspectivePairs<NV, 1>(b, slotPairs, wgt, rec, o); break;
+				case 2:  interpolatePerspectivePairs<NV, 2>(b, slotPairs, wgt, rec, o); break;
+				case 3:  interpolatePerspectivePairs<NV, 3>(b, slotPairs, wgt, rec, o); break;
+				default: interpolatePerspectivePairs<NV, 4>(b, slotPairs, wgt, rec, o); break;
+			}
+		else
+			switch (pairs)
+			{
+				case 1:  interpolateFloatPairs<NV, 1>(st, b, slotPairs, 1, wgt, rec, o); break;
+				case 2:  interpolateFloatPairs<NV, 2>(st, b, slotPairs, 2, wgt, rec, o); break;
+				case 3:  interpolateFloatPairs<NV, 3>(st, b, slotPairs, 3, wgt, rec, o); break;
+				case 4:  interpolateFloatPairs<NV, 4>(st, b, slotPairs, 4, wgt, rec, o); break;
+				default: interpolateFloatPairs<NV, 0>(st, b, slotPairs, pairs, wgt, rec, o); break;
+			}
 	}
 	else
 	{
@@ -354,7 +386,7 @@ __device__ __forceinline__ uint32_t coverTriangleRow(
 
 /* fragment stage of one covered pixel of a triangle: the pixel's remaining x steps, depth /
  * 1/w interpolation (interpolateDepthAndWTriangle, interpolation.c:34-47) and emitFragment */
-template <bool SIMPLE>
+template <int SIMPLE>
 __device__ __forceinline__ void shadeTriangleFragment(
 	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, const RowStart& rs, const TriStep& ts,
 	Pixel& px, FragCounters& cnt, int x, int y)
@@ -386,7 +418,7 @@ __device__ __forceinline__ void shadeTriangleFragment(
  * warp's block.  The touching entries are compacted in order (t = 0 .. n-1); row lanes decide
  * coverage, 8 triangles x 4 rows per round; pixel threads gather the bits of their pixel --
  * bit t of `cov` <=> triangle t covers my pixel -- and shade them in order. */
-template <bool SIMPLE>
+template <int SIMPLE>
 __device__ __forceinline__ void visitTriangles(
 	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, bool mine, uint32_t recSlot, int rowLo, int rowCnt,
 	WarpStep& ws, Pixel (&px)[SRPD_PX], FragCounters& cnt, int x, int y0, int bx0, int by0, int lane)
@@ -501,7 +533,7 @@ __device__ __forceinline__ void visitLine(
 			const float recW = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(iw0, w0), __fmul_rn(iw1, t)));
 			const float depth = __fadd_rn(__fmul_rn(zw0, w0), __fmul_rn(zw1, t));
 			Pixel cur = getSel(px, which);
-			emitFragment<2, false>(a.d.st, fr, cur, cnt, ipx, ipy, (float) ((double) ipx + 0.5), (float) ((double) ipy + 0.5),
+			emitFragment<2, 0>(a.d.st, fr, cur, cnt, ipx, ipy, (float) ((double) ipx + 0.5), (float) ((double) ipy + 0.5),
 			                depth, recW, recW, true, q3.w, rec + SRPD_REC_HEADER_BYTES, wgt);
 			setSel(px, which, cur);
 		}
@@ -535,7 +567,7 @@ __device__ __forceinline__ void visitPoint(
 			continue;
 		const uint4 q2 = __ldg(h + 2), q3 = __ldg(h + 3);
 		Pixel cur = getSel(px, k);
-		emitFragment<1, false>(a.d.st, fr, cur, cnt, x, y, pcx, pcy, __uint_as_float(q2.x), 0.f, __uint_as_float(q2.y),
+		emitFragment<1, 0>(a.d.st, fr, cur, cnt, x, y, pcx, pcy, __uint_as_float(q2.x), 0.f, __uint_as_float(q2.y),
 		                true, q3.w, rec + SRPD_REC_HEADER_BYTES, nullptr);
 		setSel(px, k, cur);
 	}
@@ -555,7 +587,7 @@ template <int KIND> struct TileSharedK : TileShared {};
 template <> struct TileSharedK<SRPD_KIND_TRIANGLE> : TileShared { WarpStep step[SRPD_TILE_WARPS]; };
 
 /* One tile: filter the candidate list, visit the primitives in order, write the tile back. */
-template <int KIND, bool SIMPLE>
+template <int KIND, int SIMPLE>
 __device__ __forceinline__ void processTile(
 	const SrpdTileArgs& a, const SrpdFrame& fr, uint32_t frame, int tileX, int tileY, TileSharedK<KIND>& sm, FragCounters& cnt)
 {
@@ -725,7 +757,7 @@ __device__ __forceinline__ void clearTile(const SrpdState& st, const SrpdFrame& 
  * Register budget: both launch-bound arguments are given explicitly (under device LTO a
  * missing minimum makes the linker's code generator cap the kernel at 64 registers and
  * spill).  Triangles and points fit two 512-thread CTAs per SM; the line walker does not. */
-template <int KIND, bool BATCH, bool SIMPLE>
+template <int KIND, bool BATCH, int SIMPLE>
 __global__ void __launch_bounds__(SRPD_TILE_THREADS, KIND == SRPD_KIND_LINE ? SRPD_TILE_CTAS_PER_SM / 2 : SRPD_TILE_CTAS_PER_SM)
 srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 {
@@ -836,7 +868,7 @@ void srpdLaunchClear(uint32_t* color, float* depth, size_t nPixels, cudaStream_t
 	srpdClearKernel<<<grid, 256, 0, stream>>>((uint4*) color, (uint4*) depth, nVec, color + nVec * 4, depth + nVec * 4, nTail);
 }
 
-template <int KIND, bool BATCH, bool SIMPLE>
+template <int KIND, bool BATCH, int SIMPLE>
 static void launchTileKernelS(const SrpdTileArgs& a, unsigned grid, cudaStream_t stream)
 {
 	static bool configured = false;
@@ -857,13 +889,25 @@ static void launchTileKernel(const SrpdTileArgs& a, unsigned grid, cudaStream_t 
 	{
 		if (simple)
 		{
-			if (a.frames) launchTileKernelS<KIND, true, true>(a, grid, stream);
-			else          launchTileKernelS<KIND, false, true>(a, grid, stream);
+			/* all floats PERSPECTIVE (mode 0, two bits each) and at most four pairs of them */
+			const uint32_t used = st.nFloats >= 16 ? 0xFFFFFFFFu : ((1u << (2 * st.nFloats)) - 1u);
+			const bool perspective = st.nFloats >= 1 && st.nFloats <= 8 && (st.floatModes & used) == 0u
+				&& SRP_INTERPOLATION_MODE_PERSPECTIVE == 0;
+			if (perspective)
+			{
+				if (a.frames) launchTileKernelS<KIND, true, 2>(a, grid, stream);
+				else          launchTileKernelS<KIND, false, 2>(a, grid, stream);
+			}
+			else
+			{
+				if (a.frames) launchTileKernelS<KIND, true, 1>(a, grid, stream);
+				else          launchTileKernelS<KIND, false, 1>(a, grid, stream);
+			}
 			return;
 		}
 	}
-	if (a.frames) launchTileKernelS<KIND, true, false>(a, grid, stream);
-	else          launchTileKernelS<KIND, false, false>(a, grid, stream);
+	if (a.frames) launchTileKernelS<KIND, true, 0>(a, grid, stream);
+	else          launchTileKernelS<KIND, false, 0>(a, grid, stream);
 }
 
 void srpdLaunchTiles(const SrpdTileArgs& a0, cudaStream_t stream)

@@ -393,8 +393,11 @@ __device__ __noinline__ ClipResult clipChunk(
 		sl.origSlot[0] = (uint8_t) slot0; sl.origSlot[1] = (uint8_t) slot1; sl.origSlot[2] = (uint8_t) slot2;
 		sl.list[0][0] = 0; sl.list[0][1] = 1; sl.list[0][2] = 2;
 		int n = 3, nPool = 3, cur = 0;
-		for (int plane = 0; plane < 6 && n > 0; plane++)
+		#pragma unroll      /* the plane becomes a constant: its distance is one add, not a jump table */
+		for (int plane = 0; plane < 6; plane++)
 		{
+			if (n == 0)
+				break;
 			const uint8_t* src = sl.list[cur];
 			uint8_t* dst = sl.list[cur ^ 1];
 			int o = 0;

@@ -46,30 +46,37 @@ srpdBinCountKernel(const __grid_constant__ SrpdBinArgs a)
 	extern __shared__ uint32_t sCount[];
 	const uint32_t nSuper = a.superX * a.superY;
 	const uint32_t nStored = a.frameCounts[1];
-	for (uint32_t s = threadIdx.x; s < nSuper; s += SRPD_BIN_THREADS)
-		sCount[s] = 0;
-	__syncthreads();
-	const uint32_t first = blockIdx.x * SRPD_BIN_CHUNK;
-	for (uint32_t o = threadIdx.x; o < SRPD_BIN_CHUNK; o += SRPD_BIN_THREADS)
+	const uint32_t nChunks = (nStored + SRPD_BIN_CHUNK - 1) / SRPD_BIN_CHUNK;
+	/* the grid is sized for the machine, not for the record capacity: the CTAs stride over the
+	 * chunks that exist (nobody reads the counts of chunks past the end) */
+	for (uint32_t chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x)
 	{
-		const uint32_t r = first + o;
-		if (r >= nStored)
-			break;
-		const uint32_t rect = superRect(a.bboxes[r], a.superX, a.superY, a.superShift);
-		if (rectEmpty(rect))
-			continue;
-		for (uint32_t sy = (rect >> 8) & 0xFFu; sy <= (rect >> 24); sy++)
-			for (uint32_t sx = rect & 0xFFu; sx <= ((rect >> 16) & 0xFFu); sx++)
-				atomicAdd(&sCount[sy * a.superX + sx], 1u);
+		for (uint32_t s = threadIdx.x; s < nSuper; s += SRPD_BIN_THREADS)
+			sCount[s] = 0;
+		__syncthreads();
+		const uint32_t first = chunk * SRPD_BIN_CHUNK;
+		for (uint32_t o = threadIdx.x; o < SRPD_BIN_CHUNK; o += SRPD_BIN_THREADS)
+		{
+			const uint32_t r = first + o;
+			if (r >= nStored)
+				break;
+			const uint32_t rect = superRect(a.bboxes[r], a.superX, a.superY, a.superShift);
+			if (rectEmpty(rect))
+				continue;
+			for (uint32_t sy = (rect >> 8) & 0xFFu; sy <= (rect >> 24); sy++)
+				for (uint32_t sx = rect & 0xFFu; sx <= ((rect >> 16) & 0xFFu); sx++)
+					atomicAdd(&sCount[sy * a.superX + sx], 1u);
+		}
+		__syncthreads();
+		for (uint32_t s = threadIdx.x; s < nSuper; s += SRPD_BIN_THREADS)
+			a.chunkCounts[(size_t) chunk * nSuper + s] = sCount[s];
+		__syncthreads();
 	}
-	__syncthreads();
-	for (uint32_t s = threadIdx.x; s < nSuper; s += SRPD_BIN_THREADS)
-		a.chunkCounts[(size_t) blockIdx.x * nSuper + s] = sCount[s];
 }
 
 /* Scan pass 1: thread = supertile column; exclusive scan over the chunks (independent,
  * coalesced loads -- only the running sum is serial), total per supertile. */
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32)
 srpdBinScanColumnsKernel(const __grid_constant__ SrpdBinArgs a)
 {
 	const uint32_t nSuper = a.superX * a.superY;
@@ -80,6 +87,20 @@ srpdBinScanColumnsKernel(const __grid_constant__ SrpdBinArgs a)
 		return;
 	uint32_t run = 0;
 	uint32_t c = 0;
+	/* the running sum is the only serial part: keep many independent loads in flight */
+	for (; c + 32 <= nChunks; c += 32)
+	{
+		uint32_t n[32];
+		#pragma unroll
+		for (int u = 0; u < 32; u++)
+			n[u] = a.chunkCounts[(size_t) (c + u) * nSuper + s];
+		#pragma unroll
+		for (int u = 0; u < 32; u++)
+		{
+			a.chunkCounts[(size_t) (c + u) * nSuper + s] = run;
+			run += n[u];
+		}
+	}
 	for (; c + 8 <= nChunks; c += 8)
 	{
 		uint32_t n[8];
@@ -103,13 +124,15 @@ srpdBinScanColumnsKernel(const __grid_constant__ SrpdBinArgs a)
 	a.superTotals[s] = run;
 }
 
-/* Scan pass 2: one CTA, exclusive scan of the supertile totals -> superOffsets */
+/* Scan pass 2: one CTA, exclusive scan of the supertile totals -> superOffsets (warp-shuffle
+ * scans: lanes, then the 32 warp totals, one barrier pair per 1024 supertiles) */
 __global__ void __launch_bounds__(1024)
 srpdBinScanKernel(const __grid_constant__ SrpdBinArgs a)
 {
-	__shared__ uint32_t sTotals[1024];
+	__shared__ uint32_t sWarp[32];
 	__shared__ uint32_t sCarry;
 	const uint32_t nSuper = a.superX * a.superY;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	if (threadIdx.x == 0)
 		sCarry = 0;
 	__syncthreads();
@@ -117,24 +140,35 @@ srpdBinScanKernel(const __grid_constant__ SrpdBinArgs a)
 	{
 		const uint32_t s = s0 + threadIdx.x;
 		const uint32_t run = s < nSuper ? a.superTotals[s] : 0;
-		sTotals[threadIdx.x] = run;
-		__syncthreads();
 		uint32_t v = run;
-		for (uint32_t o = 1; o < 1024; o <<= 1)
+		#pragma unroll
+		for (uint32_t o = 1; o < 32; o <<= 1)
 		{
-			const uint32_t add = threadIdx.x >= o ? sTotals[threadIdx.x - o] : 0;
-			__syncthreads();
-			v += add;
-			sTotals[threadIdx.x] = v;
-			__syncthreads();
+			const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, v, o);
+			if (lane >= o) v += n;
 		}
+		if (lane == 31)
+			sWarp[warp] = v;
+		__syncthreads();
+		if (warp == 0)
+		{
+			uint32_t w = sWarp[lane];
+			#pragma unroll
+			for (uint32_t o = 1; o < 32; o <<= 1)
+			{
+				const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, w, o);
+				if (lane >= o) w += n;
+			}
+			sWarp[lane] = w;      /* inclusive over the warps */
+		}
+		__syncthreads();
 		const uint32_t carry = sCarry;
-		const uint32_t excl = carry + v - run;
+		const uint32_t excl = carry + (warp ? sWarp[warp - 1] : 0u) + v - run;
 		if (s < nSuper)
 			a.superOffsets[s] = excl < a.listCapacity ? excl : a.listCapacity;
 		__syncthreads();
-		if (threadIdx.x == 1023)
-			sCarry = carry + v;
+		if (threadIdx.x == 0)
+			sCarry = carry + sWarp[31];
 		__syncthreads();
 	}
 	if (threadIdx.x == 0)
@@ -170,12 +204,13 @@ srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 	extern __shared__ uint32_t sFill[];                   /* [FILL_WARPS][nSuper] cursors, then [FILL_WARPS][nSuper] lane masks */
 	const uint32_t nSuper = a.superX * a.superY;
 	const uint32_t nStored = a.frameCounts[1];
-	const uint32_t first = blockIdx.x * SRPD_BIN_CHUNK;
-	if (first >= nStored)
-		return;
+	const uint32_t nChunks = (nStored + SRPD_BIN_CHUNK - 1) / SRPD_BIN_CHUNK;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	uint32_t* sCnt = sFill + (size_t) warp * nSuper;
 	uint32_t* sMask = sFill + (size_t) (FILL_WARPS + warp) * nSuper;
+	for (uint32_t chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x)      /* grid sized for the machine */
+	{
+	const uint32_t first = chunk * SRPD_BIN_CHUNK;
 
 	for (uint32_t i = tid; i < 2 * FILL_WARPS * nSuper; i += FILL_WARPS * 32)
 		sFill[i] = 0;
@@ -197,7 +232,7 @@ srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 	__syncthreads();
 	for (uint32_t s = tid; s < nSuper; s += FILL_WARPS * 32)
 	{
-		uint32_t run = a.superOffsets[s] + a.chunkCounts[(size_t) blockIdx.x * nSuper + s];
+		uint32_t run = a.superOffsets[s] + a.chunkCounts[(size_t) chunk * nSuper + s];
 		for (int w = 0; w < FILL_WARPS; w++)
 		{
 			const uint32_t c = sFill[(size_t) w * nSuper + s];
@@ -248,6 +283,8 @@ srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 				}
 		__syncwarp();
 	}
+	__syncthreads();      /* the next chunk re-initialises the cursors */
+	}   /* chunk */
 }
 
 static int gBinLaunches = 0;
@@ -256,8 +293,11 @@ int srpdBinLaunchCount(void) { return gBinLaunches; }
 void srpdLaunchBin(const SrpdBinArgs& a, cudaStream_t stream)
 {
 	const uint32_t nSuper = a.superX * a.superY;
-	srpdBinCountKernel<<<a.nChunksMax, SRPD_BIN_THREADS, nSuper * sizeof(uint32_t), stream>>>(a);
-	srpdBinScanColumnsKernel<<<(nSuper + 127) / 128, 128, 0, stream>>>(a);
+	uint32_t grid = a.smCount * 3u;      /* the CTAs stride over the chunks that turn out to exist */
+	if (grid > a.nChunksMax) grid = a.nChunksMax;
+	if (grid == 0) grid = 1;
+	srpdBinCountKernel<<<grid, SRPD_BIN_THREADS, nSuper * sizeof(uint32_t), stream>>>(a);
+	srpdBinScanColumnsKernel<<<(nSuper + 31) / 32, 32, 0, stream>>>(a);      /* one warp per CTA: the columns spread over the SMs */
 	srpdBinScanKernel<<<1, 1024, 0, stream>>>(a);
 	/* as many warps per chunk as the cursor matrix allows in shared memory */
 	const size_t budget = 160 * 1024;
@@ -266,21 +306,21 @@ void srpdLaunchBin(const SrpdBinArgs& a, cudaStream_t stream)
 		const size_t bytes = 2 * 8 * (size_t) nSuper * sizeof(uint32_t);
 		static bool configured8 = false;
 		if (!configured8) { cudaFuncSetAttribute(srpdBinFillKernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget); configured8 = true; }
-		srpdBinFillKernel<8><<<a.nChunksMax, 8 * 32, bytes, stream>>>(a);
+		srpdBinFillKernel<8><<<grid, 8 * 32, bytes, stream>>>(a);
 	}
 	else if (2 * 4 * (size_t) nSuper * sizeof(uint32_t) <= budget)
 	{
 		const size_t bytes = 2 * 4 * (size_t) nSuper * sizeof(uint32_t);
 		static bool configured4 = false;
 		if (!configured4) { cudaFuncSetAttribute(srpdBinFillKernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget); configured4 = true; }
-		srpdBinFillKernel<4><<<a.nChunksMax, 4 * 32, bytes, stream>>>(a);
+		srpdBinFillKernel<4><<<grid, 4 * 32, bytes, stream>>>(a);
 	}
 	else
 	{
 		const size_t bytes = 2 * 2 * (size_t) nSuper * sizeof(uint32_t);
 		static bool configured2 = false;
 		if (!configured2) { cudaFuncSetAttribute(srpdBinFillKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget); configured2 = true; }
-		srpdBinFillKernel<2><<<a.nChunksMax, 2 * 32, bytes, stream>>>(a);
+		srpdBinFillKernel<2><<<grid, 2 * 32, bytes, stream>>>(a);
 	}
 	gBinLaunches += 4;
 }

@@ -137,7 +137,8 @@ struct SrpdBinArgs
 {
 	const uint2* bboxes;
 	const uint32_t* frameCounts;      /* [0][1] = number of stored records               */
-	uint32_t nChunksMax;              /* grid size of the chunk kernels                  */
+	uint32_t nChunksMax;              /* chunks at full record capacity                  */
+	uint32_t smCount;
 	uint32_t superX, superY;          /* supertile grid                                  */
 	uint32_t superShift;              /* supertile = (1 << superShift)^2 tiles           */
 	uint32_t* superTotals;            /* [nSuper] entries per supertile (scan pass 1 -> 2)*/

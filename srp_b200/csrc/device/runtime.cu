@@ -35,6 +35,8 @@ struct Runtime
 	cudaEvent_t bandEvents[SRPD_MAX_BANDS] = {};
 	cudaEvent_t copyDone = nullptr;
 	cudaEvent_t submitted = nullptr;       /* async downloads: "everything enqueued so far" on the submission stream */
+	cudaStream_t auxStream = nullptr;      /* work off the critical path of a draw (checkpoint pre-pass) */
+	cudaEvent_t geomDone = nullptr, ckptDone = nullptr;
 	SrpcuMirror mirror = { nullptr, nullptr, nullptr };
 	int* mirrorDone = nullptr;
 	bool copyPending = false;
@@ -172,6 +174,9 @@ int srpcuInit(void)
 		CU(cudaEventCreateWithFlags(&g.bandEvents[i], cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&g.copyDone, cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&g.submitted, cudaEventDisableTiming));
+	CU(cudaStreamCreateWithFlags(&g.auxStream, cudaStreamNonBlocking));
+	CU(cudaEventCreateWithFlags(&g.geomDone, cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&g.ckptDone, cudaEventDisableTiming));
 	CU(cudaMalloc(&g.stats, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
 	CU(cudaMemset(g.stats, 0, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
 	CU(cudaMallocHost(&g.statsHost, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
@@ -457,21 +462,6 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ga.stats = g.stats;
 	g.launches += (unsigned long long) srpdLaunchGeom(ga, g.stream);
 	CU(cudaGetLastError());
-	if (ckptEntries)
-	{
-		SrpdCkptArgs ca;
-		memset(&ca, 0, sizeof ca);
-		ca.records = ga.records;
-		ca.recCapacity = recCapacity;
-		ca.recStride = recStride;
-		ca.largeCount = ga.largeCount;
-		ca.largeList = ga.largeList;
-		ca.largeCapacity = largeCapacity;
-		ca.ckptTable = (float*) g.ckptTable.ptr;
-		srpdLaunchCheckpoints(ca, g.stream);
-		g.launches++;
-		CU(cudaGetLastError());
-	}
 	mark();
 
 	/* supertile size from the expected record density: aim at <= ~1.5 k candidates per tile */
@@ -499,6 +489,35 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		&& superX <= 256 && superY <= 256;
 	if (g.forceBinning == 0) binned = false;
 	if (g.forceBinning == 1 && nFrames == 1 && nSuper <= 8192 && superX <= 256 && superY <= 256) binned = true;
+
+	/* barycentric checkpoints of large triangles: needed by the tiles only, so with binning in
+	 * between the (usually empty) pre-pass runs beside the binning kernels on the auxiliary stream */
+	bool ckptAside = false;
+	if (ckptEntries)
+	{
+		SrpdCkptArgs ca;
+		memset(&ca, 0, sizeof ca);
+		ca.records = ga.records;
+		ca.recCapacity = recCapacity;
+		ca.recStride = recStride;
+		ca.largeCount = ga.largeCount;
+		ca.largeList = ga.largeList;
+		ca.largeCapacity = largeCapacity;
+		ca.ckptTable = (float*) g.ckptTable.ptr;
+		cudaStream_t where = g.stream;
+		if (binned)
+		{
+			CU(cudaEventRecord(g.geomDone, g.stream));
+			CU(cudaStreamWaitEvent(g.auxStream, g.geomDone, 0));
+			where = g.auxStream;
+			ckptAside = true;
+		}
+		srpdLaunchCheckpoints(ca, where);
+		g.launches++;
+		CU(cudaGetLastError());
+		if (ckptAside)
+			CU(cudaEventRecord(g.ckptDone, g.auxStream));
+	}
 
 	SrpdTileArgs ta;
 	memset(&ta, 0, sizeof ta);
@@ -534,6 +553,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		ba.bboxes = ga.bboxesOrdered;
 		ba.frameCounts = ga.frameCounts;
 		ba.nChunksMax = (recCapacity + SRPD_BIN_CHUNK - 1) / SRPD_BIN_CHUNK;
+		ba.smCount = (uint32_t) g.smCount;
 		ba.superX = superX;
 		ba.superY = superY;
 		ba.superShift = superShift;
@@ -583,6 +603,8 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	    && (uint64_t) st.width * st.height >= (1u << 20) && !getenv("SRP_B200_NO_BANDS"))
 		nBands = rows >= 64 ? 4 : 1;
 	mark();
+	if (ckptAside)
+		CU(cudaStreamWaitEvent(g.stream, g.ckptDone, 0));
 	if (nBands == 1)
 	{
 		srpdLaunchTiles(ta, g.stream);

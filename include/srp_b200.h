@@ -71,6 +71,30 @@ void* srpB200FramebufferDevicePlane(const SRPFramebuffer* fb, int which);
 SRPTexture* srpB200NewTextureFromMemory(const uint8_t* rgb, int width, int height,
                                         SRPTextureWrappingMode wrappingModeX, SRPTextureWrappingMode wrappingModeY);
 
+/* ---- I/O neighbours of the draw path ------------------------------------------------
+ * What a program does right before it fills its buffers and right after it has its pixels
+ * (plain host code).  srpB200LoadOBJ reads a Wavefront OBJ the way the reference's examples do
+ * (examples/utility/objparser.c:8-79, `loadOBJMesh`): every corner of an
+ * `f p/t/n p/t/n p/t/n` face becomes its own vertex {vec3 position, vec2 uv, vec3 normal}
+ * (32 bytes, the reference's OBJVertex) and the indices are 0..n-1 -- the same arrays bit for
+ * bit, ready for srpVertexBufferCopyData / srpIndexBufferCopyData(SRP_UINT32) -- without that
+ * loader's fixed 65536-element tables.  Returns 0 on success; other face forms are skipped with
+ * a warning.  srpB200WritePNG / srpB200SaveFramebufferPNG write the colour plane as an 8-bit
+ * RGBA PNG with alpha 255 (tests/utils/save.c:4-33, `saveFramebufferToImage`); the framebuffer
+ * variant first brings the host mirror up to date.  Both return 0 on success. */
+typedef struct SRPB200Mesh
+{
+	float* vertices;            /* vertexCount * 8 floats: position.xyz, uv.xy, normal.xyz */
+	size_t vertexCount;
+	size_t bytesPerVertex;      /* 32 */
+	uint32_t* indices;          /* indexCount entries, 0..vertexCount-1 */
+	size_t indexCount;
+} SRPB200Mesh;
+int srpB200LoadOBJ(const char* path, SRPB200Mesh* mesh);
+void srpB200FreeMesh(SRPB200Mesh* mesh);
+int srpB200WritePNG(const char* path, size_t width, size_t height, const uint32_t* color);
+int srpB200SaveFramebufferPNG(const SRPFramebuffer* fb, const char* path);
+
 /* ---- frame-parallel batch ----------------------------------------------------------
  * One call = nFrames independent srpFramebufferClear + srpDrawIndexBuffer pairs that
  * share buffers, program and context state and differ in uniform and target:

@@ -95,6 +95,11 @@ class SRPB200Stats(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class SRPB200Mesh(C.Structure):
+    _fields_ = [("vertices", C.POINTER(C.c_float)), ("vertexCount", C.c_size_t), ("bytesPerVertex", C.c_size_t),
+                ("indices", C.POINTER(C.c_uint32)), ("indexCount", C.c_size_t)]
+
+
 MESSAGE_FUNC = C.CFUNCTYPE(None, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_void_p)
 
 
@@ -218,6 +223,10 @@ class SrpLibrary:
             "srpB200FramebufferWait": (None, [C.POINTER(SRPFramebuffer)]),
             "srpB200NewFramebufferOnDevice": (C.POINTER(SRPFramebuffer), [sz, sz, vp, vp, vp]),
             "srpB200FramebufferDevicePlane": (vp, [C.POINTER(SRPFramebuffer), i32]),
+            "srpB200LoadOBJ": (i32, [C.c_char_p, C.POINTER(SRPB200Mesh)]),
+            "srpB200FreeMesh": (None, [C.POINTER(SRPB200Mesh)]),
+            "srpB200WritePNG": (i32, [C.c_char_p, sz, sz, vp]),
+            "srpB200SaveFramebufferPNG": (i32, [C.POINTER(SRPFramebuffer), C.c_char_p]),
             "srpB200DrawBatch": (None, [vp, vp, C.POINTER(C.POINTER(SRPFramebuffer)), sz,
                                         C.POINTER(SRPShaderProgram), vp, sz, i32, sz, sz, i32]),
             "srpB200SetRowRange": (None, [sz, sz]),
@@ -299,6 +308,25 @@ class SrpLibrary:
         return getattr(self.dll, fn)(*[float(a) for a in args]).numpy()
 
     # -- product-only ---------------------------------------------------------------------
+    def load_obj(self, path):
+        """srpB200LoadOBJ -> (vertices [n, 8] float32, indices uint32), copies"""
+        m = SRPB200Mesh()
+        if self.dll.srpB200LoadOBJ(str(path).encode(), C.byref(m)) != 0:
+            raise OSError(f"srpB200LoadOBJ({path}) failed: {self.messages[-1:]}")
+        try:
+            n = int(m.vertexCount)
+            v = np.ctypeslib.as_array(m.vertices, shape=(n, 8)).copy() if n else np.zeros((0, 8), np.float32)
+            i = np.ctypeslib.as_array(m.indices, shape=(int(m.indexCount),)).copy() if n else np.zeros(0, np.uint32)
+        finally:
+            self.dll.srpB200FreeMesh(C.byref(m))
+        return v, i
+
+    def write_png(self, path, color: np.ndarray):
+        """srpB200WritePNG of a [H, W] uint32 colour plane (R in the top byte)"""
+        c = np.ascontiguousarray(color, dtype=np.uint32)
+        if self.dll.srpB200WritePNG(str(path).encode(), c.shape[1], c.shape[0], c.ctypes.data) != 0:
+            raise OSError(f"srpB200WritePNG({path}) failed")
+
     def stage_times(self) -> dict:
         ms = (C.c_double * 3)()
         n = int(self.dll.srpB200CollectStageTimes(ms))

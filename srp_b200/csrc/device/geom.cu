@@ -366,6 +366,22 @@ __device__ __forceinline__ const unsigned char* clipVary(const ClipSlot& sl, con
 	return v < 3 ? vvary + (size_t) sl.origSlot[v] * slotSize : fresh + (size_t) (v - 3) * slotSize;
 }
 
+/* a fan triangle through the polygon mode; the filled case inline (the clipper warp has the
+ * registers for it, and its latency is what the clipper pass consists of) */
+template <bool WRITE>
+__device__ __forceinline__ void emitFanTriangle(Emitter& em, const SrpdState& st, const SrpdPos p[3], const unsigned char* const vary[3])
+{
+	if (st.polygonMode == SRP_POLYGON_MODE_FILL)
+	{
+		SrpdTriSetup s;
+		bool stored;
+		if (setupAndClassify(st, p, s, stored))
+			writeTriangle<WRITE>(em, st, s, stored, vary);
+	}
+	else
+		emitPolygonModeTriangle<WRITE>(em, st, p, vary);
+}
+
 struct ClipResult { uint32_t nEmit, nStore; bool overflow; };
 enum { SRPD_CLIP_COUNT = 1, SRPD_CLIP_WRITE = 2 };
 
@@ -373,7 +389,7 @@ enum { SRPD_CLIP_COUNT = 1, SRPD_CLIP_WRITE = 2 };
  * mode: COUNT = clip + count the fan triangles (returns, in the owner lanes, the ids / records
  * their triangle produces); WRITE = emit them from idBase / storeBase of their owner, from the
  * slots the COUNT call left behind.  Called by all 32 lanes. */
-__device__ __noinline__ ClipResult clipChunk(
+__device__ __forceinline__ ClipResult clipChunk(
 	Emitter em, const SrpdState& st, int mode, unsigned char* slots, uint32_t chunkMask,
 	const float4* vpos, const unsigned char* vvary, uint32_t slot0, uint32_t slot1, uint32_t slot2,
 	uint32_t idBase, uint32_t storeBase)
@@ -495,7 +511,7 @@ __device__ __noinline__ ClipResult clipChunk(
 			em.idBase = 0; em.storeBase = 0; em.nEmit = 0; em.nStore = 0; em.overflow = false;
 			if (!writing)
 			{
-				emitPolygonModeTriangle<false>(em, st, tp, tv);
+				emitFanTriangle<false>(em, st, tp, tv);
 				os.cnt[i][0] = (uint16_t) em.nEmit; os.cnt[i][1] = (uint16_t) em.nStore;
 			}
 			else if (os.cnt[i][1] != 0)
@@ -504,7 +520,7 @@ __device__ __noinline__ ClipResult clipChunk(
 				for (int j = 0; j < i; j++) { preE += os.cnt[j][0]; preS += os.cnt[j][1]; }
 				em.idBase = os.idBase + preE;
 				em.storeBase = os.storeBase + preS;
-				emitPolygonModeTriangle<true>(em, st, tp, tv);
+				emitFanTriangle<true>(em, st, tp, tv);
 				if (em.overflow) res.overflow = true;
 			}
 		}

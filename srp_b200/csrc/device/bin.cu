@@ -53,14 +53,21 @@ srpdBinCountKernel(const __grid_constant__ SrpdBinArgs a)
 	{
 		for (uint32_t s = threadIdx.x; s < nSuper; s += SRPD_BIN_THREADS)
 			sCount[s] = 0;
-		__syncthreads();
 		const uint32_t first = chunk * SRPD_BIN_CHUNK;
-		for (uint32_t o = threadIdx.x; o < SRPD_BIN_CHUNK; o += SRPD_BIN_THREADS)
+		/* all of the thread's boxes are requested before the first one is used (the loads overlap) */
+		constexpr int PER = SRPD_BIN_CHUNK / SRPD_BIN_THREADS;
+		uint2 bb[PER];
+		#pragma unroll
+		for (int k = 0; k < PER; k++)
 		{
-			const uint32_t r = first + o;
-			if (r >= nStored)
-				break;
-			const uint32_t rect = superRect(a.bboxes[r], a.superX, a.superY, a.superShift);
+			const uint32_t r = first + k * SRPD_BIN_THREADS + threadIdx.x;
+			bb[k] = r < nStored ? a.bboxes[r] : make_uint2(0u, 0u);      /* an empty box */
+		}
+		__syncthreads();      /* (the counters are zero) */
+		#pragma unroll
+		for (int k = 0; k < PER; k++)
+		{
+			const uint32_t rect = superRect(bb[k], a.superX, a.superY, a.superShift);
 			if (rectEmpty(rect))
 				continue;
 			for (uint32_t sy = (rect >> 8) & 0xFFu; sy <= (rect >> 24); sy++)

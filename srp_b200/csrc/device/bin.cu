@@ -38,6 +38,14 @@ __device__ __forceinline__ uint32_t superRect(uint2 bb, uint32_t superX, uint32_
 }
 __device__ __forceinline__ bool rectEmpty(uint32_t r) { return (r & 0xFFu) > ((r >> 16) & 0xFFu); }
 
+/* Records per chunk: SRPD_BIN_CHUNK, or a quarter of it while the draw stores so few records that
+ * full chunks would leave most of the machine idle (cfg3: 130 k records = 64 chunks of 2048 on 148
+ * SMs).  Every binning kernel derives it from the same record count. */
+__device__ __forceinline__ uint32_t binChunkRecords(uint32_t nStored)
+{
+	return nStored <= SRPD_BIN_SMALL_RECORDS ? SRPD_BIN_CHUNK / 4 : SRPD_BIN_CHUNK;
+}
+
 } // namespace
 
 __global__ void __launch_bounds__(SRPD_BIN_THREADS)
@@ -46,22 +54,23 @@ srpdBinCountKernel(const __grid_constant__ SrpdBinArgs a)
 	extern __shared__ uint32_t sCount[];
 	const uint32_t nSuper = a.superX * a.superY;
 	const uint32_t nStored = a.frameCounts[1];
-	const uint32_t nChunks = (nStored + SRPD_BIN_CHUNK - 1) / SRPD_BIN_CHUNK;
+	const uint32_t chunkRecords = binChunkRecords(nStored);
+	const uint32_t nChunks = (nStored + chunkRecords - 1) / chunkRecords;
 	/* the grid is sized for the machine, not for the record capacity: the CTAs stride over the
 	 * chunks that exist (nobody reads the counts of chunks past the end) */
 	for (uint32_t chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x)
 	{
 		for (uint32_t s = threadIdx.x; s < nSuper; s += SRPD_BIN_THREADS)
 			sCount[s] = 0;
-		const uint32_t first = chunk * SRPD_BIN_CHUNK;
+		const uint32_t first = chunk * chunkRecords;
 		/* all of the thread's boxes are requested before the first one is used (the loads overlap) */
 		constexpr int PER = SRPD_BIN_CHUNK / SRPD_BIN_THREADS;
 		uint2 bb[PER];
 		#pragma unroll
 		for (int k = 0; k < PER; k++)
 		{
-			const uint32_t r = first + k * SRPD_BIN_THREADS + threadIdx.x;
-			bb[k] = r < nStored ? a.bboxes[r] : make_uint2(0u, 0u);      /* an empty box */
+			const uint32_t o = k * SRPD_BIN_THREADS + threadIdx.x;
+			bb[k] = (o < chunkRecords && first + o < nStored) ? a.bboxes[first + o] : make_uint2(0u, 0u);      /* an empty box */
 		}
 		__syncthreads();      /* (the counters are zero) */
 		#pragma unroll
@@ -88,7 +97,8 @@ srpdBinScanColumnsKernel(const __grid_constant__ SrpdBinArgs a)
 {
 	const uint32_t nSuper = a.superX * a.superY;
 	const uint32_t nStored = a.frameCounts[1];
-	const uint32_t nChunks = (nStored + SRPD_BIN_CHUNK - 1) / SRPD_BIN_CHUNK;
+	const uint32_t chunkRecords = binChunkRecords(nStored);
+	const uint32_t nChunks = (nStored + chunkRecords - 1) / chunkRecords;
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= nSuper)
 		return;
@@ -206,28 +216,30 @@ template <int FILL_WARPS>
 __global__ void __launch_bounds__(FILL_WARPS * 32, 1)
 srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 {
-	constexpr int SPAN = SRPD_BIN_CHUNK / FILL_WARPS;     /* records per warp      */
-	constexpr int ROUNDS = SPAN / 32;                     /* steps of 32 per warp  */
+	constexpr int ROUNDS = SRPD_BIN_CHUNK / FILL_WARPS / 32;      /* steps of 32 per warp, at most */
 	extern __shared__ uint32_t sFill[];                   /* [FILL_WARPS][nSuper] cursors, then [FILL_WARPS][nSuper] lane masks */
 	const uint32_t nSuper = a.superX * a.superY;
 	const uint32_t nStored = a.frameCounts[1];
-	const uint32_t nChunks = (nStored + SRPD_BIN_CHUNK - 1) / SRPD_BIN_CHUNK;
+	const uint32_t chunkRecords = binChunkRecords(nStored);
+	const uint32_t nChunks = (nStored + chunkRecords - 1) / chunkRecords;
+	const uint32_t span = chunkRecords / FILL_WARPS;              /* records per warp */
+	const int rounds = (int) (span / 32);
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	uint32_t* sCnt = sFill + (size_t) warp * nSuper;
 	uint32_t* sMask = sFill + (size_t) (FILL_WARPS + warp) * nSuper;
 	for (uint32_t chunk = blockIdx.x; chunk < nChunks; chunk += gridDim.x)      /* grid sized for the machine */
 	{
-	const uint32_t first = chunk * SRPD_BIN_CHUNK;
+	const uint32_t first = chunk * chunkRecords;
 
 	for (uint32_t i = tid; i < 2 * FILL_WARPS * nSuper; i += FILL_WARPS * 32)
 		sFill[i] = 0;
 	uint32_t rect[ROUNDS];
-	const uint32_t warpFirst = first + warp * SPAN;
+	const uint32_t warpFirst = first + warp * span;
 	#pragma unroll
 	for (int r = 0; r < ROUNDS; r++)
 	{
 		const uint32_t rec = warpFirst + r * 32 + lane;
-		rect[r] = rec < nStored ? superRect(a.bboxes[rec], a.superX, a.superY, a.superShift) : 0x00000101u;
+		rect[r] = (r < rounds && rec < nStored) ? superRect(a.bboxes[rec], a.superX, a.superY, a.superShift) : 0x00000101u;
 	}
 	__syncthreads();
 	#pragma unroll

@@ -72,6 +72,7 @@ constexpr int SRPD_STATS_SLOTS = 1024;   /* SrpdStats[slots]: counters are sprea
 
 constexpr int SRPD_BIN_THREADS = 256;
 constexpr int SRPD_BIN_CHUNK = 2048;     /* records per coarse-binning CTA                  */
+constexpr uint32_t SRPD_BIN_SMALL_RECORDS = 1u << 18;   /* up to here chunks are SRPD_BIN_CHUNK / 4 (bin.cu) */
 
 /* Per-draw zero-filled header in front of the scan state: word 0 batch ticket, 1 abort flag,
  * 2 tile work counter, 3 records a frame needed (max over frames), 4 coarse-list entries needed,

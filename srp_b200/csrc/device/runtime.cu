@@ -553,6 +553,12 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		ba.bboxes = ga.bboxesOrdered;
 		ba.frameCounts = ga.frameCounts;
 		ba.nChunksMax = (recCapacity + SRPD_BIN_CHUNK - 1) / SRPD_BIN_CHUNK;
+		/* draws that store few records use quarter-size chunks (bin.cu): room for those too */
+		{
+			const uint32_t small = recCapacity < SRPD_BIN_SMALL_RECORDS ? recCapacity : SRPD_BIN_SMALL_RECORDS;
+			const uint32_t smallChunks = (small + SRPD_BIN_CHUNK / 4 - 1) / (SRPD_BIN_CHUNK / 4);
+			if (ba.nChunksMax < smallChunks) ba.nChunksMax = smallChunks;
+		}
 		ba.smCount = (uint32_t) g.smCount;
 		ba.superX = superX;
 		ba.superY = superY;

@@ -494,15 +494,21 @@ __device__ __forceinline__ void visitTriangles(
 	__syncwarp();      /* the next step overwrites this warp's scratch */
 }
 
-/* rasterizeLine for one pixel, reference line.c:34-77: every lane replays the DDA chain of
- * the record's segment (<= SRPD_LINE_SEG fragments, starting from the chain state the
- * geometry kernel recorded) and keeps the fragments that land on its own linear index
- * y*W + x -- including the ones the reference's unchecked indexing wraps to the next row
- * (App. B-1). */
+/* rasterizeLine for the warp's pixel block, reference line.c:34-77.  A record is a segment of
+ * <= SRPD_LINE_SEG (16) consecutive DDA fragments with the chain state at its first one.  Lane k
+ * walks the chain to fragment k -- k float additions per coordinate, exactly the reference's
+ * sequence, all fragments side by side instead of every lane replaying all of them -- and rounds
+ * it to its pixel once.  The fragments that land in this block are then matched to the lanes
+ * that own their pixels, and every lane shades its own pixels' fragments in DDA order, all lanes
+ * at once: a fragment is matched through its linear index
+ * y*W + x, which is also how the reference's unchecked indexing wraps x == width onto the next
+ * row (App. B-1).  Must be called by all 32 lanes. */
+static_assert(SRPD_LINE_SEG <= 32, "one lane per fragment of a segment");
 __device__ __forceinline__ void visitLine(
 	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, Pixel (&px)[SRPD_PX], FragCounters& cnt,
 	int x, int y0, const bool (&valid)[SRPD_PX])
 {
+	const int lane = threadIdx.x & 31;
 	const uint4* h = (const uint4*) rec;
 	const uint4 q0 = __ldg(h + 0), q1 = __ldg(h + 1), q2 = __ldg(h + 2), q3 = __ldg(h + 3);
 	float fx = __uint_as_float(q0.x), fy = __uint_as_float(q0.y);
@@ -517,29 +523,69 @@ __device__ __forceinline__ void visitLine(
 	#pragma unroll
 	for (int k = 0; k < SRPD_PX; k++)
 		mine[k] = valid[k] ? (long long) (y0 + 4 * k) * W + x : -1;
-	for (int i = 0; i < count; i++)
-	{
-		const int ipx = srpdRoundToInt(fx), ipy = srpdRoundToInt(fy);
-		const long long idx = (long long) ipy * W + ipx;
-		int which = -1;
-		#pragma unroll
-		for (int k = 0; k < SRPD_PX; k++)
-			if (idx == mine[k]) which = k;
-		if (which >= 0)
+	/* lane k: k steps of the chain */
+	for (int i = 0; i + 1 < count; i++)
+		if (i < lane)
 		{
-			const float w0 = __fsub_rn(1.0f, t);
-			const float wgt[2] = { w0, t };
+			fx = __fadd_rn(fx, xInc);
+			fy = __fadd_rn(fy, yInc);
+			t = __fadd_rn(t, tInc);
+		}
+	const int myX = srpdRoundToInt(fx), myY = srpdRoundToInt(fy);
+	/* does my fragment land in this warp's block (columns bx0 .. bx0+7, rows by0 .. by0+7)? */
+	bool inBlock = false;
+	if (lane < count)
+	{
+		const long long idx = (long long) myY * W + myX;
+		if (idx >= 0 && idx < W * (long long) a.d.st.height)
+		{
+			const int bx0 = x - (lane % SRPD_BLK_W), by0 = y0 - (lane / SRPD_BLK_W);
+			const int pxl = (int) (idx % W), pyl = (int) (idx / W);
+			inBlock = pxl >= bx0 && pxl < bx0 + SRPD_BLK_W && pyl >= by0 && pyl < by0 + SRPD_BLK_H;
+		}
+	}
+	/* which fragments hit my pixels?  bit k of hits[j] = fragment k lands on my j-th pixel */
+	uint32_t hits[SRPD_PX];
+	#pragma unroll
+	for (int j = 0; j < SRPD_PX; j++)
+		hits[j] = 0u;
+	for (uint32_t m = __ballot_sync(0xFFFFFFFFu, inBlock); m != 0u; m &= m - 1u)
+	{
+		const int k = __ffs(m) - 1;
+		const int ipx = __shfl_sync(0xFFFFFFFFu, myX, k), ipy = __shfl_sync(0xFFFFFFFFu, myY, k);
+		const long long idx = (long long) ipy * W + ipx;
+		#pragma unroll
+		for (int j = 0; j < SRPD_PX; j++)
+			if (idx == mine[j]) hits[j] |= 1u << k;
+	}
+	/* every lane shades the fragments of its own pixels, in DDA order per pixel; different
+	 * pixels are independent, so the lanes work side by side (a line rarely visits a pixel twice) */
+	for (;;)
+	{
+		uint32_t any = hits[0];
+		#pragma unroll
+		for (int j = 1; j < SRPD_PX; j++)
+			any |= hits[j];
+		if (!__any_sync(0xFFFFFFFFu, any != 0u))
+			break;
+		const int which = pickPending(hits);
+		const uint32_t hsel = getSel(hits, which);
+		const int k = any ? __ffs(hsel) - 1 : 0;
+		const int ipx = __shfl_sync(0xFFFFFFFFu, myX, k), ipy = __shfl_sync(0xFFFFFFFFu, myY, k);
+		const float tk = __shfl_sync(0xFFFFFFFFu, t, k);
+		if (any)
+		{
+			setSel(hits, which, hsel & (hsel - 1u));
+			const float w0 = __fsub_rn(1.0f, tk);
+			const float wgt[2] = { w0, tk };
 			/* interpolateDepthAndWLine, interpolation.c:49-60 */
-			const float recW = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(iw0, w0), __fmul_rn(iw1, t)));
-			const float depth = __fadd_rn(__fmul_rn(zw0, w0), __fmul_rn(zw1, t));
+			const float recW = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(iw0, w0), __fmul_rn(iw1, tk)));
+			const float depth = __fadd_rn(__fmul_rn(zw0, w0), __fmul_rn(zw1, tk));
 			Pixel cur = getSel(px, which);
 			emitFragment<2, 0>(a.d.st, fr, cur, cnt, ipx, ipy, (float) ((double) ipx + 0.5), (float) ((double) ipy + 0.5),
 			                depth, recW, recW, true, q3.w, rec + SRPD_REC_HEADER_BYTES, wgt);
 			setSel(px, which, cur);
 		}
-		fx = __fadd_rn(fx, xInc);
-		fy = __fadd_rn(fy, yInc);
-		t = __fadd_rn(t, tInc);
 	}
 }
 

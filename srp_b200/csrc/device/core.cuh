@@ -431,10 +431,13 @@ SRP_HD void srpdLineSegment(const SrpdState& st, const SrpdLineSetup& ln, float&
 	const long long W = st.width, total = (long long) st.width * st.height;
 	for (int k = 0; k < n; k++)
 	{
-		const long long idx = (long long) srpdRoundToInt(y) * W + srpdRoundToInt(x);
+		const int ix = srpdRoundToInt(x), iy = srpdRoundToInt(y);
+		const long long idx = (long long) iy * W + ix;
 		if (idx >= 0 && idx < total)
 		{
-			const long long px = idx % W, py = idx / W;
+			/* a fragment inside the row needs no 64-bit division: idx = iy*W + ix with 0 <= ix < W */
+			const bool inRow = ix >= 0 && ix < W;
+			const long long px = inRow ? ix : idx % W, py = inRow ? iy : idx / W;
 			x0 = px < x0 ? px : x0; x1 = px > x1 ? px : x1;
 			y0 = py < y0 ? py : y0; y1 = py > y1 ? py : y1;
 		}

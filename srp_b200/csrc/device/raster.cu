@@ -540,7 +540,8 @@ __device__ __forceinline__ void visitLine(
 		if (idx >= 0 && idx < W * (long long) a.d.st.height)
 		{
 			const int bx0 = x - (lane % SRPD_BLK_W), by0 = y0 - (lane / SRPD_BLK_W);
-			const int pxl = (int) (idx % W), pyl = (int) (idx / W);
+			const bool inRow = myX >= 0 && myX < W;      /* the usual case needs no 64-bit division */
+			const int pxl = inRow ? myX : (int) (idx % W), pyl = inRow ? myY : (int) (idx / W);
 			inBlock = pxl >= bx0 && pxl < bx0 + SRPD_BLK_W && pyl >= by0 && pyl < by0 + SRPD_BLK_H;
 		}
 	}

@@ -24,6 +24,11 @@ extern "C" __device__ void srpB200DeviceFS(int programId, SRPFragmentShaderIn* i
 #ifndef SRPD_TILE_CTAS_PER_SM
 #define SRPD_TILE_CTAS_PER_SM 5
 #endif
+/* the line variant of the tile kernel (general fragment stage, no SIMPLE variant): measured on
+ * cfg4's 1 M-line draw with 2 / 3 / 4 / 5 CTAs per SM: 3.20 / 2.38 / 2.04 / 2.08 ms */
+#ifndef SRPD_TILE_LINE_CTAS_PER_SM
+#define SRPD_TILE_LINE_CTAS_PER_SM 4
+#endif
 constexpr int SRPD_TILE_W = 32;          /* pixels; one 128-byte colour row per tile row   */
 constexpr int SRPD_TILE_H = SRPD_TILE_H_PX;
 constexpr int SRPD_BLK_W = 8;            /* pixels owned by one warp: 8 x (4 * pixels per thread) */

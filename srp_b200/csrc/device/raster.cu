@@ -805,7 +805,7 @@ __device__ __forceinline__ void clearTile(const SrpdState& st, const SrpdFrame& 
  * missing minimum makes the linker's code generator cap the kernel at 64 registers and
  * spill).  Triangles and points fit two 512-thread CTAs per SM; the line walker does not. */
 template <int KIND, bool BATCH, int SIMPLE>
-__global__ void __launch_bounds__(SRPD_TILE_THREADS, KIND == SRPD_KIND_LINE ? SRPD_TILE_CTAS_PER_SM / 2 : SRPD_TILE_CTAS_PER_SM)
+__global__ void __launch_bounds__(SRPD_TILE_THREADS, KIND == SRPD_KIND_LINE ? SRPD_TILE_LINE_CTAS_PER_SM : SRPD_TILE_CTAS_PER_SM)
 srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 {
 	extern __shared__ __align__(16) unsigned char srpdTileSmem[];
@@ -967,7 +967,7 @@ void srpdLaunchTiles(const SrpdTileArgs& a0, cudaStream_t stream)
 	/* persistent grid: resident CTAs per SM x SM count (no more CTAs than work items) */
 	const uint32_t tilesPerFrame = a.tilesX * rows;
 	const uint64_t nItems = (uint64_t) ((tilesPerFrame + a.tilesPerItem - 1) / a.tilesPerItem) * a.d.nFrames;
-	const uint32_t perSm = a.d.kind == SRPD_KIND_LINE ? SRPD_TILE_CTAS_PER_SM / 2 : SRPD_TILE_CTAS_PER_SM;
+	const uint32_t perSm = a.d.kind == SRPD_KIND_LINE ? SRPD_TILE_LINE_CTAS_PER_SM : SRPD_TILE_CTAS_PER_SM;
 	uint64_t grid = (uint64_t) a.smCount * perSm;
 	if (grid > nItems) grid = nItems;
 	if (grid == 0) return;

@@ -427,24 +427,28 @@ SRP_HD void srpdLineSegment(const SrpdState& st, const SrpdLineSetup& ln, float&
 	seg.w[6] = srpdF2U(ln.zw[0]); seg.w[7] = srpdF2U(ln.zw[1]);
 	seg.w[8] = srpdF2U(ln.invW[0]); seg.w[9] = srpdF2U(ln.invW[1]);
 	seg.w[10] = srpdF2U(t);
-	long long x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
+	int x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
 	const long long W = st.width, total = (long long) st.width * st.height;
-	for (int k = 0; k < n; k++)
-	{
-		const int ix = srpdRoundToInt(x), iy = srpdRoundToInt(y);
-		const long long idx = (long long) iy * W + ix;
-		if (idx >= 0 && idx < total)
+	/* a fixed trip count with the body under `k < n`: the lanes of a warp (one line each, of
+	 * different lengths) stay together instead of peeling off one by one (measured: two lanes
+	 * active in the data-dependent loop) */
+	for (int k = 0; k < SRPD_LINE_SEG; k++)
+		if (k < n)
 		{
-			/* a fragment inside the row needs no 64-bit division: idx = iy*W + ix with 0 <= ix < W */
-			const bool inRow = ix >= 0 && ix < W;
-			const long long px = inRow ? ix : idx % W, py = inRow ? iy : idx / W;
-			x0 = px < x0 ? px : x0; x1 = px > x1 ? px : x1;
-			y0 = py < y0 ? py : y0; y1 = py > y1 ? py : y1;
+			const int ix = srpdRoundToInt(x), iy = srpdRoundToInt(y);
+			const long long idx = (long long) iy * W + ix;
+			if (idx >= 0 && idx < total)
+			{
+				/* a fragment inside the row needs no 64-bit division: idx = iy*W + ix with 0 <= ix < W */
+				const bool inRow = ix >= 0 && ix < W;
+				const int px = inRow ? ix : (int) (idx % W), py = inRow ? iy : (int) (idx / W);
+				x0 = px < x0 ? px : x0; x1 = px > x1 ? px : x1;
+				y0 = py < y0 ? py : y0; y1 = py > y1 ? py : y1;
+			}
+			x = SRP_FADD(x, ln.xInc);
+			y = SRP_FADD(y, ln.yInc);
+			t = SRP_FADD(t, ln.tInc);
 		}
-		x = SRP_FADD(x, ln.xInc);
-		y = SRP_FADD(y, ln.yInc);
-		t = SRP_FADD(t, ln.tInc);
-	}
 	seg.any = x1 >= 0;
 	seg.minX = (uint16_t) (seg.any ? x0 : 0); seg.maxX = (uint16_t) (seg.any ? x1 + 1 : 0);
 	seg.minY = (uint16_t) (seg.any ? y0 : 0); seg.maxY = (uint16_t) (seg.any ? y1 + 1 : 0);

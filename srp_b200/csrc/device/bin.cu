@@ -90,55 +90,78 @@ srpdBinCountKernel(const __grid_constant__ SrpdBinArgs a)
 	}
 }
 
-/* Scan pass 1: thread = supertile column; exclusive scan over the chunks (independent,
- * coalesced loads -- only the running sum is serial), total per supertile. */
-__global__ void __launch_bounds__(32)
+/* Scan pass 1: exclusive scan over the chunks for every supertile column, total per supertile.
+ * A CTA takes 32 columns (one per lane: coalesced rows); its 8 warps split the chunk rows, sum
+ * their parts (loads only, 32 in flight), exchange the 8 partial sums per column through shared
+ * memory and then rewrite their rows with the running sums -- the serial depth is two batches of
+ * loads per 256 chunks instead of one dependent batch per 8 (or 32) chunks. */
+constexpr int SRPD_SCAN_COL_WARPS = 8;
+__global__ void __launch_bounds__(SRPD_SCAN_COL_WARPS * 32)
 srpdBinScanColumnsKernel(const __grid_constant__ SrpdBinArgs a)
 {
+	__shared__ uint32_t sPart[SRPD_SCAN_COL_WARPS][32];
 	const uint32_t nSuper = a.superX * a.superY;
 	const uint32_t nStored = a.frameCounts[1];
 	const uint32_t chunkRecords = binChunkRecords(nStored);
 	const uint32_t nChunks = (nStored + chunkRecords - 1) / chunkRecords;
-	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= nSuper)
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const uint32_t s = blockIdx.x * 32u + lane;
+	const bool valid = s < nSuper;
+	const uint32_t rows = (nChunks + SRPD_SCAN_COL_WARPS - 1) / SRPD_SCAN_COL_WARPS;
+	const uint32_t c0 = min(warp * rows, nChunks), c1 = min(c0 + rows, nChunks);
+	uint32_t* col = a.chunkCounts + s;
+
+	uint32_t sum = 0;
+	if (valid)
+	{
+		uint32_t c = c0;
+		for (; c + 32 <= c1; c += 32)
+		{
+			uint32_t n[32];
+			#pragma unroll
+			for (int u = 0; u < 32; u++)
+				n[u] = col[(size_t) (c + u) * nSuper];
+			#pragma unroll
+			for (int u = 0; u < 32; u++)
+				sum += n[u];
+		}
+		for (; c < c1; c++)
+			sum += col[(size_t) c * nSuper];
+	}
+	sPart[warp][lane] = sum;
+	__syncthreads();
+	uint32_t run = 0, total = 0;
+	#pragma unroll
+	for (int w = 0; w < SRPD_SCAN_COL_WARPS; w++)
+	{
+		const uint32_t p = sPart[w][lane];
+		if ((uint32_t) w < warp) run += p;
+		total += p;
+	}
+	if (!valid)
 		return;
-	uint32_t run = 0;
-	uint32_t c = 0;
-	/* the running sum is the only serial part: keep many independent loads in flight */
-	for (; c + 32 <= nChunks; c += 32)
+	uint32_t c = c0;
+	for (; c + 32 <= c1; c += 32)
 	{
 		uint32_t n[32];
 		#pragma unroll
 		for (int u = 0; u < 32; u++)
-			n[u] = a.chunkCounts[(size_t) (c + u) * nSuper + s];
+			n[u] = col[(size_t) (c + u) * nSuper];
 		#pragma unroll
 		for (int u = 0; u < 32; u++)
 		{
-			a.chunkCounts[(size_t) (c + u) * nSuper + s] = run;
+			col[(size_t) (c + u) * nSuper] = run;
 			run += n[u];
 		}
 	}
-	for (; c + 8 <= nChunks; c += 8)
+	for (; c < c1; c++)
 	{
-		uint32_t n[8];
-		#pragma unroll
-		for (int u = 0; u < 8; u++)
-			n[u] = a.chunkCounts[(size_t) (c + u) * nSuper + s];
-		#pragma unroll
-		for (int u = 0; u < 8; u++)
-		{
-			a.chunkCounts[(size_t) (c + u) * nSuper + s] = run;
-			run += n[u];
-		}
-	}
-	for (; c < nChunks; c++)
-	{
-		const size_t at = (size_t) c * nSuper + s;
-		const uint32_t n = a.chunkCounts[at];
-		a.chunkCounts[at] = run;
+		const uint32_t n = col[(size_t) c * nSuper];
+		col[(size_t) c * nSuper] = run;
 		run += n;
 	}
-	a.superTotals[s] = run;
+	if (warp == 0)
+		a.superTotals[s] = total;
 }
 
 /* Scan pass 2: one CTA, exclusive scan of the supertile totals -> superOffsets (warp-shuffle
@@ -316,7 +339,7 @@ void srpdLaunchBin(const SrpdBinArgs& a, cudaStream_t stream)
 	if (grid > a.nChunksMax) grid = a.nChunksMax;
 	if (grid == 0) grid = 1;
 	srpdBinCountKernel<<<grid, SRPD_BIN_THREADS, nSuper * sizeof(uint32_t), stream>>>(a);
-	srpdBinScanColumnsKernel<<<(nSuper + 31) / 32, 32, 0, stream>>>(a);      /* one warp per CTA: the columns spread over the SMs */
+	srpdBinScanColumnsKernel<<<(nSuper + 31) / 32, SRPD_SCAN_COL_WARPS * 32, 0, stream>>>(a);
 	srpdBinScanKernel<<<1, 1024, 0, stream>>>(a);
 	/* as many warps per chunk as the cursor matrix allows in shared memory */
 	const size_t budget = 160 * 1024;

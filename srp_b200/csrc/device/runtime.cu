@@ -343,7 +343,8 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	/* A single frame whose uniform fits travels inside the kernel argument blocks (constant
 	 * bank, kernels.cuh); everything else -- batches, large or NULL uniforms -- binds per-frame
 	 * device copies: one 256-byte aligned block per frame */
-	const bool inlineUniform = nFrames == 1 && uniforms && uniformBytes > 0 && uniformBytes <= (size_t) SRPD_INLINE_UNIFORM_BYTES;
+	static const bool noInline = getenv("SRP_B200_NO_INLINE_UNIFORM") != nullptr;      /* tests: force the bound path */
+	const bool inlineUniform = nFrames == 1 && uniforms && uniformBytes > 0 && uniformBytes <= (size_t) SRPD_INLINE_UNIFORM_BYTES && !noInline;
 	const size_t ublock = (uniformBytes + 255) & ~(size_t) 255;
 	unsigned char* uniDev = nullptr;
 	if (uniforms && uniformBytes && !inlineUniform)

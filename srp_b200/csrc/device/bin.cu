@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(SRPD_BIN_THREADS)
 srpdBinCountKernel(const __grid_constant__ SrpdBinArgs a)
 {
 	extern __shared__ uint32_t sCount[];
+	srpdGridDependencyEnter();
 	const uint32_t nSuper = a.superX * a.superY;
 	const uint32_t nStored = a.frameCounts[1];
 	const uint32_t chunkRecords = binChunkRecords(nStored);
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(SRPD_SCAN_COL_WARPS * 32)
 srpdBinScanColumnsKernel(const __grid_constant__ SrpdBinArgs a)
 {
 	__shared__ uint32_t sPart[SRPD_SCAN_COL_WARPS][32];
+	srpdGridDependencyEnter();
 	const uint32_t nSuper = a.superX * a.superY;
 	const uint32_t nStored = a.frameCounts[1];
 	const uint32_t chunkRecords = binChunkRecords(nStored);
@@ -171,6 +173,7 @@ srpdBinScanKernel(const __grid_constant__ SrpdBinArgs a)
 {
 	__shared__ uint32_t sWarp[32];
 	__shared__ uint32_t sCarry;
+	srpdGridDependencyEnter();
 	const uint32_t nSuper = a.superX * a.superY;
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	if (threadIdx.x == 0)
@@ -241,6 +244,7 @@ srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 {
 	constexpr int ROUNDS = SRPD_BIN_CHUNK / FILL_WARPS / 32;      /* steps of 32 per warp, at most */
 	extern __shared__ uint32_t sFill[];                   /* [FILL_WARPS][nSuper] cursors, then [FILL_WARPS][nSuper] lane masks */
+	srpdGridDependencyEnter();
 	const uint32_t nSuper = a.superX * a.superY;
 	const uint32_t nStored = a.frameCounts[1];
 	const uint32_t chunkRecords = binChunkRecords(nStored);
@@ -332,15 +336,20 @@ srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 static int gBinLaunches = 0;
 int srpdBinLaunchCount(void) { return gBinLaunches; }
 
-void srpdLaunchBin(const SrpdBinArgs& a, cudaStream_t stream)
+void srpdLaunchBin(const SrpdBinArgs& a, cudaStream_t stream, cudaEvent_t joinBeforeFill)
 {
 	const uint32_t nSuper = a.superX * a.superY;
 	uint32_t grid = a.smCount * 3u;      /* the CTAs stride over the chunks that turn out to exist */
 	if (grid > a.nChunksMax) grid = a.nChunksMax;
 	if (grid == 0) grid = 1;
-	srpdBinCountKernel<<<grid, SRPD_BIN_THREADS, nSuper * sizeof(uint32_t), stream>>>(a);
-	srpdBinScanColumnsKernel<<<(nSuper + 31) / 32, SRPD_SCAN_COL_WARPS * 32, 0, stream>>>(a);
-	srpdBinScanKernel<<<1, 1024, 0, stream>>>(a);
+	srpdLaunchKernel(srpdBinCountKernel, grid, SRPD_BIN_THREADS, nSuper * sizeof(uint32_t), stream, a);
+	srpdLaunchKernel(srpdBinScanColumnsKernel, (nSuper + 31) / 32, SRPD_SCAN_COL_WARPS * 32, 0, stream, a);
+	srpdLaunchKernel(srpdBinScanKernel, 1, 1024, 0, stream, a);
+	/* work of another stream that the kernel AFTER the fill needs (the checkpoint pre-pass, for
+	 * the tiles) joins here: the fill then starts after it, and the tile kernel's programmatic
+	 * dependency on the fill covers it */
+	if (joinBeforeFill)
+		cudaStreamWaitEvent(stream, joinBeforeFill, 0);
 	/* as many warps per chunk as the cursor matrix allows in shared memory */
 	const size_t budget = 160 * 1024;
 	if (2 * 8 * (size_t) nSuper * sizeof(uint32_t) <= budget / 2)
@@ -348,21 +357,21 @@ void srpdLaunchBin(const SrpdBinArgs& a, cudaStream_t stream)
 		const size_t bytes = 2 * 8 * (size_t) nSuper * sizeof(uint32_t);
 		static bool configured8 = false;
 		if (!configured8) { cudaFuncSetAttribute(srpdBinFillKernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget); configured8 = true; }
-		srpdBinFillKernel<8><<<grid, 8 * 32, bytes, stream>>>(a);
+		srpdLaunchKernel(srpdBinFillKernel<8>, grid, 8 * 32, bytes, stream, a);
 	}
 	else if (2 * 4 * (size_t) nSuper * sizeof(uint32_t) <= budget)
 	{
 		const size_t bytes = 2 * 4 * (size_t) nSuper * sizeof(uint32_t);
 		static bool configured4 = false;
 		if (!configured4) { cudaFuncSetAttribute(srpdBinFillKernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget); configured4 = true; }
-		srpdBinFillKernel<4><<<grid, 4 * 32, bytes, stream>>>(a);
+		srpdLaunchKernel(srpdBinFillKernel<4>, grid, 4 * 32, bytes, stream, a);
 	}
 	else
 	{
 		const size_t bytes = 2 * 2 * (size_t) nSuper * sizeof(uint32_t);
 		static bool configured2 = false;
 		if (!configured2) { cudaFuncSetAttribute(srpdBinFillKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget); configured2 = true; }
-		srpdBinFillKernel<2><<<grid, 2 * 32, bytes, stream>>>(a);
+		srpdLaunchKernel(srpdBinFillKernel<2>, grid, 2 * 32, bytes, stream, a);
 	}
 	gBinLaunches += 4;
 }

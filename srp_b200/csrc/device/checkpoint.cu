@@ -16,6 +16,7 @@
 __global__ void __launch_bounds__(128)
 srpdCheckpointKernel(const __grid_constant__ SrpdCkptArgs a)
 {
+	srpdGridDependencyEnter();
 	uint32_t nLarge = *a.largeCount;
 	if (nLarge > a.largeCapacity)
 		nLarge = a.largeCapacity;
@@ -59,5 +60,5 @@ srpdCheckpointKernel(const __grid_constant__ SrpdCkptArgs a)
 
 void srpdLaunchCheckpoints(const SrpdCkptArgs& a, cudaStream_t stream)
 {
-	srpdCheckpointKernel<<<296, 128, 0, stream>>>(a);
+	srpdLaunchKernel(srpdCheckpointKernel, 296, 128, 0, stream, a);
 }

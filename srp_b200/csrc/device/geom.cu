@@ -647,6 +647,7 @@ __global__ void __launch_bounds__(CLIPPER ? 32 : SRPD_GEOM_THREADS, CLIPPER ? 16
 srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
+	srpdGridDependencyEnter();
 	const SrpdDraw& d = a.d;
 	const SrpdState& st = d.st;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -885,6 +886,7 @@ srpdBatchScanKernel(const __grid_constant__ SrpdGeomArgs a)
 	constexpr int WARPS = SRPD_SCAN_CHUNK / 4 / 32;
 	__shared__ uint32_t sWarpE[WARPS], sWarpS[WARPS];
 	__shared__ uint32_t sBase[2];
+	srpdGridDependencyEnter();
 	const uint32_t frame = blockIdx.x / a.chunksPerFrame, chunk = blockIdx.x - frame * a.chunksPerFrame;
 	const uint32_t first = frame * a.batchesPerFrame;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -947,6 +949,7 @@ srpdBatchScanKernel(const __grid_constant__ SrpdGeomArgs a)
 __global__ void __launch_bounds__(256)
 srpdRecordOrderKernel(const __grid_constant__ SrpdGeomArgs a)
 {
+	srpdGridDependencyEnter();
 	const uint32_t batch = blockIdx.x * 8 + (threadIdx.x >> 5);
 	const uint32_t lane = threadIdx.x & 31;
 	if (batch >= a.batchesPerFrame * a.d.nFrames)
@@ -979,7 +982,7 @@ static void launchGeomKernel(const SrpdGeomArgs& a, unsigned grid, cudaStream_t 
 		cudaFuncSetAttribute(srpdGeomKernel<BATCH, CLIPPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 		configured = true;
 	}
-	srpdGeomKernel<BATCH, CLIPPER><<<grid, CLIPPER ? 32 : SRPD_GEOM_THREADS, geomCtaBytes(a.d.st.slotSize, CLIPPER), stream>>>(a);
+	srpdLaunchKernel(srpdGeomKernel<BATCH, CLIPPER>, grid, CLIPPER ? 32 : SRPD_GEOM_THREADS, geomCtaBytes(a.d.st.slotSize, CLIPPER), stream, a);
 }
 
 /* Small draws: one launch, every batch by a clipper warp.  Large draws: the main pass, then the
@@ -1010,8 +1013,8 @@ int srpdLaunchGeom(const SrpdGeomArgs& a0, cudaStream_t stream)
 		else          launchGeomKernel<false, true>(a, clipGrid, stream);
 		launches = 2;
 	}
-	srpdBatchScanKernel<<<a.d.nFrames * a.chunksPerFrame, SRPD_SCAN_CHUNK / 4, 0, stream>>>(a);
-	srpdRecordOrderKernel<<<(batches + 7) / 8, 256, 0, stream>>>(a);
+	srpdLaunchKernel(srpdBatchScanKernel, a.d.nFrames * a.chunksPerFrame, SRPD_SCAN_CHUNK / 4, 0, stream, a);
+	srpdLaunchKernel(srpdRecordOrderKernel, (batches + 7) / 8, 256, 0, stream, a);
 	launches += 2;
 	gGeomLaunches += launches;
 	return launches;

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 #include "core.cuh"
 
 /* User program table (defined by SRP_B200_DEFINE_PROGRAM_TABLE in the executable's
@@ -185,9 +186,47 @@ struct SrpdTileArgs
 	SrpdStats* stats;
 };
 
+/* ---- programmatic dependent launch ---------------------------------------------------
+ * A draw is a chain of ~10 dependent kernels, several of them only 3-10 us long, so the gaps
+ * between them (grid drain + launch latency of the next one) are a visible share of a frame.
+ * Every kernel is launched with the programmatic-stream-serialisation attribute and starts with
+ * srpdGridDependencyEnter(): `griddepcontrol.wait` blocks until the preceding kernel of the
+ * stream has completed and its memory is visible (so the dependency itself is unchanged --
+ * nothing is read or written before it), then `griddepcontrol.launch_dependents` lets the NEXT
+ * kernel's CTAs be scheduled as soon as all of this kernel's CTAs have got that far: they become
+ * resident on SMs as these drain and sit in their own wait, so the next kernel starts the
+ * moment this one ends.  Without the launch attribute both instructions are no-ops.
+ * SRP_B200_PDL=0/1 switches the attribute (runtime.cu). */
+__device__ __forceinline__ void srpdGridDependencyEnter()
+{
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#ifndef SRPD_PDL_DEFAULT
+#define SRPD_PDL_DEFAULT 0
+#endif
+bool srpdPdlEnabled(void);
+
+template <typename Arg>
+inline cudaError_t srpdLaunchKernel(void (*kernel)(Arg), unsigned grid, unsigned block, size_t smemBytes, cudaStream_t stream, const Arg& a)
+{
+	cudaLaunchConfig_t cfg;
+	memset(&cfg, 0, sizeof cfg);
+	cfg.gridDim = dim3(grid, 1, 1);
+	cfg.blockDim = dim3(block, 1, 1);
+	cfg.dynamicSmemBytes = smemBytes;
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = srpdPdlEnabled() ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
 /* launchers (defined next to their kernels) */
 int srpdLaunchGeom(const SrpdGeomArgs& a, cudaStream_t stream);
-void srpdLaunchBin(const SrpdBinArgs& a, cudaStream_t stream);
+void srpdLaunchBin(const SrpdBinArgs& a, cudaStream_t stream, cudaEvent_t joinBeforeFill);
 void srpdLaunchTiles(const SrpdTileArgs& a, cudaStream_t stream);
 void srpdLaunchClear(uint32_t* color, float* depth, size_t nPixels, cudaStream_t stream);
 int srpdGeomLaunchCount(void);

@@ -811,6 +811,7 @@ srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 	extern __shared__ __align__(16) unsigned char srpdTileSmem[];
 	TileSharedK<KIND>& sm = *reinterpret_cast<TileSharedK<KIND>*>(srpdTileSmem);
 
+	srpdGridDependencyEnter();
 	if (*a.abortFlag)      /* a scratch pool overflowed: the host repeats the draw with larger pools */
 		return;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -890,6 +891,7 @@ srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
  * to be materialised without a draw), reference core/framebuffer.c:57-62 */
 __global__ void __launch_bounds__(256) srpdClearKernel(uint4* color, uint4* depth, size_t nVec, uint32_t* colorTail, float* depthTail, int nTail)
 {
+	srpdGridDependencyEnter();
 	const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
 	const uint32_t m1 = 0xBF800000u;   /* -1.0f */
 	const uint4 minusOne = make_uint4(m1, m1, m1, m1);
@@ -925,7 +927,7 @@ static void launchTileKernelS(const SrpdTileArgs& a, unsigned grid, cudaStream_t
 		cudaFuncSetAttribute(srpdTileKernel<KIND, BATCH, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 		configured = true;
 	}
-	srpdTileKernel<KIND, BATCH, SIMPLE><<<grid, SRPD_TILE_THREADS, bytes, stream>>>(a);
+	srpdLaunchKernel(srpdTileKernel<KIND, BATCH, SIMPLE>, grid, SRPD_TILE_THREADS, (size_t) bytes, stream, a);
 }
 template <int KIND>
 static void launchTileKernel(const SrpdTileArgs& a, unsigned grid, cudaStream_t stream)

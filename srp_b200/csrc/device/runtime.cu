@@ -111,6 +111,23 @@ void mark()
 	g.pendingEvents.push_back(e);
 }
 
+} // namespace
+
+/* programmatic dependent launch of the draw's kernel chain (kernels.cuh); SRP_B200_PDL=0 turns
+ * the launch attribute off (the kernels' griddepcontrol instructions are then no-ops) */
+bool srpdPdlEnabled(void)
+{
+	static int enabled = -1;
+	if (enabled < 0)
+	{
+		const char* e = getenv("SRP_B200_PDL");
+		enabled = e ? (atoi(e) != 0) : SRPD_PDL_DEFAULT;
+	}
+	return enabled != 0;
+}
+
+namespace {
+
 int envInt(const char* name, int fallback)
 {
 	const char* v = getenv(name);
@@ -580,7 +597,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		ba.abortFlag = ga.abortFlag;
 		ba.needed = ga.needed;
 		ba.stats = g.stats;
-		srpdLaunchBin(ba, g.stream);
+		srpdLaunchBin(ba, g.stream, ckptAside ? g.ckptDone : (cudaEvent_t) nullptr);     /* (ckptAside implies binned) */
 		g.launches += 4;
 		CU(cudaGetLastError());
 		ta.superOffsets = ba.superOffsets;
@@ -610,8 +627,6 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	    && (uint64_t) st.width * st.height >= (1u << 20) && !getenv("SRP_B200_NO_BANDS"))
 		nBands = rows >= 64 ? 4 : 1;
 	mark();
-	if (ckptAside)
-		CU(cudaStreamWaitEvent(g.stream, g.ckptDone, 0));
 	if (nBands == 1)
 	{
 		srpdLaunchTiles(ta, g.stream);

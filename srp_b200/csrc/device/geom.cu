@@ -23,10 +23,10 @@
  *      slots from the frame's bump allocator and publishes its totals;
  *   5. records are written (unclipped triangles from the set-up kept in step 3, clipped
  *      ones are clipped again) with batch-local primitive ids.
- * Two small kernels then restore the reference's serial order (primitive_assembly.c:64,90-91:
- * `primitiveID++` over emitted primitives): srpdBatchScanKernel prefix-sums the batch totals
- * in batch order, srpdRecordOrderKernel adds the id prefix to every record and builds the
- * id-ordered view (ordered bounding boxes + permutation) that binning and tiles consume.
+ * One small kernel then restores the reference's serial order (primitive_assembly.c:64,90-91:
+ * `primitiveID++` over emitted primitives): srpdBatchOrderKernel prefix-sums the batch totals
+ * in batch order, adds the id prefix to every record and builds the id-ordered view (ordered
+ * bounding boxes + permutation) that binning and tiles consume.
  *
  * HBM traffic per input triangle: 3 indices + (amortised) its vertices in, one record
  * (80 B header + 3 blobs) + one 8-byte bbox out. */
@@ -824,7 +824,7 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	/* 4. warp scan of both counts.  No warp ever waits for another one: the batch takes a
 	 * contiguous range of record slots from the frame's bump allocator (arrival order) and leaves
 	 * its counts behind; the batch-order prefix sums and the id-ordered view of the records are
-	 * built afterwards (srpdBatchScanKernel, srpdRecordOrderKernel). */
+	 * built afterwards (srpdBatchOrderKernel). */
 	const uint32_t incE = warpInclusiveScan(myEmit, lane);
 	const uint32_t incS = warpInclusiveScan(myStore, lane);
 	const uint32_t totE = __shfl_sync(0xFFFFFFFFu, incE, 31), totS = __shfl_sync(0xFFFFFFFFu, incS, 31);
@@ -833,7 +833,7 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	{
 		physBase = totS ? atomicAdd(&a.frameBump[frame], totS) : 0u;
 		a.batchInfo[batch] = make_uint4(physBase, totE, totS, 0u);
-		/* totals of the scan chunk this batch belongs to (srpdBatchScanKernel adds up the chunks before its own) */
+		/* totals of the scan chunk this batch belongs to (srpdBatchOrderKernel adds up the chunks before its own) */
 		uint2* cs = a.chunkSums + (size_t) frame * a.chunksPerFrame + b / SRPD_SCAN_CHUNK;
 		if (totE) atomicAdd(&cs->x, totE);
 		if (totS) atomicAdd(&cs->y, totS);
@@ -876,20 +876,30 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	}   /* batch */
 }
 
-/* Exclusive prefix sums of (ids, records) over the batches of a frame, in batch order: this is
- * the reference's serial `primitiveID++`.  One CTA per chunk of SRPD_SCAN_CHUNK batches; the
- * geometry warps have already accumulated every chunk's totals, so a CTA adds up the chunks in
- * front of its own and scans its own batches (4 per thread, warp-shuffle scans). */
-__global__ void __launch_bounds__(SRPD_SCAN_CHUNK / 4)
-srpdBatchScanKernel(const __grid_constant__ SrpdGeomArgs a)
+/* Batch order -> primitive order, one CTA per chunk of SRPD_SCAN_CHUNK batches of a frame.
+ * (1) Exclusive prefix sums of (ids, records) over the batches, in batch order: this is the
+ * reference's serial `primitiveID++`.  The geometry warps have already accumulated every
+ * chunk's totals, so a CTA adds up the chunks in front of its own and scans its own batches
+ * (one per thread, warp-shuffle scans).  (2) The id-ordered view: the chunk's records occupy a
+ * contiguous range of positions in primitive order; the threads stride over those positions
+ * (an even split whatever the batches' record counts -- most batches of a mesh around the
+ * camera store nothing), find the owning batch in the chunk's prefix array in shared memory,
+ * add the batch's id prefix to the record and write its bounding box and physical slot at its
+ * position.  Binning and the tile kernel only ever walk this view. */
+constexpr int SRPD_ORDER_THREADS = 1024;      /* the first SRPD_SCAN_CHUNK of them scan; all of them move records */
+__global__ void __launch_bounds__(SRPD_ORDER_THREADS)
+srpdBatchOrderKernel(const __grid_constant__ SrpdGeomArgs a)
 {
-	constexpr int WARPS = SRPD_SCAN_CHUNK / 4 / 32;
+	constexpr int WARPS = SRPD_SCAN_CHUNK / 32;
 	__shared__ uint32_t sWarpE[WARPS], sWarpS[WARPS];
 	__shared__ uint32_t sBase[2];
+	__shared__ uint32_t sOrd[SRPD_SCAN_CHUNK + 1];      /* records in front of the batch within the chunk; [CHUNK] = the chunk's total */
+	__shared__ uint32_t sPhys[SRPD_SCAN_CHUNK];         /* the batch's first record slot */
+	__shared__ uint32_t sIds[SRPD_SCAN_CHUNK];          /* primitive ids in front of the batch within the frame */
 	srpdGridDependencyEnter();
 	const uint32_t frame = blockIdx.x / a.chunksPerFrame, chunk = blockIdx.x - frame * a.chunksPerFrame;
 	const uint32_t first = frame * a.batchesPerFrame;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint2* cs = a.chunkSums + (size_t) frame * a.chunksPerFrame;
 	if (warp == 0)
 	{
@@ -903,72 +913,71 @@ srpdBatchScanKernel(const __grid_constant__ SrpdGeomArgs a)
 		ps = __reduce_add_sync(0xFFFFFFFFu, ps);
 		if (lane == 0) { sBase[0] = pe; sBase[1] = ps; }
 	}
-	const uint32_t b = chunk * SRPD_SCAN_CHUNK + threadIdx.x * 4;
-	uint32_t e[4], s[4];
-	uint32_t sumE = 0, sumS = 0;
-	#pragma unroll
-	for (int i = 0; i < 4; i++)
+	const bool scanner = tid < SRPD_SCAN_CHUNK;      /* (whole warps) */
+	const uint32_t b = chunk * SRPD_SCAN_CHUNK + tid;
+	uint32_t e = 0, s = 0, phys0 = 0;
+	if (scanner && b < a.batchesPerFrame)
 	{
-		e[i] = 0; s[i] = 0;
-		if (b + i < a.batchesPerFrame)
-		{
-			const uint4 info = a.batchInfo[first + b + i];
-			e[i] = info.y; s[i] = info.z;
-		}
-		sumE += e[i]; sumS += s[i];
+		const uint4 info = a.batchInfo[first + b];
+		phys0 = info.x; e = info.y; s = info.z;
 	}
-	const uint32_t incE = warpInclusiveScan(sumE, lane), incS = warpInclusiveScan(sumS, lane);
-	if (lane == 31) { sWarpE[warp] = incE; sWarpS[warp] = incS; }
+	uint32_t incE = 0, incS = 0;
+	if (scanner)
+	{
+		incE = warpInclusiveScan(e, lane); incS = warpInclusiveScan(s, lane);
+		if (lane == 31) { sWarpE[warp] = incE; sWarpS[warp] = incS; }
+	}
 	__syncthreads();
-	uint32_t baseE = sBase[0], baseS = sBase[1];
-	for (int w = 0; w < warp; w++) { baseE += sWarpE[w]; baseS += sWarpS[w]; }
-	uint32_t pe = baseE + incE - sumE, ps = baseS + incS - sumS;
-	#pragma unroll
-	for (int i = 0; i < 4; i++)
+	uint32_t inE = incE - e, inS = incS - s;      /* exclusive, within the chunk */
+	if (scanner)
+		for (int w = 0; w < warp; w++) { inE += sWarpE[w]; inS += sWarpS[w]; }
+	const uint32_t baseE = sBase[0], baseS = sBase[1];
+	if (scanner)
 	{
-		if (b + i < a.batchesPerFrame)
-			a.batchPrefix[first + b + i] = make_uint2(pe, ps);
-		pe += e[i]; ps += s[i];
+		sOrd[tid] = inS;
+		sPhys[tid] = phys0;
+		sIds[tid] = baseE + inE;
 	}
-	if (chunk == a.chunksPerFrame - 1 && threadIdx.x == SRPD_SCAN_CHUNK / 4 - 1)
+	if (tid == SRPD_SCAN_CHUNK - 1)
 	{
-		/* the frame's totals (the last thread of the last chunk has seen everything) */
-		a.frameCounts[2 * frame + 0] = pe;
-		a.frameCounts[2 * frame + 1] = ps < a.recCapacity ? ps : a.recCapacity;
-		if (ps > a.recCapacity)
-			atomicMax(&a.needed[0], ps);
-		atomicAdd(&a.stats->primsIn, (unsigned long long) a.d.nInputPrims);
-		atomicAdd(&a.stats->primsEmitted, (unsigned long long) pe);
-		atomicAdd(&a.stats->primsStored, (unsigned long long) ps);
+		sOrd[SRPD_SCAN_CHUNK] = inS + s;
+		if (chunk == a.chunksPerFrame - 1)
+		{
+			/* the frame's totals (the last thread of the last chunk has seen everything) */
+			const uint32_t pe = baseE + inE + e, ps = baseS + inS + s;
+			a.frameCounts[2 * frame + 0] = pe;
+			a.frameCounts[2 * frame + 1] = ps < a.recCapacity ? ps : a.recCapacity;
+			if (ps > a.recCapacity)
+				atomicMax(&a.needed[0], ps);
+			atomicAdd(&a.stats->primsIn, (unsigned long long) a.d.nInputPrims);
+			atomicAdd(&a.stats->primsEmitted, (unsigned long long) pe);
+			atomicAdd(&a.stats->primsStored, (unsigned long long) ps);
+		}
 	}
-}
-
-/* The id-ordered view: one warp per batch adds the batch's id prefix to its records and
- * writes, at the records' positions in primitive order, their bounding boxes and physical
- * slots.  Binning and the tile kernel only ever walk this view. */
-__global__ void __launch_bounds__(256)
-srpdRecordOrderKernel(const __grid_constant__ SrpdGeomArgs a)
-{
-	srpdGridDependencyEnter();
-	const uint32_t batch = blockIdx.x * 8 + (threadIdx.x >> 5);
-	const uint32_t lane = threadIdx.x & 31;
-	if (batch >= a.batchesPerFrame * a.d.nFrames)
-		return;
-	const uint32_t frame = batch / a.batchesPerFrame;
-	const uint4 info = a.batchInfo[batch];
-	const uint2 prefix = a.batchPrefix[batch];
+	__syncthreads();
+	const uint32_t total = sOrd[SRPD_SCAN_CHUNK];
 	const size_t base = (size_t) frame * a.recCapacity;
-	for (uint32_t j = lane; j < info.z; j += 32)
+	for (uint32_t j = tid; j < total; j += SRPD_ORDER_THREADS)
 	{
-		const uint32_t phys = info.x + j, ord = prefix.y + j;
+		/* the owning batch: the last one with sOrd[t] <= j (batches without records share their
+		 * successor's value and are stepped over) */
+		uint32_t lo = 0, hi = SRPD_SCAN_CHUNK;
+		#pragma unroll
+		for (int step = 0; step < 8; step++)      /* log2(SRPD_SCAN_CHUNK) */
+		{
+			const uint32_t mid = (lo + hi) >> 1;
+			if (sOrd[mid] <= j) lo = mid; else hi = mid;
+		}
+		const uint32_t phys = sPhys[lo] + (j - sOrd[lo]), ord = baseS + j;
 		if (phys >= a.recCapacity || ord >= a.recCapacity)
-			break;
+			continue;      /* (a pool overflowed: the draw is repeated with larger pools) */
 		a.bboxesOrdered[base + ord] = a.bboxes[base + phys];
 		a.perm[base + ord] = phys;
 		uint32_t* id = (uint32_t*) (a.records + (base + phys) * a.recStride) + 15;
-		*id += prefix.x;
+		*id += sIds[lo];
 	}
 }
+static_assert(SRPD_SCAN_CHUNK == 256, "srpdBatchOrderKernel: one batch per thread, 8 search steps");
 
 static int gGeomLaunches = 0;
 int srpdGeomLaunchCount(void) { return gGeomLaunches; }
@@ -1013,9 +1022,8 @@ int srpdLaunchGeom(const SrpdGeomArgs& a0, cudaStream_t stream)
 		else          launchGeomKernel<false, true>(a, clipGrid, stream);
 		launches = 2;
 	}
-	srpdLaunchKernel(srpdBatchScanKernel, a.d.nFrames * a.chunksPerFrame, SRPD_SCAN_CHUNK / 4, 0, stream, a);
-	srpdLaunchKernel(srpdRecordOrderKernel, (batches + 7) / 8, 256, 0, stream, a);
-	launches += 2;
+	srpdLaunchKernel(srpdBatchOrderKernel, a.d.nFrames * a.chunksPerFrame, SRPD_ORDER_THREADS, 0, stream, a);
+	launches += 1;
 	gGeomLaunches += launches;
 	return launches;
 }

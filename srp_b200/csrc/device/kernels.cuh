@@ -58,7 +58,7 @@ constexpr int SRPD_GEOM_WARPS = SRPD_GEOM_WARPS_PER_CTA;
 #ifndef SRPD_GEOM_CTAS_PER_SM
 #define SRPD_GEOM_CTAS_PER_SM (32 / SRPD_GEOM_WARPS_PER_CTA)
 #endif
-constexpr int SRPD_SCAN_CHUNK = 1024;    /* batches per CTA of the batch-order scan */
+constexpr int SRPD_SCAN_CHUNK = 256;     /* batches per CTA of the batch-order kernel (one per thread) */
 /* draws of at most this many batches run as one launch of clipper warps (geom.cu) */
 constexpr unsigned SRPD_GEOM_SMALL_DRAW_BATCHES = 512;
 constexpr int SRPD_GEOM_THREADS = 32 * SRPD_GEOM_WARPS;
@@ -105,7 +105,6 @@ struct SrpdGeomArgs
 	uint32_t deferred;                /* set by srpdLaunchGeom: this launch works off the list  */
 	uint32_t smCount;
 	uint4* batchInfo;                 /* [nFrames * batchesPerFrame] {first slot, ids, records, -} */
-	uint2* batchPrefix;               /* [nFrames * batchesPerFrame] exclusive {ids, records} in batch order */
 	uint32_t* abortFlag;              /* zeroed per draw; set when a scratch pool overflows: the
 	                                     tile kernel then leaves the framebuffer untouched  */
 	uint32_t* needed;                 /* [0] records needed per frame (max), [1] coarse-list entries needed */
@@ -203,7 +202,7 @@ __device__ __forceinline__ void srpdGridDependencyEnter()
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 #ifndef SRPD_PDL_DEFAULT
-#define SRPD_PDL_DEFAULT 0
+#define SRPD_PDL_DEFAULT 1
 #endif
 bool srpdPdlEnabled(void);
 

@@ -42,7 +42,7 @@ struct Runtime
 	bool copyPending = false;
 	std::string lastError;
 	Pool records, bboxes, scan, frameCounts, chunkCounts, superOffsets, superTotals, listIds, uniforms, frames;
-	Pool ckptTable, largeList, bboxesOrdered, perm, batchInfo, batchPrefix, deferList;
+	Pool ckptTable, largeList, bboxesOrdered, perm, batchInfo, deferList;
 	int smCount = 148;
 	uint64_t recFloor = 0, listFloor = 0;  /* minimum pool capacities, raised by srpcuTakeOverflow() */
 	SrpdStats* stats = nullptr;            /* device, SRPD_STATS_SLOTS slots */
@@ -50,6 +50,7 @@ struct Runtime
 	unsigned long long launches = 0, h2d = 0, d2h = 0;
 	int forceBinning = -1;                 /* SRP_B200_BINNING=0/1 overrides the heuristic */
 	uint32_t binThreshold = 4096;
+	bool ckptAside = true;               /* checkpoint pre-pass beside the binning kernels (auxiliary stream) */
 	/* optional per-stage timing: 4 events per draw (start, after geometry, after binning,
 	 * after tiles) on the submission stream, summed when collected */
 	bool profile = false;
@@ -199,6 +200,7 @@ int srpcuInit(void)
 	CU(cudaMallocHost(&g.statsHost, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
 	g.forceBinning = envInt("SRP_B200_BINNING", -1);
 	g.binThreshold = (uint32_t) envInt("SRP_B200_BIN_THRESHOLD", 4096);
+	g.ckptAside = envInt("SRP_B200_CKPT_ASIDE", 1) != 0;
 	g.failed = false;
 	g.ready = true;
 	return 0;
@@ -447,13 +449,11 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	if (!grow(g.bboxesOrdered, (size_t) recCapacity * sizeof(uint2) * nFrames)) return 1;
 	if (!grow(g.perm, (size_t) recCapacity * sizeof(uint32_t) * nFrames)) return 1;
 	if (!grow(g.batchInfo, sizeof(uint4) * (size_t) batchesPerFrame * nFrames)) return 1;
-	if (!grow(g.batchPrefix, sizeof(uint2) * (size_t) batchesPerFrame * nFrames)) return 1;
 	if (!grow(g.deferList, sizeof(uint32_t) * (size_t) batchesPerFrame * nFrames)) return 1;
 	ga.deferList = (uint32_t*) g.deferList.ptr;
 	ga.bboxesOrdered = (uint2*) g.bboxesOrdered.ptr;
 	ga.perm = (uint32_t*) g.perm.ptr;
 	ga.batchInfo = (uint4*) g.batchInfo.ptr;
-	ga.batchPrefix = (uint2*) g.batchPrefix.ptr;
 	ga.batchesPerFrame = batchesPerFrame;
 	ga.chunksPerFrame = chunksPerFrame;
 	ga.chunkSums = (uint2*) ((unsigned char*) g.scan.ptr + SRPD_DRAW_HEADER_BYTES + scanStateBytes + occBytes);
@@ -523,7 +523,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		ca.largeCapacity = largeCapacity;
 		ca.ckptTable = (float*) g.ckptTable.ptr;
 		cudaStream_t where = g.stream;
-		if (binned)
+		if (binned && g.ckptAside)
 		{
 			CU(cudaEventRecord(g.geomDone, g.stream));
 			CU(cudaStreamWaitEvent(g.auxStream, g.geomDone, 0));

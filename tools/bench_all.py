@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Secondary measurements (not the driver's JSON line): kernel-only frame times and stage
 split of every BASELINE config on one GPU, incl. the frame-parallel batch (cfg5).
-Run under gpurun; writes gpurun_out/bench_all.json."""
+Run under gpurun; writes gpurun_out/bench_all.json.  usage: bench_all.py [cfg1 cfg2 cfg2_4k cfg3 cfg3_r12 cfg4 cfg5_frame cfg5 ...]"""
 import ctypes as C
 import json
 import sys
@@ -85,14 +85,21 @@ def time_batch(lib, n_frames=1024, size=1024, steps=3):
 def main():
     lib = H.load_product()
     out = {"version": lib.dll.srpB200Version().decode(), "results": []}
-    for make in (S.cfg1_textured_cube, S.cfg2_teapot, lambda: S.cfg2_teapot(3840, 2160), S.cfg3_shell,
-                 lambda: S.cfg3_shell(radius=1.2), S.cfg4_subpixel, lambda: S.cfg5_frame(0)):
+    makers = {"cfg1": S.cfg1_textured_cube, "cfg2": S.cfg2_teapot, "cfg2_4k": lambda: S.cfg2_teapot(3840, 2160),
+              "cfg3": S.cfg3_shell, "cfg3_r12": lambda: S.cfg3_shell(radius=1.2), "cfg4": S.cfg4_subpixel,
+              "cfg5_frame": lambda: S.cfg5_frame(0)}
+    only = sys.argv[1:]      # optional: names of the configs to run
+    for name, make in makers.items():
+        if only and name not in only:
+            continue
         r = time_scene(lib, make())
         print(json.dumps(r)); out["results"].append(r)
-    r = time_batch(lib)
-    print(json.dumps(r)); out["results"].append(r)
+    if not only or "cfg5" in only:
+        r = time_batch(lib)
+        print(json.dumps(r)); out["results"].append(r)
     Path(ROOT / "gpurun_out").mkdir(exist_ok=True)
-    (ROOT / "gpurun_out" / "bench_all.json").write_text(json.dumps(out, indent=1))
+    tag = ("_" + "_".join(only)) if only else ""
+    (ROOT / "gpurun_out" / f"bench_all{tag}.json").write_text(json.dumps(out, indent=1))
 
 
 if __name__ == "__main__":

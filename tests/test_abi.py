@@ -113,3 +113,24 @@ def test_reference_and_product_host_math_agree(reference):
     for fn, args in (("mat4ConstructRotate", (1.1, -0.4, 2.5)), ("mat4ConstructOrthogonalProjection", (-2, 3, -1, 1, 0.5, 9)),
                      ("mat4ConstructPerspectiveProjection", (-1, 1, -1, 1, 0.3, 6)), ("mat4ConstructTRS", (1, 2, 3, 0.1, 0.2, 0.3, 2, 2, 0.5))):
         assert np.array_equal(lib.mat4(fn, *args), reference.mat4(fn, *args)), fn
+
+
+def test_every_kernel_waits_for_its_predecessor():
+    """The draw's kernels are launched with the programmatic-stream-serialisation attribute
+    (kernels.cuh: srpdLaunchKernel), which is only safe if EVERY kernel blocks in
+    `griddepcontrol.wait` before touching memory.  Check the SASS of the shipped library: each
+    srpd* kernel contains the wait (ACQBULK) and the early trigger (PREEXIT)."""
+    sass = subprocess.run(["cuobjdump", "-sass", str(host.PRODUCT_SO)], capture_output=True, text=True)
+    if sass.returncode != 0 or "Function :" not in sass.stdout:
+        pytest.skip("cuobjdump not available")
+    kernels, cur = {}, None
+    for line in sass.stdout.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip()
+            kernels[cur] = set()
+        elif cur and ("ACQBULK" in line or "PREEXIT" in line):
+            kernels[cur].add("ACQBULK" if "ACQBULK" in line else "PREEXIT")
+    ours = {k: v for k, v in kernels.items() if "srpd" in k and "Kernel" in k}
+    assert len(ours) >= 9, sorted(kernels)
+    bad = [k for k, v in ours.items() if v != {"ACQBULK", "PREEXIT"}]
+    assert not bad, f"kernels without the dependency prologue: {bad}"

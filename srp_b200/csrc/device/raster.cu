@@ -374,8 +374,18 @@ __device__ __forceinline__ uint32_t coverTriangleRow(
 	#pragma unroll
 	for (int i = 0; i < SRPD_BLK_W; i++)
 	{
+#ifdef SRPD_COVER_CHAINED_SETP
+		/* experiment (leads for round 2): the three edge tests as one chain of
+		 * predicated compares instead of three compares combined through selects */
+		uint32_t bit;
+		asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\tsetp.gt.and.f32 p, %3, %4, p;\n\tsetp.gt.and.f32 p, %5, %6, p;\n\t"
+		    "selp.u32 %0, %7, 0, p;\n\t}"
+		    : "=r"(bit) : "f"(l0), "f"(t0), "f"(l1), "f"(t1), "f"(l2), "f"(t2), "r"(1u << i));
+		bits |= bit;
+#else
 		if (l0 > t0 && l1 > t1 && l2 > t2)
 			bits |= 1u << i;
+#endif
 		if (i + 1 < SRPD_BLK_W)
 		{
 			l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);

@@ -409,7 +409,13 @@ __device__ __forceinline__ ClipResult clipChunk(
 		sl.origSlot[0] = (uint8_t) slot0; sl.origSlot[1] = (uint8_t) slot1; sl.origSlot[2] = (uint8_t) slot2;
 		sl.list[0][0] = 0; sl.list[0][1] = 1; sl.list[0][2] = 2;
 		int n = 3, nPool = 3, cur = 0;
+#ifdef SRPD_CLIP_ROLLED
+		/* experiment (leads for round 2): a sixth of the code on the clipper pass's path,
+		 * which stalls on instruction fetch a third of the time */
+		#pragma unroll 1
+#else
 		#pragma unroll      /* the plane becomes a constant: its distance is one add, not a jump table */
+#endif
 		for (int plane = 0; plane < 6; plane++)
 		{
 			if (n == 0)

@@ -122,8 +122,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------ CPU reference
 def _ref_worker(args):
     workload, frames, warm = args
-    from srp_b200 import host as H, scenes as S
-    ref = H.load_oracle_reference()
+    from srp_b200 import scenes as S
+    from oracle.refhost import load_oracle_reference      # the checker / baseline, never the product path
+    ref = load_oracle_reference()
     p = S.Prepared(ref, make_scene(workload))
     for _ in range(warm):
         p.draw_all()
@@ -139,8 +140,8 @@ def _ref_worker(args):
 def run_reference(workload, frames_per_worker, workers, warm=1):
     """frame-parallel CPU run of the unmodified reference: `workers` processes (the library is
     single-threaded with global state), each renders `frames_per_worker` frames"""
-    from srp_b200 import host as H
-    if not H.REFERENCE_SO.exists():
+    from oracle import refhost
+    if not refhost.available():
         return None
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
@@ -149,6 +150,51 @@ def run_reference(workload, frames_per_worker, workers, warm=1):
     wall = time.perf_counter() - t0
     slowest = max(r[0] for r in res)
     return {"frames": frames_per_worker * workers, "seconds": slowest, "wall_with_setup": wall, "covered": res[0][1]}
+
+
+def parity_vs_reference(lib, scene, label):
+    """One frame of `scene` through the product (already the CUDA path) and through the unmodified
+    reference, outside any timed region: are the three planes bit-identical?  The reference has no
+    fragment counters, so the product's deterministic counts are reported, not compared."""
+    from srp_b200 import scenes as S
+    from oracle import refhost
+    if not refhost.available():
+        return {"config": label, "planes_equal": None, "why": "oracle/_ref not present on this box"}
+    lib.dll.srpB200ResetStats()
+    got = S.render(lib, scene)
+    st = lib.stats()
+    t0 = time.perf_counter()
+    want = S.render(refhost.load_oracle_reference(), scene)
+    ref_s = time.perf_counter() - t0
+    diff = {n: int((a != b).sum()) for n, a, b in zip(("color", "depth", "stencil"), got, want)}
+    return {"config": label, "planes_equal": all(v == 0 for v in diff.values()), "differing_pixels": diff,
+            "pixels": int(got[0].size), "covered_pixels": int((want[0] != 0).sum()),
+            "frags_emitted": st["fragsEmitted"], "frags_shaded": st["fragsShaded"], "prims_emitted": st["primsEmitted"],
+            "frags_emitted_equal": None, "frags_note": "the unmodified reference exposes no fragment counter; planes are compared bit for bit",
+            "reference_frame_s": ref_s, "checker": "unmodified reference (oracle/_ref), one frame, outside the timed region"}
+
+
+def kernel_only_fps(lib, torch, stream, flush, scene, steps, warm):
+    """device-timed frames/s of a secondary scene (same method as the headline value)"""
+    from srp_b200 import host as H, scenes as S
+    lib.dll.srpB200SetSyncMode(H.SRP_B200_SYNC_EXPLICIT)
+    p = S.Prepared(lib, scene)
+    for _ in range(warm):
+        p.draw_all()
+    lib.dll.srpB200Finish()
+    lib.dll.srpB200ResetStats()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    with torch.cuda.stream(stream):
+        for a, b in ev:
+            flush.fill_(3)
+            a.record(stream); p.draw_all(); b.record(stream)
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    st = lib.stats()
+    p.free()
+    lib.dll.srpB200SetSyncMode(H.SRP_B200_SYNC_DRAW)
+    return {"frames_per_s": 1e3 / ms, "ms_per_frame": ms, "frags_emitted_per_frame": st["fragsEmitted"] / steps,
+            "prims_emitted_per_frame": st["primsEmitted"] / steps, "prims_stored_per_frame": st["primsStored"] / steps}
 
 
 def host_cores():
@@ -175,14 +221,17 @@ def main():
     W = max(args.warmup, 3)
     K = args.steps
     wl = WORKLOADS[args.workload]
-    config = {"workload": wl["desc"], "frames_per_step_per_gpu": 1, "partition": "frame-parallel" if world > 1 else "single GPU",
-              "l2": "flushed between timed steps (256 MiB fill)", "data": "synthetic"}
+    # the same dict in both arms (the driver compares them): what differs between the arms -- GPUs
+    # vs host processes -- is stated under n_gpus / cpu_baseline.cores
+    config = {"workload": wl["desc"], "frames_per_step_per_worker": 1,
+              "partition": "frame-parallel: every worker (GPU rank / host process) renders its own frames of the same scene",
+              "l2": "ours: flushed between timed steps (256 MiB fill); reference arm: n/a (host caches)", "data": "synthetic"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        from srp_b200 import host as H
-        if not H.REFERENCE_SO.exists():
+        from oracle import refhost
+        if not refhost.available():
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref_host.so was not built (needs /root/reference at build time)"}))
             return
         cores = host_cores()
@@ -192,7 +241,7 @@ def main():
         line = {"impl": "reference", "metric": f"frames_per_s_{args.workload}", "value": value, "unit": "frames/s",
                 "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * r["seconds"] / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(config, partition=f"frame-parallel over {workers} host processes"),
+                "config": config,
                 "cpu_baseline": {"value": value, "unit": "frames/s", "cores": workers, "kind": "reference",
                                  "sample": f"{r['frames']} frames of the same workload ({K} per process), unmodified reference built by oracle/Makefile"},
                 "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -403,6 +452,16 @@ def main():
             "version": lib.dll.srpB200Version().decode(),
         }
         if world == 1 and args.cpu_seconds > 0:
+            # parity of the benchmarked workload itself, at full size, against the unmodified reference
+            line["parity"] = parity_vs_reference(lib, scene, wl["desc"])
+            if args.workload == "cfg3":
+                # BASELINE config 3 says "heavy near-plane clipping": the r = 3 shell of the headline
+                # clips 0.2 % of its triangles, so the r = 1.2 shell (every triangle near the camera
+                # straddles the near plane) is timed and checked as well
+                heavy = S.cfg3_shell(radius=1.2)
+                sec = kernel_only_fps(lib, torch, stream, flush, heavy, K, W)
+                sec["parity"] = parity_vs_reference(lib, heavy, "cfg3 with shell radius 1.2 (heavy near-plane clipping)")
+                line.setdefault("secondary", {})["cfg3_r1.2_heavy_clipping"] = sec
             cores = host_cores()
             workers = min(cores, 64)
             per_frame_guess = 0.6 if args.workload == "cfg3" else 0.03

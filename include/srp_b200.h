@@ -124,7 +124,9 @@ typedef struct SRPB200Stats
 	unsigned long long fragsEmitted, fragsShaded;
 	unsigned long long kernelLaunches;     /* kernels of this library launched            */
 	unsigned long long h2dBytes, d2hBytes; /* bytes this library copied across PCIe       */
-	unsigned long long overflow;           /* draws dropped because a pool was too small  */
+	unsigned long long overflow;           /* guard, expected 0: draws that hit a scratch-pool limit (pools hold the worst case) */
+	unsigned long long subDraws;           /* kernel chains submitted: > draws when a draw's worst case exceeded the
+	                                          scratch budget and it was split into ranges of input primitives */
 } SRPB200Stats;
 void srpB200GetStats(SRPB200Stats* out);   /* synchronises */
 void srpB200ResetStats(void);

@@ -16,14 +16,15 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
-from srp_b200 import host as H, scenes as S   # noqa: E402
+from srp_b200 import host as H, scenes as S
+from oracle.refhost import load_oracle_reference   # noqa: E402
 import synthetic_scenes                        # noqa: E402
 
 
 def main():
     out = ROOT / "tests" / "golden" / "synthetic"
     out.mkdir(parents=True, exist_ok=True)
-    ref = H.load_oracle_reference()
+    ref = load_oracle_reference()
     assert ref.dll.srpbIsReferenceBuild() == 1
     manifest = {}
     for name, scene in synthetic_scenes.all_scenes().items():

@@ -4,6 +4,6 @@ The product is the C library (include/srp/*.h + include/srp_b200.h, sources unde
 srp_b200/csrc, built by srp_b200/build.py); this package only holds the build recipe and a
 ctypes mirror of the C API used by the tests and the benchmark.  Importing the package does
 not load CUDA; `load_product()` does and raises if the library has not been built."""
-from .host import load_product, load_oracle_reference, SrpLibrary  # noqa: F401
+from .host import load_product, SrpLibrary  # noqa: F401
 
-__all__ = ["load_product", "load_oracle_reference", "SrpLibrary"]
+__all__ = ["load_product", "SrpLibrary"]

@@ -2,12 +2,12 @@
  *
  * The reference has no binning (it rasterises primitive-at-a-time, src/pipeline/draw.c:
  * 101-122); this stage exists so that a tile CTA only looks at the primitives near it
- * while still visiting them in primitive-id order.  Records are already stored in id
- * order by the geometry kernel, so "in order" means "in increasing record index".
+ * while still visiting them in primitive-id order.  The id-ordered view (srpdBatchOrderKernel)
+ * lists the stored primitives in primitive order, so "in order" means "in increasing position".
  *
  * Bins are supertiles of 2^k x 2^k tiles (k = 3: 256x128 px, down to k = 1 for dense
- * sub-pixel geometry; chosen per draw).  Three passes over the 8-byte bounding
- * boxes (HBM-bound; the records themselves are not touched):
+ * sub-pixel geometry; chosen per draw).  Three passes over the bounding boxes of the id-ordered
+ * view (16-byte entries, 8 bytes of box each; the records themselves are not touched):
  *   count : one CTA per chunk of 2048 records counts, per supertile, how many of the
  *           chunk's records overlap it            -> chunkCounts[chunk][supertile]
  *   scan  : per supertile an exclusive scan over the chunks, then an exclusive scan over
@@ -71,7 +71,7 @@ srpdBinCountKernel(const __grid_constant__ SrpdBinArgs a)
 		for (int k = 0; k < PER; k++)
 		{
 			const uint32_t o = k * SRPD_BIN_THREADS + threadIdx.x;
-			bb[k] = (o < chunkRecords && first + o < nStored) ? a.bboxes[first + o] : make_uint2(0u, 0u);      /* an empty box */
+			bb[k] = (o < chunkRecords && first + o < nStored) ? *(const uint2*) (a.ordered + first + o) : make_uint2(0u, 0u);      /* an empty box */
 		}
 		__syncthreads();      /* (the counters are zero) */
 		#pragma unroll
@@ -220,9 +220,12 @@ srpdBinScanKernel(const __grid_constant__ SrpdBinArgs a)
 		a.superOffsets[nSuper] = total < a.listCapacity ? total : a.listCapacity;
 		if (total > a.listCapacity)
 		{
-			atomicAdd(&a.stats->overflow, 1ull);
-			atomicExch(a.abortFlag, 1u);
+			/* the coarse lists do not fit: this draw's tiles scan all records instead (slow but
+			 * exact, no host round trip), and the host is told how large the pool has to be */
+			*a.listOverflow = 1u;
 			a.needed[1] = total;
+			*(volatile uint32_t*) (a.hostNotes + 1) = total;
+			__threadfence_system();
 		}
 	}
 }
@@ -266,7 +269,7 @@ srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 	for (int r = 0; r < ROUNDS; r++)
 	{
 		const uint32_t rec = warpFirst + r * 32 + lane;
-		rect[r] = (r < rounds && rec < nStored) ? superRect(a.bboxes[rec], a.superX, a.superY, a.superShift) : 0x00000101u;
+		rect[r] = (r < rounds && rec < nStored) ? superRect(*(const uint2*) (a.ordered + rec), a.superX, a.superY, a.superShift) : 0x00000101u;
 	}
 	__syncthreads();
 	#pragma unroll

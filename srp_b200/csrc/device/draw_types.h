@@ -82,10 +82,16 @@ typedef struct SrpdDraw
 	uint32_t topology;               /* SRPD_TOPO_*                                      */
 	uint64_t startIndex;
 	uint64_t count;                  /* stream indices                                   */
-	uint32_t nInputPrims;
+	uint32_t nInputPrims;            /* input primitives of THIS sub-draw                */
 	uint32_t kind;                   /* SRPD_KIND_* of the emitted primitives            */
-	uint32_t maxOutPerInput;         /* 1, 7 or 21                                       */
+	uint32_t maxOutPerInput;         /* worst-case records one input primitive stores    */
 	uint32_t nFrames;
+	/* A draw whose worst-case record count exceeds the scratch budget is submitted as several
+	 * sub-draws over consecutive ranges of its input primitives (srp_draw.c): firstPrim is the
+	 * range's first input primitive, chunkIndex > 0 continues the primitive ids of the
+	 * previous sub-draw (kept on the device), so no scratch pool can ever overflow. */
+	uint32_t firstPrim;
+	uint32_t chunkIndex;
 	/* sort-first strips: only tile rows [tileRow0, tileRow1) are rasterised          */
 	uint32_t tileRow0, tileRow1;
 } SrpdDraw;

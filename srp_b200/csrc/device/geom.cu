@@ -1,35 +1,35 @@
-/* srp-b200 -- geometry front-end kernel (sm_100a).
+/* srp-b200 -- geometry front-end kernels (sm_100a).
  *
- * One CTA = one batch of 256 consecutive input primitives of one frame.  Replaces, for
- * that batch, the reference's per-primitive loop in
+ * One WARP = one batch of SRPD_GEOM_PRIMS (30) consecutive input primitives of one frame; the
+ * warps of a CTA share nothing and there is no CTA barrier.  Replaces, for that batch, the
+ * reference's per-primitive loop in
  *   src/pipeline/primitive_assembly.c:37-135 (assembleTrianglesGeneric),
  *   :137-178 (assembleLines), :221-254 (assemblePoints)
  * and everything it calls: topology.c:24-83, core/buffer.c:102-128 (typed index fetch),
  * vertex_processing.c:38-74 (post-VS cache + vertex shader), clipping.c:68-258,
  * raster/triangle.c:113-160 / line.c:79-86 / point.c:76-79 (setup).
  *
- * Stages inside the CTA:
- *   1. topology + index fetch: every thread resolves the 1..3 vertex indices of its
- *      input primitive;
- *   2. post-VS cache = index de-duplication in shared memory: the indices are inserted
- *      into a 1024-slot open-addressing table, the distinct ones are numbered by a CTA
- *      scan, and the user vertex shader runs ONCE per distinct index of the batch with
- *      its outputs (clip position + varyings blob) kept in shared memory;
- *   3. per primitive: outcodes, trivial accept/reject, Sutherland-Hodgman (triangles) or
- *      Liang-Barsky (lines) clipping on the rare path, polygon-mode expansion, setup,
- *      face / degenerate culling -- first only counting how many primitive ids the input
- *      primitive consumes and how many records it stores;
- *   4. CTA exclusive scan of both counts; the batch reserves a contiguous range of record
- *      slots from the frame's bump allocator and publishes its totals;
- *   5. records are written (unclipped triangles from the set-up kept in step 3, clipped
- *      ones are clipped again) with batch-local primitive ids.
- * One small kernel then restores the reference's serial order (primitive_assembly.c:64,90-91:
- * `primitiveID++` over emitted primitives): srpdBatchOrderKernel prefix-sums the batch totals
- * in batch order, adds the id prefix to every record and builds the id-ordered view (ordered
- * bounding boxes + permutation) that binning and tiles consume.
+ * Stages of a batch (srpdGeomKernel):
+ *   1. topology + index fetch: every lane resolves the 1..3 vertex indices of its primitive;
+ *   2. post-VS cache = index de-duplication in shared memory: the indices go into a warp-private
+ *      128-slot open-addressing table, the distinct ones are numbered by a warp scan, and the
+ *      user vertex shader runs ONCE per distinct index of the batch, outputs kept in shared memory;
+ *   3. per primitive: outcodes, trivial accept / reject inline; lines, points and polygon-mode
+ *      expansion on an out-of-line path; setup, face / degenerate culling, the exact zero-coverage
+ *      test of tiny triangles -- counting primitive ids and records first;
+ *   4. warp scan of both counts; the batch takes a contiguous range of record slots from the
+ *      frame's bump allocator (arrival order) and publishes its totals;
+ *   5. records are written with batch-local primitive ids.
+ * A batch that contains a triangle crossing a clip plane is not processed by the main pass at
+ * all: it is appended to a deferred list and a second launch (`CLIPPER`: one warp per CTA, more
+ * registers, clip slots in shared memory) takes all deferred batches at once (clipChunk).
+ * srpdBatchOrderKernel then restores the reference's serial order (primitive_assembly.c:64,
+ * 90-91: `primitiveID++` over emitted primitives): it prefix-sums the batch totals in batch order
+ * and writes the id-ordered view -- per stored primitive its bounding box, its record slot and
+ * the id prefix of its batch -- that binning and tiles consume; the records are not touched again.
  *
- * HBM traffic per input triangle: 3 indices + (amortised) its vertices in, one record
- * (80 B header + 3 blobs) + one 8-byte bbox out. */
+ * HBM traffic per input triangle: 3 indices + (amortised) its vertices in; per STORED triangle
+ * one record (80 B header + 3 blobs), one 8-byte box and one 16-byte ordered-view entry out. */
 #include "kernels.cuh"
 
 namespace {
@@ -223,8 +223,21 @@ __device__ __forceinline__ void writeTriangle(Emitter& em, const SrpdState& st, 
 				const uint32_t cols = (uint32_t) (s.maxX - 1) / SRPD_TILE_W - (uint32_t) s.minX / SRPD_TILE_W + 1;
 				const uint32_t entries = rows * cols;
 				const uint32_t slot = em.storeBase + em.nStore;
-				const uint32_t off = atomicAdd(em.a->ckptCursor, entries);
-				if (off + entries <= em.a->ckptCapacity && slot < em.a->recCapacity)
+				/* reserve with a compare-and-swap so that the cursor never passes the capacity (it
+				 * cannot wrap, whatever the number of large triangles of a draw or batch) */
+				const uint32_t cap = em.a->ckptCapacity;
+				uint32_t off = cap;
+				if (entries <= cap)
+				{
+					uint32_t cur = *(volatile uint32_t*) em.a->ckptCursor;
+					while (cur <= cap - entries)
+					{
+						const uint32_t prev = atomicCAS(em.a->ckptCursor, cur, cur + entries);
+						if (prev == cur) { off = cur; break; }
+						cur = prev;
+					}
+				}
+				if ((uint64_t) off + entries <= (uint64_t) cap && slot < em.a->recCapacity)
 				{
 					const uint32_t q = atomicAdd(em.a->largeCount, 1u);
 					if (q < em.a->largeCapacity)
@@ -682,8 +695,10 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	/* single draw: the uniform block sits in the argument block (constant bank) */
 	const void* uniform = BATCH ? a.frames[frame].uniform : (const void*) a.uniformInline;
 
-	const uint32_t k = b * SRPD_GEOM_PRIMS + lane;
-	const bool active = lane < SRPD_GEOM_PRIMS && k < d.nInputPrims;
+	/* (a sub-draw covers input primitives [firstPrim, firstPrim + nInputPrims) of the draw) */
+	const uint32_t kLocal = b * SRPD_GEOM_PRIMS + lane;
+	const uint32_t k = d.firstPrim + kLocal;
+	const bool active = lane < SRPD_GEOM_PRIMS && kLocal < d.nInputPrims;
 
 	/* 1. topology + typed index fetch */
 	uint32_t vi[3] = { 0, 0, 0 };
@@ -889,9 +904,10 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
  * (one per thread, warp-shuffle scans).  (2) The id-ordered view: the chunk's records occupy a
  * contiguous range of positions in primitive order; the threads stride over those positions
  * (an even split whatever the batches' record counts -- most batches of a mesh around the
- * camera store nothing), find the owning batch in the chunk's prefix array in shared memory,
- * add the batch's id prefix to the record and write its bounding box and physical slot at its
- * position.  Binning and the tile kernel only ever walk this view. */
+ * camera store nothing), find the owning batch in the chunk's prefix array in shared memory and
+ * write {bounding box, record slot, id prefix of the batch} at its position: 16 bytes, write-only
+ * (the records keep their batch-local ids; the tile kernel adds the prefix when it shades).
+ * Binning and the tile kernel only ever walk this view. */
 constexpr int SRPD_ORDER_THREADS = 1024;      /* the first SRPD_SCAN_CHUNK of them scan; all of them move records */
 __global__ void __launch_bounds__(SRPD_ORDER_THREADS)
 srpdBatchOrderKernel(const __grid_constant__ SrpdGeomArgs a)
@@ -937,7 +953,9 @@ srpdBatchOrderKernel(const __grid_constant__ SrpdGeomArgs a)
 	uint32_t inE = incE - e, inS = incS - s;      /* exclusive, within the chunk */
 	if (scanner)
 		for (int w = 0; w < warp; w++) { inE += sWarpE[w]; inS += sWarpS[w]; }
-	const uint32_t baseE = sBase[0], baseS = sBase[1];
+	/* a later sub-draw of a split draw continues the ids of the previous one (draw_types.h) */
+	const uint32_t carry = a.d.chunkIndex ? a.idCarry[frame] : 0u;
+	const uint32_t baseE = sBase[0] + carry, baseS = sBase[1];
 	if (scanner)
 	{
 		sOrd[tid] = inS;
@@ -953,10 +971,11 @@ srpdBatchOrderKernel(const __grid_constant__ SrpdGeomArgs a)
 			const uint32_t pe = baseE + inE + e, ps = baseS + inS + s;
 			a.frameCounts[2 * frame + 0] = pe;
 			a.frameCounts[2 * frame + 1] = ps < a.recCapacity ? ps : a.recCapacity;
+			a.idCarryOut[frame] = pe;
 			if (ps > a.recCapacity)
 				atomicMax(&a.needed[0], ps);
 			atomicAdd(&a.stats->primsIn, (unsigned long long) a.d.nInputPrims);
-			atomicAdd(&a.stats->primsEmitted, (unsigned long long) pe);
+			atomicAdd(&a.stats->primsEmitted, (unsigned long long) (pe - carry));
 			atomicAdd(&a.stats->primsStored, (unsigned long long) ps);
 		}
 	}
@@ -976,11 +995,10 @@ srpdBatchOrderKernel(const __grid_constant__ SrpdGeomArgs a)
 		}
 		const uint32_t phys = sPhys[lo] + (j - sOrd[lo]), ord = baseS + j;
 		if (phys >= a.recCapacity || ord >= a.recCapacity)
-			continue;      /* (a pool overflowed: the draw is repeated with larger pools) */
-		a.bboxesOrdered[base + ord] = a.bboxes[base + phys];
-		a.perm[base + ord] = phys;
-		uint32_t* id = (uint32_t*) (a.records + (base + phys) * a.recStride) + 15;
-		*id += sIds[lo];
+			continue;      /* (cannot happen: the pools hold the worst case; kept as a guard) */
+		/* write-only: the record keeps its batch-local id, the view carries the batch's id prefix */
+		const uint2 bb = a.bboxes[base + phys];
+		a.ordered[base + ord] = make_uint4(bb.x, bb.y, phys, sIds[lo]);
 	}
 }
 static_assert(SRPD_SCAN_CHUNK == 256, "srpdBatchOrderKernel: one batch per thread, 8 search steps");

@@ -80,7 +80,7 @@ constexpr int SRPD_BIN_THREADS = 256;
 constexpr int SRPD_BIN_CHUNK = 2048;     /* records per coarse-binning CTA                  */
 constexpr uint32_t SRPD_BIN_SMALL_RECORDS = 1u << 18;   /* up to here chunks are SRPD_BIN_CHUNK / 4 (bin.cu) */
 
-/* Per-draw zero-filled header in front of the scan state: word 0 batch ticket, 1 abort flag,
+/* Per-draw zero-filled header in front of the scan state: word 0 coarse-list overflow flag, 1 abort flag,
  * 2 tile work counter, 3 records a frame needed (max over frames), 4 coarse-list entries needed,
  * 5 checkpoint-table cursor (entries), 6 number of large triangles, 7 deferred batches */
 constexpr int SRPD_DRAW_HEADER_BYTES = 64;   /* words 8..15: tile work counters of up to 8 bands */
@@ -97,8 +97,10 @@ struct SrpdGeomArgs
 	uint2* bboxes;                    /* [nFrames][recCapacity] x0|y0<<16, x1|y1<<16 (half-open, pixels) */
 	uint32_t recCapacity;
 	uint32_t recStride;
-	uint2* bboxesOrdered;             /* the same boxes at their position in primitive order */
-	uint32_t* perm;                   /* [nFrames][recCapacity] position in primitive order -> record slot */
+	uint4* ordered;                   /* [nFrames][recCapacity] the id-ordered view: entry i = the i-th stored primitive
+	                                     in primitive order: {box.x, box.y, record slot, id prefix of its batch} */
+	uint32_t* idCarry;                /* [nFrames] ids handed out by the previous sub-draw of a split draw (read if d.chunkIndex) */
+	uint32_t* idCarryOut;             /* [nFrames] written by every sub-draw (the other one of two arrays: the CTAs of srpdBatchOrderKernel run concurrently) */
 	uint32_t* frameBump;              /* [nFrames], zeroed per draw: record slots handed out */
 	uint32_t* deferCount;             /* header word 7, zeroed per draw: batches the main pass left to the clipper pass */
 	uint32_t* deferList;              /* [nFrames * batchesPerFrame] their indices              */
@@ -141,7 +143,7 @@ void srpdLaunchCheckpoints(const SrpdCkptArgs& a, cudaStream_t stream);
 
 struct SrpdBinArgs
 {
-	const uint2* bboxes;
+	const uint4* ordered;             /* the id-ordered view (.x, .y = bounding box) */
 	const uint32_t* frameCounts;      /* [0][1] = number of stored records               */
 	uint32_t nChunksMax;              /* chunks at full record capacity                  */
 	uint32_t smCount;
@@ -152,8 +154,10 @@ struct SrpdBinArgs
 	uint32_t* superOffsets;           /* [nSuper + 1]                                    */
 	uint32_t* listIds;                /* [listCapacity] record indices, id order per supertile */
 	uint32_t listCapacity;
-	uint32_t* abortFlag;
+	uint32_t* listOverflow;           /* zeroed per draw; set when the coarse lists do not fit listCapacity: the tile
+	                                     kernel then ignores them and lets every tile scan all records (slow, exact) */
 	uint32_t* needed;
+	uint32_t* hostNotes;              /* pinned, mapped: [1] = coarse-list entries a draw needed (the host raises the pool) */
 	SrpdStats* stats;
 };
 
@@ -164,13 +168,13 @@ struct SrpdTileArgs
 	const SrpdFrame* frames;          /* nullptr: frame0 + uniformInline                 */
 	alignas(16) unsigned char uniformInline[SRPD_INLINE_UNIFORM_BYTES];
 	const unsigned char* records;
-	const uint2* bboxes;              /* in primitive order */
-	const uint32_t* perm;             /* position in primitive order -> record slot */
+	const uint4* ordered;             /* the id-ordered view: {box.x, box.y, record slot, id prefix} */
 	uint32_t recCapacity;
 	uint32_t recStride;
 	const uint32_t* frameCounts;
 	const uint32_t* superOffsets;     /* nullptr: direct path, every tile scans all records */
 	const uint32_t* listIds;
+	const uint32_t* listOverflow;     /* != 0: the coarse lists are incomplete, scan all records instead */
 	uint32_t superX;
 	uint32_t superShift;
 	uint32_t tilesX, tilesY;

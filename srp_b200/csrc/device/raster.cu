@@ -291,6 +291,7 @@ struct WarpStep
 {
 	RowStart row[32 * SRPD_BLK_H];       /* [compact triangle][block row]                          */
 	TriStep  tri[32];                    /* [compact triangle]                                     */
+	uint32_t idBase[32];                 /* [compact triangle] id prefix of the triangle's batch   */
 	alignas(16) uint8_t bits[SRPD_BLK_H * 32];   /* [block row][compact triangle]: the row's 8 coverage bits */
 	uint8_t  pair[SRPD_BLK_H * 32];      /* work list of the row lanes: triangle * SRPD_BLK_H + row   */
 };
@@ -398,7 +399,7 @@ __device__ __forceinline__ uint32_t coverTriangleRow(
  * 1/w interpolation (interpolateDepthAndWTriangle, interpolation.c:34-47) and emitFragment */
 template <int SIMPLE>
 __device__ __forceinline__ void shadeTriangleFragment(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, const RowStart& rs, const TriStep& ts,
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, const RowStart& rs, const TriStep& ts, uint32_t idBase,
 	Pixel& px, FragCounters& cnt, int x, int y)
 {
 	float l0 = rs.l0, l1 = rs.l1, l2 = rs.l2;
@@ -433,7 +434,7 @@ __device__ __forceinline__ void shadeTriangleFragment(
 	                              __fmul_rn(__uint_as_float(q3.z), l2));
 	/* pixel centre: (float) ((double) x + 0.5) is exact, and so is the float sum for these magnitudes */
 	emitFragment<3, SIMPLE>(a.d.st, fr, px, cnt, x, y, __fadd_rn((float) x, 0.5f), __fadd_rn((float) y, 0.5f),
-	                depth, recW, recW, (flags & 8u) != 0, q3.w, rec + SRPD_REC_HEADER_BYTES, wgt);
+	                depth, recW, recW, (flags & 8u) != 0, q3.w + idBase, rec + SRPD_REC_HEADER_BYTES, wgt);
 }
 
 /* One list step of a warp.  `mine` = this lane's list entry (record slot `recSlot`) touches the
@@ -442,7 +443,7 @@ __device__ __forceinline__ void shadeTriangleFragment(
  * bit t of `cov` <=> triangle t covers my pixel -- and shade them in order. */
 template <int SIMPLE>
 __device__ __forceinline__ void visitTriangles(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, bool mine, uint32_t recSlot, int rowLo, int rowCnt,
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, bool mine, uint32_t recSlot, uint32_t idBase, int rowLo, int rowCnt,
 	WarpStep& ws, Pixel (&px)[SRPD_PX], FragCounters& cnt, int x, int y0, int bx0, int by0, int lane)
 {
 	const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
@@ -460,6 +461,7 @@ __device__ __forceinline__ void visitTriangles(
 	{
 		const int t = __popc(m & ((1u << lane) - 1u));
 		ws.tri[t].rec = recSlot;
+		ws.idBase[t] = idBase;
 		uint8_t* out = ws.pair + (inc - (uint32_t) rowCnt);
 		for (int r = 0; r < rowCnt; r++)
 			out[r] = (uint8_t) (t * SRPD_BLK_H + rowLo + r);
@@ -509,7 +511,7 @@ __device__ __forceinline__ void visitTriangles(
 			const int t = __ffs(c) - 1;
 			setSel(cov, h, c & (c - 1u));
 			Pixel cur = getSel(px, h);
-			shadeTriangleFragment<SIMPLE>(a, fr, records, ws.row[t * SRPD_BLK_H + ly + 4 * h], ws.tri[t], cur, cnt, x, y0 + 4 * h);
+			shadeTriangleFragment<SIMPLE>(a, fr, records, ws.row[t * SRPD_BLK_H + ly + 4 * h], ws.tri[t], ws.idBase[t], cur, cnt, x, y0 + 4 * h);
 			setSel(px, h, cur);
 		}
 	}
@@ -527,7 +529,7 @@ __device__ __forceinline__ void visitTriangles(
  * row (App. B-1).  Must be called by all 32 lanes. */
 static_assert(SRPD_LINE_SEG <= 32, "one lane per fragment of a segment");
 __device__ __forceinline__ void visitLine(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, Pixel (&px)[SRPD_PX], FragCounters& cnt,
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, uint32_t idBase, Pixel (&px)[SRPD_PX], FragCounters& cnt,
 	int x, int y0, const bool (&valid)[SRPD_PX])
 {
 	const int lane = threadIdx.x & 31;
@@ -606,7 +608,7 @@ __device__ __forceinline__ void visitLine(
 			const float depth = __fadd_rn(__fmul_rn(zw0, w0), __fmul_rn(zw1, tk));
 			Pixel cur = getSel(px, which);
 			emitFragment<2, 0>(a.d.st, fr, cur, cnt, ipx, ipy, (float) ((double) ipx + 0.5), (float) ((double) ipy + 0.5),
-			                depth, recW, recW, true, q3.w, rec + SRPD_REC_HEADER_BYTES, wgt);
+			                depth, recW, recW, true, q3.w + idBase, rec + SRPD_REC_HEADER_BYTES, wgt);
 			setSel(px, which, cur);
 		}
 	}
@@ -614,7 +616,7 @@ __device__ __forceinline__ void visitLine(
 
 /* rasterizePoint for the thread's pixels, reference point.c:32-74 */
 __device__ __forceinline__ void visitPoint(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, Pixel (&px)[SRPD_PX], FragCounters& cnt,
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, uint32_t idBase, Pixel (&px)[SRPD_PX], FragCounters& cnt,
 	int x, int y0, const bool (&valid)[SRPD_PX])
 {
 	const uint4* h = (const uint4*) rec;
@@ -637,7 +639,7 @@ __device__ __forceinline__ void visitPoint(
 		const uint4 q2 = __ldg(h + 2), q3 = __ldg(h + 3);
 		Pixel cur = getSel(px, k);
 		emitFragment<1, 0>(a.d.st, fr, cur, cnt, x, y, pcx, pcy, __uint_as_float(q2.x), 0.f, __uint_as_float(q2.y),
-		                true, q3.w, rec + SRPD_REC_HEADER_BYTES, nullptr);
+		                true, q3.w + idBase, rec + SRPD_REC_HEADER_BYTES, nullptr);
 		setSel(px, k, cur);
 	}
 }
@@ -648,6 +650,7 @@ __device__ __forceinline__ void visitPoint(
 struct TileShared
 {
 	uint32_t ids[SRPD_TILE_THREADS];     /* record slots of the tile's list chunk */
+	uint32_t idBase[SRPD_TILE_THREADS];  /* id prefix of their batches (records hold batch-local ids) */
 	uint2    box[SRPD_TILE_THREADS];     /* their boxes */
 	uint32_t warpCnt[32];
 	uint32_t item[2];
@@ -667,7 +670,7 @@ __device__ __forceinline__ void processTile(
 	/* candidate list of this tile */
 	uint32_t begin = 0, end;
 	const uint32_t* ids = nullptr;
-	if (a.superOffsets)
+	if (a.superOffsets && *a.listOverflow == 0u)
 	{
 		const uint32_t s = ((uint32_t) tileY >> a.superShift) * a.superX + ((uint32_t) tileX >> a.superShift);
 		begin = a.superOffsets[s];
@@ -678,8 +681,7 @@ __device__ __forceinline__ void processTile(
 		end = a.frameCounts[2 * frame + 1];
 
 	const unsigned char* records = a.records + (size_t) frame * a.recCapacity * a.recStride;
-	const uint2* bboxes = a.bboxes + (size_t) frame * a.recCapacity;
-	const uint32_t* perm = a.perm + (size_t) frame * a.recCapacity;
+	const uint4* ordered = a.ordered + (size_t) frame * a.recCapacity;
 
 	/* pixel ownership: warp w -> block (w % 4, w / 4) of 8 x SRPD_BLK_H pixels;
 	 * lane -> column lane % 8, rows lane / 8 (+ 4 for the thread's second pixel) */
@@ -715,12 +717,13 @@ __device__ __forceinline__ void processTile(
 		/* CTA: keep the candidates whose bbox touches the tile, in order */
 		const uint32_t i = c + tid;
 		bool hit = false;
-		uint32_t rid = 0;
+		uint4 ent = make_uint4(0u, 0u, 0u, 0u);
 		uint2 bb = make_uint2(0u, 0u);
 		if (i < end)
 		{
-			rid = ids ? ids[i] : i;          /* position in primitive order */
-			bb = bboxes[rid];
+			const uint32_t rid = ids ? ids[i] : i;          /* position in primitive order */
+			ent = ordered[rid];                              /* {box, record slot, id prefix} */
+			bb = make_uint2(ent.x, ent.y);
 			const int x0 = (int) (bb.x & 0xFFFFu), y0b = (int) (bb.x >> 16);
 			const int x1 = (int) (bb.y & 0xFFFFu), y1b = (int) (bb.y >> 16);
 			hit = x0 < tx0 + SRPD_TILE_W && x1 > tx0 && y0b < ty0 + SRPD_TILE_H && y1b > ty0;
@@ -739,7 +742,8 @@ __device__ __forceinline__ void processTile(
 		if (hit)
 		{
 			const uint32_t pos = base + __popc(ballot & ((1u << lane) - 1u));
-			sm.ids[pos] = perm[rid];         /* record slot */
+			sm.ids[pos] = ent.z;             /* record slot */
+			sm.idBase[pos] = ent.w;
 			sm.box[pos] = bb;
 		}
 		__syncthreads();
@@ -749,7 +753,7 @@ __device__ __forceinline__ void processTile(
 		{
 			const uint32_t j = j0 + lane;
 			bool mine = false;
-			uint32_t slot = 0u;
+			uint32_t slot = 0u, idBase = 0u;
 			int rowLo = 0, rowCnt = 0;
 			if (j < total)
 			{
@@ -758,11 +762,12 @@ __device__ __forceinline__ void processTile(
 				const int x1 = (int) (b2.y & 0xFFFFu), y1b = (int) (b2.y >> 16);
 				mine = x0 < bx0 + SRPD_BLK_W && x1 > bx0 && y0b < by0 + SRPD_BLK_H && y1b > by0;
 				slot = sm.ids[j];
+				idBase = sm.idBase[j];
 				rowLo = max(y0b, by0) - by0;
 				rowCnt = min(y1b, by0 + SRPD_BLK_H) - by0 - rowLo;
 			}
 			if constexpr (KIND == SRPD_KIND_TRIANGLE)
-				visitTriangles<SIMPLE>(a, fr, records, mine, slot, rowLo, rowCnt, sm.step[warp], px, cnt, x, y0, bx0, by0, lane);
+				visitTriangles<SIMPLE>(a, fr, records, mine, slot, idBase, rowLo, rowCnt, sm.step[warp], px, cnt, x, y0, bx0, by0, lane);
 			else
 			{
 				uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
@@ -771,10 +776,11 @@ __device__ __forceinline__ void processTile(
 					const int bit = __ffs(m) - 1;
 					m &= m - 1;
 					const unsigned char* rec = records + (size_t) sm.ids[j0 + bit] * a.recStride;
+					const uint32_t recIdBase = sm.idBase[j0 + bit];
 					if (KIND == SRPD_KIND_LINE)
-						visitLine(a, fr, rec, px, cnt, x, y0, valid);
+						visitLine(a, fr, rec, recIdBase, px, cnt, x, y0, valid);
 					else
-						visitPoint(a, fr, rec, px, cnt, x, y0, valid);
+						visitPoint(a, fr, rec, recIdBase, px, cnt, x, y0, valid);
 				}
 			}
 		}

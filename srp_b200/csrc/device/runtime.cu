@@ -36,15 +36,28 @@ struct Runtime
 	cudaEvent_t copyDone = nullptr;
 	cudaEvent_t submitted = nullptr;       /* async downloads: "everything enqueued so far" on the submission stream */
 	cudaStream_t auxStream = nullptr;      /* work off the critical path of a draw (checkpoint pre-pass) */
+	cudaStream_t uploadStream = nullptr;   /* srp*BufferCopyData: ordered behind the last draw that reads the buffer only */
+	cudaEvent_t uploadDone = nullptr;
+	/* pinned staging ring for per-draw host data (uniform blocks, frame bindings): the caller's
+	 * memory has been read when the draw call returns, whatever kind of memory it is */
+	unsigned char* ring = nullptr;
+	size_t ringBytes = 0, ringHead = 0;
+	cudaEvent_t ringWrapped = nullptr;     /* recorded on the submission stream when the ring wraps */
+	bool ringWrapPending = false;
+	uint32_t* hostNotes = nullptr;         /* pinned + mapped, written by kernels: [0] draws that hit a pool limit (a bug
+	                                          guard), [1] coarse-list entries a draw needed */
+	uint32_t* hostNotesDev = nullptr;      /* device alias */
+	unsigned long long guardSeen = 0;
+	size_t poolBudget = 0;                 /* bytes the per-record scratch arrays of one sub-draw may take */
 	cudaEvent_t geomDone = nullptr, ckptDone = nullptr;
 	SrpcuMirror mirror = { nullptr, nullptr, nullptr };
 	int* mirrorDone = nullptr;
 	bool copyPending = false;
 	std::string lastError;
 	Pool records, bboxes, scan, frameCounts, chunkCounts, superOffsets, superTotals, listIds, uniforms, frames;
-	Pool ckptTable, largeList, bboxesOrdered, perm, batchInfo, deferList;
+	Pool ckptTable, largeList, ordered, batchInfo, deferList, idCarry;
 	int smCount = 148;
-	uint64_t recFloor = 0, listFloor = 0;  /* minimum pool capacities, raised by srpcuTakeOverflow() */
+	uint64_t listFloor = 0;                /* minimum coarse-list capacity, raised when a draw reported it needed more */
 	SrpdStats* stats = nullptr;            /* device, SRPD_STATS_SLOTS slots */
 	SrpdStats* statsHost = nullptr;        /* pinned */
 	unsigned long long launches = 0, h2d = 0, d2h = 0;
@@ -195,6 +208,19 @@ int srpcuInit(void)
 	CU(cudaStreamCreateWithFlags(&g.auxStream, cudaStreamNonBlocking));
 	CU(cudaEventCreateWithFlags(&g.geomDone, cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&g.ckptDone, cudaEventDisableTiming));
+	CU(cudaStreamCreateWithFlags(&g.uploadStream, cudaStreamNonBlocking));
+	CU(cudaEventCreateWithFlags(&g.uploadDone, cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&g.ringWrapped, cudaEventDisableTiming));
+	g.ringBytes = (size_t) 8 << 20;
+	CU(cudaMallocHost((void**) &g.ring, g.ringBytes));
+	CU(cudaHostAlloc((void**) &g.hostNotes, 64, cudaHostAllocMapped));
+	memset(g.hostNotes, 0, 64);
+	CU(cudaHostGetDevicePointer((void**) &g.hostNotesDev, g.hostNotes, 0));
+	{
+		/* scratch budget of one sub-draw: an eighth of the device memory unless told otherwise */
+		const int mb = envInt("SRP_B200_POOL_BUDGET_MB", 0);
+		g.poolBudget = mb > 0 ? (size_t) mb << 20 : prop.totalGlobalMem / 8;
+	}
 	CU(cudaMalloc(&g.stats, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
 	CU(cudaMemset(g.stats, 0, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
 	CU(cudaMallocHost(&g.statsHost, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
@@ -214,6 +240,7 @@ void* srpcuMalloc(size_t bytes)
 	cudaError_t e = cudaMalloc(&p, bytes);
 	if (e != cudaSuccess) { fail("cudaMalloc", e); return nullptr; }
 	cudaMemsetAsync(p, 0, bytes, g.stream);
+	cudaStreamSynchronize(g.stream);      /* uploads run on their own stream */
 	return p;
 }
 void srpcuFree(void* p)
@@ -254,12 +281,71 @@ void srpcuPrefetchToDevice(void* p, size_t bytes)
 	cudaMemPrefetchAsync(p, bytes, g.device, g.stream);
 }
 
-int srpcuUpload(void* dst, const void* src, size_t bytes)
+/* Pinned staging for small per-draw host data: copies `bytes` from the caller into the ring and
+ * returns the staged address (nullptr if it cannot fit).  Space is reused after a wrap, once the
+ * submission stream has passed the event recorded at the wrap. */
+static unsigned char* ringReserve(size_t bytes)
+{
+	const size_t need = (bytes + 255) & ~(size_t) 255;
+	if (need > g.ringBytes / 2)
+		return nullptr;
+	if (g.ringHead + need > g.ringBytes)
+	{
+		/* everything staged so far has been consumed once the stream gets here */
+		cudaEventRecord(g.ringWrapped, g.stream);
+		cudaEventSynchronize(g.ringWrapped);
+		g.ringHead = 0;
+	}
+	unsigned char* at = g.ring + g.ringHead;
+	g.ringHead += need;
+	return at;
+}
+static unsigned char* stageHostData(const void* src, size_t bytes)
+{
+	unsigned char* at = ringReserve(bytes);
+	if (at)
+		memcpy(at, src, bytes);
+	return at;
+}
+
+/* srp*BufferCopyData: memcpy semantics -- when the call returns the caller may reuse `src`.
+ * The copy runs on the upload stream, ordered behind `lastUse` (the last draw that reads the
+ * destination; may be null) instead of behind everything the submission stream still has
+ * queued, and later draws are ordered behind the copy.  Pageable sources are staged by the CUDA
+ * runtime before the call returns; pinned, registered and device sources are waited for. */
+int srpcuUpload(void* dst, const void* src, size_t bytes, void* lastUse)
+{
+	if (srpcuInit()) return 1;
+	if (bytes == 0) return 0;
+	if (lastUse)
+		CU(cudaStreamWaitEvent(g.uploadStream, (cudaEvent_t) lastUse, 0));
+	CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, g.uploadStream));
+	cudaPointerAttributes attr;
+	bool pageable = false;
+	if (cudaPointerGetAttributes(&attr, src) == cudaSuccess)
+		pageable = attr.type == cudaMemoryTypeUnregistered;
+	else
+		cudaGetLastError();
+	if (!pageable)
+		CU(cudaStreamSynchronize(g.uploadStream));
+	CU(cudaEventRecord(g.uploadDone, g.uploadStream));
+	CU(cudaStreamWaitEvent(g.stream, g.uploadDone, 0));
+	g.h2d += bytes;
+	return 0;
+}
+/* plain stream-ordered copy on the submission stream (framebuffer uploads; synchronised by the caller) */
+int srpcuUploadInStream(void* dst, const void* src, size_t bytes)
 {
 	if (srpcuInit()) return 1;
 	if (bytes == 0) return 0;
 	CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, g.stream));
 	g.h2d += bytes;
+	return 0;
+}
+int srpcuRecordEvent(void* event)
+{
+	if (!g.ready || !event) return 0;
+	CU(cudaEventRecord((cudaEvent_t) event, g.stream));
 	return 0;
 }
 int srpcuDownload(void* dstHost, const void* srcDevice, size_t bytes)
@@ -370,10 +456,26 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	{
 		if (!grow(g.uniforms, ublock * nFrames)) return 1;
 		uniDev = (unsigned char*) g.uniforms.ptr;
-		if (nFrames == 1)
-			CU(cudaMemcpyAsync(uniDev, uniforms, uniformBytes, cudaMemcpyDefault, g.stream));
+		/* through the pinned staging ring, so that the caller's uniform memory -- pageable or
+		 * pinned -- has been read when the draw call returns (the reference reads it during the
+		 * call; a caller may overwrite it right afterwards) */
+		const size_t packed = ublock * (nFrames - 1) + uniformBytes;
+		unsigned char* staged = ringReserve(packed);
+		if (staged)
+		{
+			for (uint32_t f = 0; f < nFrames; f++)
+				memcpy(staged + (size_t) f * ublock, (const unsigned char*) uniforms + (size_t) f * uniformStride, uniformBytes);
+			CU(cudaMemcpyAsync(uniDev, staged, packed, cudaMemcpyHostToDevice, g.stream));
+		}
 		else
-			CU(cudaMemcpy2DAsync(uniDev, ublock, uniforms, uniformStride, uniformBytes, nFrames, cudaMemcpyDefault, g.stream));
+		{
+			/* larger than the ring: copy and wait */
+			if (nFrames == 1)
+				CU(cudaMemcpyAsync(uniDev, uniforms, uniformBytes, cudaMemcpyDefault, g.stream));
+			else
+				CU(cudaMemcpy2DAsync(uniDev, ublock, uniforms, uniformStride, uniformBytes, nFrames, cudaMemcpyDefault, g.stream));
+			CU(cudaStreamSynchronize(g.stream));
+		}
 		g.h2d += uniformBytes * nFrames;
 	}
 
@@ -384,33 +486,30 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	if (!inlineUniform)
 	{
 		if (!grow(g.frames, sizeof(SrpdFrame) * nFrames)) return 1;
-		SrpdFrame* tmp = (SrpdFrame*) malloc(sizeof(SrpdFrame) * nFrames);
+		const size_t bytes = sizeof(SrpdFrame) * nFrames;
+		SrpdFrame* tmp = (SrpdFrame*) malloc(bytes);
+		if (!tmp) { g.lastError = "srp-b200: out of host memory"; return 1; }
 		for (uint32_t f = 0; f < nFrames; f++)
 		{
 			tmp[f] = framesHost[f];
 			tmp[f].uniform = uniDev ? uniDev + (size_t) f * ublock : nullptr;
 		}
-		cudaError_t e = cudaMemcpyAsync(g.frames.ptr, tmp, sizeof(SrpdFrame) * nFrames, cudaMemcpyHostToDevice, g.stream);
-		/* pageable source: the copy has been staged when the call returns */
+		unsigned char* staged = stageHostData(tmp, bytes);
+		cudaError_t e = cudaMemcpyAsync(g.frames.ptr, staged ? (const void*) staged : (const void*) tmp, bytes, cudaMemcpyHostToDevice, g.stream);
+		if (e == cudaSuccess && !staged)
+			e = cudaStreamSynchronize(g.stream);      /* pageable source larger than the ring */
 		free(tmp);
 		if (e != cudaSuccess) { fail("cudaMemcpyAsync(frames)", e); return 1; }
-		g.h2d += sizeof(SrpdFrame) * nFrames;
+		g.h2d += bytes;
 		framesDev = (const SrpdFrame*) g.frames.ptr;
 	}
 
-	/* scratch sizing.  Worst case per input primitive is d.maxOutPerInput records; the
-	 * pools are sized for 2x the input (+ slack) and a draw that would exceed them sets
-	 * the overflow counter, which the host turns into a retry at the worst-case size. */
+	/* scratch sizing: the pools hold the WORST case of this sub-draw (d.maxOutPerInput records
+	 * per input primitive), so they cannot overflow whatever the geometry turns out to be; the
+	 * host layer splits a draw whose worst case exceeds the budget (srpcuMaxPrimsPerSubDraw). */
 	const int nVerts = srpdVertsOfKind(d.kind);
 	const uint32_t recStride = srpdRecordStride(st, nVerts);
-	const uint64_t worst = (uint64_t) d.nInputPrims * d.maxOutPerInput;
-	uint64_t cap = (d.maxOutPerInput == 1) ? worst : (uint64_t) d.nInputPrims * 2 + 4096;
-	if (d.kind == SRPD_KIND_LINE)          /* lines are stored as 16-fragment segments */
-		cap = (uint64_t) d.nInputPrims * (d.st.polygonMode == SRP_POLYGON_MODE_LINE ? 12 : 4) + 65536;
-	else if (d.st.polygonMode != SRP_POLYGON_MODE_FILL && d.maxOutPerInput > 1)
-		cap = (uint64_t) d.nInputPrims * 4 + 4096;
-	if (cap < g.recFloor) cap = g.recFloor;     /* raised after an overflow to what that draw needed */
-	if (getenv("SRP_B200_WORST_CASE_POOLS") || cap > worst) cap = worst;
+	uint64_t cap = (uint64_t) d.nInputPrims * d.maxOutPerInput;
 	if (cap > 0x7FFFFFF0ull) cap = 0x7FFFFFF0ull;
 	const uint32_t recCapacity = (uint32_t) cap;
 	const uint32_t batchesPerFrame = (d.nInputPrims + SRPD_GEOM_PRIMS - 1) / SRPD_GEOM_PRIMS;
@@ -446,13 +545,14 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ga.abortFlag = (uint32_t*) g.scan.ptr + 1;
 	ga.needed = (uint32_t*) g.scan.ptr + 3;
 	ga.frameBump = (uint32_t*) ((unsigned char*) g.scan.ptr + SRPD_DRAW_HEADER_BYTES);
-	if (!grow(g.bboxesOrdered, (size_t) recCapacity * sizeof(uint2) * nFrames)) return 1;
-	if (!grow(g.perm, (size_t) recCapacity * sizeof(uint32_t) * nFrames)) return 1;
+	if (!grow(g.ordered, (size_t) recCapacity * sizeof(uint4) * nFrames)) return 1;
+	if (!grow(g.idCarry, sizeof(uint32_t) * 2 * (size_t) nFrames)) return 1;
 	if (!grow(g.batchInfo, sizeof(uint4) * (size_t) batchesPerFrame * nFrames)) return 1;
 	if (!grow(g.deferList, sizeof(uint32_t) * (size_t) batchesPerFrame * nFrames)) return 1;
 	ga.deferList = (uint32_t*) g.deferList.ptr;
-	ga.bboxesOrdered = (uint2*) g.bboxesOrdered.ptr;
-	ga.perm = (uint32_t*) g.perm.ptr;
+	ga.ordered = (uint4*) g.ordered.ptr;
+	ga.idCarry = (uint32_t*) g.idCarry.ptr + (size_t) ((d.chunkIndex + 1) & 1u) * nFrames;      /* what the previous sub-draw wrote */
+	ga.idCarryOut = (uint32_t*) g.idCarry.ptr + (size_t) (d.chunkIndex & 1u) * nFrames;
 	ga.batchInfo = (uint4*) g.batchInfo.ptr;
 	ga.batchesPerFrame = batchesPerFrame;
 	ga.chunksPerFrame = chunksPerFrame;
@@ -545,8 +645,8 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	if (inlineUniform)
 		memcpy(ta.uniformInline, uniforms, uniformBytes);
 	ta.records = ga.records;
-	ta.bboxes = ga.bboxesOrdered;
-	ta.perm = ga.perm;
+	ta.ordered = ga.ordered;
+	ta.listOverflow = (uint32_t*) g.scan.ptr + 0;
 	ta.recCapacity = recCapacity;
 	ta.recStride = recStride;
 	ta.frameCounts = ga.frameCounts;
@@ -568,7 +668,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	{
 		SrpdBinArgs ba;
 		memset(&ba, 0, sizeof ba);
-		ba.bboxes = ga.bboxesOrdered;
+		ba.ordered = ga.ordered;
 		ba.frameCounts = ga.frameCounts;
 		ba.nChunksMax = (recCapacity + SRPD_BIN_CHUNK - 1) / SRPD_BIN_CHUNK;
 		/* draws that store few records use quarter-size chunks (bin.cu): room for those too */
@@ -581,9 +681,18 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		ba.superX = superX;
 		ba.superY = superY;
 		ba.superShift = superShift;
-		uint64_t listCap = (uint64_t) recCapacity * 2 + (uint64_t) nSuper * 64 + 65536;
+		/* coarse lists: their worst case (every record in every supertile) is not affordable, so
+		 * the pool is sized generously and a draw that still exceeds it falls back, on the device,
+		 * to tiles that scan all records (bin.cu); the note it leaves raises the pool for later draws */
+		if (g.hostNotes[1])
+		{
+			const uint64_t need = g.hostNotes[1];
+			if (need + need / 8 + 1024 > g.listFloor) g.listFloor = need + need / 8 + 1024;
+			g.hostNotes[1] = 0;
+		}
+		uint64_t listCap = (uint64_t) (expected < recCapacity ? expected : recCapacity) * (d.kind == SRPD_KIND_LINE ? 8 : 4) + (uint64_t) nSuper * 64 + 65536;
 		if (listCap < g.listFloor) listCap = g.listFloor;
-		if (getenv("SRP_B200_WORST_CASE_POOLS")) listCap = (uint64_t) recCapacity * nSuper;
+		if (const char* e = getenv("SRP_B200_LIST_CAPACITY")) listCap = (uint64_t) atoll(e);      /* tests: force the fallback */
 		if (listCap > 0x7FFFFFF0ull) listCap = 0x7FFFFFF0ull;
 		ba.listCapacity = (uint32_t) listCap;
 		if (!grow(g.chunkCounts, sizeof(uint32_t) * (size_t) ba.nChunksMax * nSuper)) return 1;
@@ -594,8 +703,9 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		ba.superOffsets = (uint32_t*) g.superOffsets.ptr;
 		ba.superTotals = (uint32_t*) g.superTotals.ptr;
 		ba.listIds = (uint32_t*) g.listIds.ptr;
-		ba.abortFlag = ga.abortFlag;
+		ba.listOverflow = (uint32_t*) g.scan.ptr + 0;
 		ba.needed = ga.needed;
+		ba.hostNotes = g.hostNotesDev;
 		ba.stats = g.stats;
 		srpdLaunchBin(ba, g.stream, ckptAside ? g.ckptDone : (cudaEvent_t) nullptr);     /* (ckptAside implies binned) */
 		g.launches += 4;
@@ -698,10 +808,10 @@ void srpcuGetStats(SrpdStats* out, unsigned long long* launches, unsigned long l
 	}
 }
 
-/* 1 if a scratch pool overflowed since the previous call (synchronises; small copies).  The
- * kernels record what the overflowing draw would have needed (records per frame, coarse-list
- * entries); the pool floors are raised to that, so repeating the draw succeeds.
- * Only slot 0 of the counter array is used for overflow accounting. */
+/* Guard: 1 if a draw hit a record-pool limit since the previous call (synchronises).  The pools
+ * are sized for the worst case of every sub-draw, so this is never expected; a draw that does
+ * trip it leaves its framebuffer (and a pending clear) untouched, and the host reports it.
+ * Only slot 0 of the counter array is used for this accounting. */
 int srpcuTakeOverflow(void)
 {
 	static unsigned long long seen = 0;
@@ -712,14 +822,23 @@ int srpcuTakeOverflow(void)
 	const unsigned long long now = g.statsHost[0].overflow;
 	const int fresh = now > seen;
 	seen = now;
-	if (fresh && g.scan.ptr)
-	{
-		uint32_t needed[2] = { 0, 0 };
-		cudaMemcpy(needed, (uint32_t*) g.scan.ptr + 3, sizeof needed, cudaMemcpyDeviceToHost);
-		if (needed[0]) g.recFloor = (uint64_t) needed[0] + needed[0] / 8 + 1024;
-		if (needed[1]) g.listFloor = (uint64_t) needed[1] + needed[1] / 8 + 1024;
-	}
 	return fresh;
+}
+
+/* How many input primitives of `d` one sub-draw may take so that the worst-case per-record
+ * scratch (record + box + ordered-view entry, for every frame of a batch) stays within the
+ * budget (SRP_B200_POOL_BUDGET_MB, default an eighth of the device memory). */
+uint32_t srpcuMaxPrimsPerSubDraw(const SrpdDraw* d)
+{
+	if (srpcuInit()) return d->nInputPrims;
+	const uint64_t perRecord = (uint64_t) srpdRecordStride(d->st, srpdVertsOfKind(d->kind)) + sizeof(uint2) + sizeof(uint4);
+	const uint64_t perPrim = perRecord * (d->maxOutPerInput ? d->maxOutPerInput : 1) * (d->nFrames ? d->nFrames : 1);
+	uint64_t n = g.poolBudget / (perPrim ? perPrim : 1);
+	const uint64_t byIndex = 0x7FFFFFF0ull / (d->maxOutPerInput ? d->maxOutPerInput : 1);      /* 32-bit record slots */
+	if (n > byIndex) n = byIndex;
+	if (n < (uint64_t) SRPD_GEOM_PRIMS) n = SRPD_GEOM_PRIMS;
+	n -= n % SRPD_GEOM_PRIMS;      /* whole batches */
+	return n > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t) n;
 }
 
 /* per-stage device time: enable, run draws, collect {geometry, binning, tiles} in ms */

@@ -27,8 +27,12 @@ void srpcuFreeHost(void* p);
 void* srpcuMallocManaged(size_t bytes);          /* managed memory (textures)            */
 void srpcuFreeManaged(void* p);
 void srpcuPrefetchToDevice(void* p, size_t bytes);
-/* stream-ordered copy of caller memory of any kind (host, pinned, device) to the device */
-int srpcuUpload(void* dst, const void* src, size_t bytes);
+/* copy of caller memory of any kind (pageable, pinned, device) to the device with memcpy
+ * semantics: the caller may reuse `src` on return.  Runs on the upload stream behind `lastUse`
+ * (event of the last draw that reads `dst`, or NULL); later draws are ordered behind it. */
+int srpcuUpload(void* dst, const void* src, size_t bytes, void* lastUse);
+int srpcuUploadInStream(void* dst, const void* src, size_t bytes);   /* on the submission stream; enqueue only */
+int srpcuRecordEvent(void* event);                                  /* on the submission stream */
 int srpcuDownload(void* dstHost, const void* srcDevice, size_t bytes);   /* enqueue only */
 int srpcuSynchronize(void);
 
@@ -64,10 +68,11 @@ int srpcuDownloadPlanesAsync(const SrpcuMirror* host, const void* dColor, const 
 int srpcuHostWaitEvent(void* event);
 int srpcuStreamWaitEvent(void* event);
 
-/* 1 if a scratch pool overflowed since the previous call (the affected draw left the
- * framebuffer untouched); the pools' minimum sizes have then been raised to what that draw
- * needed, so the host simply repeats it. */
+/* Guard: 1 if a draw hit a record-pool limit since the previous call (never expected: the pools
+ * hold the worst case of every sub-draw); synchronises. */
 int srpcuTakeOverflow(void);
+/* input primitives one sub-draw of `d` may take within the scratch budget (whole batches) */
+uint32_t srpcuMaxPrimsPerSubDraw(const SrpdDraw* d);
 
 void srpcuSetProfiling(int on);
 unsigned long long srpcuCollectStageTimes(double outMs[3]);

@@ -1,9 +1,12 @@
 /* srp-b200 host layer -- vertex / index buffer objects.
  * API behaviour of reference src/core/buffer.c:20-128 (grow-only storage, the element
  * count is nBytesData / element size, index types u8/u16/u32/u64), but the payload is
- * device-resident: *CopyData is a stream-ordered upload (the source may be pageable or
- * pinned host memory, or -- through unified addressing -- device memory, e.g. a buffer
- * another GPU broadcast over NVLink). */
+ * device-resident: *CopyData is an upload with the reference's memcpy semantics -- the caller
+ * may reuse its memory when the call returns -- whatever the source is (pageable or pinned
+ * host memory, or, through unified addressing, device memory, e.g. a buffer another GPU
+ * broadcast over NVLink).  The copy is ordered behind the last draw that reads the buffer
+ * (its `lastUse` event under the explicit policy), not behind everything that is queued, so
+ * next frame's geometry crosses PCIe while this frame is still being rasterised. */
 #include <stdlib.h>
 #include "srp_internal.h"
 
@@ -39,7 +42,7 @@ void srpVertexBufferCopyData(SRPVertexBuffer* vb, size_t nBytesPerVertex, size_t
 	}
 	vb->nBytesPerVertex = nBytesPerVertex;
 	vb->nVertices = nBytesPerVertex ? nBytesData / nBytesPerVertex : 0;
-	if (srpcuUpload(vb->data, data, nBytesData))
+	if (srpcuUpload(vb->data, data, nBytesData, vb->lastUse))
 		srpFatalMessage(__func__, "%s", srpcuLastError());
 }
 
@@ -47,6 +50,7 @@ void srpFreeVertexBuffer(SRPVertexBuffer* vb)
 {
 	if (!vb) return;
 	srpcuFree(vb->data);
+	srpcuFreeEvent(vb->lastUse);
 	free(vb);
 }
 
@@ -76,7 +80,7 @@ void srpIndexBufferCopyData(SRPIndexBuffer* ib, SRPType indicesType, size_t nByt
 	ib->indicesType = indicesType;
 	ib->nBytesPerIndex = elem;
 	ib->nIndices = nBytesData / elem;
-	if (srpcuUpload(ib->data, data, nBytesData))
+	if (srpcuUpload(ib->data, data, nBytesData, ib->lastUse))
 		srpFatalMessage(__func__, "%s", srpcuLastError());
 }
 
@@ -84,5 +88,6 @@ void srpFreeIndexBuffer(SRPIndexBuffer* ib)
 {
 	if (!ib) return;
 	srpcuFree(ib->data);
+	srpcuFreeEvent(ib->lastUse);
 	free(ib);
 }

@@ -14,7 +14,7 @@
 #include "srp_internal.h"
 
 static size_t gRow0 = 0, gRow1 = SIZE_MAX;
-static unsigned long long gDraws = 0;
+static unsigned long long gDraws = 0, gSubDraws = 0;
 
 void srpB200SetRowRange(size_t row0, size_t row1) { gRow0 = row0; gRow1 = row1; }
 size_t srpB200TileWidth(void) { return (size_t) srpcuTileWidth(); }
@@ -38,8 +38,9 @@ void srpB200GetStats(SRPB200Stats* out)
 	out->h2dBytes = h2d;
 	out->d2hBytes = d2h;
 	out->overflow = s.overflow;
+	out->subDraws = gSubDraws;
 }
-void srpB200ResetStats(void) { gDraws = 0; srpcuResetStats(); }
+void srpB200ResetStats(void) { gDraws = 0; gSubDraws = 0; srpcuResetStats(); }
 void srpB200SetProfiling(int enable) { srpcuSetProfiling(enable); }
 unsigned long long srpB200CollectStageTimes(double outMs[3]) { return srpcuCollectStageTimes(outMs); }
 
@@ -239,16 +240,17 @@ static bool buildDraw(
 	d->startIndex = startIndex;
 	d->count = count;
 	d->nInputPrims = (uint32_t) nPrims;
-	/* worst-case records per input primitive: a clipped triangle fans into <= 7; a line is
-	 * stored as segments of 16 DDA fragments and has <= max(W, H) + 1 of them */
+	/* worst-case records per input primitive: the clipper keeps at most 10 polygon vertices, i.e.
+	 * a clipped triangle fans into <= 8 (geom.cu: SRPD_CLIP_MAX_VERTS); a line is stored as
+	 * segments of 16 DDA fragments and has <= max(W, H) + 2 fragments */
 	const uint32_t maxDim = (uint32_t) (fb->width > fb->height ? fb->width : fb->height);
-	const uint32_t segmentsPerLine = (maxDim + 1) / 16 + 2;
+	const uint32_t segmentsPerLine = (maxDim + 2) / 16 + 2;
 	if (isTriangle)
 	{
 		d->kind = st->polygonMode == SRP_POLYGON_MODE_FILL ? SRPD_KIND_TRIANGLE
 		        : st->polygonMode == SRP_POLYGON_MODE_LINE ? SRPD_KIND_LINE : SRPD_KIND_POINT;
-		d->maxOutPerInput = st->polygonMode == SRP_POLYGON_MODE_FILL ? 7
-		                  : st->polygonMode == SRP_POLYGON_MODE_LINE ? 21 * segmentsPerLine : 21;
+		d->maxOutPerInput = st->polygonMode == SRP_POLYGON_MODE_FILL ? 8
+		                  : st->polygonMode == SRP_POLYGON_MODE_LINE ? 24 * segmentsPerLine : 24;
 	}
 	else
 	{
@@ -265,14 +267,24 @@ static bool buildDraw(
 	return true;
 }
 
+/* under the explicit policy the draw is still in flight when the call returns: remember where the
+ * stream was, so that a later *CopyData into this buffer waits for exactly this draw */
+static void markBufferUse(void** lastUse)
+{
+	if (*lastUse == NULL)
+		*lastUse = srpcuNewEvent();
+	if (*lastUse)
+		srpcuRecordEvent(*lastUse);
+}
+
 static void submit(
 	const SRPIndexBuffer* ib, const SRPVertexBuffer* vb, SRPFramebuffer* const* fbs, size_t nFrames,
 	const SRPShaderProgram* sp, const void* uniforms, size_t uniformStride,
 	SRPPrimitive primitive, size_t startIndex, size_t count, bool clearFirst)
 {
-	if (count == 0 || nFrames == 0 || checkOOB(ib, vb, startIndex, count))
+	if (nFrames == 0)
 		return;
-
+	bool enqueued = false;
 	SRPFramebufferImpl** impls = malloc(nFrames * sizeof *impls);
 	SrpdFrame* frames = malloc(nFrames * sizeof *frames);
 	if (!impls || !frames) abort();
@@ -284,34 +296,48 @@ static void submit(
 		{
 			srpFatalMessage("srpDraw", "framebuffer %zu is not a live srp framebuffer of the batch's size", f);
 			ok = false;
+			nFrames = f;      /* (only the ones seen so far are touched below) */
 			break;
 		}
-		srpFramebufferBeforeWrite(impls[f]);
 		if (clearFirst)
 			srpFramebufferClear(fbs[f]);
 	}
 
 	SrpdDraw d;
 	const SRPProgramEntry* prog = NULL;
-	if (ok && buildDraw(&d, ib, vb, fbs[0], sp, primitive, startIndex, count, &prog))
+	if (ok && count != 0 && !checkOOB(ib, vb, startIndex, count)
+	    && buildDraw(&d, ib, vb, fbs[0], sp, primitive, startIndex, count, &prog))
 	{
+		for (size_t f = 0; f < nFrames; f++)
+			srpFramebufferBeforeWrite(impls[f]);
 		d.nFrames = (uint32_t) nFrames;
-		for (int attempt = 0; attempt < 3; attempt++)
+		/* The scratch pools of a (sub-)draw hold its worst case, so nothing can overflow and nothing
+		 * ever has to be repeated -- under either synchronisation policy.  A draw whose worst case
+		 * exceeds the scratch budget is submitted as consecutive ranges of its input primitives;
+		 * primitive ids continue across the ranges on the device. */
+		const uint32_t total = d.nInputPrims;
+		const uint32_t perSub = srpcuMaxPrimsPerSubDraw(&d);
+		uint32_t chunk = 0;
+		for (uint32_t first = 0; first < total; first += perSub, chunk++)
 		{
+			d.firstPrim = first;
+			d.nInputPrims = total - first < perSub ? total - first : perSub;
+			d.chunkIndex = chunk;
+			const bool last = first + d.nInputPrims >= total;
 			for (size_t f = 0; f < nFrames; f++)
 			{
 				frames[f].uniform = NULL;
 				frames[f].color = impls[f]->dColor;
 				frames[f].depth = impls[f]->dDepth;
 				frames[f].stencil = impls[f]->dStencil;
-				frames[f].clearPending = impls[f]->clearPending;
+				frames[f].clearPending = chunk == 0 && impls[f]->clearPending;
 				frames[f].pad = 0;
 			}
 			const size_t ubytes = uniforms ? prog->uniformSize : 0;
-			/* default policy: the draw itself may refresh the host mirror band by band, overlapping
-			 * the copies with rasterisation (it reports back whether it did) */
+			/* default policy: the (last sub-)draw itself may refresh the host mirror band by band,
+			 * overlapping the copies with rasterisation (it reports back whether it did) */
 			int mirrored = 0;
-			if (nFrames == 1 && srpB200GetSyncMode() == SRP_B200_SYNC_DRAW)
+			if (last && nFrames == 1 && srpB200GetSyncMode() == SRP_B200_SYNC_DRAW)
 			{
 				const int planes = srpMirrorPlanes();
 				const bool wantStencil = (planes & SRP_B200_MIRROR_STENCIL) && (impls[0]->stencilTouched || d.st.stencilEnabled);
@@ -325,24 +351,26 @@ static void submit(
 				srpFatalMessage("srpDraw", "%s", srpcuLastError());
 				break;
 			}
-			gDraws++;
-			if (srpB200GetSyncMode() != SRP_B200_SYNC_DRAW || !srpcuTakeOverflow())
+			gDraws += chunk == 0;
+			gSubDraws++;
+			enqueued = true;
+			if (chunk == 0)
+				for (size_t f = 0; f < nFrames; f++)
+					impls[f]->clearPending = false;      /* consumed by the first sub-draw's tiles */
+			if (last)
 			{
+				if (srpB200GetSyncMode() != SRP_B200_SYNC_DRAW)
+				{
+					markBufferUse(&((SRPVertexBuffer*) vb)->lastUse);
+					if (ib) markBufferUse(&((SRPIndexBuffer*) ib)->lastUse);
+				}
 				srpFramebufferAfterDraw(impls, nFrames, d.st.stencilEnabled, mirrored != 0);
-				break;
-			}
-			/* A scratch pool was too small for this draw (heavy clipping / long lines).  The
-			 * kernels raised the draw's abort flag, so the tile kernel left the framebuffer
-			 * (and a pending clear) untouched, and recorded what the draw needs; the pools'
-			 * floors are now at that size: repeat. */
-			if (attempt == 2)
-			{
-				srpFatalMessage("srpDraw", "scratch pools overflowed repeatedly; draw is incomplete");
-				srpFramebufferAfterDraw(impls, nFrames, d.st.stencilEnabled, false);
-				break;
 			}
 		}
 	}
+	if (!enqueued)
+		for (size_t f = 0; f < nFrames; f++)
+			srpFramebufferAfterSkippedDraw(fbs[f]);
 	free(frames);
 	free(impls);
 }

@@ -9,7 +9,9 @@
  * mirror that is refreshed by a device-to-host copy: after every draw (default policy)
  * or on request (include/srp_b200.h).  A clear only sets a flag; the next draw's tile
  * kernel starts from the clear values instead of loading the planes, and writes every
- * tile, so clear + draw costs one write of the planes and no read. */
+ * tile, so clear + draw costs one write of the planes and no read.  If the next draw call
+ * turns out to draw nothing, or the planes are requested first, the clear is materialised
+ * then (srpFramebufferAfterSkippedDraw, materializeClear). */
 #include <stdlib.h>
 #include <string.h>
 #include "srp_internal.h"
@@ -125,6 +127,25 @@ static void materializeClear(SRPFramebufferImpl* fb)
 	fb->clearPending = false;
 }
 
+/* A draw call that enqueued nothing (srp_draw.c) after srpFramebufferClear: under the default
+ * policy the caller may read fb->color / fb->depth right after the call and must find the clear
+ * there, as with the reference's immediate memset (core/framebuffer.c:57-62).  The device planes
+ * are cleared by a kernel; the host mirror is written directly (no PCIe round trip). */
+void srpFramebufferAfterSkippedDraw(const SRPFramebuffer* pub)
+{
+	SRPFramebufferImpl* fb = srpFramebufferImpl(pub);
+	if (!fb || !fb->clearPending || gSyncMode != SRP_B200_SYNC_DRAW)
+		return;
+	materializeClear(fb);
+	const size_t n = fb->pub.size;
+	if (gMirrorPlanes & SRP_B200_MIRROR_COLOR)
+		memset(fb->pub.color, 0, n * sizeof(uint32_t));
+	if (gMirrorPlanes & SRP_B200_MIRROR_DEPTH)
+		for (size_t i = 0; i < n; i++)
+			fb->pub.depth[i] = -1.0f;
+	/* (mirrorStale stays set: only srp_io.c looks at it, and a redundant download is harmless) */
+}
+
 static void enqueueDownload(SRPFramebufferImpl* fb, int planes)
 {
 	materializeClear(fb);
@@ -208,9 +229,9 @@ void srpB200FramebufferUpload(const SRPFramebuffer* pub)
 	srpFramebufferBeforeWrite(fb);
 	const size_t n = fb->pub.size;
 	fb->clearPending = false;
-	int err = srpcuUpload(fb->dColor, fb->pub.color, n * sizeof(uint32_t));
-	err |= srpcuUpload(fb->dDepth, fb->pub.depth, n * sizeof(float));
-	err |= srpcuUpload(fb->dStencil, fb->pub.stencil, n * sizeof(uint8_t));
+	int err = srpcuUploadInStream(fb->dColor, fb->pub.color, n * sizeof(uint32_t));
+	err |= srpcuUploadInStream(fb->dDepth, fb->pub.depth, n * sizeof(float));
+	err |= srpcuUploadInStream(fb->dStencil, fb->pub.stencil, n * sizeof(uint8_t));
 	if (err || srpcuSynchronize())
 		srpFatalMessage(__func__, "%s", srpcuLastError());
 }
@@ -226,7 +247,6 @@ void srpFramebufferAfterDraw(SRPFramebufferImpl* const* fbs, size_t n, bool sten
 {
 	for (size_t i = 0; i < n; i++)
 	{
-		fbs[i]->clearPending = false;
 		fbs[i]->mirrorStale = true;
 		if (stencilEnabled)
 			fbs[i]->stencilTouched = true;

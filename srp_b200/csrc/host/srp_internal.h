@@ -18,6 +18,7 @@ struct SRPVertexBuffer
 	size_t nVertices;
 	size_t nBytesAllocated;
 	void* data;                 /* device */
+	void* lastUse;              /* event behind the last asynchronous draw that reads `data` (explicit policy) */
 };
 
 struct SRPIndexBuffer
@@ -27,6 +28,7 @@ struct SRPIndexBuffer
 	size_t nIndices;
 	size_t nBytesAllocated;
 	void* data;                 /* device */
+	void* lastUse;              /* as in SRPVertexBuffer */
 };
 
 /* The public SRPFramebuffer (host-visible mirror pointers) is the first member, so the
@@ -78,6 +80,9 @@ SRPFramebufferImpl* srpFramebufferImpl(const SRPFramebuffer* fb);
  * asynchronous download that may still be reading them */
 void srpFramebufferBeforeWrite(SRPFramebufferImpl* fb);
 void srpFramebufferAfterDraw(SRPFramebufferImpl* const* fbs, size_t n, bool stencilEnabled, bool alreadyMirrored);
+/* a draw call that enqueued nothing (count 0, out-of-range, culled away, unregistered program ...):
+ * under the default policy the host-visible planes must still show a clear issued before it */
+void srpFramebufferAfterSkippedDraw(const SRPFramebuffer* fb);
 
 int srpMirrorPlanes(void);
 

@@ -1,16 +1,11 @@
 """Host-side mirror of the srp C API (ctypes), the way a C program would call it.
 
-The same class drives two shared objects that export the identical C ABI
-(include/srp/api.h):
-
-  * srp_b200/lib/libsrp_b200.so   -- the product: host C layer + sm_100a kernels
-  * oracle/_ref/libref_host.so    -- TEST INFRASTRUCTURE: the unmodified reference
-                                     (kitrofimov/srp) built by oracle/Makefile
-
-so a parity test issues literally the same calls against both and compares the
-framebuffer planes.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline /
-reference arm may load the oracle; `load_product()` never does, and it raises if the CUDA
-library is missing -- there is no CPU fallback on the product path.
+`SrpLibrary` wraps any shared object that exports the srp C ABI (include/srp/api.h).  The
+product is srp_b200/lib/libsrp_b200.so (host C layer + sm_100a kernels); `load_product()` loads
+it and raises if it is missing -- there is no CPU fallback on the product path and nothing in
+this package knows where the oracle lives.  The tests drive the unmodified reference through
+the same class (oracle/refhost.py, test infrastructure), so a parity test issues literally the
+same calls against both and compares the framebuffer planes.
 
 Function names, argument meaning and error behaviour are the reference's
 (include/srp/{context,buffer,framebuffer,texture,shaders}.h); numpy only carries bytes.
@@ -25,7 +20,6 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
 PRODUCT_SO = ROOT / "srp_b200" / "lib" / "libsrp_b200.so"
-REFERENCE_SO = ROOT / "oracle" / "_ref" / "libref_host.so"
 
 # ---- enums (include/srp/api.h) ------------------------------------------------------
 SRP_FLOAT, SRP_DOUBLE, SRP_INT8, SRP_INT16, SRP_INT32, SRP_INT64, SRP_UINT8, SRP_UINT16, SRP_UINT32, SRP_UINT64 = range(10)
@@ -89,7 +83,7 @@ class SrpbProgramInfo(C.Structure):
 class SRPB200Stats(C.Structure):
     _fields_ = [(n, C.c_ulonglong) for n in (
         "draws", "primsIn", "primsEmitted", "primsStored", "fragsEmitted", "fragsShaded",
-        "kernelLaunches", "h2dBytes", "d2hBytes", "overflow")]
+        "kernelLaunches", "h2dBytes", "d2hBytes", "overflow", "subDraws")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -354,12 +348,3 @@ def load_product() -> SrpLibrary:
                 "srp_b200 has no CPU implementation to fall back to.")
         _loaded["product"] = SrpLibrary(PRODUCT_SO, is_product=True)
     return _loaded["product"]
-
-
-def load_oracle_reference() -> SrpLibrary:
-    """TEST INFRASTRUCTURE ONLY: the unmodified reference built into oracle/_ref."""
-    if "reference" not in _loaded:
-        if not REFERENCE_SO.exists():
-            raise FileNotFoundError(f"{REFERENCE_SO} is missing (it is built from /root/reference by oracle/Makefile)")
-        _loaded["reference"] = SrpLibrary(REFERENCE_SO, is_product=False)
-    return _loaded["reference"]

@@ -208,23 +208,24 @@ def cube_mesh():
     return np.array(verts, f32), np.array(idx, np.uint8)
 
 
-def procedural_texture(size=480, seed=7):
-    """deterministic RGB8 'stone wall' stand-in (the reference asset is not shipped)"""
-    y, x = np.mgrid[0:size, 0:size]
-    rng = np.random.RandomState(seed)
-    noise = rng.randint(0, 48, (size, size))
-    brick = (((x // 60 + (y // 30) % 2 * 30 // 30) % 2) * 40 + ((y % 30) < 2) * 60 + ((x + (y // 30 % 2) * 30) % 60 < 2) * 60)
-    r = np.clip(96 + brick + noise, 0, 255)
-    g = np.clip(80 + brick // 2 + noise, 0, 255)
-    b = np.clip(64 + noise * 2, 0, 255)
-    return np.stack([r, g, b], -1).astype(np.uint8)
+ASSETS = ROOT / "tests" / "_build" / "res"      # the reference's examples/res, copied there by srp_b200.build
 
 
-def _find_res(rel):
-    for base in (ROOT / "oracle" / "_ref" / "res", ROOT / "tests" / "_build" / "res"):
-        if (base / rel).exists():
-            return base / rel
-    return None
+def asset_path(rel):
+    """A resource of the reference's examples (teapot OBJ, stone-wall texture).  The build copies
+    examples/res next to the scene executables; the snapshot that travels to the GPU box carries
+    it.  A missing asset is an error: no config is ever rendered with a stand-in."""
+    p = ASSETS / rel
+    if not p.exists():
+        raise FileNotFoundError(f"{p} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` where /root/reference exists")
+    return p
+
+
+def stone_wall_texture():
+    """examples/res/textures/stoneWall.png (480x480) as RGB8, the texture of cfg1"""
+    from PIL import Image
+    with Image.open(asset_path("textures/stoneWall.png")) as im:
+        return np.ascontiguousarray(np.asarray(im.convert("RGB"), dtype=np.uint8))
 
 
 def load_obj(path):
@@ -248,32 +249,10 @@ def load_obj(path):
     return verts, np.arange(len(verts), dtype=np.uint32)
 
 
-def torus_mesh(n_major=53, n_minor=11):
-    """1166-triangle stand-in for the teapot when the asset is unavailable (same vertex
-    format, same de-indexed layout: 3498 vertices, identity indices)."""
-    tris = []
-    def p(i, j):
-        a, b = 2 * np.pi * i / n_major, 2 * np.pi * j / n_minor
-        c = np.array([np.cos(a) * (2 + 0.8 * np.cos(b)), 0.8 * np.sin(b) + 1.2, np.sin(a) * (2 + 0.8 * np.cos(b))])
-        n = np.array([np.cos(a) * np.cos(b), np.sin(b), np.sin(a) * np.cos(b)])
-        return list(c) + [i / n_major, j / n_minor] + list(n)
-    for i in range(n_major):
-        for j in range(n_minor):
-            q = [p(i, j), p(i + 1, j), p(i + 1, j + 1), p(i, j + 1)]
-            tris += [q[0], q[1], q[2], q[0], q[2], q[3]]
-    verts = np.array(tris, f32)
-    return verts, np.arange(len(verts), dtype=np.uint32)
-
-
 def teapot_mesh():
-    """(vertices [n, 8] float32, indices u32, source) -- the Utah teapot of the reference's
-    examples/res when the build copied it next to the oracle, else the torus stand-in."""
-    path = _find_res("objects/utah_teapot.obj")
-    if path is not None:
-        v, i = load_obj(path)
-        return v, i, "utah_teapot.obj"
-    v, i = torus_mesh()
-    return v, i, "synthetic torus (teapot asset unavailable)"
+    """(vertices [n, 8] float32, indices u32, source): the Utah teapot of the reference's examples/res"""
+    v, i = load_obj(asset_path("objects/utah_teapot.obj"))
+    return v, i, "utah_teapot.obj"
 
 
 def sphere_shell(n=708, radius=3.0):
@@ -354,7 +333,7 @@ def texcube_uniform(model, view_m, proj):
 def cfg1_textured_cube(width=800, height=600, frame=70, texture=None):
     """cfg1: textured cube, cull BACK / front CCW, depth test, perspective-correct uv"""
     verts, idx = cube_mesh()
-    tex = texture if texture is not None else procedural_texture()
+    tex = texture if texture is not None else stone_wall_texture()
     model = rotate(frame / 100.0, frame / 200.0, frame / 500.0)
     d = Draw("texcube", H.SRP_PRIM_TRIANGLES, verts, 20, indices=idx,
              uniform=texcube_uniform(model, view((0, 0, -3)), perspective(-1, 1, -1, 1, 1, 50)),

@@ -58,7 +58,7 @@ def product():
 
 @pytest.fixture(scope="session")
 def reference():
-    from srp_b200 import host
-    if not host.REFERENCE_SO.exists():
+    from oracle import refhost
+    if not refhost.available():
         pytest.skip("oracle/_ref/libref_host.so not built (needs /root/reference at build time)")
-    return host.load_oracle_reference()
+    return refhost.load_oracle_reference()

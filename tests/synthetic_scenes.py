@@ -25,6 +25,18 @@ IDENT = np.eye(4, dtype=f32)
 COLOR_VARY = [(3, H.SRP_FLOAT, H.SRP_INTERPOLATION_MODE_PERSPECTIVE)]
 
 
+def procedural_texture(size=480, seed=7):
+    """deterministic RGB8 test texture (bricks + noise)"""
+    y, x = np.mgrid[0:size, 0:size]
+    rng = np.random.RandomState(seed)
+    noise = rng.randint(0, 48, (size, size))
+    brick = (((x // 60 + (y // 30) % 2 * 30 // 30) % 2) * 40 + ((y % 30) < 2) * 60 + ((x + (y // 30 % 2) * 30) % 60 < 2) * 60)
+    r = np.clip(96 + brick + noise, 0, 255)
+    g = np.clip(80 + brick // 2 + noise, 0, 255)
+    b = np.clip(64 + noise * 2, 0, 255)
+    return np.stack([r, g, b], -1).astype(np.uint8)
+
+
 def _xf(model=IDENT, view=IDENT, proj=IDENT):
     return S.transform_bytes(model, view, proj)
 
@@ -245,7 +257,7 @@ def all_scenes() -> dict:
     # ---- texture wrap modes ----
     tverts, tidx = S.cube_mesh()
     tverts = tverts.copy(); tverts[:, 3:] = tverts[:, 3:] * 2.5 - 0.75        # uv outside [0, 1]
-    tex = S.procedural_texture(64, seed=3)
+    tex = procedural_texture(64, seed=3)
     for wx, wy, tag in ((H.TW_REPEAT, H.TW_REPEAT, "repeat"), (H.TW_CLAMP_TO_EDGE, H.TW_CLAMP_TO_EDGE, "clamp"),
                         (H.TW_REPEAT, H.TW_CLAMP_TO_EDGE, "mixed")):
         add(S.Scene(f"texture_wrap_{tag}_222x222", 222, 222, [

@@ -98,13 +98,43 @@ def test_load_obj_matches_the_reference_loader_semantics(tmp_path):
         pass
 
 
-def test_load_obj_teapot_equals_numpy_restatement():
-    path = S._find_res("objects/utah_teapot.obj")
-    if path is None:
-        import pytest
-        pytest.skip("teapot asset travels with the oracle build only")
+def _reference_load_obj(reference, path):
+    """the reference's own loader (examples/utility/objparser.c: loadOBJMesh), linked into the oracle library"""
+    import ctypes as C
+
+    class OBJMesh(C.Structure):
+        _fields_ = [("vertices", C.POINTER(C.c_float)), ("vertexCount", C.c_size_t),
+                    ("indices", C.POINTER(C.c_uint32)), ("indexCount", C.c_size_t)]
+    m = OBJMesh()
+    reference.dll.loadOBJMesh.restype = C.c_bool
+    reference.dll.loadOBJMesh.argtypes = [C.c_char_p, C.POINTER(OBJMesh)]
+    reference.dll.freeOBJMesh.argtypes = [C.POINTER(OBJMesh)]
+    assert reference.dll.loadOBJMesh(str(path).encode(), C.byref(m))
+    v = np.ctypeslib.as_array(m.vertices, shape=(int(m.vertexCount), 8)).copy()
+    i = np.ctypeslib.as_array(m.indices, shape=(int(m.indexCount),)).copy()
+    reference.dll.freeOBJMesh(C.byref(m))
+    return v, i
+
+
+def test_load_obj_equals_the_reference_loader(reference, tmp_path):
+    """srpB200LoadOBJ against the reference's loadOBJMesh itself: the teapot asset and the
+    hand-written file above (quads, missing uv, out-of-range index) give the same arrays bit for bit"""
+    import pytest
     lib = host.load_product()
-    v, i = lib.load_obj(path)
-    wv, wi = S.load_obj(path)
-    assert v.shape == wv.shape == (3498, 8)
-    assert np.array_equal(v.view(np.uint32), wv.view(np.uint32)) and np.array_equal(i, wi)
+    small = tmp_path / "m.obj"
+    small.write_text(OBJ_TEXT.replace("f 1/1/1 2/2/2 9/1/1\n", ""))     # (the reference reads out of range there: undefined)
+    paths = [small]
+    try:
+        paths.append(S.asset_path("objects/utah_teapot.obj"))
+    except FileNotFoundError:
+        pass
+    for path in paths:
+        v, i = lib.load_obj(path)
+        wv, wi = _reference_load_obj(reference, path)
+        assert v.shape == wv.shape and np.array_equal(v.view(np.uint32), wv.view(np.uint32)), path
+        assert np.array_equal(i, wi), path
+    if len(paths) == 2:
+        assert lib.load_obj(paths[1])[0].shape == (3498, 8)
+        # the Python description of the scenes uses the same semantics
+        sv, si = S.load_obj(paths[1])
+        assert np.array_equal(sv.view(np.uint32), wv.view(np.uint32)) and np.array_equal(si, wi)

@@ -6,6 +6,7 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np
 from srp_b200 import host as H, scenes as S
+from oracle.refhost import load_oracle_reference
 
 
 def diff(name, a, b):
@@ -23,7 +24,7 @@ def diff(name, a, b):
 def main():
     prod = H.load_product()
     print(prod.dll.srpB200Version().decode())
-    ref = H.load_oracle_reference()
+    ref = load_oracle_reference()
     which = sys.argv[1:] or ["cfg1", "cfg2", "cfg3s", "cfg4s"]
     table = {
         "cfg1": lambda: S.cfg1_textured_cube(),

@@ -7,7 +7,7 @@
 Workload (BASELINE.json: "frames/s & Gfrag/s (teapot 4K, 1M-tri mesh)"): cfg3, the synthetic
 1 002 528-triangle shell at 3840x2160 with the camera inside the mesh, Gouraud shader, depth
 test.  A step = srpFramebufferClear + srpDrawIndexBuffer of one frame per
-GPU.  With N GPUs the work is frame-parallel (every rank renders its own frames of the same
+GPU.  With N GPUs the headline is frame-parallel (every rank renders its own frames of the same
 scene; rank 0 builds the mesh and broadcasts vertex / index buffers over NCCL once, no
 collective in the timed region): weak scaling, value = N * K / max-over-ranks time.
 
@@ -18,17 +18,27 @@ collective in the timed region): weak scaling, value = N * K / max-over-ranks ti
              clears, draws and brings the colour + depth planes back into the host-visible
              framebuffer; wall clock.  Headline: two frames in flight (explicit policy,
              srpB200FramebufferDownloadAsync / Wait); `synchronous`: the default policy, one
-             frame at a time, every draw returning with the mirror up to date
+             frame at a time, every draw returning with the mirror up to date.  `host_link`
+             puts it next to the measured ceiling of the host link (profiles/)
   roofline   the dominant kernel's algorithmic bytes / its measured duration vs the measured
              HBM copy bandwidth (MEASURED_PEAKS.json), plus the whole-frame figure
+  parity     the benchmarked frame, at full size, against the unmodified reference (N = 1)
+  secondary  cfg3 with heavy near-plane clipping (N = 1); cfg5 = BASELINE config 5, 1024 teapot
+             frames of 1024x1024 split frame-parallel over the N ranks (srpB200DrawBatch)
+  strips     (N > 1) ONE cfg3 frame split into N sort-first strips: every rank runs the geometry
+             front-end and rasterises its rows straight into the root GPU's framebuffer over
+             NVLink (CUDA IPC peer memory; flags in the root's memory signal completion), next
+             to the NCCL send/recv gather as the baseline; bit-exactness vs one GPU is checked
   cpu_baseline  the unmodified reference (oracle/_ref) on the host cores, bounded sample
 
 `--impl reference` times that reference instead (frame-parallel over all host cores).
-The oracle is only used as the CPU baseline / reference arm here, never on the product path.
+The oracle is only used as the CPU baseline / reference arm / parity checker here, never on the
+product path.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import multiprocessing as mp
 import os
@@ -204,6 +214,146 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+# ------------------------------------------------------------------------------------ secondary: cfg5 batch
+def cfg5_batch(lib, torch, dist, stream, world, rank, total_frames=1024, size=1024, steps=3):
+    """BASELINE config 5: `total_frames` teapot frames of size x size, frame f rotated by f / 200,
+    split frame-parallel over the ranks (multigpu.frame_partition), each rank's share in one
+    srpB200DrawBatch call; device time of the call, max over ranks.  Returns rank-0's record."""
+    from srp_b200 import host as H, multigpu as M, scenes as S
+    mine = M.frame_partition(total_frames, world, rank)
+    n = len(mine)
+    mesh = S.teapot_mesh()
+    draws = [S.teapot_draw(f, mesh) for f in mine]
+    lib.new_context()
+    for fn, *args in draws[0].state:
+        getattr(lib.dll, fn)(*args)
+    vb = lib.vertex_buffer(mesh[0], 32); ib = lib.index_buffer(mesh[1])
+    prog = lib.program("gouraud", S.GOURAUD_VARYINGS, 12)
+    fbs = [lib.framebuffer(size, size) for _ in range(n)]
+    arr = (C.POINTER(H.SRPFramebuffer) * n)(*[f.ptr for f in fbs])
+    uni = np.frombuffer(b"".join(d.uniform for d in draws), dtype=np.uint8).copy()
+    stride = len(draws[0].uniform)
+    prog.set_uniform(draws[0].uniform)
+    lib.dll.srpB200SetSyncMode(H.SRP_B200_SYNC_EXPLICIT)
+    call = lambda: lib.dll.srpB200DrawBatch(ib, vb, arr, n, C.byref(prog.sp), uni.ctypes.data, stride,
+                                            H.SRP_PRIM_TRIANGLES, 0, len(mesh[1]), 1)
+    call(); lib.dll.srpB200Finish()
+    lib.dll.srpB200ResetStats(); lib.dll.srpB200SetProfiling(1); lib.stage_times()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(); torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    with torch.cuda.stream(stream):
+        for a, b in ev:
+            a.record(stream); call(); b.record(stream)
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    st = lib.stage_times(); lib.dll.srpB200SetProfiling(0)
+    stats = lib.stats()
+    # one frame of the batch against a single clear + draw of the same frame (this process, same library)
+    probe = fbs[n // 2].planes()
+    lib.dll.srpB200SetSyncMode(H.SRP_B200_SYNC_DRAW)
+    single = S.render(lib, S.cfg5_frame(mine[n // 2], size, mesh))
+    same = all(bool(np.array_equal(a, b)) for a, b in zip(probe, single))
+    for f in fbs:
+        f.free()
+    lib.dll.srpFreeVertexBuffer(vb); lib.dll.srpFreeIndexBuffer(ib)
+    if world > 1:
+        t = torch.tensor([ms, 0.0 if same else 1.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, same = float(t[0]), float(t[1]) == 0.0
+    per_frame_bytes = size * size * 9 + mesh[0].nbytes + mesh[1].nbytes
+    return {"what": f"{total_frames} teapot frames {size}x{size} ({mesh[2]}), frame-parallel over {world} rank(s), one srpB200DrawBatch per rank",
+            "frames_per_s": total_frames / ms * 1e3, "ms_per_batch": ms, "frames_per_rank": n,
+            "stage_ms_per_batch_rank0": {k: st[k] / steps for k in ("geometry_ms", "binning_ms", "tiles_ms")},
+            "frags_emitted_per_frame_rank0": stats["fragsEmitted"] / steps / n,
+            "hbm_gbs_per_gpu_algorithmic": n * per_frame_bytes / ms / 1e6,
+            "batch_frame_equals_single_draw": same}
+
+
+# ------------------------------------------------------------------------------------ strips (N > 1)
+def strips(lib, torch, dist, stream, world, rank, prep, scene, steps, warm, single_planes):
+    """ONE frame split into `world` sort-first strips.  (a) fused: the other ranks' tile kernels
+    write their strips into the root's framebuffer over NVLink (multigpu.StripTarget);
+    (b) baseline: every rank renders locally, NCCL send/recv gathers the strips.  Device time on
+    the root from the first frame's submission to the last frame being complete in its memory."""
+    from srp_b200 import host as H, multigpu as M
+    lib.dll.srpB200SetSyncMode(H.SRP_B200_SYNC_EXPLICIT)
+    keep = prep.fb
+    out = {"ranks": world, "rows_per_rank": [list(M.strip_rows(scene.height, int(lib.dll.srpB200TileHeight()), world, r)) for r in range(world)]}
+
+    def draw_into(fb):
+        prep.fb = fb
+        prep.draw_all()
+
+    # (a) fused peer write
+    target = M.StripTarget(lib, scene.width, scene.height, ring=3, root=0)
+    def run(n):
+        for _ in range(n):
+            target.render(draw_into)
+            if rank == 0:
+                target.complete()
+    run(warm)
+    lib.dll.srpB200Finish()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream); run(steps); e1.record(stream)
+    lib.dll.srpB200Finish()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    exact = None
+    if rank == 0:
+        last = target.fbs[(target.frame - 1) % target.ring]
+        got = last.planes()
+        exact = all(bool(np.array_equal(a, b)) for a, b in zip(got, single_planes))
+    dist.barrier()
+    peer_bytes = 0 if rank == 0 else (target.rows[1] - target.rows[0]) * scene.width * 8      # colour + depth rows written remotely
+    tb = torch.tensor([float(peer_bytes)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tb)
+    target.free()
+    out["fused_peer_write"] = {"frames_per_s": steps / (float(t[0]) / 1e3), "ms_per_frame": float(t[0]) / steps,
+                               "bit_exact_vs_single_gpu": exact, "nvlink_bytes_per_frame": int(tb[0]),
+                               "what": "tile kernels of ranks 1.. store their strips into rank 0's planes (CUDA IPC peer memory) as part of the tile "
+                                       "write-back; per frame and rank one flag store in rank 0's memory signals completion, ring of 3 framebuffers"}
+
+    # (b) NCCL gather baseline
+    th = int(lib.dll.srpB200TileHeight())
+    r0, r1 = M.strip_rows(scene.height, th, world, rank)
+    fb = lib.framebuffer(scene.width, scene.height)
+    planes = [M.device_plane_tensor(lib, fb, w) for w in range(3)]
+    def run_gather(n):
+        for _ in range(n):
+            lib.dll.srpB200SetRowRange(r0, r1)
+            draw_into(fb)
+            lib.dll.srpB200SetRowRange(0, 2 ** 64 - 1)
+            with torch.cuda.stream(stream):
+                M.gather_strips_inplace(planes, scene.height, th, dst=0)
+    run_gather(warm)
+    lib.dll.srpB200Finish(); torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+    run_gather(steps)
+    with torch.cuda.stream(stream):
+        e1.record(stream)
+    lib.dll.srpB200Finish(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    exact2 = None
+    if rank == 0:
+        exact2 = all(bool(np.array_equal(a, b)) for a, b in zip(fb.planes(), single_planes))
+    fb.free()
+    out["nccl_gather"] = {"frames_per_s": steps / (float(t[0]) / 1e3), "ms_per_frame": float(t[0]) / steps,
+                          "bit_exact_vs_single_gpu": exact2,
+                          "what": "every rank renders its strip locally; one batch of ncclSend / ncclRecv per frame moves the strips of the three planes to rank 0"}
+    prep.fb = keep
+    lib.dll.srpB200SetSyncMode(H.SRP_B200_SYNC_DRAW)
+    return out
+
+
 # ------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -212,7 +362,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample (0: skip, e.g. under ncu)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample (0: skip it and the secondary legs, e.g. under ncu)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -251,6 +401,10 @@ def main():
 
     # ---------------------------------------------------------------- ours
     os.environ["SRP_B200_DEVICE"] = str(local_rank)
+    # NUMA placement of this rank's host side BEFORE anything pins memory: the pinned framebuffer
+    # mirrors and staging buffers then live next to the rank's GPU (srp_b200/numa.py)
+    from srp_b200 import numa
+    numa_note = numa.bind_to_gpu(local_rank) if os.environ.get("SRP_B200_NUMA_BIND", "1") != "0" else "off (SRP_B200_NUMA_BIND=0)"
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
@@ -391,12 +545,28 @@ def main():
     lib.dll.srpB200SetMirrorPlanes(1)
     e2e_color_s = timed(prep.draw_all)
     lib.dll.srpB200SetMirrorPlanes(7)
-    checksum = int(np.ctypeslib.as_array(prep.fb.ptr.contents.color, shape=(scene.width * scene.height,))[::4099].sum())
+    single_planes = prep.fb.planes()
+    checksum = int(single_planes[0].reshape(-1)[::4099].sum())
 
     if world > 1:
         t = torch.tensor([dev_ms, e2e_s * 1e3, e2e_static_s * 1e3, e2e_color_s * 1e3, e2e_pipe_s * 1e3], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_s, e2e_static_s, e2e_color_s, e2e_pipe_s = float(t[0]), float(t[1]) / 1e3, float(t[2]) / 1e3, float(t[3]) / 1e3, float(t[4]) / 1e3
+
+    # ---- secondary legs that need every rank
+    secondary = {}
+    strips_rec = None
+    full = args.cpu_seconds > 0
+    if full and world > 1 and args.workload == "cfg3":
+        try:
+            strips_rec = strips(lib, torch, dist, stream, world, rank, prep, scene, K, W, single_planes)
+        except Exception as e:      # noqa: BLE001 -- a secondary leg must not cost the headline line
+            strips_rec = {"error": f"{type(e).__name__}: {e}"}
+    if full:
+        try:
+            secondary["cfg5_batch_frame_parallel"] = cfg5_batch(lib, torch, dist, stream, world, rank)
+        except Exception as e:      # noqa: BLE001
+            secondary["cfg5_batch_frame_parallel"] = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         peaks = {}
@@ -416,10 +586,18 @@ def main():
         achieved = dom_bytes / (per[dom] / 1e3) / 1e9 if per[dom] > 0 else 0.0
         frame_gbs = alg["total"] * (value / world) / 1e9
         traffic = None
-        tr = ROOT / "profiles" / "r01_cfg3_ncu_summary_traffic.json"
+        tr = ROOT / "profiles" / "r02_cfg3_ncu_summary_traffic.json"
         dom_kernel = {"geometry_ms": "srpdGeomKernel", "binning_ms": "srpdBinFillKernel", "tiles_ms": "srpdTileKernel"}[dom]
         if tr.exists() and args.workload == "cfg3":
             traffic = json.loads(tr.read_text())["kernels"].get(dom_kernel, {}).get("dram_bytes")
+        ceiling = None
+        cf = ROOT / "profiles" / f"r02_pcie_ceiling_n{world}.json"
+        if cf.exists():
+            c = json.loads(cf.read_text())
+            ceiling = {"frames_per_s_ceiling": c["frames_per_s_ceiling_aggregate"], "d2h_gbs_per_rank": c["d2h_alone_gbs_per_rank"],
+                       "h2d_gbs_per_rank": c["h2d_alone_gbs_per_rank"], "both_gbs_per_rank": c["both_gbs_per_rank"],
+                       "fraction_of_ceiling": (world * K / e2e_pipe_s) / c["frames_per_s_ceiling_aggregate"],
+                       "source": f"profiles/r02_pcie_ceiling_n{world}.json: pinned copies of one frame's traffic (28 MB up, 66 MB down) on every rank at once"}
         line = {
             "metric": f"frames_per_s_{args.workload}", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
@@ -431,13 +609,14 @@ def main():
             "stage_ms_per_frame": per,
             "roofline": {"bound": "hbm", "kernel": {"geometry_ms": "srpdGeomKernel", "binning_ms": "srpdBin*Kernel", "tiles_ms": "srpdTileKernel"}[dom],
                          "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
-                         "traffic_source": "profiles/r01_cfg3_ncu_summary_traffic.json (ncu --set full, one full-frame launch; the 126 MB L2 absorbs most of the plane writes within the launch)" if traffic else None,
+                         "traffic_source": "profiles/r02_cfg3_ncu_summary_traffic.json (ncu --set full, one full-frame launch; the 126 MB L2 absorbs part of the plane writes within the launch)" if traffic else None,
                          "algorithmic_bytes_per_launch": dom_bytes, "peak_source": peak_src,
                          "frame": {"algorithmic_bytes": alg, "achieved": frame_gbs, "frac": frame_gbs / hbm}},
             "e2e": {"value": world * K / e2e_pipe_s, "unit": "frames/s",
                     "h2d_bytes_per_step": st3["h2dBytes"] // K, "d2h_bytes_per_step": st3["d2hBytes"] // K,
                     "ms_per_step": 1e3 * e2e_pipe_s / K, "result_checksum": pipe_checksum,
                     "result_checksum_matches_synchronous": pipe_checksum == checksum and len(set(pipe_checks)) == 1,
+                    "host_link": ceiling, "numa": numa_note,
                     "what": "throughput with two frames in flight through the public C API (explicit synchronisation policy): per step "
                             "srpVertexBufferCopyData + srpIndexBufferCopyData from pinned host memory, srpFramebufferClear, "
                             "srpDrawIndexBuffer, srpB200FramebufferDownloadAsync (colour + depth into the host-visible framebuffer), and "
@@ -451,7 +630,9 @@ def main():
             "clocks": clocks,
             "version": lib.dll.srpB200Version().decode(),
         }
-        if world == 1 and args.cpu_seconds > 0:
+        if strips_rec is not None:
+            line["strips"] = strips_rec
+        if world == 1 and full:
             # parity of the benchmarked workload itself, at full size, against the unmodified reference
             line["parity"] = parity_vs_reference(lib, scene, wl["desc"])
             if args.workload == "cfg3":
@@ -461,7 +642,7 @@ def main():
                 heavy = S.cfg3_shell(radius=1.2)
                 sec = kernel_only_fps(lib, torch, stream, flush, heavy, K, W)
                 sec["parity"] = parity_vs_reference(lib, heavy, "cfg3 with shell radius 1.2 (heavy near-plane clipping)")
-                line.setdefault("secondary", {})["cfg3_r1.2_heavy_clipping"] = sec
+                secondary["cfg3_r1.2_heavy_clipping"] = sec
             cores = host_cores()
             workers = min(cores, 64)
             per_frame_guess = 0.6 if args.workload == "cfg3" else 0.03
@@ -475,6 +656,8 @@ def main():
             else:
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference",
                                         "sample": "oracle/_ref not present on this box"}
+        if secondary:
+            line["secondary"] = secondary
         print(json.dumps(line))
     prep.free()
     if world > 1:

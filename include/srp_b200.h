@@ -59,6 +59,9 @@ void srpB200FramebufferUpload(const SRPFramebuffer* fb);    /* host mirror -> de
  * behind it, so results never tear. */
 void srpB200FramebufferDownloadAsync(const SRPFramebuffer* fb);
 void srpB200FramebufferWait(const SRPFramebuffer* fb);
+/* stream-side counterpart of Wait: everything enqueued after this call is ordered behind the
+ * framebuffer's in-flight asynchronous download (the host does not block) */
+void srpB200FramebufferFence(const SRPFramebuffer* fb);
 
 /* ---- device-resident objects -------------------------------------------------------
  * Framebuffer on caller-owned device memory (e.g. planes of a torch tensor that NCCL
@@ -113,6 +116,27 @@ void srpB200DrawBatch(const SRPIndexBuffer* ib, const SRPVertexBuffer* vb,
 void srpB200SetRowRange(size_t row0, size_t row1);
 size_t srpB200TileWidth(void);
 size_t srpB200TileHeight(void);
+
+/* Multi-GPU form of the strips (one process per GPU): the framebuffer lives on
+ * ONE GPU (the root); the other ranks map its three planes through CUDA IPC and their tile
+ * kernels write their strips straight into the root's memory over NVLink as part of the tile
+ * write-back -- no staging copy and no separate gather step.
+ *   root:   srpB200IpcExport() of srpB200FramebufferDevicePlane(fb, 0..2) -> three 64-byte handles
+ *           that travel to the other ranks (torch.distributed / any byte transport);
+ *   others: srpB200IpcOpen() each handle, srpB200NewFramebufferOnDevice() on the mapped planes,
+ *           srpB200SetRowRange(own strip), then the usual srpFramebufferClear + srpDraw*Buffer.
+ * Completion is signalled through 32-bit flags in (peer) device memory with two stream-ordered
+ * calls: srpB200StreamSignal stores `value` once everything enqueued before it has finished and
+ * its writes are visible system-wide; srpB200StreamWait holds this process's stream until the
+ * flag is >= value.  srpB200DeviceAlloc gives zero-filled device memory that can be exported. */
+typedef struct SRPB200IpcHandle { unsigned char bytes[64]; } SRPB200IpcHandle;
+void* srpB200DeviceAlloc(size_t bytes);
+void srpB200DeviceFree(void* devicePtr);
+int srpB200IpcExport(const void* devicePtr, SRPB200IpcHandle* handle);   /* 0 on success */
+void* srpB200IpcOpen(const SRPB200IpcHandle* handle);                     /* NULL on failure */
+void srpB200IpcClose(void* mappedPtr);
+void srpB200StreamSignal(uint32_t* flag, uint32_t value);
+void srpB200StreamWait(const uint32_t* flag, uint32_t value);
 
 /* ---- counters ----------------------------------------------------------------------
  * Accumulated since the last reset over all draws (deterministic; equal to the

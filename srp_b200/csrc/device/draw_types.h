@@ -40,6 +40,8 @@ typedef struct SrpdStencilFace
 typedef struct SrpdState
 {
 	int32_t width, height;           /* framebuffer, pixels                              */
+	int32_t stripY0, stripY1;        /* pixel rows [stripY0, stripY1) this process rasterises (sort-first strips;
+	                                    the whole frame otherwise): primitives outside keep their id, store nothing */
 	/* raster */
 	uint8_t frontFaceCW, cullFace, polygonMode, provokingFirst;
 	float   pointSize;

@@ -203,6 +203,10 @@ __device__ __forceinline__ bool setupAndClassify(const SrpdState& st, const Srpd
 	 * that exactly; such a triangle keeps its primitive id but needs no record. */
 	if (stored && srpdTriangleIsSmall(s) && !srpdSmallTriangleCoversAnyPixel(s))
 		stored = false;
+	/* sort-first strips: a primitive whose box misses this process's rows keeps its id (every
+	 * rank runs the same scan) but needs no record here */
+	if (stored && ((int) s.maxY <= st.stripY0 || (int) s.minY >= st.stripY1))
+		stored = false;
 	return true;
 }
 
@@ -284,7 +288,7 @@ __device__ __noinline__ void emitLine(Emitter& em, const SrpdState& st, const Sr
 		SrpdLineSegment seg;
 		const int n = total - i < SRPD_LINE_SEG ? total - i : SRPD_LINE_SEG;
 		srpdLineSegment(st, ln, x, y, t, n, seg);
-		if (!seg.any)
+		if (!seg.any || (int) seg.maxY <= st.stripY0 || (int) seg.minY >= st.stripY1)      /* (outside this process's strip) */
 			continue;
 		unsigned char* blobs = beginRecord<WRITE>(em, seg.w, seg.minX, seg.minY, seg.maxX, seg.maxY);
 		if (WRITE && blobs)
@@ -299,7 +303,7 @@ template <bool WRITE>
 __device__ __noinline__ void emitPoint(Emitter& em, const SrpdState& st, const SrpdPos& p, const unsigned char* vary)
 {
 	SrpdPointSetup s;
-	if (srpdSetupPoint(st, p, s))
+	if (srpdSetupPoint(st, p, s) && (int) s.maxY > st.stripY0 && (int) s.minY < st.stripY1)
 	{
 		unsigned char* blob = beginRecord<WRITE>(em, s.w, s.minX, s.minY, s.maxX, s.maxY);
 		if (WRITE && blob)

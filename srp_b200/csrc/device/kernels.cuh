@@ -12,32 +12,23 @@ extern "C" __device__ void srpB200DeviceVS(int programId, SRPVertexShaderIn* in,
 extern "C" __device__ void srpB200DeviceFS(int programId, SRPFragmentShaderIn* in, SRPFragmentShaderOut* out);
 
 /* ---- launch geometry -------------------------------------------------------------- */
-/* pixels per thread of the tile kernel (1 or 2): a thread owns rows ly and ly + 4 of its column */
-#ifndef SRPD_PX_PER_THREAD
-#define SRPD_PX_PER_THREAD 2
-#endif
-#ifndef SRPD_TILE_H_PX
-#define SRPD_TILE_H_PX (8 * SRPD_PX_PER_THREAD)
-#endif
-/* 256-thread CTAs, five per SM (47 registers): measured on cfg3 against three (78 registers,
- * -11 %), four (62, -4 %); the kernel is bound by instruction issue and every extra resident
- * warp fills issue slots.  Six do not fit the per-warp step scratch in shared memory. */
+/* Tiles.  Geometry, occupancy bitmap, coarse binning and the strips' row ranges work on 32x16
+ * tiles (SRPD_TILE_W x SRPD_TILE_H).  The tile kernel rasterises WARP TILES of 32x8 pixels --
+ * half a tile: one 128-byte colour row per tile row, 8 rows -- each owned by one warp that
+ * shares nothing with the other warps of its CTA (no CTA barrier anywhere).  128-thread CTAs,
+ * eight per SM (32 warps, <= 64 registers, ~6.6 KB of shared memory per warp: the warp tile's
+ * pixels, a 128-entry fragment queue, the step's triangle data and a ring of list entries). */
 #ifndef SRPD_TILE_CTAS_PER_SM
-#define SRPD_TILE_CTAS_PER_SM 5
+#define SRPD_TILE_CTAS_PER_SM 8
 #endif
-/* the line variant of the tile kernel (general fragment stage, no SIMPLE variant): measured on
- * cfg4's 1 M-line draw with 2 / 3 / 4 / 5 CTAs per SM: 3.20 / 2.38 / 2.04 / 2.08 ms */
-#ifndef SRPD_TILE_LINE_CTAS_PER_SM
-#define SRPD_TILE_LINE_CTAS_PER_SM 4
-#endif
-constexpr int SRPD_TILE_W = 32;          /* pixels; one 128-byte colour row per tile row   */
-constexpr int SRPD_TILE_H = SRPD_TILE_H_PX;
-constexpr int SRPD_BLK_W = 8;            /* pixels owned by one warp: 8 x (4 * pixels per thread) */
-constexpr int SRPD_PX = SRPD_PX_PER_THREAD;
-static_assert(SRPD_PX == 1 || SRPD_PX == 2, "a thread owns one or two pixels");
-constexpr int SRPD_BLK_H = 4 * SRPD_PX;
-constexpr int SRPD_TILE_THREADS = SRPD_TILE_W * SRPD_TILE_H / SRPD_PX;
+constexpr int SRPD_TILE_W = 32;
+constexpr int SRPD_TILE_H = 16;
+constexpr int SRPD_WT_W = 32;            /* warp tile */
+constexpr int SRPD_WT_H = 8;
+constexpr int SRPD_WT_PIXELS = SRPD_WT_W * SRPD_WT_H;
+constexpr int SRPD_TILE_THREADS = 128;
 constexpr int SRPD_TILE_WARPS = SRPD_TILE_THREADS / 32;
+static_assert(SRPD_WT_W == SRPD_TILE_W && SRPD_TILE_H == 2 * SRPD_WT_H, "a tile is two warp tiles, one above the other");
 /* coarse bins ("supertiles") are 2^k x 2^k tiles with k = superShift chosen per draw from the
  * expected record density: 8x8 tiles (256x128 px) for ordinary meshes down to 2x2 for
  * millions of sub-pixel primitives, so that a tile never filters more than ~1-2 k candidates */

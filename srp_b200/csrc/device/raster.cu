@@ -1,5 +1,5 @@
 /* srp-b200 -- tile kernel: coverage, interpolation, fragment shading and the whole
- * per-fragment test sequence, one CTA per 32x16-pixel framebuffer tile (sm_100a).
+ * per-fragment test sequence (sm_100a).
  *
  * Replaces the reference's immediate-mode inner loops
  *   src/raster/triangle.c:73-111 (rasterizeTriangle), line.c:34-77 (rasterizeLine),
@@ -7,40 +7,48 @@
  *   pipeline/interpolation.c:34-163, core/color.c:14-23 (colorPack)
  * and srpFramebufferClear (core/framebuffer.c:57-62), which is fused in here.
  *
- * Ownership model: every thread owns TWO pixels of the tile (same column, rows ly and ly + 4
- * of its warp's 8x8 block) for the whole draw and keeps their colour / depth / stencil in
- * registers; the tile's primitives are visited in primitive-id order, so the reference's
- * "later primitive wins" semantics (no blending, depth EQUAL/ALWAYS, stencil counters) hold
- * with no atomics.  Work distribution (CTA = 8 warps = one 32x16 tile):
- *   - the CTA scans its candidate list (all records of the frame, or the coarse bin of
- *     its supertile) one record per thread at a time and compacts the ones whose bounding
- *     box touches the tile into shared memory with a ballot + warp reductions (order kept);
- *   - each warp walks that list 32 entries per step and keeps those touching its block;
- *   - triangles: "row lanes" -- one lane per (triangle, block row) -- walk the barycentric
- *     chain to their row and decide the coverage of its 8 pixels; the pixel threads then
- *     gather the bits of their own pixels and shade their covering triangles in order.
+ * ONE WARP = ONE WARP TILE of 32x8 pixels.  The warp tile's colour / depth / stencil live in the
+ * warp's SHARED MEMORY for as long as it works on the tile: loaded once (or, with a pending
+ * clear, just initialised), tested and updated there by every fragment of the draw, written
+ * back once with 16-byte stores in full 128-byte rows.  The warp is the only one that touches
+ * these pixels, and it visits the tile's primitives in primitive-id order, so the reference's
+ * "later primitive wins" semantics (no blending, depth EQUAL / ALWAYS, stencil counters) hold
+ * with no atomics; the warps of a CTA share nothing and there is no CTA barrier.  Per tile:
+ *   - LIST: the warp scans the candidate list (the coarse bin of its supertile, or all records)
+ *     32 entries at a time and appends those whose bounding box touches the tile to a ring in
+ *     shared memory (ballot compaction, order kept); 32 collected entries make a step;
+ *   - COVERAGE (triangles): "row lanes" -- one lane per (triangle, tile row) -- walk the
+ *     barycentric chain to their row and along it.  Each edge function moves monotonically
+ *     along the row (float addition of a constant is monotone), so a row's covered pixels are ONE
+ *     interval: the lane walks to its first covered pixel, counts to its last, and a warp scan
+ *     gives every lane its place in the warp's FRAGMENT QUEUE, where it leaves
+ *     {lambda0, lambda1, lambda2, triangle, pixel} per covered pixel (queue = primitive order);
+ *   - SHADING: the lanes take the queue 32 fragments at a time -- whichever pixels they belong
+ *     to, so every lane has a fragment -- and run the fragment stage on the pixel's state in
+ *     shared memory; two fragments of one pass that hit the same pixel (different triangles)
+ *     are found with match.any and run one after the other, in queue order.
  * Exact arithmetic: a pixel's barycentrics are NOT evaluated in closed form; the reference's
  * incremental chain is replayed -- (y - minY) float additions of dlambda/dy from the value at
  * the bounding-box corner, then (x - minX) additions of dlambda/dx (triangle.c:102-109) --
- * which is what makes depth bit-exact.  Lines replay the DDA chain of
- * line.c:56-76 the same way.
+ * which is what makes depth bit-exact; the row lane that decides coverage
+ * is the one that walks the chain, so no pixel replays any part of it.  Lines replay the DDA
+ * chain of line.c:56-76 the same way.
  *
  * Framebuffer traffic per tile: at most one read and one write of 9 B/px; with a pending
- * clear no read at all.  Stores leave straight from the registers, every warp store as four
- * full 32-byte sectors (the eight lanes of a block row hold eight neighbouring pixels). */
+ * clear no read at all.  Algorithmic bytes of a launch: 9 B x the pixels of the frame(s). */
 #include "kernels.cuh"
 
 namespace {
 
-struct Pixel
-{
-	uint32_t color;
-	float depth;
-	uint32_t stencil;
-	uint32_t dirty;      /* bit0 colour, bit1 depth, bit2 stencil */
-};
-
 struct FragCounters { uint32_t emitted, shaded; };
+
+/* the pixel a fragment lands on: its three plane entries in the tile's shared-memory state */
+struct PixelRef
+{
+	uint32_t* color;
+	float* depth;
+	uint8_t* stencil;
+};
 
 /* float varyings of one fragment, two per step; PAIRS > 0: compile-time trip count */
 template <int NV, int PAIRS>
@@ -73,14 +81,9 @@ __device__ __forceinline__ void interpolateFloatPairs(
 	}
 }
 
-/* emitFragment, reference src/raster/fragment.c:63-125.  `sx, sy` are the (unwrapped)
- * integer fragment coordinates the scissor test sees; interpolation of the varyings is
- * deferred until the early tests have passed (it is pure). */
-/* SIMPLE (compile-time) = 1: no scissor, no stencil, the shader does not write depth and all
- * varyings are floats -- the state almost every draw has; the tests on the draw state then
- * disappear from the fragment stage instead of being evaluated per fragment. */
-/* SIMPLE = 2: additionally every varying is PERSPECTIVE (what Gouraud colours and texture
- * coordinates are): the two mode bits per float are not decoded per fragment at all. */
+/* all-PERSPECTIVE floats (what Gouraud colours and texture coordinates are): no mode decode.
+ * QUADS: the blobs are 16 bytes apart and 16-byte aligned (1-4 floats per vertex in a 16-byte
+ * slot: records are 16-byte aligned and the header is 80 bytes), one 16-byte load per vertex */
 template <int NV, int PAIRS>
 __device__ __forceinline__ void interpolatePerspectivePairs(const float2* b, int slotPairs, const float* wgt, float rec, float2* out)
 {
@@ -101,10 +104,40 @@ __device__ __forceinline__ void interpolatePerspectivePairs(const float2* b, int
 		out[e] = make_float2(__fmul_rn(vx, rec), __fmul_rn(vy, rec));
 	}
 }
+template <int NV, int FLOATS>
+__device__ __forceinline__ void interpolatePerspectiveQuad(const float4* b, const float* wgt, float rec, float* out)
+{
+	float4 in[NV];
+	#pragma unroll
+	for (int i = 0; i < NV; i++)
+		in[i] = __ldg(b + i);
+	float v[4] = { 0.f, 0.f, 0.f, 0.f };
+	#pragma unroll
+	for (int i = 0; i < NV; i++)
+	{
+		v[0] = __fadd_rn(v[0], __fmul_rn(in[i].x, wgt[i]));
+		v[1] = __fadd_rn(v[1], __fmul_rn(in[i].y, wgt[i]));
+		v[2] = __fadd_rn(v[2], __fmul_rn(in[i].z, wgt[i]));
+		if (FLOATS == 4)
+			v[3] = __fadd_rn(v[3], __fmul_rn(in[i].w, wgt[i]));
+	}
+	#pragma unroll
+	for (int e = 0; e < FLOATS; e++)
+		out[e] = __fmul_rn(v[e], rec);
+}
 
+/* emitFragment, reference src/raster/fragment.c:63-125.  `sx, sy` are the (unwrapped)
+ * integer fragment coordinates the scissor test sees; interpolation of the varyings is
+ * deferred until the early tests have passed (it is pure).
+ * SIMPLE (compile-time) = 1: no scissor, no stencil, the shader does not write depth and all
+ * varyings are floats -- the state almost every draw has; the tests on the draw state then
+ * disappear from the fragment stage instead of being evaluated per fragment.
+ * SIMPLE = 2: additionally every varying is PERSPECTIVE: the two mode bits per float are not
+ * decoded per fragment at all.
+ * `dirty` collects which planes the thread changed (bit0 colour, bit1 depth, bit2 stencil). */
 template <int NV, int SIMPLE>
 __device__ __forceinline__ void emitFragment(
-	const SrpdState& st, const SrpdFrame& fr, Pixel& px, FragCounters& cnt,
+	const SrpdState& st, const SrpdFrame& fr, const PixelRef& px, uint32_t& dirty, FragCounters& cnt,
 	int sx, int sy, float fragX, float fragY, float depth, float rec, float fragW,
 	bool frontFacing, uint32_t primitiveID,
 	const unsigned char* blobs, const float* wgt)
@@ -117,15 +150,15 @@ __device__ __forceinline__ void emitFragment(
 	if (scissorEnabled && !srpdScissor(st, sx, sy))
 		return;
 
-	const float storedDepth = px.depth;
+	const float storedDepth = *px.depth;
 	if (stencilEnabled)
 	{
 		const SrpdStencilFace& sf = frontFacing ? st.stencilFront : st.stencilBack;
-		const uint8_t storedStencil = (uint8_t) px.stencil;
+		const uint8_t storedStencil = *px.stencil;
 		if (!srpdCompareU8(sf.func, (uint8_t) (sf.ref & sf.mask), (uint8_t) (storedStencil & sf.mask)))
 		{
-			px.stencil = srpdStencilWrite(storedStencil, srpdStencilOp(sf.sfailOp, storedStencil, sf.ref), sf.writeMask);
-			px.dirty |= 4u;
+			*px.stencil = srpdStencilWrite(storedStencil, srpdStencilOp(sf.sfailOp, storedStencil, sf.ref), sf.writeMask);
+			dirty |= 4u;
 			return;
 		}
 	}
@@ -134,14 +167,14 @@ __device__ __forceinline__ void emitFragment(
 		if (stencilEnabled)
 		{
 			const SrpdStencilFace& sf = frontFacing ? st.stencilFront : st.stencilBack;
-			const uint8_t storedStencil = (uint8_t) px.stencil;
-			px.stencil = srpdStencilWrite(storedStencil, srpdStencilOp(sf.dfailOp, storedStencil, sf.ref), sf.writeMask);
-			px.dirty |= 4u;
+			const uint8_t storedStencil = *px.stencil;
+			*px.stencil = srpdStencilWrite(storedStencil, srpdStencilOp(sf.dfailOp, storedStencil, sf.ref), sf.writeMask);
+			dirty |= 4u;
 		}
 		return;
 	}
 
-	alignas(8) unsigned char interpolated[SRPD_MAX_VARYING_BYTES];
+	alignas(16) unsigned char interpolated[SRPD_MAX_VARYING_BYTES];
 	if (NV == 1)
 	{
 		for (int k = 0; k < st.slotSize / 4; k++)
@@ -157,13 +190,21 @@ __device__ __forceinline__ void emitFragment(
 		float2* o = (float2*) interpolated;
 		const int pairs = (st.nFloats + 1) >> 1, slotPairs = st.slotSize / 8;
 		if (SIMPLE == 2)
-			switch (pairs)      /* 1..4 (launchTileKernel) */
+		{
+			if (st.slotSize == 16)      /* 3 or 4 floats (launchTileKernel: 1..8 floats); warp-uniform */
 			{
-				case 1:  interpolatePerspectivePairs<NV, 1>(b, slotPairs, wgt, rec, o); break;
-				case 2:  interpolatePerspectivePairs<NV, 2>(b, slotPairs, wgt, rec, o); break;
-				case 3:  interpolatePerspectivePairs<NV, 3>(b, slotPairs, wgt, rec, o); break;
-				default: interpolatePerspectivePairs<NV, 4>(b, slotPairs, wgt, rec, o); break;
+				if (st.nFloats == 3) interpolatePerspectiveQuad<NV, 3>((const float4*) blobs, wgt, rec, (float*) interpolated);
+				else                 interpolatePerspectiveQuad<NV, 4>((const float4*) blobs, wgt, rec, (float*) interpolated);
 			}
+			else
+				switch (pairs)
+				{
+					case 1:  interpolatePerspectivePairs<NV, 1>(b, slotPairs, wgt, rec, o); break;
+					case 2:  interpolatePerspectivePairs<NV, 2>(b, slotPairs, wgt, rec, o); break;
+					case 3:  interpolatePerspectivePairs<NV, 3>(b, slotPairs, wgt, rec, o); break;
+					default: interpolatePerspectivePairs<NV, 4>(b, slotPairs, wgt, rec, o); break;
+				}
+		}
 		else
 			switch (pairs)
 			{
@@ -203,9 +244,9 @@ __device__ __forceinline__ void emitFragment(
 			if (stencilEnabled)
 			{
 				const SrpdStencilFace& sf = frontFacing ? st.stencilFront : st.stencilBack;
-				const uint8_t storedStencil = (uint8_t) px.stencil;
-				px.stencil = srpdStencilWrite(storedStencil, srpdStencilOp(sf.dfailOp, storedStencil, sf.ref), sf.writeMask);
-				px.dirty |= 4u;
+				const uint8_t storedStencil = *px.stencil;
+				*px.stencil = srpdStencilWrite(storedStencil, srpdStencilOp(sf.dfailOp, storedStencil, sf.ref), sf.writeMask);
+				dirty |= 4u;
 			}
 			return;
 		}
@@ -213,36 +254,19 @@ __device__ __forceinline__ void emitFragment(
 	if (stencilEnabled)
 	{
 		const SrpdStencilFace& sf = frontFacing ? st.stencilFront : st.stencilBack;
-		const uint8_t storedStencil = (uint8_t) px.stencil;
-		px.stencil = srpdStencilWrite(storedStencil, srpdStencilOp(sf.passOp, storedStencil, sf.ref), sf.writeMask);
-		px.dirty |= 4u;
+		const uint8_t storedStencil = *px.stencil;
+		*px.stencil = srpdStencilWrite(storedStencil, srpdStencilOp(sf.passOp, storedStencil, sf.ref), sf.writeMask);
+		dirty |= 4u;
 	}
-	px.color = srpdColorPack(out.color);
-	px.dirty |= 1u;
+	*px.color = srpdColorPack(out.color);
+	dirty |= 1u;
 	if (st.depthTest && st.depthWrite)
 	{
-		px.depth = depth;
-		px.dirty |= 2u;
+		*px.depth = depth;
+		dirty |= 2u;
 	}
 }
 
-/* Triangle coverage, one LANE per (TRIANGLE, BLOCK ROW).
- *
- * The reference reaches pixel (x, y) of a triangle by (y - minY) float additions of
- * dlambda/dy from the value at the bounding-box corner, then (x - minX) additions of
- * dlambda/dx (triangle.c:102-109).  The 8 pixels of a block row share that chain up to the
- * row's first pixel, and only a handful of the (up to 32) triangles of a list step touch a
- * warp's 8x4 block, so coverage is not decided by the pixel threads (most of which would
- * only find out that they are outside) but by "row lanes": lane 4*k + r takes row r of the
- * k-th touching triangle, walks the chain down to its row and right to the first column
- * (from the box corner, or from the (row, tile column) checkpoint of a large triangle),
- * tests the row's <= 8 pixels with the top-left rule and leaves
- *   - the row's 8 coverage bits (combined by shuffles into the triangle's 32-bit block mask),
- *   - lambda at the first column, for the pixel threads to resume from.
- * The pixel threads then transpose the masks (bit t of `cov` = triangle t covers my pixel)
- * and shade their own covered triangles in primitive order, resuming the chain with their
- * <= 7 remaining x steps: every value goes through exactly the reference's sequence of
- * additions => bit-exact. */
 __device__ __forceinline__ uint32_t warpInclusiveScan(uint32_t v, int lane)
 {
 	#pragma unroll
@@ -254,47 +278,41 @@ __device__ __forceinline__ uint32_t warpInclusiveScan(uint32_t v, int lane)
 	return v;
 }
 
-/* A thread owns SRPD_PX pixels of its column (rows ly and ly + 4 of the warp's block).  Their
- * state lives in small arrays that are only ever indexed by compile-time constants, so they
- * stay in registers; a run-time choice between them goes through selects (getSel / setSel),
- * which lets the long fragment stage exist once in the code instead of once per pixel. */
-template <typename T>
-__device__ __forceinline__ T getSel(const T (&v)[SRPD_PX], int h)
+/* ---- shared memory: one of these per warp ------------------------------------------- */
+
+/* what the shading lanes need of a triangle, copied from its record once per list step:
+ * a = {z0*iw0, z1*iw1, z2*iw2, primitive id}, b = {iw0, iw1, iw2, record slot | checkpointed << 30 | frontFacing << 31} */
+struct TriInfo { uint4 a, b; };
+constexpr uint32_t SRPD_TRI_SLOT_MASK = 0x3FFFFFFFu;      /* record slots are < 2^30 (runtime.cu clamps the pools) */
+constexpr uint32_t SRPD_TRI_CKPT_BIT = 1u << 30, SRPD_TRI_FRONT_BIT = 1u << 31;
+
+constexpr int SRPD_QUEUE = 128;          /* fragment queue entries */
+constexpr int SRPD_RING = 64;            /* list entries waiting for a step (< 32 left over + <= 32 new) */
+
+/* the warp tile's pixels: plane entry of pixel (x, y), x = 0..31, y = 0..7.  Rows are 32 words;
+ * the 4-pixel (16-byte) chunks of a row are XOR-swizzled with the row so that the pixels of one
+ * column -- what the fragments of a small triangle in one shading pass are made of -- fall into
+ * different banks, while a chunk stays a chunk for the 16-byte loads / stores of the write-back */
+__device__ __forceinline__ int pixelEntry(int x, int y)
 {
-	T r = v[0];
-	#pragma unroll
-	for (int i = 1; i < SRPD_PX; i++)
-		if (h == i) r = v[i];
-	return r;
-}
-template <typename T>
-__device__ __forceinline__ void setSel(T (&v)[SRPD_PX], int h, const T& x)
-{
-	#pragma unroll
-	for (int i = 0; i < SRPD_PX; i++)
-		if (h == i) v[i] = x;
-}
-__device__ __forceinline__ int pickPending(const uint32_t (&cov)[SRPD_PX])
-{
-	int h = 0;
-	#pragma unroll
-	for (int i = SRPD_PX - 1; i > 0; i--)
-		if (cov[i] != 0u && cov[0] == 0u) h = i;
-	return h;
+	return y * SRPD_WT_W + ((((x >> 2) ^ y) & 7) << 2) + (x & 3);
 }
 
-struct RowStart { float l0, l1, l2; int xs; };          /* lambda at column xs of the row          */
-struct TriStep  { float dx0, dx1, dx2; uint32_t rec; };  /* dlambda/dx and the record slot          */
-
-/* per-warp scratch of one list step (shared memory) */
-struct WarpStep
+struct WarpTile
 {
-	RowStart row[32 * SRPD_BLK_H];       /* [compact triangle][block row]                          */
-	TriStep  tri[32];                    /* [compact triangle]                                     */
-	uint32_t idBase[32];                 /* [compact triangle] id prefix of the triangle's batch   */
-	alignas(16) uint8_t bits[SRPD_BLK_H * 32];   /* [block row][compact triangle]: the row's 8 coverage bits */
-	uint8_t  pair[SRPD_BLK_H * 32];      /* work list of the row lanes: triangle * SRPD_BLK_H + row   */
+	alignas(16) uint32_t color[SRPD_WT_PIXELS];
+	alignas(16) float    depth[SRPD_WT_PIXELS];
+	alignas(16) uint8_t  stencil[SRPD_WT_PIXELS];
+	uint4 ring[SRPD_RING];               /* {box.x, box.y, record slot, id prefix} of the tile's next primitives */
 };
+struct WarpTileTri : WarpTile
+{
+	uint4   frag[SRPD_QUEUE];            /* fragment queue: lambda0..2 (float bits), triangle | x << 5 | y << 10 */
+	TriInfo tri[32];                     /* [triangle of the step] */
+	uint8_t pair[SRPD_WT_H * 32];        /* work list of the row lanes: triangle * 8 + row */
+};
+template <int KIND> struct WarpTileK { typedef WarpTile type; };
+template <> struct WarpTileK<SRPD_KIND_TRIANGLE> { typedef WarpTileTri type; };
 
 /* top-left rule as ONE comparison per edge: the reference accepts lambda when
  * lambda > 0 || (|lambda| <= 1e-9 && edgeTL) (triangle.c:82-87).  With F = the largest float
@@ -305,32 +323,37 @@ __device__ __forceinline__ float coverageThreshold(bool topLeft)
 	return topLeft ? __uint_as_float(0xB0897060u) : 0.0f;      /* 0xB089705F = -F; one ulp further from zero */
 }
 
-__device__ __forceinline__ uint32_t coverTriangleRow(
-	const unsigned char* rec, const float* ckptTable, int bx0, int y, RowStart* rowOut, TriStep* triOut)
+/* A row lane's walk: the chain to the row's first pixel inside the tile -- from the box corner,
+ * or from the (row, tile column) checkpoint of a large triangle -- then along the row to its
+ * first covered pixel and on to its last.  The reference tests every pixel of the box row
+ * (triangle.c:80-110); lambda_i(x) is a chain of float additions of one constant, hence monotone
+ * in x, hence {x : lambda_i(x) passes} is a prefix or a suffix of the row for each edge and the
+ * covered pixels are one interval: once coverage has begun and ended nothing further can be
+ * covered, so the walk stops there.  Returns the number of covered pixels; `first` = the first
+ * one (tile-relative x), (s0, s1, s2) = lambda there, (dx0, dx1, dx2) = dlambda/dx. */
+__device__ __forceinline__ int coverTriangleRow(
+	const unsigned char* rec, bool checkpointed, const float* ckptTable, int tx0, int y,
+	float& s0, float& s1, float& s2, float& dx0, float& dx1, float& dx2, int& first)
 {
 	const uint4* h = (const uint4*) rec;
 	const uint4 q0 = __ldg(h + 0), q1 = __ldg(h + 1), q2 = __ldg(h + 2);
 	const int minX = (int) (q0.w & 0xFFFFu), maxX = (int) (q0.w >> 16);
-	const int minY = (int) (q1.w & 0xFFFFu), maxY = (int) (q1.w >> 16);
-	const float dx0 = __uint_as_float(q1.x), dx1 = __uint_as_float(q1.y), dx2 = __uint_as_float(q1.z);
-	triOut->dx0 = dx0; triOut->dx1 = dx1; triOut->dx2 = dx2;      /* (every row lane of the triangle writes the same values) */
-	const int xs = max(bx0, minX);
-	const int n = min(bx0 + SRPD_BLK_W, maxX) - xs;
-	if (y < minY || y >= maxY || n <= 0)
-		return 0u;
+	const int minY = (int) (q1.w & 0xFFFFu);
+	dx0 = __uint_as_float(q1.x); dx1 = __uint_as_float(q1.y); dx2 = __uint_as_float(q1.z);
+	const int xs = max(tx0, minX);
+	const int n = min(tx0 + SRPD_WT_W, maxX) - xs;      /* > 0: the box touches the tile (and y is inside the box) */
 	float l0, l1, l2;
 	int nx;
-	const uint32_t ckpt = __ldg((const uint32_t*) rec + 19);
-	if (ckpt)
+	if (checkpointed)
 	{
-		/* large triangle: resume from the checkpoint of (row, this tile's column), written by
+		/* large triangle: resume from the checkpoint of (row, this tile column), written by
 		 * srpdCheckpointKernel with the reference's own sequence of additions */
+		const uint32_t ckpt = __ldg((const uint32_t*) rec + 19);
 		const int col0 = minX / SRPD_TILE_W;
 		const int cols = (maxX - 1) / SRPD_TILE_W - col0 + 1;
-		const int tileX0 = (bx0 / SRPD_TILE_W) * SRPD_TILE_W;
-		const float* e = ckptTable + 3 * ((size_t) (ckpt - 1) + (size_t) (y - minY) * cols + (bx0 / SRPD_TILE_W - col0));
+		const float* e = ckptTable + 3 * ((size_t) (ckpt - 1) + (size_t) (y - minY) * cols + (tx0 / SRPD_TILE_W - col0));
 		l0 = __ldg(e + 0); l1 = __ldg(e + 1); l2 = __ldg(e + 2);
-		nx = xs - max(tileX0, minX);
+		nx = 0;      /* the checkpoint is at max(tile column start, minX) = xs */
 	}
 	else
 	{
@@ -353,186 +376,189 @@ __device__ __forceinline__ uint32_t coverTriangleRow(
 			}
 		nx = xs - minX;
 	}
-	for (; nx >= 4; nx -= 4)
+	for (; nx > 0; nx--)      /* (only a box that starts left of the tile) */
 	{
-		#pragma unroll
-		for (int u = 0; u < 4; u++)
-		{
-			l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
-		}
+		l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
 	}
-	#pragma unroll
-	for (int u = 0; u < 3; u++)
-		if (u < nx)
-		{
-			l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
-		}
-	rowOut->l0 = l0; rowOut->l1 = l1; rowOut->l2 = l2; rowOut->xs = xs;
-	/* the row's pixels; values past the row's last pixel are computed but masked off */
 	const uint32_t flags = q2.w;
 	const float t0 = coverageThreshold(flags & 1u), t1 = coverageThreshold(flags & 2u), t2 = coverageThreshold(flags & 4u);
-	uint32_t bits = 0u;
-	#pragma unroll
-	for (int i = 0; i < SRPD_BLK_W; i++)
+	/* to the first covered pixel */
+	int i = 0;
+	while (i < n && !(l0 > t0 && l1 > t1 && l2 > t2))
 	{
-#ifdef SRPD_COVER_CHAINED_SETP
-		/* experiment (leads for round 2): the three edge tests as one chain of
-		 * predicated compares instead of three compares combined through selects */
-		uint32_t bit;
-		asm("{\n\t.reg .pred p;\n\tsetp.gt.f32 p, %1, %2;\n\tsetp.gt.and.f32 p, %3, %4, p;\n\tsetp.gt.and.f32 p, %5, %6, p;\n\t"
-		    "selp.u32 %0, %7, 0, p;\n\t}"
-		    : "=r"(bit) : "f"(l0), "f"(t0), "f"(l1), "f"(t1), "f"(l2), "f"(t2), "r"(1u << i));
-		bits |= bit;
-#else
-		if (l0 > t0 && l1 > t1 && l2 > t2)
-			bits |= 1u << i;
-#endif
-		if (i + 1 < SRPD_BLK_W)
-		{
-			l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
-		}
+		l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
+		i++;
 	}
-	return (bits & ((1u << n) - 1u)) << (xs - bx0);
+	first = xs - tx0 + i;
+	s0 = l0; s1 = l1; s2 = l2;
+	/* on to the last one */
+	int count = 0;
+	while (i < n && (l0 > t0 && l1 > t1 && l2 > t2))
+	{
+		l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
+		i++;
+		count++;
+	}
+	return count;
 }
 
-/* fragment stage of one covered pixel of a triangle: the pixel's remaining x steps, depth /
- * 1/w interpolation (interpolateDepthAndWTriangle, interpolation.c:34-47) and emitFragment */
+/* Two fragments of one shading pass that land on the same pixel must run one after the other,
+ * in queue order (the queue is in primitive order).  `key` = the pixel for lanes that hold a
+ * fragment, a value no other lane has otherwise.  Returns this lane's turn (0 = first) and,
+ * through `turns`, how many turns the pass needs (1 unless pixels collide). */
+__device__ __forceinline__ uint32_t fragmentTurn(uint32_t key, int lane, uint32_t& turns)
+{
+	const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+	const uint32_t turn = __popc(peers & ((1u << lane) - 1u));
+	turns = __reduce_max_sync(0xFFFFFFFFu, turn) + 1u;
+	return turn;
+}
+
+/* fragment stage of one queued triangle fragment: depth / 1/w interpolation
+ * (interpolateDepthAndWTriangle, interpolation.c:34-47) and emitFragment */
 template <int SIMPLE>
 __device__ __forceinline__ void shadeTriangleFragment(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, const RowStart& rs, const TriStep& ts, uint32_t idBase,
-	Pixel& px, FragCounters& cnt, int x, int y)
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, const uint4& frag, const TriInfo& ti,
+	WarpTile& wt, int tx0, int ty0, uint32_t& dirty, FragCounters& cnt)
 {
-	float l0 = rs.l0, l1 = rs.l1, l2 = rs.l2;
-	const int nx = x - rs.xs;      /* 0..7 */
-#ifndef SRPD_NO_STEP_IN_REGS
-	/* ONE 16-byte shared load of the triangle's step, pinned by `volatile`: left to itself the
-	 * compiler, at the 48-register cap, re-loads it under every predicated step below (7 LDS.128
-	 * per fragment) and spills around the loop; measured on cfg3: tiles 0.194 -> 0.186 ms */
-	float dx0, dx1, dx2;
-	uint32_t recSlot;
-	asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=f"(dx0), "=f"(dx1), "=f"(dx2), "=r"(recSlot)
-	             : "r"((uint32_t) __cvta_generic_to_shared(&ts)));
-#else
-	const float dx0 = ts.dx0, dx1 = ts.dx1, dx2 = ts.dx2;
-	const uint32_t recSlot = ts.rec;
-#endif
-	#pragma unroll
-	for (int i = 0; i < SRPD_BLK_W - 1; i++)
-		if (i < nx)
-		{
-			l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
-		}
-	const unsigned char* rec = records + (size_t) recSlot * a.recStride;
-	const uint4* h = (const uint4*) rec;
-	const uint4 q3 = __ldg(h + 3), q4 = __ldg(h + 4);
-	const uint32_t flags = __ldg((const uint32_t*) rec + 11);
+	const float l0 = __uint_as_float(frag.x), l1 = __uint_as_float(frag.y), l2 = __uint_as_float(frag.z);
+	const int lx = (int) ((frag.w >> 5) & 31u), ly = (int) (frag.w >> 10);
+	const uint4 A = ti.a, B = ti.b;
 	const float wgt[3] = { l0, l1, l2 };
-	const float iwSum = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(q4.x), l0), __fmul_rn(__uint_as_float(q4.y), l1)),
-	                              __fmul_rn(__uint_as_float(q4.z), l2));
+	const float iwSum = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(B.x), l0), __fmul_rn(__uint_as_float(B.y), l1)),
+	                              __fmul_rn(__uint_as_float(B.z), l2));
 	const float recW = __fdiv_rn(1.0f, iwSum);
-	const float depth = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(q3.x), l0), __fmul_rn(__uint_as_float(q3.y), l1)),
-	                              __fmul_rn(__uint_as_float(q3.z), l2));
+	const float depth = __fadd_rn(__fadd_rn(__fmul_rn(__uint_as_float(A.x), l0), __fmul_rn(__uint_as_float(A.y), l1)),
+	                              __fmul_rn(__uint_as_float(A.z), l2));
+	const int x = tx0 + lx, y = ty0 + ly;
+	const unsigned char* rec = records + (size_t) (B.w & SRPD_TRI_SLOT_MASK) * a.recStride;
+	const int p = pixelEntry(lx, ly);
+	PixelRef px;
+	px.color = wt.color + p; px.depth = wt.depth + p; px.stencil = wt.stencil + p;
 	/* pixel centre: (float) ((double) x + 0.5) is exact, and so is the float sum for these magnitudes */
-	emitFragment<3, SIMPLE>(a.d.st, fr, px, cnt, x, y, __fadd_rn((float) x, 0.5f), __fadd_rn((float) y, 0.5f),
-	                depth, recW, recW, (flags & 8u) != 0, q3.w + idBase, rec + SRPD_REC_HEADER_BYTES, wgt);
+	emitFragment<3, SIMPLE>(a.d.st, fr, px, dirty, cnt, x, y, __fadd_rn((float) x, 0.5f), __fadd_rn((float) y, 0.5f),
+	                depth, recW, recW, (B.w & SRPD_TRI_FRONT_BIT) != 0u, A.w, rec + SRPD_REC_HEADER_BYTES, wgt);
 }
 
-/* One list step of a warp.  `mine` = this lane's list entry (record slot `recSlot`) touches the
- * warp's block.  The touching entries are compacted in order (t = 0 .. n-1); row lanes decide
- * coverage, 8 triangles x 4 rows per round; pixel threads gather the bits of their pixel --
- * bit t of `cov` <=> triangle t covers my pixel -- and shade them in order. */
+/* one shading pass: queue entries [f0, f0 + 32) */
+template <int SIMPLE>
+__device__ __forceinline__ void shadePass(
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, WarpTileTri& wt, int f0, int nFrags, bool several,
+	int tx0, int ty0, uint32_t& dirty, FragCounters& cnt, int lane)
+{
+	const int f = f0 + lane;
+	const bool has = f < nFrags;
+	uint4 frag = make_uint4(0u, 0u, 0u, 0u);
+	if (has)
+		frag = wt.frag[f];
+	uint32_t turn = 0u, turns = 1u;
+	if (several)
+		turn = fragmentTurn(has ? (frag.w >> 5) : (uint32_t) (SRPD_WT_PIXELS + lane), lane, turns);
+	for (uint32_t r = 0; r < turns; r++)
+	{
+		if (has && turn == r)
+			shadeTriangleFragment<SIMPLE>(a, fr, records, frag, wt.tri[frag.w & 31u], wt, tx0, ty0, dirty, cnt);
+		if (turns > 1u)
+			__syncwarp();
+	}
+	if (several)
+		__syncwarp();      /* a later pass may hold another triangle's fragment for one of this pass's pixels */
+}
+
+/* One step: the next `n` (<= 32) primitives of the tile, entries ring[head ..] (all of them touch
+ * the tile).  Their shading data goes to shared memory; the (triangle, row) pairs -- only the tile
+ * rows inside a triangle's box -- form a work list that the row lanes take 32 at a time:
+ * coverage (coverTriangleRow), then a warp scan places every lane's fragments in the queue, in
+ * (triangle, row, x) order, SRPD_QUEUE fragments per turn; the shading passes empty the queue;
+ * lanes whose pixels did not fit take the next turn. */
 template <int SIMPLE>
 __device__ __forceinline__ void visitTriangles(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, bool mine, uint32_t recSlot, uint32_t idBase, int rowLo, int rowCnt,
-	WarpStep& ws, Pixel (&px)[SRPD_PX], FragCounters& cnt, int x, int y0, int bx0, int by0, int lane)
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, WarpTileTri& wt, int head, int n,
+	int tx0, int ty0, uint32_t& dirty, FragCounters& cnt, int lane)
 {
-	const uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
-	if (m == 0u)
-		return;
-	const int n = __popc(m);
-	/* work list of (triangle, row) pairs: only the block rows inside a triangle's bounding box,
-	 * so the row lanes are (nearly) all busy whatever the triangles' heights */
-	const uint32_t inc = warpInclusiveScan(mine ? (uint32_t) rowCnt : 0u, lane);
+	int rowLo = 0, rowCnt = 0;
+	if (lane < n)
+	{
+		const uint4 ent = wt.ring[(head + lane) & (SRPD_RING - 1)];
+		const int y0b = (int) (ent.x >> 16), y1b = (int) (ent.y >> 16);
+		rowLo = max(y0b, ty0) - ty0;
+		rowCnt = min(y1b, ty0 + SRPD_WT_H) - ty0 - rowLo;
+		const unsigned char* rec = records + (size_t) ent.z * a.recStride;
+		const uint4 q3 = __ldg((const uint4*) rec + 3), q4 = __ldg((const uint4*) rec + 4);
+		const uint32_t flags = __ldg((const uint32_t*) rec + 11);
+		TriInfo ti;
+		ti.a = make_uint4(q3.x, q3.y, q3.z, q3.w + ent.w);      /* batch-local id + the batch's id prefix */
+		ti.b = make_uint4(q4.x, q4.y, q4.z, ent.z | (q4.w ? SRPD_TRI_CKPT_BIT : 0u) | ((flags & 8u) ? SRPD_TRI_FRONT_BIT : 0u));
+		wt.tri[lane] = ti;
+	}
+	const uint32_t inc = warpInclusiveScan((uint32_t) rowCnt, lane);
 	const int nPairs = (int) __shfl_sync(0xFFFFFFFFu, inc, 31);
-	#pragma unroll
-	for (int i = 0; i < SRPD_BLK_H * 32 / 4 / 32; i++)
-		((uint32_t*) ws.bits)[lane + 32 * i] = 0u;
-	if (mine)
 	{
-		const int t = __popc(m & ((1u << lane) - 1u));
-		ws.tri[t].rec = recSlot;
-		ws.idBase[t] = idBase;
-		uint8_t* out = ws.pair + (inc - (uint32_t) rowCnt);
+		uint8_t* out = wt.pair + (inc - (uint32_t) rowCnt);
 		for (int r = 0; r < rowCnt; r++)
-			out[r] = (uint8_t) (t * SRPD_BLK_H + rowLo + r);
+			out[r] = (uint8_t) (lane * SRPD_WT_H + rowLo + r);
 	}
 	__syncwarp();
-	for (int q = lane; q < nPairs; q += 32)
+	for (int q0 = 0; q0 < nPairs; q0 += 32)
 	{
-		const int pr = ws.pair[q];
-		const int t = pr / SRPD_BLK_H, row = pr % SRPD_BLK_H;
-		const uint32_t bits = coverTriangleRow(records + (size_t) ws.tri[t].rec * a.recStride, a.ckptTable, bx0, by0 + row,
-		                                       &ws.row[pr], &ws.tri[t]);
-		ws.bits[row * 32 + t] = (uint8_t) bits;
-	}
-	__syncwarp();
-	/* gather: byte t of a row's 32 bytes holds the row's coverage of triangle t; bit (lane % 8)
-	 * of it is my pixel.  Four triangles per 32-bit word: isolate the bit in each byte, then
-	 * one multiply moves the four bits next to each other (no carries: all partial products
-	 * land on distinct bit positions). */
-	const int ly = lane / SRPD_BLK_W, lx = lane % SRPD_BLK_W;
-	uint32_t cov[SRPD_PX];
-	#pragma unroll
-	for (int h = 0; h < SRPD_PX; h++)
-	{
-		cov[h] = 0u;
-		const uint32_t* rowBits = (const uint32_t*) (ws.bits + (ly + 4 * h) * 32);
-		for (int w = 0; w * 4 < n; w++)
+		/* coverage: one lane per (triangle, row) */
+		const int q = q0 + lane;
+		uint32_t tRow = 0u;
+		float l0 = 0.f, l1 = 0.f, l2 = 0.f, dx0 = 0.f, dx1 = 0.f, dx2 = 0.f;
+		int x = 0, left = 0;
+		if (q < nPairs)
 		{
-			const uint32_t four = (rowBits[w] >> lx) & 0x01010101u;
-			cov[h] |= (((four * 0x00204081u) >> 21) & 0xFu) << (4 * w);
+			tRow = wt.pair[q];
+			const uint32_t slotWord = wt.tri[tRow / SRPD_WT_H].b.w;
+			left = coverTriangleRow(records + (size_t) (slotWord & SRPD_TRI_SLOT_MASK) * a.recStride, (slotWord & SRPD_TRI_CKPT_BIT) != 0u,
+			                        a.ckptTable, tx0, ty0 + (int) (tRow % SRPD_WT_H), l0, l1, l2, dx0, dx1, dx2, x);
 		}
-		if (n < 32)
-			cov[h] &= (1u << n) - 1u;      /* bytes of triangles beyond n are stale */
-	}
-	/* shade: every lane works through the covering triangles of its own pixel(s), in order */
-	for (;;)
-	{
-		uint32_t any = cov[0];
-		#pragma unroll
-		for (int h = 1; h < SRPD_PX; h++)
-			any |= cov[h];
-		if (!__any_sync(0xFFFFFFFFu, any != 0u))
-			break;
-		if (any)
+		/* do two triangles meet in this round?  (only then can two fragments share a pixel) */
+		const uint32_t firstTri = __shfl_sync(0xFFFFFFFFu, tRow / SRPD_WT_H, 0);
+		const bool several = __any_sync(0xFFFFFFFFu, left != 0 && tRow / SRPD_WT_H != firstTri);
+		uint32_t meta = (tRow / SRPD_WT_H) | ((uint32_t) x << 5) | ((tRow % SRPD_WT_H) << 10);
+		while (__any_sync(0xFFFFFFFFu, left != 0))
 		{
-			const int h = pickPending(cov);
-			const uint32_t c = getSel(cov, h);
-			const int t = __ffs(c) - 1;
-			setSel(cov, h, c & (c - 1u));
-			Pixel cur = getSel(px, h);
-			shadeTriangleFragment<SIMPLE>(a, fr, records, ws.row[t * SRPD_BLK_H + ly + 4 * h], ws.tri[t], ws.idBase[t], cur, cnt, x, y0 + 4 * h);
-			setSel(px, h, cur);
+			/* a turn: the next fragments in strict (lane, x) = (primitive, row, x) order, as many as
+			 * the queue holds: the lanes in front queue all they have left, one lane may get in
+			 * only a part of its row, the lanes behind it wait for the next turn (a lane behind
+			 * may belong to a later triangle that covers the same pixels) */
+			const uint32_t want = (uint32_t) left;
+			const uint32_t incF = warpInclusiveScan(want, lane);
+			const uint32_t excl = incF - want;
+			const int nFrags = min((int) __shfl_sync(0xFFFFFFFFu, incF, 31), SRPD_QUEUE);
+			const int k = excl >= (uint32_t) SRPD_QUEUE ? 0 : min((int) want, SRPD_QUEUE - (int) excl);
+			uint4* out = wt.frag + excl;
+			for (int j = 0; j < k; j++)
+			{
+				/* lambda at the covered pixels: the chain goes on with the same additions */
+				out[j] = make_uint4(__float_as_uint(l0), __float_as_uint(l1), __float_as_uint(l2), meta);
+				l0 = __fadd_rn(l0, dx0); l1 = __fadd_rn(l1, dx1); l2 = __fadd_rn(l2, dx2);
+				meta += 1u << 5;
+			}
+			left -= k;
+			__syncwarp();
+			for (int f0 = 0; f0 < nFrags; f0 += 32)
+				shadePass<SIMPLE>(a, fr, records, wt, f0, nFrags, several, tx0, ty0, dirty, cnt, lane);
+			__syncwarp();      /* the next turn overwrites the queue */
 		}
 	}
-	__syncwarp();      /* the next step overwrites this warp's scratch */
+	__syncwarp();      /* the next step overwrites the triangle data and the pair list */
 }
 
-/* rasterizeLine for the warp's pixel block, reference line.c:34-77.  A record is a segment of
+/* rasterizeLine for the warp tile, reference line.c:34-77.  A record is a segment of
  * <= SRPD_LINE_SEG (16) consecutive DDA fragments with the chain state at its first one.  Lane k
  * walks the chain to fragment k -- k float additions per coordinate, exactly the reference's
- * sequence, all fragments side by side instead of every lane replaying all of them -- and rounds
- * it to its pixel once.  The fragments that land in this block are then matched to the lanes
- * that own their pixels, and every lane shades its own pixels' fragments in DDA order, all lanes
- * at once: a fragment is matched through its linear index
- * y*W + x, which is also how the reference's unchecked indexing wraps x == width onto the next
- * row (App. B-1).  Must be called by all 32 lanes. */
+ * sequence, all fragments side by side -- and rounds it to its pixel once.  A fragment that
+ * lands in this warp's tile is shaded by the lane that walked to it, on the pixel's state in
+ * shared memory; a fragment is placed through its linear index y*W + x, which is also how the
+ * reference's unchecked indexing wraps x == width onto the next row (App. B-1).  Two fragments
+ * of the segment on one pixel run in DDA order.  Must be called by all 32 lanes. */
 static_assert(SRPD_LINE_SEG <= 32, "one lane per fragment of a segment");
 __device__ __forceinline__ void visitLine(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, uint32_t idBase, Pixel (&px)[SRPD_PX], FragCounters& cnt,
-	int x, int y0, const bool (&valid)[SRPD_PX])
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, uint32_t idBase,
+	WarpTile& wt, int tx0, int ty0, uint32_t& dirty, FragCounters& cnt, int lane)
 {
-	const int lane = threadIdx.x & 31;
 	const uint4* h = (const uint4*) rec;
 	const uint4 q0 = __ldg(h + 0), q1 = __ldg(h + 1), q2 = __ldg(h + 2), q3 = __ldg(h + 3);
 	float fx = __uint_as_float(q0.x), fy = __uint_as_float(q0.y);
@@ -543,10 +569,6 @@ __device__ __forceinline__ void visitLine(
 	const float iw0 = __uint_as_float(q2.x), iw1 = __uint_as_float(q2.y);
 	float t = __uint_as_float(q2.z);
 	const long long W = a.d.st.width;
-	long long mine[SRPD_PX];
-	#pragma unroll
-	for (int k = 0; k < SRPD_PX; k++)
-		mine[k] = valid[k] ? (long long) (y0 + 4 * k) * W + x : -1;
 	/* lane k: k steps of the chain */
 	for (int i = 0; i + 1 < count; i++)
 		if (i < lane)
@@ -556,123 +578,244 @@ __device__ __forceinline__ void visitLine(
 			t = __fadd_rn(t, tInc);
 		}
 	const int myX = srpdRoundToInt(fx), myY = srpdRoundToInt(fy);
-	/* does my fragment land in this warp's block (columns bx0 .. bx0+7, rows by0 .. by0+7)? */
-	bool inBlock = false;
+	/* does my fragment land in this warp's tile? */
+	bool inTile = false;
+	int lx = 0, ly = 0;
 	if (lane < count)
 	{
 		const long long idx = (long long) myY * W + myX;
 		if (idx >= 0 && idx < W * (long long) a.d.st.height)
 		{
-			const int bx0 = x - (lane % SRPD_BLK_W), by0 = y0 - (lane / SRPD_BLK_W);
 			const bool inRow = myX >= 0 && myX < W;      /* the usual case needs no 64-bit division */
 			const int pxl = inRow ? myX : (int) (idx % W), pyl = inRow ? myY : (int) (idx / W);
-			inBlock = pxl >= bx0 && pxl < bx0 + SRPD_BLK_W && pyl >= by0 && pyl < by0 + SRPD_BLK_H;
+			inTile = pxl >= tx0 && pxl < tx0 + SRPD_WT_W && pyl >= ty0 && pyl < ty0 + SRPD_WT_H;
+			lx = pxl - tx0; ly = pyl - ty0;
 		}
 	}
-	/* which fragments hit my pixels?  bit k of hits[j] = fragment k lands on my j-th pixel */
-	uint32_t hits[SRPD_PX];
-	#pragma unroll
-	for (int j = 0; j < SRPD_PX; j++)
-		hits[j] = 0u;
-	for (uint32_t m = __ballot_sync(0xFFFFFFFFu, inBlock); m != 0u; m &= m - 1u)
+	if (!__any_sync(0xFFFFFFFFu, inTile))
+		return;
+	uint32_t turns;
+	const uint32_t turn = fragmentTurn(inTile ? (uint32_t) (ly * SRPD_WT_W + lx) : (uint32_t) (SRPD_WT_PIXELS + lane), lane, turns);
+	for (uint32_t r = 0; r < turns; r++)
 	{
-		const int k = __ffs(m) - 1;
-		const int ipx = __shfl_sync(0xFFFFFFFFu, myX, k), ipy = __shfl_sync(0xFFFFFFFFu, myY, k);
-		const long long idx = (long long) ipy * W + ipx;
-		#pragma unroll
-		for (int j = 0; j < SRPD_PX; j++)
-			if (idx == mine[j]) hits[j] |= 1u << k;
-	}
-	/* every lane shades the fragments of its own pixels, in DDA order per pixel; different
-	 * pixels are independent, so the lanes work side by side (a line rarely visits a pixel twice) */
-	for (;;)
-	{
-		uint32_t any = hits[0];
-		#pragma unroll
-		for (int j = 1; j < SRPD_PX; j++)
-			any |= hits[j];
-		if (!__any_sync(0xFFFFFFFFu, any != 0u))
-			break;
-		const int which = pickPending(hits);
-		const uint32_t hsel = getSel(hits, which);
-		const int k = any ? __ffs(hsel) - 1 : 0;
-		const int ipx = __shfl_sync(0xFFFFFFFFu, myX, k), ipy = __shfl_sync(0xFFFFFFFFu, myY, k);
-		const float tk = __shfl_sync(0xFFFFFFFFu, t, k);
-		if (any)
+		if (inTile && turn == r)
 		{
-			setSel(hits, which, hsel & (hsel - 1u));
-			const float w0 = __fsub_rn(1.0f, tk);
-			const float wgt[2] = { w0, tk };
+			const float w0 = __fsub_rn(1.0f, t);
+			const float wgt[2] = { w0, t };
 			/* interpolateDepthAndWLine, interpolation.c:49-60 */
-			const float recW = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(iw0, w0), __fmul_rn(iw1, tk)));
-			const float depth = __fadd_rn(__fmul_rn(zw0, w0), __fmul_rn(zw1, tk));
-			Pixel cur = getSel(px, which);
-			emitFragment<2, 0>(a.d.st, fr, cur, cnt, ipx, ipy, (float) ((double) ipx + 0.5), (float) ((double) ipy + 0.5),
+			const float recW = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(iw0, w0), __fmul_rn(iw1, t)));
+			const float depth = __fadd_rn(__fmul_rn(zw0, w0), __fmul_rn(zw1, t));
+			const int p = pixelEntry(lx, ly);
+			PixelRef px;
+			px.color = wt.color + p; px.depth = wt.depth + p; px.stencil = wt.stencil + p;
+			emitFragment<2, 0>(a.d.st, fr, px, dirty, cnt, myX, myY, (float) ((double) myX + 0.5), (float) ((double) myY + 0.5),
 			                depth, recW, recW, true, q3.w + idBase, rec + SRPD_REC_HEADER_BYTES, wgt);
-			setSel(px, which, cur);
 		}
+		if (turns > 1u)
+			__syncwarp();
 	}
 }
 
-/* rasterizePoint for the thread's pixels, reference point.c:32-74 */
+/* rasterizePoint for the warp tile, reference point.c:32-74: lane = pixel column; the lanes whose
+ * column lies in the point's square walk down its rows inside the tile */
 __device__ __forceinline__ void visitPoint(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, uint32_t idBase, Pixel (&px)[SRPD_PX], FragCounters& cnt,
-	int x, int y0, const bool (&valid)[SRPD_PX])
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, uint32_t idBase,
+	WarpTile& wt, int tx0, int ty0, uint32_t& dirty, FragCounters& cnt, int lane)
 {
 	const uint4* h = (const uint4*) rec;
-	const uint4 q1 = __ldg(h + 1);
-	if (x < (int) q1.x || x > (int) q1.y)
+	const uint4 q1 = __ldg(h + 1);      /* pixel box, inclusive: minX, maxX, minY, maxY */
+	const int x = tx0 + lane;
+	if (x < (int) q1.x || x > (int) q1.y || x >= a.d.st.width)
 		return;
 	const uint4 q0 = __ldg(h + 0);
 	const float pcx = (float) ((double) x + 0.5);
 	if (pcx < __uint_as_float(q0.x) || pcx >= __uint_as_float(q0.z))
 		return;
-	#pragma unroll 1
-	for (int k = 0; k < SRPD_PX; k++)
+	const uint4 q2 = __ldg(h + 2), q3 = __ldg(h + 3);
+	const int yLo = max((int) q1.z, ty0), yHi = min(min((int) q1.w, ty0 + SRPD_WT_H - 1), a.d.st.height - 1);
+	for (int y = yLo; y <= yHi; y++)
 	{
-		const int y = y0 + 4 * k;
-		if (!getSel(valid, k) || y < (int) q1.z || y > (int) q1.w)
-			continue;
 		const float pcy = (float) ((double) y + 0.5);
 		if (pcy < __uint_as_float(q0.y) || pcy >= __uint_as_float(q0.w))
 			continue;
-		const uint4 q2 = __ldg(h + 2), q3 = __ldg(h + 3);
-		Pixel cur = getSel(px, k);
-		emitFragment<1, 0>(a.d.st, fr, cur, cnt, x, y, pcx, pcy, __uint_as_float(q2.x), 0.f, __uint_as_float(q2.y),
+		const int p = pixelEntry(lane, y - ty0);
+		PixelRef px;
+		px.color = wt.color + p; px.depth = wt.depth + p; px.stencil = wt.stencil + p;
+		emitFragment<1, 0>(a.d.st, fr, px, dirty, cnt, x, y, pcx, pcy, __uint_as_float(q2.x), 0.f, __uint_as_float(q2.y),
 		                true, q3.w + idBase, rec + SRPD_REC_HEADER_BYTES, nullptr);
-		setSel(px, k, cur);
+	}
+}
+
+/* ---- warp tile: global memory <-> shared memory ---------------------------------------
+ * A tile row is 32 pixels = 128 bytes of colour / depth = eight 16-byte chunks of 4 pixels and
+ * 32 bytes of stencil.  Lane l moves chunks l and l + 32 of the 64 chunks of a plane (chunk c =
+ * row c / 8, pixels 4 * (c % 8) ..), so eight neighbouring lanes move one full 128-byte row.
+ * The 16-byte path needs the row pitch and the plane base to keep the chunks aligned (width a
+ * multiple of 4 pixels, 16 for stencil); other framebuffers take the element-wise path. */
+struct TileIO
+{
+	bool vec4;       /* colour / depth rows can move as 16-byte chunks */
+	bool vec16;      /* stencil rows can move as 16-byte chunks */
+};
+
+__device__ __forceinline__ TileIO tileIO(const SrpdState& st, const SrpdFrame& fr)
+{
+	TileIO io;
+	io.vec4 = (st.width % 4) == 0 && ((((uintptr_t) fr.color) | ((uintptr_t) fr.depth)) & 15u) == 0;
+	io.vec16 = (st.width % 16) == 0 && (((uintptr_t) fr.stencil) & 15u) == 0;
+	return io;
+}
+
+/* the planes the draw reads (or, with a pending clear, the clear values) -> shared memory */
+__device__ __forceinline__ void loadWarpTile(const SrpdState& st, const SrpdFrame& fr, const TileIO& io, bool stencilEnabled,
+                                             WarpTile& wt, int tx0, int ty0, int lane)
+{
+	const bool loadColor = !fr.clearPending, loadDepth = !fr.clearPending && st.depthTest;
+	#pragma unroll
+	for (int k = 0; k < 2; k++)
+	{
+		const int c = lane + 32 * k;
+		const int row = c / 8, col = (c % 8) * 4;
+		const int x = tx0 + col, y = ty0 + row;
+		const int e = pixelEntry(col, row);
+		uint4 vc = make_uint4(0u, 0u, 0u, 0u);                                              /* colour 0 */
+		uint4 vd = make_uint4(0xBF800000u, 0xBF800000u, 0xBF800000u, 0xBF800000u);          /* depth -1 */
+		if ((loadColor || loadDepth) && y < st.height && x < st.width)
+		{
+			const size_t at = (size_t) y * st.width + x;
+			if (io.vec4)
+			{
+				if (loadColor) vc = *(const uint4*) (fr.color + at);
+				if (loadDepth) vd = *(const uint4*) (fr.depth + at);
+			}
+			else
+			{
+				uint32_t* pc = &vc.x; uint32_t* pd = &vd.x;
+				for (int i = 0; i < 4; i++)
+					if (x + i < st.width)
+					{
+						if (loadColor) pc[i] = fr.color[at + i];
+						if (loadDepth) pd[i] = __float_as_uint(fr.depth[at + i]);
+					}
+			}
+		}
+		*(uint4*) (wt.color + e) = vc;
+		*(uint4*) (wt.depth + e) = vd;
+	}
+	/* stencil: 64 chunks of 4 bytes, two per lane */
+	#pragma unroll
+	for (int k = 0; k < 2; k++)
+	{
+		const int c = lane + 32 * k;
+		const int row = c / 8, col = (c % 8) * 4;
+		const int x = tx0 + col, y = ty0 + row;
+		uint32_t v = 0u;
+		if (stencilEnabled && y < st.height && x < st.width)
+		{
+			const uint8_t* src = fr.stencil + (size_t) y * st.width + x;
+			if (io.vec4 && (((uintptr_t) fr.stencil) & 3u) == 0)
+				v = *(const uint32_t*) src;
+			else
+				for (int i = 0; i < 4; i++)
+					if (x + i < st.width) v |= (uint32_t) src[i] << (8 * i);
+		}
+		*(uint32_t*) (wt.stencil + pixelEntry(col, row)) = v;
+	}
+}
+
+/* shared memory -> the planes.  With a pending clear every pixel of colour and depth is written
+ * (untouched ones with the clear values); otherwise only the planes that some fragment changed
+ * (`dirty`: bit0 colour, bit1 depth, bit2 stencil) -- their other pixels go back as they were
+ * loaded.  Full 128-byte rows of colour / depth, 32-byte rows of stencil. */
+__device__ __forceinline__ void storeWarpTile(const SrpdState& st, const SrpdFrame& fr, const TileIO& io, uint32_t dirty,
+                                              const WarpTile& wt, int tx0, int ty0, int lane)
+{
+	const bool storeColor = fr.clearPending || (dirty & 1u), storeDepth = fr.clearPending || (dirty & 2u);
+	if (storeColor || storeDepth)
+	{
+		#pragma unroll
+		for (int k = 0; k < 2; k++)
+		{
+			const int c = lane + 32 * k;
+			const int row = c / 8, col = (c % 8) * 4;
+			const int x = tx0 + col, y = ty0 + row;
+			if (y >= st.height || x >= st.width)
+				continue;
+			const int e = pixelEntry(col, row);
+			const size_t at = (size_t) y * st.width + x;
+			const uint4 vc = *(const uint4*) (wt.color + e), vd = *(const uint4*) (wt.depth + e);
+			if (io.vec4)
+			{
+				if (storeColor) *(uint4*) (fr.color + at) = vc;
+				if (storeDepth) *(uint4*) (fr.depth + at) = vd;
+			}
+			else
+			{
+				const uint32_t* pc = &vc.x; const uint32_t* pd = &vd.x;
+				for (int i = 0; i < 4; i++)
+					if (x + i < st.width)
+					{
+						if (storeColor) fr.color[at + i] = pc[i];
+						if (storeDepth) fr.depth[at + i] = __uint_as_float(pd[i]);
+					}
+			}
+		}
+	}
+	if (dirty & 4u)
+	{
+		if (io.vec16)
+		{
+			/* lanes 0..15: one 16-pixel half row each = four swizzled 4-byte chunks */
+			if (lane < 16)
+			{
+				const int row = lane / 2, col = (lane % 2) * 16;
+				const int x = tx0 + col, y = ty0 + row;
+				if (y < st.height && x < st.width)
+				{
+					uint4 v;
+					v.x = *(const uint32_t*) (wt.stencil + pixelEntry(col + 0, row));
+					v.y = *(const uint32_t*) (wt.stencil + pixelEntry(col + 4, row));
+					v.z = *(const uint32_t*) (wt.stencil + pixelEntry(col + 8, row));
+					v.w = *(const uint32_t*) (wt.stencil + pixelEntry(col + 12, row));
+					*(uint4*) (fr.stencil + (size_t) y * st.width + x) = v;
+				}
+			}
+		}
+		else
+		{
+			#pragma unroll
+			for (int k = 0; k < 2; k++)
+			{
+				const int c = lane + 32 * k;
+				const int row = c / 8, col = (c % 8) * 4;
+				const int x = tx0 + col, y = ty0 + row;
+				if (y >= st.height || x >= st.width)
+					continue;
+				const uint32_t v = *(const uint32_t*) (wt.stencil + pixelEntry(col, row));
+				uint8_t* dst = fr.stencil + (size_t) y * st.width + x;
+				for (int i = 0; i < 4; i++)
+					if (x + i < st.width) dst[i] = (uint8_t) (v >> (8 * i));
+			}
+		}
 	}
 }
 
 } // namespace
 
-/* shared memory of the tile kernel (dynamic: with the per-warp step scratch it exceeds 48 KB) */
-struct TileShared
-{
-	uint32_t ids[SRPD_TILE_THREADS];     /* record slots of the tile's list chunk */
-	uint32_t idBase[SRPD_TILE_THREADS];  /* id prefix of their batches (records hold batch-local ids) */
-	uint2    box[SRPD_TILE_THREADS];     /* their boxes */
-	uint32_t warpCnt[32];
-	uint32_t item[2];
-};
-template <int KIND> struct TileSharedK : TileShared {};
-template <> struct TileSharedK<SRPD_KIND_TRIANGLE> : TileShared { WarpStep step[SRPD_TILE_WARPS]; };
-
-/* One tile: filter the candidate list, visit the primitives in order, write the tile back. */
+/* One warp tile: load its state, collect the primitives that touch it, visit them in order, write it back. */
 template <int KIND, int SIMPLE>
-__device__ __forceinline__ void processTile(
-	const SrpdTileArgs& a, const SrpdFrame& fr, uint32_t frame, int tileX, int tileY, TileSharedK<KIND>& sm, FragCounters& cnt)
+__device__ __forceinline__ void processWarpTile(
+	const SrpdTileArgs& a, const SrpdFrame& fr, uint32_t frame, int tileX, int tileY8, typename WarpTileK<KIND>::type& wt, FragCounters& cnt, int lane)
 {
 	const SrpdState& st = a.d.st;
 	const bool stencilEnabled = SIMPLE ? false : (bool) st.stencilEnabled;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
 	/* candidate list of this tile */
 	uint32_t begin = 0, end;
 	const uint32_t* ids = nullptr;
 	if (a.superOffsets && *a.listOverflow == 0u)
 	{
-		const uint32_t s = ((uint32_t) tileY >> a.superShift) * a.superX + ((uint32_t) tileX >> a.superShift);
+		const uint32_t s = ((uint32_t) tileY8 >> (a.superShift + 1)) * a.superX + ((uint32_t) tileX >> a.superShift);
 		begin = a.superOffsets[s];
 		end = a.superOffsets[s + 1];
 		ids = a.listIds;
@@ -682,168 +825,131 @@ __device__ __forceinline__ void processTile(
 
 	const unsigned char* records = a.records + (size_t) frame * a.recCapacity * a.recStride;
 	const uint4* ordered = a.ordered + (size_t) frame * a.recCapacity;
+	const int tx0 = tileX * SRPD_WT_W, ty0 = tileY8 * SRPD_WT_H;
+	const TileIO io = tileIO(st, fr);
+	uint32_t dirty = 0u;
 
-	/* pixel ownership: warp w -> block (w % 4, w / 4) of 8 x SRPD_BLK_H pixels;
-	 * lane -> column lane % 8, rows lane / 8 (+ 4 for the thread's second pixel) */
-	const int tx0 = tileX * SRPD_TILE_W, ty0 = tileY * SRPD_TILE_H;
-	const int bx0 = tx0 + (warp % (SRPD_TILE_W / SRPD_BLK_W)) * SRPD_BLK_W;
-	const int by0 = ty0 + (warp / (SRPD_TILE_W / SRPD_BLK_W)) * SRPD_BLK_H;
-	const int x = bx0 + (lane % SRPD_BLK_W), y0 = by0 + (lane / SRPD_BLK_W);
+	loadWarpTile(st, fr, io, stencilEnabled, wt, tx0, ty0, lane);
+	__syncwarp();
 
-	Pixel px[SRPD_PX];
-	bool valid[SRPD_PX];
-	#pragma unroll
-	for (int k = 0; k < SRPD_PX; k++)
+	int head = 0, waiting = 0;      /* the ring: entries [head, head + waiting) */
+	for (uint32_t c = begin; c < end; c += 32)
 	{
-		const int y = y0 + 4 * k;
-		valid[k] = x < st.width && y < st.height;
-		px[k].color = 0u; px[k].depth = -1.0f; px[k].stencil = 0u; px[k].dirty = 0u;
-		if (valid[k] && (!fr.clearPending || stencilEnabled))
-		{
-			const size_t pixelIndex = (size_t) y * st.width + x;
-			if (!fr.clearPending)
-			{
-				px[k].color = fr.color[pixelIndex];
-				if (st.depthTest)
-					px[k].depth = fr.depth[pixelIndex];
-			}
-			if (stencilEnabled)
-				px[k].stencil = fr.stencil[pixelIndex];
-		}
-	}
-
-	for (uint32_t c = begin; c < end; c += SRPD_TILE_THREADS)
-	{
-		/* CTA: keep the candidates whose bbox touches the tile, in order */
-		const uint32_t i = c + tid;
+		/* keep the candidates whose box touches the tile, in order */
+		const uint32_t i = c + lane;
 		bool hit = false;
 		uint4 ent = make_uint4(0u, 0u, 0u, 0u);
-		uint2 bb = make_uint2(0u, 0u);
 		if (i < end)
 		{
 			const uint32_t rid = ids ? ids[i] : i;          /* position in primitive order */
 			ent = ordered[rid];                              /* {box, record slot, id prefix} */
-			bb = make_uint2(ent.x, ent.y);
-			const int x0 = (int) (bb.x & 0xFFFFu), y0b = (int) (bb.x >> 16);
-			const int x1 = (int) (bb.y & 0xFFFFu), y1b = (int) (bb.y >> 16);
-			hit = x0 < tx0 + SRPD_TILE_W && x1 > tx0 && y0b < ty0 + SRPD_TILE_H && y1b > ty0;
+			const int x0 = (int) (ent.x & 0xFFFFu), y0b = (int) (ent.x >> 16);
+			const int x1 = (int) (ent.y & 0xFFFFu), y1b = (int) (ent.y >> 16);
+			hit = x0 < tx0 + SRPD_WT_W && x1 > tx0 && y0b < ty0 + SRPD_WT_H && y1b > ty0;
 		}
 		const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
-		/* (no barrier needed here: whoever gets this far has passed the previous chunk's second
-		 * barrier, which every warp reaches only after it has read that chunk's counters; and the
-		 * list itself is rewritten only after the next barrier, which every warp reaches only
-		 * after it has finished walking the previous list) */
-		if (lane == 0)
-			sm.warpCnt[warp] = __popc(ballot);
-		__syncthreads();
-		const uint32_t wc = lane < SRPD_TILE_WARPS ? sm.warpCnt[lane] : 0u;
-		const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, wc);
-		const uint32_t base = __reduce_add_sync(0xFFFFFFFFu, lane < warp ? wc : 0u);
-		if (hit)
-		{
-			const uint32_t pos = base + __popc(ballot & ((1u << lane) - 1u));
-			sm.ids[pos] = ent.z;             /* record slot */
-			sm.idBase[pos] = ent.w;
-			sm.box[pos] = bb;
-		}
-		__syncthreads();
-
-		/* warp: visit, in order, the entries that touch this warp's block */
-		for (uint32_t j0 = 0; j0 < total; j0 += 32)
-		{
-			const uint32_t j = j0 + lane;
-			bool mine = false;
-			uint32_t slot = 0u, idBase = 0u;
-			int rowLo = 0, rowCnt = 0;
-			if (j < total)
-			{
-				const uint2 b2 = sm.box[j];
-				const int x0 = (int) (b2.x & 0xFFFFu), y0b = (int) (b2.x >> 16);
-				const int x1 = (int) (b2.y & 0xFFFFu), y1b = (int) (b2.y >> 16);
-				mine = x0 < bx0 + SRPD_BLK_W && x1 > bx0 && y0b < by0 + SRPD_BLK_H && y1b > by0;
-				slot = sm.ids[j];
-				idBase = sm.idBase[j];
-				rowLo = max(y0b, by0) - by0;
-				rowCnt = min(y1b, by0 + SRPD_BLK_H) - by0 - rowLo;
-			}
-			if constexpr (KIND == SRPD_KIND_TRIANGLE)
-				visitTriangles<SIMPLE>(a, fr, records, mine, slot, idBase, rowLo, rowCnt, sm.step[warp], px, cnt, x, y0, bx0, by0, lane);
-			else
-			{
-				uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
-				while (m)
-				{
-					const int bit = __ffs(m) - 1;
-					m &= m - 1;
-					const unsigned char* rec = records + (size_t) sm.ids[j0 + bit] * a.recStride;
-					const uint32_t recIdBase = sm.idBase[j0 + bit];
-					if (KIND == SRPD_KIND_LINE)
-						visitLine(a, fr, rec, recIdBase, px, cnt, x, y0, valid);
-					else
-						visitPoint(a, fr, rec, recIdBase, px, cnt, x, y0, valid);
-				}
-			}
-		}
-	}
-
-	/* write-back, straight from the registers: the eight lanes of a block row hold eight
-	 * neighbouring pixels, so every store instruction of the warp leaves as four full 32-byte
-	 * sectors (one per row); no staging in shared memory and no barrier -- a warp that is done
-	 * with its block moves on to the next tile's list.  With a pending clear every pixel is
-	 * written (untouched ones with the clear values), otherwise only what a fragment changed. */
-	#pragma unroll
-	for (int k = 0; k < SRPD_PX; k++)
-	{
-		if (!valid[k])
+		if (ballot == 0u)
 			continue;
-		const size_t pixelIndex = (size_t) (y0 + 4 * k) * st.width + x;
-		if (fr.clearPending || (px[k].dirty & 1u))
-			fr.color[pixelIndex] = px[k].color;
-		if (fr.clearPending || (px[k].dirty & 2u))
-			fr.depth[pixelIndex] = px[k].depth;
-		if (px[k].dirty & 4u)
-			fr.stencil[pixelIndex] = (uint8_t) px[k].stencil;
-	}
-}
-
-/* A tile no primitive touches while a clear is pending: just write the clear values
- * (colour 0, depth -1; reference core/framebuffer.c:57-62), one 128-byte row per warp. */
-__device__ __forceinline__ void clearTile(const SrpdState& st, const SrpdFrame& fr, int tileX, int tileY)
-{
-	const int x = tileX * SRPD_TILE_W + (threadIdx.x % SRPD_TILE_W);
-	#pragma unroll
-	for (int k = 0; k < SRPD_PX; k++)
-	{
-		const int y = tileY * SRPD_TILE_H + (threadIdx.x / SRPD_TILE_W) + k * (SRPD_TILE_H / SRPD_PX);
-		if (x < st.width && y < st.height)
+		if (hit)
+			wt.ring[(head + waiting + __popc(ballot & ((1u << lane) - 1u))) & (SRPD_RING - 1)] = ent;
+		waiting += __popc(ballot);
+		__syncwarp();
+		if (waiting >= 32 || c + 32 >= end)
 		{
-			const size_t i = (size_t) y * st.width + x;
-			fr.color[i] = 0u;
-			fr.depth[i] = -1.0f;
+			const int n = min(waiting, 32);
+			if constexpr (KIND == SRPD_KIND_TRIANGLE)
+				visitTriangles<SIMPLE>(a, fr, records, wt, head, n, tx0, ty0, dirty, cnt, lane);
+			else
+				for (int k = 0; k < n; k++)
+				{
+					const uint4 e = wt.ring[(head + k) & (SRPD_RING - 1)];
+					const unsigned char* rec = records + (size_t) e.z * a.recStride;
+					if (KIND == SRPD_KIND_LINE)
+						visitLine(a, fr, rec, e.w, wt, tx0, ty0, dirty, cnt, lane);
+					else
+						visitPoint(a, fr, rec, e.w, wt, tx0, ty0, dirty, cnt, lane);
+					__syncwarp();      /* the next primitive sees this one's pixels */
+				}
+			head = (head + n) & (SRPD_RING - 1);
+			waiting -= n;
 		}
 	}
+	/* what is left in the ring (fewer than 32; the loop's last chunk may have been empty) */
+	if (waiting > 0)
+	{
+		if constexpr (KIND == SRPD_KIND_TRIANGLE)
+			visitTriangles<SIMPLE>(a, fr, records, wt, head, waiting, tx0, ty0, dirty, cnt, lane);
+		else
+			for (int k = 0; k < waiting; k++)
+			{
+				const uint4 e = wt.ring[(head + k) & (SRPD_RING - 1)];
+				const unsigned char* rec = records + (size_t) e.z * a.recStride;
+				if (KIND == SRPD_KIND_LINE)
+					visitLine(a, fr, rec, e.w, wt, tx0, ty0, dirty, cnt, lane);
+				else
+					visitPoint(a, fr, rec, e.w, wt, tx0, ty0, dirty, cnt, lane);
+				__syncwarp();
+			}
+	}
+
+	dirty = __reduce_or_sync(0xFFFFFFFFu, dirty);
+	__syncwarp();
+	storeWarpTile(st, fr, io, dirty, wt, tx0, ty0, lane);
+	__syncwarp();      /* the next tile re-initialises the state */
 }
 
-/* Persistent tile kernel: the grid is sized to the machine (CTAs per SM x SM count) and the
- * CTAs pull work items -- groups of `tilesPerItem` consecutive tiles of one frame -- from an
+/* A warp tile no primitive touches while a clear is pending: just write the clear values
+ * (colour 0, depth -1; reference core/framebuffer.c:57-62), full 128-byte rows. */
+__device__ __forceinline__ void clearWarpTile(const SrpdState& st, const SrpdFrame& fr, int tileX, int tileY8, int lane)
+{
+	const bool vec4 = (st.width % 4) == 0 && ((((uintptr_t) fr.color) | ((uintptr_t) fr.depth)) & 15u) == 0;
+	#pragma unroll
+	for (int k = 0; k < 2; k++)
+	{
+		const int c = lane + 32 * k;
+		const int x = tileX * SRPD_WT_W + (c % 8) * 4, y = tileY8 * SRPD_WT_H + c / 8;
+		if (y >= st.height || x >= st.width)
+			continue;
+		const size_t at = (size_t) y * st.width + x;
+		if (vec4)
+		{
+			*(uint4*) (fr.color + at) = make_uint4(0u, 0u, 0u, 0u);
+			*(uint4*) (fr.depth + at) = make_uint4(0xBF800000u, 0xBF800000u, 0xBF800000u, 0xBF800000u);
+		}
+		else
+			for (int i = 0; i < 4; i++)
+				if (x + i < st.width)
+				{
+					fr.color[at + i] = 0u;
+					fr.depth[at + i] = -1.0f;
+				}
+	}
+}
+
+/* Persistent tile kernel: the grid is sized to the machine (CTAs per SM x SM count) and every
+ * WARP pulls work items -- groups of `tilesPerItem` consecutive warp tiles of one frame -- from an
  * atomic counter, so neither empty tiles (skipped through the occupancy bitmap the geometry
- * kernel filled) nor hundreds of frames of a batch cost a CTA launch each.
+ * kernel filled) nor hundreds of frames of a batch cost a launch each, and a warp that draws a
+ * heavy tile holds nobody up.
  *
  * Register budget: both launch-bound arguments are given explicitly (under device LTO a
- * missing minimum makes the linker's code generator cap the kernel at 64 registers and
- * spill).  Triangles and points fit two 512-thread CTAs per SM; the line walker does not. */
+ * missing minimum makes the linker's code generator cap the kernel at 64 registers and spill). */
 template <int KIND, bool BATCH, int SIMPLE>
-__global__ void __launch_bounds__(SRPD_TILE_THREADS, KIND == SRPD_KIND_LINE ? SRPD_TILE_LINE_CTAS_PER_SM : SRPD_TILE_CTAS_PER_SM)
+__global__ void __launch_bounds__(SRPD_TILE_THREADS, SRPD_TILE_CTAS_PER_SM)
 srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 {
+	typedef typename WarpTileK<KIND>::type Shared;
 	extern __shared__ __align__(16) unsigned char srpdTileSmem[];
-	TileSharedK<KIND>& sm = *reinterpret_cast<TileSharedK<KIND>*>(srpdTileSmem);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	Shared& wt = reinterpret_cast<Shared*>(srpdTileSmem)[warp];
 
 	srpdGridDependencyEnter();
-	if (*a.abortFlag)      /* a scratch pool overflowed: the host repeats the draw with larger pools */
+	if (*a.abortFlag)      /* guard (never expected, runtime.cu): leave the framebuffer untouched */
 		return;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t rows = a.d.tileRow1 - a.d.tileRow0;
+	/* warp-tile rows of the row range: two per tile row, the last tile row may have one */
+	const uint32_t rows8All = ((uint32_t) a.d.st.height + SRPD_WT_H - 1) / SRPD_WT_H;
+	const uint32_t row8Lo = a.d.tileRow0 * 2u, row8Hi = min(a.d.tileRow1 * 2u, rows8All);
+	const uint32_t rows = row8Hi > row8Lo ? row8Hi - row8Lo : 0u;
 	const uint32_t tilesPerFrame = a.tilesX * rows;
 	const uint32_t itemsPerFrame = (tilesPerFrame + a.tilesPerItem - 1) / a.tilesPerItem;
 	const uint32_t nItems = itemsPerFrame * a.d.nFrames;
@@ -851,16 +957,14 @@ srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 	FragCounters cnt;
 	cnt.emitted = 0; cnt.shaded = 0;
 
-	if (tid == 0)
-		sm.item[0] = atomicAdd(a.workCounter, 1u);
-	__syncthreads();
-	for (uint32_t it = 0;; it++)
+	for (;;)
 	{
-		const uint32_t item = sm.item[it & 1];
+		uint32_t item = 0u;
+		if (lane == 0)
+			item = atomicAdd(a.workCounter, 1u);
+		item = __shfl_sync(0xFFFFFFFFu, item, 0);
 		if (item >= nItems)
 			break;
-		if (tid == 0)      /* fetch the next item while this one is processed */
-			sm.item[(it + 1) & 1] = atomicAdd(a.workCounter, 1u);
 		/* BATCH: many frames, bindings in a device array; otherwise the one frame of the argument block */
 		uint32_t frame = 0u, inFrame = item;
 		if (BATCH)
@@ -884,22 +988,22 @@ srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 		 * first * tilesX < 2^40 (tiles per frame < 2^23, tilesX <= 2^11) */
 		uint32_t rowInBand = (uint32_t) (((uint64_t) first * a.tilesXInv) >> 40);
 		int tileX = (int) (first - rowInBand * a.tilesX);
-		int tileY = (int) (a.d.tileRow0 + rowInBand);
+		int tileY8 = (int) (row8Lo + rowInBand);
 		for (uint32_t t = first; t < last; t++)
 		{
-			const uint32_t tileIndex = (uint32_t) tileY * a.tilesX + (uint32_t) tileX;
+			/* (the occupancy bitmap has one bit per 32x16 tile) */
+			const uint32_t tileIndex = ((uint32_t) tileY8 >> 1) * a.tilesX + (uint32_t) tileX;
 			const bool occupied = (occ[tileIndex >> 5] >> (tileIndex & 31u)) & 1u;
 			if (occupied)
-				processTile<KIND, SIMPLE>(a, fr, frame, tileX, tileY, sm, cnt);
+				processWarpTile<KIND, SIMPLE>(a, fr, frame, tileX, tileY8, wt, cnt, lane);
 			else if (fr.clearPending)
-				clearTile(a.d.st, fr, tileX, tileY);
+				clearWarpTile(a.d.st, fr, tileX, tileY8, lane);
 			if (++tileX == (int) a.tilesX)
 			{
 				tileX = 0;
-				tileY++;
+				tileY8++;
 			}
 		}
-		__syncthreads();   /* item[(it + 1) & 1] is visible; item[it & 1] may be overwritten next round */
 	}
 
 	/* counters: warp reduction, then one atomic per warp into one of the slots, so the atomics
@@ -949,7 +1053,7 @@ template <int KIND, bool BATCH, int SIMPLE>
 static void launchTileKernelS(const SrpdTileArgs& a, unsigned grid, cudaStream_t stream)
 {
 	static bool configured = false;
-	const int bytes = (int) sizeof(TileSharedK<KIND>);
+	const int bytes = (int) (sizeof(typename WarpTileK<KIND>::type) * SRPD_TILE_WARPS);
 	if (!configured)
 	{
 		cudaFuncSetAttribute(srpdTileKernel<KIND, BATCH, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -994,12 +1098,14 @@ void srpdLaunchTiles(const SrpdTileArgs& a0, cudaStream_t stream)
 	if (rows == 0 || a.tilesX == 0)
 		return;
 	a.tilesXInv = (1ull << 40) / a.tilesX + 1ull;
-	/* persistent grid: resident CTAs per SM x SM count (no more CTAs than work items) */
-	const uint32_t tilesPerFrame = a.tilesX * rows;
+	/* persistent grid: resident CTAs per SM x SM count (no more warps than work items) */
+	const uint32_t rows8All = ((uint32_t) a.d.st.height + SRPD_WT_H - 1) / SRPD_WT_H;
+	const uint32_t row8Hi = a.d.tileRow1 * 2u < rows8All ? a.d.tileRow1 * 2u : rows8All;
+	const uint32_t rows8 = row8Hi > a.d.tileRow0 * 2u ? row8Hi - a.d.tileRow0 * 2u : 0u;
+	const uint32_t tilesPerFrame = a.tilesX * rows8;
 	const uint64_t nItems = (uint64_t) ((tilesPerFrame + a.tilesPerItem - 1) / a.tilesPerItem) * a.d.nFrames;
-	const uint32_t perSm = a.d.kind == SRPD_KIND_LINE ? SRPD_TILE_LINE_CTAS_PER_SM : SRPD_TILE_CTAS_PER_SM;
-	uint64_t grid = (uint64_t) a.smCount * perSm;
-	if (grid > nItems) grid = nItems;
+	uint64_t grid = (uint64_t) a.smCount * SRPD_TILE_CTAS_PER_SM;
+	if (grid > (nItems + SRPD_TILE_WARPS - 1) / SRPD_TILE_WARPS) grid = (nItems + SRPD_TILE_WARPS - 1) / SRPD_TILE_WARPS;
 	if (grid == 0) return;
 	if (a.d.kind == SRPD_KIND_TRIANGLE)
 		launchTileKernel<SRPD_KIND_TRIANGLE>(a, (unsigned) grid, stream);

@@ -162,8 +162,8 @@ int srpcuTileHeight(void) { return SRPD_TILE_H; }
 const char* srpcuVersion(void)
 {
 	static char buf[128];
-	snprintf(buf, sizeof buf, "srp-b200 sm_100a tile %dx%d block %dx%d geom-batch %d line-seg %d",
-	         SRPD_TILE_W, SRPD_TILE_H, SRPD_BLK_W, SRPD_BLK_H, SRPD_GEOM_PRIMS, SRPD_LINE_SEG);
+	snprintf(buf, sizeof buf, "srp-b200 sm_100a tile %dx%d warp-tile %dx%d geom-batch %d line-seg %d",
+	         SRPD_TILE_W, SRPD_TILE_H, SRPD_WT_W, SRPD_WT_H, SRPD_GEOM_PRIMS, SRPD_LINE_SEG);
 	return buf;
 }
 
@@ -423,6 +423,14 @@ int srpcuSynchronize(void)
 	}
 	CU(cudaStreamSynchronize(g.stream));
 	CU(cudaGetLastError());
+	if (g.hostNotes && g.hostNotes[2])
+	{
+		char buf[160];
+		snprintf(buf, sizeof buf, "srp-b200: srpB200StreamWait gave up waiting for a flag to reach %u (a peer never signalled)", g.hostNotes[2]);
+		g.hostNotes[2] = 0;
+		g.lastError = buf;
+		return 1;
+	}
 	return 0;
 }
 
@@ -510,7 +518,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	const int nVerts = srpdVertsOfKind(d.kind);
 	const uint32_t recStride = srpdRecordStride(st, nVerts);
 	uint64_t cap = (uint64_t) d.nInputPrims * d.maxOutPerInput;
-	if (cap > 0x7FFFFFF0ull) cap = 0x7FFFFFF0ull;
+	if (cap > 0x3FFFFFF0ull) cap = 0x3FFFFFF0ull;      /* record slots are 30-bit (raster.cu: SRPD_TRI_SLOT_MASK) */
 	const uint32_t recCapacity = (uint32_t) cap;
 	const uint32_t batchesPerFrame = (d.nInputPrims + SRPD_GEOM_PRIMS - 1) / SRPD_GEOM_PRIMS;
 
@@ -715,11 +723,12 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	}
 
 	{
-		/* work-item granularity: enough items for dynamic load balance (>= ~32 per CTA), but not
-		 * one atomic per tile when a batch has millions of mostly empty tiles */
+		/* work-item granularity (items = groups of consecutive 32x8 warp tiles, pulled by warps):
+		 * enough items for dynamic load balance (>= ~16 per warp), but not one atomic per tile
+		 * when a batch has millions of mostly empty tiles */
 		const uint32_t rows = ta.d.tileRow1 - ta.d.tileRow0;
-		const uint64_t tiles = (uint64_t) tilesX * rows * nFrames;
-		const uint64_t target = (uint64_t) g.smCount * SRPD_TILE_CTAS_PER_SM * 32;
+		const uint64_t tiles = (uint64_t) tilesX * rows * 2u * nFrames;
+		const uint64_t target = (uint64_t) g.smCount * SRPD_TILE_CTAS_PER_SM * SRPD_TILE_WARPS * 16;
 		uint32_t per = 1;
 		while (per < 32 && tiles / (per * 2) >= target) per *= 2;
 		if (const char* e = getenv("SRP_B200_TILES_PER_ITEM")) per = (uint32_t) atoi(e) > 0 ? (uint32_t) atoi(e) : per;
@@ -834,11 +843,79 @@ uint32_t srpcuMaxPrimsPerSubDraw(const SrpdDraw* d)
 	const uint64_t perRecord = (uint64_t) srpdRecordStride(d->st, srpdVertsOfKind(d->kind)) + sizeof(uint2) + sizeof(uint4);
 	const uint64_t perPrim = perRecord * (d->maxOutPerInput ? d->maxOutPerInput : 1) * (d->nFrames ? d->nFrames : 1);
 	uint64_t n = g.poolBudget / (perPrim ? perPrim : 1);
-	const uint64_t byIndex = 0x7FFFFFF0ull / (d->maxOutPerInput ? d->maxOutPerInput : 1);      /* 32-bit record slots */
+	const uint64_t byIndex = 0x3FFFFFF0ull / ((uint64_t) (d->maxOutPerInput ? d->maxOutPerInput : 1) * (d->nFrames ? d->nFrames : 1));      /* 30-bit record slots */
 	if (n > byIndex) n = byIndex;
 	if (n < (uint64_t) SRPD_GEOM_PRIMS) n = SRPD_GEOM_PRIMS;
 	n -= n % SRPD_GEOM_PRIMS;      /* whole batches */
 	return n > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t) n;
+}
+
+/* ---- peer memory and stream-ordered flags (sort-first strips, multigpu.py) ---- */
+__global__ void srpdSignalKernel(uint32_t* flag, uint32_t value)
+{
+	/* everything this stream ran before has completed (stream order); make it -- peer writes of
+	 * the tile kernel included -- visible system-wide before the flag */
+	__threadfence_system();
+	*(volatile uint32_t*) flag = value;
+	__threadfence_system();
+}
+__global__ void srpdWaitFlagKernel(const uint32_t* flag, uint32_t value, uint32_t* hostNotes)
+{
+	/* bounded: a peer that died must not hang this GPU for good (~10 s, then the stream moves on
+	 * and the host is told through hostNotes[2]) */
+	for (uint32_t spins = 0; *(volatile const uint32_t*) flag < value; spins++)
+	{
+		if (spins > 20000000u)
+		{
+			*(volatile uint32_t*) (hostNotes + 2) = value;
+			break;
+		}
+		__nanosleep(500);
+	}
+	__threadfence_system();
+}
+
+int srpcuIpcExport(const void* devicePtr, unsigned char handle[64])
+{
+	if (srpcuInit()) return 1;
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles travel as 64 bytes");
+	cudaIpcMemHandle_t h;
+	CU(cudaIpcGetMemHandle(&h, const_cast<void*>(devicePtr)));
+	memcpy(handle, &h, 64);
+	return 0;
+}
+void* srpcuIpcOpen(const unsigned char handle[64])
+{
+	if (srpcuInit()) return nullptr;
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, 64);
+	void* p = nullptr;
+	cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+	if (e != cudaSuccess) { fail("cudaIpcOpenMemHandle", e); return nullptr; }
+	return p;
+}
+int srpcuIpcClose(void* mapped)
+{
+	if (!g.ready || !mapped) return 0;
+	CU(cudaStreamSynchronize(g.stream));
+	CU(cudaIpcCloseMemHandle(mapped));
+	return 0;
+}
+int srpcuStreamSignal(uint32_t* flag, uint32_t value)
+{
+	if (srpcuInit()) return 1;
+	srpdSignalKernel<<<1, 1, 0, g.stream>>>(flag, value);
+	g.launches++;
+	CU(cudaGetLastError());
+	return 0;
+}
+int srpcuStreamWaitFlag(const uint32_t* flag, uint32_t value)
+{
+	if (srpcuInit()) return 1;
+	srpdWaitFlagKernel<<<1, 1, 0, g.stream>>>(flag, value, g.hostNotesDev);
+	g.launches++;
+	CU(cudaGetLastError());
+	return 0;
 }
 
 /* per-stage device time: enable, run draws, collect {geometry, binning, tiles} in ms */

@@ -74,6 +74,18 @@ int srpcuTakeOverflow(void);
 /* input primitives one sub-draw of `d` may take within the scratch budget (whole batches) */
 uint32_t srpcuMaxPrimsPerSubDraw(const SrpdDraw* d);
 
+/* ---- multi-GPU plumbing (one process per GPU): peer memory over NVLink ----
+ * Export device memory of this library (a framebuffer plane, srpcuMalloc) as a CUDA IPC handle
+ * (64 bytes), map another process's export into this one (peer access is enabled lazily), and
+ * two stream-ordered primitives on 32-bit flags that may live in peer memory: signal = store
+ * `value` once everything enqueued before has finished and is visible system-wide; wait = hold
+ * the stream until the flag is >= `value`. */
+int srpcuIpcExport(const void* devicePtr, unsigned char handle[64]);
+void* srpcuIpcOpen(const unsigned char handle[64]);
+int srpcuIpcClose(void* mapped);
+int srpcuStreamSignal(uint32_t* flag, uint32_t value);
+int srpcuStreamWaitFlag(const uint32_t* flag, uint32_t value);
+
 void srpcuSetProfiling(int on);
 unsigned long long srpcuCollectStageTimes(double outMs[3]);
 

@@ -23,6 +23,41 @@ const char* srpB200Version(void) { return srpcuVersion(); }
 void srpB200SetDevice(int device) { srpcuSetDevice(device); }
 void* srpB200Stream(void) { return srpcuStream(); }
 
+/* ---- multi-GPU plumbing: peer memory and stream-ordered flags (include/srp_b200.h) ---- */
+void* srpB200DeviceAlloc(size_t bytes) { return srpcuMalloc(bytes); }
+void srpB200DeviceFree(void* p) { srpcuFree(p); }
+int srpB200IpcExport(const void* devicePtr, SRPB200IpcHandle* handle)
+{
+	if (srpcuIpcExport(devicePtr, handle->bytes))
+	{
+		srpFatalMessage(__func__, "%s", srpcuLastError());
+		return 1;
+	}
+	return 0;
+}
+void* srpB200IpcOpen(const SRPB200IpcHandle* handle)
+{
+	void* p = srpcuIpcOpen(handle->bytes);
+	if (!p)
+		srpFatalMessage(__func__, "%s", srpcuLastError());
+	return p;
+}
+void srpB200IpcClose(void* mappedPtr)
+{
+	if (srpcuIpcClose(mappedPtr))
+		srpFatalMessage(__func__, "%s", srpcuLastError());
+}
+void srpB200StreamSignal(uint32_t* flag, uint32_t value)
+{
+	if (srpcuStreamSignal(flag, value))
+		srpFatalMessage(__func__, "%s", srpcuLastError());
+}
+void srpB200StreamWait(const uint32_t* flag, uint32_t value)
+{
+	if (srpcuStreamWaitFlag(flag, value))
+		srpFatalMessage(__func__, "%s", srpcuLastError());
+}
+
 void srpB200GetStats(SRPB200Stats* out)
 {
 	SrpdStats s;
@@ -264,6 +299,8 @@ static bool buildDraw(
 	if (r0 > r1) r0 = r1;
 	d->tileRow0 = (uint32_t) r0;
 	d->tileRow1 = (uint32_t) r1;
+	st->stripY0 = (int32_t) (r0 * th);
+	st->stripY1 = (int32_t) (r1 * th < fb->height ? r1 * th : fb->height);
 	return true;
 }
 

@@ -216,6 +216,15 @@ void srpB200FramebufferWait(const SRPFramebuffer* pub)
 	fb->downloadInFlight = false;
 }
 
+/* order everything enqueued from now on behind this framebuffer's in-flight asynchronous download
+ * (the strips' root releases a ring slot to its peers only once the slot's frame has left it) */
+void srpB200FramebufferFence(const SRPFramebuffer* pub)
+{
+	SRPFramebufferImpl* fb = srpFramebufferImpl(pub);
+	if (fb)
+		srpFramebufferBeforeWrite(fb);
+}
+
 void srpFramebufferBeforeWrite(SRPFramebufferImpl* fb)
 {
 	if (fb->downloadInFlight && srpcuStreamWaitEvent(fb->downloadEvent))

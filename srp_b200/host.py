@@ -215,6 +215,7 @@ class SrpLibrary:
             "srpB200FramebufferUpload": (None, [C.POINTER(SRPFramebuffer)]),
             "srpB200FramebufferDownloadAsync": (None, [C.POINTER(SRPFramebuffer)]),
             "srpB200FramebufferWait": (None, [C.POINTER(SRPFramebuffer)]),
+            "srpB200FramebufferFence": (None, [C.POINTER(SRPFramebuffer)]),
             "srpB200NewFramebufferOnDevice": (C.POINTER(SRPFramebuffer), [sz, sz, vp, vp, vp]),
             "srpB200FramebufferDevicePlane": (vp, [C.POINTER(SRPFramebuffer), i32]),
             "srpB200LoadOBJ": (i32, [C.c_char_p, C.POINTER(SRPB200Mesh)]),
@@ -224,6 +225,9 @@ class SrpLibrary:
             "srpB200DrawBatch": (None, [vp, vp, C.POINTER(C.POINTER(SRPFramebuffer)), sz,
                                         C.POINTER(SRPShaderProgram), vp, sz, i32, sz, sz, i32]),
             "srpB200SetRowRange": (None, [sz, sz]),
+            "srpB200DeviceAlloc": (vp, [sz]), "srpB200DeviceFree": (None, [vp]),
+            "srpB200IpcExport": (i32, [vp, vp]), "srpB200IpcOpen": (vp, [vp]), "srpB200IpcClose": (None, [vp]),
+            "srpB200StreamSignal": (None, [vp, C.c_uint32]), "srpB200StreamWait": (None, [vp, C.c_uint32]),
             "srpB200TileWidth": (sz, []), "srpB200TileHeight": (sz, []),
             "srpB200GetStats": (None, [C.POINTER(SRPB200Stats)]), "srpB200ResetStats": (None, []),
             "srpB200SetProfiling": (None, [i32]),

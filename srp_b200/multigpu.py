@@ -5,12 +5,22 @@ One process per GPU (torchrun), `torch.distributed` for the plumbing:
 * frame-parallel -- independent frames; `frame_partition` hands every rank a contiguous
   block, there is no collective on the data path (buffers are broadcast once at load).
 * sort-first strips -- one large frame; every rank runs the full geometry front-end (so
-  primitive ids and barycentric chains are identical everywhere) and rasterises only the
-  tile rows of its strip (`srpB200SetRowRange`); `gather_strips` collects the strips'
-  planes on the root.  The only collective of the path.  Works on CUDA tensors over NCCL
-  and on CPU tensors over gloo (the CPU tests).
+  primitive ids and barycentric chains are identical everywhere; primitives whose box misses
+  the rank's rows keep their id but store nothing) and rasterises only the tile rows of its
+  strip (`srpB200SetRowRange`).  Two ways to assemble the frame on the root:
+    - `StripTarget` (the product path): the framebuffer lives on the root GPU, the other ranks
+      map its planes through CUDA IPC and their tile kernels write their strips straight into
+      the root's memory over NVLink as part of the tile write-back; completion and
+      back-pressure go through 32-bit flags in the root's memory (srpB200StreamSignal /
+      srpB200StreamWait).  No staging copy, no separate gather step, no host round trip.
+    - `gather_strips` / `gather_strips_inplace` (the NCCL baseline named by `north_star`):
+      every rank renders into its own framebuffer and one batch of ncclSend / ncclRecv moves
+      the strips to the root.  Works on CUDA tensors over NCCL and on CPU tensors over gloo
+      (the CPU tests).
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import torch
 import torch.distributed as dist
@@ -88,3 +98,120 @@ def device_plane_tensor(lib, fb, which: int) -> torch.Tensor:
     t = torch.as_tensor(_Iface(), device="cuda")
     assert t.numel() == n and t.dtype == dtype
     return t
+
+
+class StripTarget:
+    """A ring of `ring` root-owned framebuffers that every rank renders its strip into.
+
+    Root: creates the framebuffers and a block of 32-bit flags -- flags[r] = frames rank r has
+    finished writing, flags[world] = frames the root has consumed -- and exports the three planes
+    of every framebuffer and the flags as CUDA IPC handles (srpB200IpcExport); `exchange` is any
+    function that hands the root's bytes to all ranks (a torch.distributed broadcast of objects,
+    over NCCL or gloo).  Other ranks: open the handles and wrap the mapped planes in
+    framebuffers of their own (srpB200NewFramebufferOnDevice): the tile kernel's write-back then
+    stores into the root's memory.
+
+    Frame k (every rank):  wait until the root has consumed frame k - ring (its slot is free),
+    srpB200SetRowRange(own rows), clear + draw into slot k % ring, signal flags[rank] = k + 1.
+    Root, additionally: wait for flags[r] >= k + 1 of every rank -- the frame is complete in
+    its memory --, run `consume` (e.g. an asynchronous download), signal flags[world] = k + 1.
+    Everything is enqueued on the library's stream; nothing blocks the host."""
+
+    def __init__(self, lib, width, height, ring=2, root=0, group=None, exchange=None):
+        self.lib, self.width, self.height, self.ring, self.root, self.group = lib, width, height, ring, root, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.tile_h = int(lib.dll.srpB200TileHeight())
+        self.rows = strip_rows(height, self.tile_h, self.world, self.rank)
+        self._mapped = []
+        d = lib.dll
+        payload = None
+        if self.rank == root:
+            self.fbs = [lib.framebuffer(width, height) for _ in range(ring)]
+            self.flags = d.srpB200DeviceAlloc(4 * (self.world + 1))
+            if not self.flags:
+                raise RuntimeError("srpB200DeviceAlloc failed")
+            handles = []
+            for fb in self.fbs:
+                for which in range(3):
+                    handles.append(self._export(d.srpB200FramebufferDevicePlane(fb.ptr, which)))
+            payload = {"planes": handles, "flags": self._export(self.flags)}
+        if self.world > 1:
+            box = [payload]
+            (exchange or self._broadcast)(box)
+            payload = box[0]
+        if self.rank != root:
+            planes = [self._open(h) for h in payload["planes"]]
+            self.flags = self._open(payload["flags"])
+            self.fbs = []
+            for i in range(ring):
+                ptr = d.srpB200NewFramebufferOnDevice(width, height, planes[3 * i], planes[3 * i + 1], planes[3 * i + 2])
+                if not ptr:
+                    raise RuntimeError("srpB200NewFramebufferOnDevice failed")
+                from .host import Framebuffer
+                self.fbs.append(Framebuffer(lib, ptr))
+        self.frame = 0
+
+    def _broadcast(self, box):
+        dist.broadcast_object_list(box, src=self.root, group=self.group)
+
+    def _export(self, device_ptr) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        if self.lib.dll.srpB200IpcExport(device_ptr, buf) != 0:
+            raise RuntimeError("srpB200IpcExport failed")
+        return bytes(buf)
+
+    def _open(self, handle: bytes):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        p = self.lib.dll.srpB200IpcOpen(buf)
+        if not p:
+            raise RuntimeError("srpB200IpcOpen failed: peer access between the GPUs is required")
+        self._mapped.append(p)
+        return p
+
+    def flag_ptr(self, index: int) -> int:
+        return int(self.flags) + 4 * index
+
+    def render(self, draw):
+        """enqueue one frame: `draw(fb)` issues srpFramebufferClear + the frame's draws into fb.
+        Returns the framebuffer that will hold the complete frame on the root."""
+        d = self.lib.dll
+        k = self.frame
+        fb = self.fbs[k % self.ring]
+        if k >= self.ring:
+            d.srpB200StreamWait(self.flag_ptr(self.world), k - self.ring + 1)      # the slot's previous frame was consumed
+        d.srpB200SetRowRange(self.rows[0], self.rows[1])
+        try:
+            draw(fb)
+        finally:
+            d.srpB200SetRowRange(0, 2 ** 64 - 1)
+        d.srpB200StreamSignal(self.flag_ptr(self.rank), k + 1)
+        self.frame = k + 1
+        return fb
+
+    def complete(self, consume=None):
+        """root only: order the stream behind every rank's strip of the frame enqueued last, run
+        `consume(fb)` (enqueue-only work on the complete frame), release the slot"""
+        assert self.rank == self.root
+        d = self.lib.dll
+        k = self.frame - 1
+        for r in range(self.world):
+            if r != self.rank:
+                d.srpB200StreamWait(self.flag_ptr(r), k + 1)
+        if consume is not None:
+            consume(self.fbs[k % self.ring])
+        d.srpB200StreamSignal(self.flag_ptr(self.world), k + 1)
+
+    def free(self):
+        d = self.lib.dll
+        d.srpB200Finish()
+        if dist.is_initialized() and self.world > 1:
+            dist.barrier(group=self.group)      # nobody unmaps or frees while a peer may still write
+        for fb in self.fbs:
+            fb.free()
+        if self.rank == self.root:
+            d.srpB200DeviceFree(self.flags)
+        else:
+            for p in self._mapped:
+                d.srpB200IpcClose(p)
+        self.fbs, self._mapped = [], []

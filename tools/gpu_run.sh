@@ -19,3 +19,16 @@ except Exception as e:
 PY
 timeout 120 python tools/pcie_ceiling.py > gpurun_out/pcie_$tag.log 2>&1; head -1 gpurun_out/pcie_$tag.log
 (nvidia-smi topo -m; numactl -H; lscpu | head -30; nproc) > gpurun_out/topology_$tag.txt 2>&1
+# instruction counts / durations / issue utilisation of one cfg3 frame's kernels (a handful of metrics, few replays)
+timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__thread_inst_executed_per_inst_executed.ratio,dram__bytes_read.sum,dram__bytes_write.sum \
+  --clock-control none --kernel-name regex:srpd --launch-skip 24 --launch-count 8 --csv python bench.py --steps 3 --warmup 3 --cpu-seconds 0 > gpurun_out/ncu_$tag.csv 2>/dev/null
+python - <<PY
+import csv
+rows = [l for l in open("gpurun_out/ncu_$tag.csv") if l.startswith('"')]
+last = None
+for r in csv.DictReader(rows):
+    k = r.get("Kernel Name", "?")[:40]
+    if k != last:
+        print(k); last = k
+    print("   ", r.get("Metric Name"), r.get("Metric Value"))
+PY

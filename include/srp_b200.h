@@ -28,6 +28,13 @@ typedef void (*SRPVertexShaderFunc)(SRPVertexShaderIn*, SRPVertexShaderOut*);
 typedef void (*SRPFragmentShaderFunc)(SRPFragmentShaderIn*, SRPFragmentShaderOut*);
 int srpB200RegisterProgram(SRPVertexShaderFunc hostVS, SRPFragmentShaderFunc hostFS,
                            int deviceProgramId, size_t uniformSize);
+/* The same, one shader at a time: programs that recombine shaders at run time (the reference's
+ * tests/scenes/clipping/point.c swaps the fragment shader of a copied SRPShaderProgram) register
+ * every host shader function once; a draw then looks its two functions up independently and the
+ * uniform block copied is the larger of the two sizes.  `srp_b200/twingen.py` writes these
+ * registrations -- and the __device__ twins themselves -- from a program's C source. */
+int srpB200RegisterVertexShader(SRPVertexShaderFunc hostVS, int deviceShaderId, size_t uniformSize);
+int srpB200RegisterFragmentShader(SRPFragmentShaderFunc hostFS, int deviceShaderId, size_t uniformSize);
 
 /* ---- synchronisation policy --------------------------------------------------------
  * The device planes of a framebuffer are authoritative; fb->color/depth/stencil are a

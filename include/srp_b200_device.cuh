@@ -42,8 +42,25 @@ extern "C" __device__ void srpB200DeviceFS(int programId, SRPFragmentShaderIn* i
 	extern "C" __device__ void srpB200DeviceFS(int programId, SRPFragmentShaderIn* in, SRPFragmentShaderOut* out) \
 	{ switch (programId) { TABLE(SRP_B200_FS_CASE_) default: return; } }
 
+/* Separate lists of vertex and fragment shaders (what srp_b200/twingen.py emits):
+ *   #define MY_VS(X) X(0, vsA) X(1, vsB)
+ *   #define MY_FS(X) X(0, fsA)
+ *   SRP_B200_DEFINE_SHADER_TABLES(MY_VS, MY_FS) */
+#define SRP_B200_SHADER_CASE_(id, fn) case (id): fn(in, out); return;
+#define SRP_B200_DEFINE_SHADER_TABLES(VS_TABLE, FS_TABLE) \
+	extern "C" __device__ void srpB200DeviceVS(int programId, SRPVertexShaderIn* in, SRPVertexShaderOut* out) \
+	{ switch (programId) { VS_TABLE(SRP_B200_SHADER_CASE_) default: return; } } \
+	extern "C" __device__ void srpB200DeviceFS(int programId, SRPFragmentShaderIn* in, SRPFragmentShaderOut* out) \
+	{ switch (programId) { FS_TABLE(SRP_B200_SHADER_CASE_) default: return; } }
+
 #define SRP_B200_CAT2_(a, b) a##b
 #define SRP_B200_CAT_(a, b) SRP_B200_CAT2_(a, b)
 #define SRP_B200_REGISTER_PROGRAM(hostVS, hostFS, id, uniformSize) \
 	static const int SRP_B200_CAT_(srpB200Registered_, __LINE__) = \
 		srpB200RegisterProgram((hostVS), (hostFS), (id), (uniformSize));
+#define SRP_B200_REGISTER_VERTEX_SHADER(hostVS, id, uniformSize) \
+	static const int SRP_B200_CAT_(srpB200RegisteredVS_, __LINE__) = \
+		srpB200RegisterVertexShader((hostVS), (id), (uniformSize));
+#define SRP_B200_REGISTER_FRAGMENT_SHADER(hostFS, id, uniformSize) \
+	static const int SRP_B200_CAT_(srpB200RegisteredFS_, __LINE__) = \
+		srpB200RegisterFragmentShader((hostFS), (id), (uniformSize));

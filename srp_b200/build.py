@@ -14,7 +14,8 @@ Artefacts (all git-ignored, all travel to the GPU box with the repo snapshot):
                                     reference, see oracle/Makefile
   tests/_build/scenes/<name>        (only where /root/reference exists) the reference's own
                                     tests/scenes/*.c compiled UNMODIFIED against this library
-                                    + the device twins under tests/scene_twins/
+                                    + the device twins srp_b200/twingen.py generates from the
+                                    same C sources (tests/_build/twins/)
 
 Device code: -gencode arch=compute_100a,code=lto_100a -rdc=true -fmad=false -lineinfo;
 device link: -arch=sm_100a -dlto -Xnvlink -Xnvvm=-fma=0 (no FMA contraction at LTO code
@@ -133,14 +134,15 @@ def build_oracle() -> bool:
 
 def build_scenes(jobs: int = 8) -> list[Path]:
     """The reference's own scene programs, relinked unchanged against this library."""
+    from . import twingen
     scene_root = REFERENCE / "tests" / "scenes"
-    twins = ROOT / "tests" / "scene_twins"
     if not scene_root.is_dir():
         return []
     out_dir = ROOT / "tests" / "_build" / "scenes"
     obj_dir = ROOT / "tests" / "_build" / "obj"
-    out_dir.mkdir(parents=True, exist_ok=True)
-    obj_dir.mkdir(parents=True, exist_ok=True)
+    twins = ROOT / "tests" / "_build" / "twins"      # generated from the scenes' own C sources
+    for d in (out_dir, obj_dir, twins):
+        d.mkdir(parents=True, exist_ok=True)
     archive = BUILD / "libsrp.a"
     save_o = _compile_host(ROOT / "oracle" / "ref_save_raw.c", obj_dir / "save_raw.o")
     objparser_o = obj_dir / "objparser.o"
@@ -151,11 +153,11 @@ def build_scenes(jobs: int = 8) -> list[Path]:
     def one(scene_c: Path):
         name = f"{scene_c.parent.name}_{scene_c.stem}"
         twin = twins / f"{name}.cu"
-        if not twin.exists():
-            return None
         exe = out_dir / name
-        if not _stale(exe, [scene_c, twin, archive, *HEADERS]):
+        if not _stale(exe, [scene_c, archive, PKG / "twingen.py", *HEADERS]):
             return exe
+        # the __device__ twins of the scene's shaders: its own function bodies, by the shader toolchain
+        twin.write_text(twingen.generate(scene_c.read_text(), str(scene_c)))
         scene_o = obj_dir / f"{name}.o"
         twin_o = obj_dir / f"{name}_twin.o"
         # the reference's source file, compiled where it lies, with its own C dialect

@@ -54,7 +54,7 @@ typedef struct SrpdState
 	int32_t nVaryings;
 	int32_t varyingsSize;            /* what the program declared                        */
 	int32_t slotSize;                /* bytes reserved per blob: max(declared, sum of attributes), rounded up to 8 */
-	int32_t programId;               /* device program table index                       */
+	int16_t vsProgramId, fsProgramId; /* indices into the device shader tables (vertex / fragment) */
 	/* fast path: every attribute is SRP_FLOAT and 4-byte aligned (the usual case): the blob
 	 * is nFloats consecutive floats, floatModes holds 2 bits of SRPInterpolationMode each */
 	uint32_t floatModes;

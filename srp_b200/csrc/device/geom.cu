@@ -227,27 +227,17 @@ __device__ __forceinline__ void writeTriangle(Emitter& em, const SrpdState& st, 
 				const uint32_t cols = (uint32_t) (s.maxX - 1) / SRPD_TILE_W - (uint32_t) s.minX / SRPD_TILE_W + 1;
 				const uint32_t entries = rows * cols;
 				const uint32_t slot = em.storeBase + em.nStore;
-				/* reserve with a compare-and-swap so that the cursor never passes the capacity (it
-				 * cannot wrap, whatever the number of large triangles of a draw or batch) */
-				const uint32_t cap = em.a->ckptCapacity;
-				uint32_t off = cap;
-				if (entries <= cap)
-				{
-					uint32_t cur = *(volatile uint32_t*) em.a->ckptCursor;
-					while (cur <= cap - entries)
-					{
-						const uint32_t prev = atomicCAS(em.a->ckptCursor, cur, cur + entries);
-						if (prev == cur) { off = cur; break; }
-						cur = prev;
-					}
-				}
-				if ((uint64_t) off + entries <= (uint64_t) cap && slot < em.a->recCapacity)
+				/* the cursor is 64 bits wide: it cannot wrap, whatever the number of large triangles of a
+				 * draw or batch keeps adding to it after the table is full */
+				const uint64_t cap = em.a->ckptCapacity;
+				const uint64_t off = atomicAdd(em.a->ckptCursor, (unsigned long long) entries);
+				if (off + entries <= cap && slot < em.a->recCapacity)
 				{
 					const uint32_t q = atomicAdd(em.a->largeCount, 1u);
 					if (q < em.a->largeCapacity)
 					{
 						em.a->largeList[q] = make_uint2(em.frame, slot);
-						s.w[19] = off + 1;
+						s.w[19] = (uint32_t) off + 1u;
 					}
 				}
 			}
@@ -769,7 +759,7 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 		SRPVertexShaderOut out;
 		out.clipPosition[0] = 0.f; out.clipPosition[1] = 0.f; out.clipPosition[2] = 0.f; out.clipPosition[3] = 0.f;
 		out.varyings = (SRPVarying*) (vvary + (size_t) u * st.slotSize);
-		srpB200DeviceVS(st.programId, &in, &out);
+		srpB200DeviceVS(st.vsProgramId, &in, &out);
 		ws.vpos[u] = make_float4(out.clipPosition[0], out.clipPosition[1], out.clipPosition[2], out.clipPosition[3]);
 	}
 	__syncwarp();

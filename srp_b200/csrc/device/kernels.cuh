@@ -73,9 +73,10 @@ constexpr uint32_t SRPD_BIN_SMALL_RECORDS = 1u << 18;   /* up to here chunks are
 
 /* Per-draw zero-filled header in front of the scan state: word 0 coarse-list overflow flag, 1 abort flag,
  * 2 tile work counter, 3 records a frame needed (max over frames), 4 coarse-list entries needed,
- * 5 checkpoint-table cursor (entries), 6 number of large triangles, 7 deferred batches */
-constexpr int SRPD_DRAW_HEADER_BYTES = 64;   /* words 8..15: tile work counters of up to 8 bands */
-constexpr int SRPD_MAX_BANDS = 8;
+ * 6 number of large triangles, 7 deferred batches, 8..11 tile work counters of the bands,
+ * 12-13 checkpoint-table cursor (entries, 64-bit) */
+constexpr int SRPD_DRAW_HEADER_BYTES = 64;
+constexpr int SRPD_MAX_BANDS = 4;
 
 
 struct SrpdGeomArgs
@@ -109,7 +110,7 @@ struct SrpdGeomArgs
 	uint32_t occWordsPerFrame;
 	uint32_t tilesX, tilesY;
 	/* large triangles: barycentric checkpoints (checkpoint.cu) */
-	uint32_t* ckptCursor;             /* header word 5: entries handed out               */
+	unsigned long long* ckptCursor;   /* header words 12-13 (64-bit: cannot wrap): entries handed out */
 	uint32_t* largeCount;             /* header word 6                                   */
 	uint2* largeList;                 /* [largeCapacity] {frame, record}                 */
 	uint32_t largeCapacity;

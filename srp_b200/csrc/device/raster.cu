@@ -232,7 +232,7 @@ __device__ __forceinline__ void emitFragment(
 	SRPFragmentShaderOut out;
 	out.color[0] = 0.f; out.color[1] = 0.f; out.color[2] = 0.f; out.color[3] = 0.f;
 	out.fragDepth = __int_as_float(0x7FC00000);   /* NAN */
-	srpB200DeviceFS(st.programId, &in, &out);
+	srpB200DeviceFS(st.fsProgramId, &in, &out);
 	cnt.shaded++;
 
 	if (!earlyDepth)
@@ -547,49 +547,57 @@ __device__ __forceinline__ void visitTriangles(
 }
 
 /* rasterizeLine for the warp tile, reference line.c:34-77.  A record is a segment of
- * <= SRPD_LINE_SEG (16) consecutive DDA fragments with the chain state at its first one.  Lane k
- * walks the chain to fragment k -- k float additions per coordinate, exactly the reference's
- * sequence, all fragments side by side -- and rounds it to its pixel once.  A fragment that
- * lands in this warp's tile is shaded by the lane that walked to it, on the pixel's state in
- * shared memory; a fragment is placed through its linear index y*W + x, which is also how the
- * reference's unchecked indexing wraps x == width onto the next row (App. B-1).  Two fragments
- * of the segment on one pixel run in DDA order.  Must be called by all 32 lanes. */
-static_assert(SRPD_LINE_SEG <= 32, "one lane per fragment of a segment");
-__device__ __forceinline__ void visitLine(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, uint32_t idBase,
+ * <= SRPD_LINE_SEG (16) consecutive DDA fragments with the chain state at its first one.  A pass
+ * takes TWO records: lanes 0..15 hold the fragments of the first, lanes 16..31 of the second.
+ * Lane k of a half walks the chain to fragment k -- k float additions per coordinate, exactly
+ * the reference's sequence, all fragments side by side -- and rounds it to its pixel once.  A
+ * fragment that lands in this warp's tile is shaded by the lane that walked to it, on the pixel's
+ * state in shared memory; a fragment is placed through its linear index y*W + x, which is also
+ * how the reference's unchecked indexing wraps x == width onto the next row (App. B-1).
+ * Fragments of the pass that share a pixel run in lane order = (record, DDA) order.  Must be
+ * called by all 32 lanes; `recB` may be null. */
+static_assert(SRPD_LINE_SEG <= 16, "two segments per pass: one lane per fragment of a segment");
+__device__ __forceinline__ void visitLines(
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* recA, uint32_t idBaseA, const unsigned char* recB, uint32_t idBaseB,
 	WarpTile& wt, int tx0, int ty0, uint32_t& dirty, FragCounters& cnt, int lane)
 {
-	const uint4* h = (const uint4*) rec;
-	const uint4 q0 = __ldg(h + 0), q1 = __ldg(h + 1), q2 = __ldg(h + 2), q3 = __ldg(h + 3);
-	float fx = __uint_as_float(q0.x), fy = __uint_as_float(q0.y);
-	const float xInc = __uint_as_float(q0.z), yInc = __uint_as_float(q0.w);
-	const float tInc = __uint_as_float(q1.x);
-	const int count = (int) q1.y;
-	const float zw0 = __uint_as_float(q1.z), zw1 = __uint_as_float(q1.w);
-	const float iw0 = __uint_as_float(q2.x), iw1 = __uint_as_float(q2.y);
-	float t = __uint_as_float(q2.z);
-	const long long W = a.d.st.width;
-	/* lane k: k steps of the chain */
-	for (int i = 0; i + 1 < count; i++)
-		if (i < lane)
+	const unsigned char* rec = lane < 16 ? recA : recB;
+	const uint32_t idBase = lane < 16 ? idBaseA : idBaseB;
+	const int k = lane & 15;
+	bool inTile = false;
+	int lx = 0, ly = 0, myX = 0, myY = 0;
+	float t = 0.f;
+	uint4 q1 = make_uint4(0u, 0u, 0u, 0u), q2 = q1, q3 = q1;
+	if (rec != nullptr)
+	{
+		const uint4* h = (const uint4*) rec;
+		const uint4 q0 = __ldg(h + 0);
+		q1 = __ldg(h + 1); q2 = __ldg(h + 2); q3 = __ldg(h + 3);
+		float fx = __uint_as_float(q0.x), fy = __uint_as_float(q0.y);
+		const float xInc = __uint_as_float(q0.z), yInc = __uint_as_float(q0.w);
+		const float tInc = __uint_as_float(q1.x);
+		const int count = (int) q1.y;
+		t = __uint_as_float(q2.z);
+		const long long W = a.d.st.width;
+		/* lane k of the half: k steps of the chain */
+		for (int i = 0; i < k && i + 1 < count; i++)
 		{
 			fx = __fadd_rn(fx, xInc);
 			fy = __fadd_rn(fy, yInc);
 			t = __fadd_rn(t, tInc);
 		}
-	const int myX = srpdRoundToInt(fx), myY = srpdRoundToInt(fy);
-	/* does my fragment land in this warp's tile? */
-	bool inTile = false;
-	int lx = 0, ly = 0;
-	if (lane < count)
-	{
-		const long long idx = (long long) myY * W + myX;
-		if (idx >= 0 && idx < W * (long long) a.d.st.height)
+		myX = srpdRoundToInt(fx); myY = srpdRoundToInt(fy);
+		/* does my fragment land in this warp's tile? */
+		if (k < count)
 		{
-			const bool inRow = myX >= 0 && myX < W;      /* the usual case needs no 64-bit division */
-			const int pxl = inRow ? myX : (int) (idx % W), pyl = inRow ? myY : (int) (idx / W);
-			inTile = pxl >= tx0 && pxl < tx0 + SRPD_WT_W && pyl >= ty0 && pyl < ty0 + SRPD_WT_H;
-			lx = pxl - tx0; ly = pyl - ty0;
+			const long long idx = (long long) myY * W + myX;
+			if (idx >= 0 && idx < W * (long long) a.d.st.height)
+			{
+				const bool inRow = myX >= 0 && myX < W;      /* the usual case needs no 64-bit division */
+				const int pxl = inRow ? myX : (int) (idx % W), pyl = inRow ? myY : (int) (idx / W);
+				inTile = pxl >= tx0 && pxl < tx0 + SRPD_WT_W && pyl >= ty0 && pyl < ty0 + SRPD_WT_H;
+				lx = pxl - tx0; ly = pyl - ty0;
+			}
 		}
 	}
 	if (!__any_sync(0xFFFFFFFFu, inTile))
@@ -600,6 +608,8 @@ __device__ __forceinline__ void visitLine(
 	{
 		if (inTile && turn == r)
 		{
+			const float zw0 = __uint_as_float(q1.z), zw1 = __uint_as_float(q1.w);
+			const float iw0 = __uint_as_float(q2.x), iw1 = __uint_as_float(q2.y);
 			const float w0 = __fsub_rn(1.0f, t);
 			const float wgt[2] = { w0, t };
 			/* interpolateDepthAndWLine, interpolation.c:49-60 */
@@ -616,33 +626,72 @@ __device__ __forceinline__ void visitLine(
 	}
 }
 
-/* rasterizePoint for the warp tile, reference point.c:32-74: lane = pixel column; the lanes whose
- * column lies in the point's square walk down its rows inside the tile */
-__device__ __forceinline__ void visitPoint(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* rec, uint32_t idBase,
-	WarpTile& wt, int tx0, int ty0, uint32_t& dirty, FragCounters& cnt, int lane)
+/* rasterizePoint for the warp tile, reference point.c:32-74: a step of up to 32 points, ONE LANE
+ * PER POINT.  A lane walks the pixels of its point's square inside the tile and runs the fragment
+ * stage on each; points whose squares share no pixel are independent, so the lanes work side by
+ * side.  Order where squares do overlap: every lane first learns which EARLIER points of the
+ * step overlap its square (one shuffle of the packed pixel box per point); a lane runs once all
+ * of those have run -- waves of mutually independent points, in primitive order per pixel. */
+__device__ __forceinline__ void visitPoints(
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, WarpTile& wt, int head, int n,
+	int tx0, int ty0, uint32_t& dirty, FragCounters& cnt, int lane)
 {
-	const uint4* h = (const uint4*) rec;
-	const uint4 q1 = __ldg(h + 1);      /* pixel box, inclusive: minX, maxX, minY, maxY */
-	const int x = tx0 + lane;
-	if (x < (int) q1.x || x > (int) q1.y || x >= a.d.st.width)
-		return;
-	const uint4 q0 = __ldg(h + 0);
-	const float pcx = (float) ((double) x + 0.5);
-	if (pcx < __uint_as_float(q0.x) || pcx >= __uint_as_float(q0.z))
-		return;
-	const uint4 q2 = __ldg(h + 2), q3 = __ldg(h + 3);
-	const int yLo = max((int) q1.z, ty0), yHi = min(min((int) q1.w, ty0 + SRPD_WT_H - 1), a.d.st.height - 1);
-	for (int y = yLo; y <= yHi; y++)
+	const unsigned char* rec = nullptr;
+	uint32_t idBase = 0u;
+	int xLo = 1, xHi = 0, yLo = 1, yHi = 0;      /* empty */
+	uint4 q0 = make_uint4(0u, 0u, 0u, 0u);
+	if (lane < n)
 	{
-		const float pcy = (float) ((double) y + 0.5);
-		if (pcy < __uint_as_float(q0.y) || pcy >= __uint_as_float(q0.w))
-			continue;
-		const int p = pixelEntry(lane, y - ty0);
-		PixelRef px;
-		px.color = wt.color + p; px.depth = wt.depth + p; px.stencil = wt.stencil + p;
-		emitFragment<1, 0>(a.d.st, fr, px, dirty, cnt, x, y, pcx, pcy, __uint_as_float(q2.x), 0.f, __uint_as_float(q2.y),
-		                true, q3.w + idBase, rec + SRPD_REC_HEADER_BYTES, nullptr);
+		const uint4 ent = wt.ring[(head + lane) & (SRPD_RING - 1)];
+		rec = records + (size_t) ent.z * a.recStride;
+		idBase = ent.w;
+		const uint4* h = (const uint4*) rec;
+		q0 = __ldg(h + 0);                                   /* the square: minX, minY, maxX, maxY (floats, half-open) */
+		const uint4 q1 = __ldg(h + 1);                        /* pixel box, inclusive: minX, maxX, minY, maxY */
+		xLo = max((int) q1.x, tx0); xHi = min(min((int) q1.y, tx0 + SRPD_WT_W - 1), a.d.st.width - 1);
+		yLo = max((int) q1.z, ty0); yHi = min(min((int) q1.w, ty0 + SRPD_WT_H - 1), a.d.st.height - 1);
+	}
+	const bool any = xLo <= xHi && yLo <= yHi;
+	/* tile-relative box in one word: x0 | x1 << 8 | y0 << 16 | y1 << 24 */
+	const uint32_t box = any ? (uint32_t) (xLo - tx0) | ((uint32_t) (xHi - tx0) << 8) | ((uint32_t) (yLo - ty0) << 16) | ((uint32_t) (yHi - ty0) << 24) : 0xFFFFFFFFu;
+	uint32_t blockers = 0u;      /* earlier points of the step whose squares overlap mine */
+	for (int e = 0; e + 1 < n; e++)
+	{
+		const uint32_t other = __shfl_sync(0xFFFFFFFFu, box, e);
+		if (e < lane && any && other != 0xFFFFFFFFu)
+		{
+			const int ox0 = (int) (other & 255u), ox1 = (int) ((other >> 8) & 255u), oy0 = (int) ((other >> 16) & 255u), oy1 = (int) (other >> 24);
+			if (ox0 <= xHi - tx0 && ox1 >= xLo - tx0 && oy0 <= yHi - ty0 && oy1 >= yLo - ty0)
+				blockers |= 1u << e;
+		}
+	}
+	uint32_t pending = __ballot_sync(0xFFFFFFFFu, any);
+	while (pending != 0u)
+	{
+		const bool go = ((pending >> lane) & 1u) && (blockers & pending) == 0u;
+		if (go)
+		{
+			const uint4 q2 = __ldg((const uint4*) rec + 2), q3 = __ldg((const uint4*) rec + 3);
+			for (int y = yLo; y <= yHi; y++)
+			{
+				const float pcy = (float) ((double) y + 0.5);
+				if (pcy < __uint_as_float(q0.y) || pcy >= __uint_as_float(q0.w))
+					continue;
+				for (int x = xLo; x <= xHi; x++)
+				{
+					const float pcx = (float) ((double) x + 0.5);
+					if (pcx < __uint_as_float(q0.x) || pcx >= __uint_as_float(q0.z))
+						continue;
+					const int p = pixelEntry(x - tx0, y - ty0);
+					PixelRef px;
+					px.color = wt.color + p; px.depth = wt.depth + p; px.stencil = wt.stencil + p;
+					emitFragment<1, 0>(a.d.st, fr, px, dirty, cnt, x, y, pcx, pcy, __uint_as_float(q2.x), 0.f, __uint_as_float(q2.y),
+					                true, q3.w + idBase, rec + SRPD_REC_HEADER_BYTES, nullptr);
+				}
+			}
+		}
+		pending &= ~__ballot_sync(0xFFFFFFFFu, go);
+		__syncwarp();      /* the next wave sees this one's pixels */
 	}
 }
 
@@ -833,7 +882,7 @@ __device__ __forceinline__ void processWarpTile(
 	__syncwarp();
 
 	int head = 0, waiting = 0;      /* the ring: entries [head, head + waiting) */
-	for (uint32_t c = begin; c < end; c += 32)
+	for (uint32_t c = begin; c < end || waiting > 0; c += 32)
 	{
 		/* keep the candidates whose box touches the tile, in order */
 		const uint32_t i = c + lane;
@@ -848,48 +897,30 @@ __device__ __forceinline__ void processWarpTile(
 			hit = x0 < tx0 + SRPD_WT_W && x1 > tx0 && y0b < ty0 + SRPD_WT_H && y1b > ty0;
 		}
 		const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
-		if (ballot == 0u)
-			continue;
 		if (hit)
 			wt.ring[(head + waiting + __popc(ballot & ((1u << lane) - 1u))) & (SRPD_RING - 1)] = ent;
 		waiting += __popc(ballot);
+		/* a step when 32 primitives are waiting, or what is left at the end of the list */
+		if (waiting < 32 && c + 32 < end)
+			continue;
 		__syncwarp();
-		if (waiting >= 32 || c + 32 >= end)
-		{
-			const int n = min(waiting, 32);
-			if constexpr (KIND == SRPD_KIND_TRIANGLE)
-				visitTriangles<SIMPLE>(a, fr, records, wt, head, n, tx0, ty0, dirty, cnt, lane);
-			else
-				for (int k = 0; k < n; k++)
-				{
-					const uint4 e = wt.ring[(head + k) & (SRPD_RING - 1)];
-					const unsigned char* rec = records + (size_t) e.z * a.recStride;
-					if (KIND == SRPD_KIND_LINE)
-						visitLine(a, fr, rec, e.w, wt, tx0, ty0, dirty, cnt, lane);
-					else
-						visitPoint(a, fr, rec, e.w, wt, tx0, ty0, dirty, cnt, lane);
-					__syncwarp();      /* the next primitive sees this one's pixels */
-				}
-			head = (head + n) & (SRPD_RING - 1);
-			waiting -= n;
-		}
-	}
-	/* what is left in the ring (fewer than 32; the loop's last chunk may have been empty) */
-	if (waiting > 0)
-	{
+		const int n = min(waiting, 32);
 		if constexpr (KIND == SRPD_KIND_TRIANGLE)
-			visitTriangles<SIMPLE>(a, fr, records, wt, head, waiting, tx0, ty0, dirty, cnt, lane);
-		else
-			for (int k = 0; k < waiting; k++)
+			visitTriangles<SIMPLE>(a, fr, records, wt, head, n, tx0, ty0, dirty, cnt, lane);
+		else if constexpr (KIND == SRPD_KIND_LINE)
+			for (int k = 0; k < n; k += 2)
 			{
-				const uint4 e = wt.ring[(head + k) & (SRPD_RING - 1)];
-				const unsigned char* rec = records + (size_t) e.z * a.recStride;
-				if (KIND == SRPD_KIND_LINE)
-					visitLine(a, fr, rec, e.w, wt, tx0, ty0, dirty, cnt, lane);
-				else
-					visitPoint(a, fr, rec, e.w, wt, tx0, ty0, dirty, cnt, lane);
-				__syncwarp();
+				const uint4 eA = wt.ring[(head + k) & (SRPD_RING - 1)];
+				const uint4 eB = wt.ring[(head + k + 1) & (SRPD_RING - 1)];
+				const unsigned char* recA = records + (size_t) eA.z * a.recStride;
+				const unsigned char* recB = k + 1 < n ? records + (size_t) eB.z * a.recStride : nullptr;
+				visitLines(a, fr, recA, eA.w, recB, eB.w, wt, tx0, ty0, dirty, cnt, lane);
+				__syncwarp();      /* the next primitives see these ones' pixels */
 			}
+		else
+			visitPoints(a, fr, records, wt, head, n, tx0, ty0, dirty, cnt, lane);
+		head = (head + n) & (SRPD_RING - 1);
+		waiting -= n;
 	}
 
 	dirty = __reduce_or_sync(0xFFFFFFFFu, dirty);

@@ -580,7 +580,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		if (!grow(g.ckptTable, ckptEntries * 3 * sizeof(float))) return 1;
 		if (!grow(g.largeList, sizeof(uint2) * largeCapacity)) return 1;
 	}
-	ga.ckptCursor = (uint32_t*) g.scan.ptr + 5;
+	ga.ckptCursor = (unsigned long long*) ((uint32_t*) g.scan.ptr + 12);
 	ga.largeCount = (uint32_t*) g.scan.ptr + 6;
 	ga.largeList = (uint2*) g.largeList.ptr;
 	ga.largeCapacity = ckptEntries ? largeCapacity : 0;

@@ -198,7 +198,7 @@ static bool snapshotVaryings(SrpdState* st, const SRPVertexShader* vs)
 static bool buildDraw(
 	SrpdDraw* d, const SRPIndexBuffer* ib, const SRPVertexBuffer* vb, const SRPFramebuffer* fb,
 	const SRPShaderProgram* sp, SRPPrimitive primitive, size_t startIndex, size_t count,
-	const SRPProgramEntry** outProgram)
+	SRPProgramEntry* outProgram)
 {
 	memset(d, 0, sizeof *d);
 	const SRPContext* c = &srpContext;
@@ -233,12 +233,13 @@ static bool buildDraw(
 		return false;
 	}
 
-	const SRPProgramEntry* prog = srpLookupProgram(sp->vs->shader, sp->fs->shader);
-	if (prog == NULL)
+	SRPProgramEntry prog;
+	if (!srpLookupProgram(sp->vs->shader, sp->fs->shader, &prog))
 	{
 		srpFatalMessage("srpDraw",
-			"shader program (vs %p, fs %p) has no registered __device__ twins (srpB200RegisterProgram); "
-			"nothing is drawn -- this library has no CPU path", (void*) sp->vs->shader, (void*) sp->fs->shader);
+			"shader program (vs %p, fs %p) has no registered __device__ twins (srpB200RegisterProgram / "
+			"srpB200RegisterVertexShader / srpB200RegisterFragmentShader); nothing is drawn -- this library has no CPU path",
+			(void*) sp->vs->shader, (void*) sp->fs->shader);
 		return false;
 	}
 	*outProgram = prog;
@@ -263,7 +264,8 @@ static bool buildDraw(
 	st->depthWrite = c->depth.writeEnable;
 	st->depthOp = (uint8_t) c->depth.compareOp;
 	st->earlyDepth = !sp->fs->mayOverwriteDepth;
-	st->programId = prog->deviceId;
+	st->vsProgramId = prog.vsDeviceId;
+	st->fsProgramId = prog.fsDeviceId;
 	if (!snapshotVaryings(st, sp->vs))
 		return false;
 
@@ -341,7 +343,7 @@ static void submit(
 	}
 
 	SrpdDraw d;
-	const SRPProgramEntry* prog = NULL;
+	SRPProgramEntry prog;
 	if (ok && count != 0 && !checkOOB(ib, vb, startIndex, count)
 	    && buildDraw(&d, ib, vb, fbs[0], sp, primitive, startIndex, count, &prog))
 	{
@@ -370,7 +372,7 @@ static void submit(
 				frames[f].clearPending = chunk == 0 && impls[f]->clearPending;
 				frames[f].pad = 0;
 			}
-			const size_t ubytes = uniforms ? prog->uniformSize : 0;
+			const size_t ubytes = uniforms ? prog.uniformSize : 0;
 			/* default policy: the (last sub-)draw itself may refresh the host mirror band by band,
 			 * overlapping the copies with rasterisation (it reports back whether it did) */
 			int mirrored = 0;

@@ -64,15 +64,15 @@ void srpFatalMessage(const char* sourceFunction, const char* format, ...);
 
 size_t srpSizeofType(SRPType type);
 
-/* registry (srp_registry.c) */
+/* registry (srp_registry.c): device twins of a (vertex shader, fragment shader) combination */
 typedef struct SRPProgramEntry
 {
 	SRPVertexShaderFunc vs;
 	SRPFragmentShaderFunc fs;
-	int deviceId;
-	size_t uniformSize;
+	int vsDeviceId, fsDeviceId;
+	size_t uniformSize;      /* the larger of what the two shaders read */
 } SRPProgramEntry;
-const SRPProgramEntry* srpLookupProgram(SRPVertexShaderFunc vs, SRPFragmentShaderFunc fs);
+bool srpLookupProgram(SRPVertexShaderFunc vs, SRPFragmentShaderFunc fs, SRPProgramEntry* out);
 
 /* framebuffer helpers (srp_framebuffer.c) */
 SRPFramebufferImpl* srpFramebufferImpl(const SRPFramebuffer* fb);

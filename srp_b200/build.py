@@ -164,7 +164,8 @@ def build_scenes(jobs: int = 8) -> list[Path]:
         _run([CC, "-std=c2x", "-O2", "-w", "-ffp-contract=off", f"-I{ROOT / 'include'}",
               f"-I{REFERENCE / 'examples' / 'utility'}", f"-I{REFERENCE / 'tests' / 'utils'}",
               "-c", scene_c, "-o", scene_o])
-        _run([NVCC, *DEVICE_FLAGS, *INCLUDES, "-c", twin, "-o", twin_o])
+        _run([NVCC, *DEVICE_FLAGS, *INCLUDES, f"-I{REFERENCE / 'examples' / 'utility'}", f"-I{REFERENCE / 'tests' / 'utils'}",
+              "-c", twin, "-o", twin_o])
         _run([NVCC, *DLINK_FLAGS, scene_o, twin_o, save_o, objparser_o, archive, "-o", exe, "-lz", "-lm"])
         return exe
 

@@ -8,8 +8,9 @@ the same bodies (include/srp_b200_device.cuh).  A program does not have to resta
 reads `app.c` (the unmodified source of a program written against kitrofimov/srp), and writes the
 one extra CUDA translation unit the program links with:
 
-  * every `typedef struct ... NAME;` and object-like `#define` of the file, verbatim (vertex,
-    varyings and uniform layouts),
+  * every `typedef struct ... NAME;`, object-like `#define` and `#include "..."` of the file,
+    verbatim (vertex, varyings and uniform layouts; the program's own headers are compiled with
+    the same include path as the C file),
   * every function with a shader signature -- `void f(SRPVertexShaderIn*, SRPVertexShaderOut*)`
     or `void f(SRPFragmentShaderIn*, SRPFragmentShaderOut*)` -- as `__device__ void srpTwin_f(...)`
     with the SAME body text (other top-level functions of the file, except main, come along as
@@ -143,6 +144,8 @@ def generate(source: str, origin: str = "<source>") -> str:
                          "(expected `void f(SRPVertexShaderIn* in, SRPVertexShaderOut* out)` at file scope)")
     defines = [ln.strip() for ln in clean.splitlines()
                if re.match(r"\s*#\s*define\s+\w+\s+\S", ln) and not re.match(r"\s*#\s*define\s+SRP_INCLUDE_", ln)]
+    # the program's own headers (quoted includes) may define the vertex / uniform types
+    includes = [ln.strip() for ln in clean.splitlines() if re.match(r'\s*#\s*include\s+"', ln)]
 
     def uniform_size(in_name, body):
         m = re.search(r"\(\s*(?:const\s+)?(\w+)\s*\*\s*\)\s*" + re.escape(in_name) + r"\s*->\s*uniform", body)
@@ -151,7 +154,7 @@ def generate(source: str, origin: str = "<source>") -> str:
     out = [f"/* GENERATED by srp_b200/twingen.py from {origin} -- the __device__ twins of its shaders;",
            " * the function bodies are the source's own text.  Do not edit: regenerate. */",
            "#include <srp_b200_device.cuh>", ""]
-    out += defines + ([""] if defines else [])
+    out += includes + defines + ([""] if includes or defines else [])
     for t in typedefs:
         out += [t, ""]
     for h in helpers:

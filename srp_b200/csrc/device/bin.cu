@@ -41,8 +41,16 @@ __device__ __forceinline__ bool rectEmpty(uint32_t r) { return (r & 0xFFu) > ((r
 /* Records per chunk: SRPD_BIN_CHUNK, or a quarter of it while the draw stores so few records that
  * full chunks would leave most of the machine idle (cfg3: 130 k records = 64 chunks of 2048 on 148
  * SMs).  Every binning kernel derives it from the same record count. */
-__device__ __forceinline__ uint32_t binChunkRecords(uint32_t nStored)
+__device__ __forceinline__ uint32_t binChunkRecords(uint32_t nStored, uint32_t nSuper)
 {
+	if (nSuper > SRPD_BIN_SMEM_SUPERS)
+	{
+		/* many supertiles (dense draws of small primitives): the fill runs one WARP per chunk
+		 * (srpdBinFillWarpKernel); at least 512 records per chunk, at most SRPD_BIN_WARP_CHUNKS chunks */
+		uint32_t r = (nStored + SRPD_BIN_WARP_CHUNKS - 1) / SRPD_BIN_WARP_CHUNKS;
+		r = r < 512u ? 512u : r;
+		return (r + 31u) & ~31u;
+	}
 	return nStored <= SRPD_BIN_SMALL_RECORDS ? SRPD_BIN_CHUNK / 4 : SRPD_BIN_CHUNK;
 }
 
@@ -55,7 +63,7 @@ srpdBinCountKernel(const __grid_constant__ SrpdBinArgs a)
 	srpdGridDependencyEnter();
 	const uint32_t nSuper = a.superX * a.superY;
 	const uint32_t nStored = a.frameCounts[1];
-	const uint32_t chunkRecords = binChunkRecords(nStored);
+	const uint32_t chunkRecords = binChunkRecords(nStored, nSuper);
 	const uint32_t nChunks = (nStored + chunkRecords - 1) / chunkRecords;
 	/* the grid is sized for the machine, not for the record capacity: the CTAs stride over the
 	 * chunks that exist (nobody reads the counts of chunks past the end) */
@@ -64,25 +72,28 @@ srpdBinCountKernel(const __grid_constant__ SrpdBinArgs a)
 		for (uint32_t s = threadIdx.x; s < nSuper; s += SRPD_BIN_THREADS)
 			sCount[s] = 0;
 		const uint32_t first = chunk * chunkRecords;
-		/* all of the thread's boxes are requested before the first one is used (the loads overlap) */
-		constexpr int PER = SRPD_BIN_CHUNK / SRPD_BIN_THREADS;
-		uint2 bb[PER];
-		#pragma unroll
-		for (int k = 0; k < PER; k++)
-		{
-			const uint32_t o = k * SRPD_BIN_THREADS + threadIdx.x;
-			bb[k] = (o < chunkRecords && first + o < nStored) ? *(const uint2*) (a.ordered + first + o) : make_uint2(0u, 0u);      /* an empty box */
-		}
 		__syncthreads();      /* (the counters are zero) */
-		#pragma unroll
-		for (int k = 0; k < PER; k++)
+		for (uint32_t part = 0; part < chunkRecords; part += SRPD_BIN_CHUNK)
 		{
-			const uint32_t rect = superRect(bb[k], a.superX, a.superY, a.superShift);
-			if (rectEmpty(rect))
-				continue;
-			for (uint32_t sy = (rect >> 8) & 0xFFu; sy <= (rect >> 24); sy++)
-				for (uint32_t sx = rect & 0xFFu; sx <= ((rect >> 16) & 0xFFu); sx++)
-					atomicAdd(&sCount[sy * a.superX + sx], 1u);
+			/* all of the thread's boxes are requested before the first one is used (the loads overlap) */
+			constexpr int PER = SRPD_BIN_CHUNK / SRPD_BIN_THREADS;
+			uint2 bb[PER];
+			#pragma unroll
+			for (int k = 0; k < PER; k++)
+			{
+				const uint32_t o = part + k * SRPD_BIN_THREADS + threadIdx.x;
+				bb[k] = (o < chunkRecords && first + o < nStored) ? *(const uint2*) (a.ordered + first + o) : make_uint2(0u, 0u);      /* an empty box */
+			}
+			#pragma unroll
+			for (int k = 0; k < PER; k++)
+			{
+				const uint32_t rect = superRect(bb[k], a.superX, a.superY, a.superShift);
+				if (rectEmpty(rect))
+					continue;
+				for (uint32_t sy = (rect >> 8) & 0xFFu; sy <= (rect >> 24); sy++)
+					for (uint32_t sx = rect & 0xFFu; sx <= ((rect >> 16) & 0xFFu); sx++)
+						atomicAdd(&sCount[sy * a.superX + sx], 1u);
+			}
 		}
 		__syncthreads();
 		for (uint32_t s = threadIdx.x; s < nSuper; s += SRPD_BIN_THREADS)
@@ -104,7 +115,7 @@ srpdBinScanColumnsKernel(const __grid_constant__ SrpdBinArgs a)
 	srpdGridDependencyEnter();
 	const uint32_t nSuper = a.superX * a.superY;
 	const uint32_t nStored = a.frameCounts[1];
-	const uint32_t chunkRecords = binChunkRecords(nStored);
+	const uint32_t chunkRecords = binChunkRecords(nStored, nSuper);
 	const uint32_t nChunks = (nStored + chunkRecords - 1) / chunkRecords;
 	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 	const uint32_t s = blockIdx.x * 32u + lane;
@@ -250,7 +261,7 @@ srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 	srpdGridDependencyEnter();
 	const uint32_t nSuper = a.superX * a.superY;
 	const uint32_t nStored = a.frameCounts[1];
-	const uint32_t chunkRecords = binChunkRecords(nStored);
+	const uint32_t chunkRecords = binChunkRecords(nStored, nSuper);
 	const uint32_t nChunks = (nStored + chunkRecords - 1) / chunkRecords;
 	const uint32_t span = chunkRecords / FILL_WARPS;              /* records per warp */
 	const int rounds = (int) (span / 32);
@@ -336,6 +347,88 @@ srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 	}   /* chunk */
 }
 
+/* Fill for draws with MANY supertiles (dense small primitives: cfg4's 10 M sub-pixel triangles bin
+ * into 4080 supertiles), where a per-warp cursor matrix no longer fits shared memory.  One WARP
+ * per chunk; its cursors are its own row of chunkCounts in global memory (after the scans:
+ * records of earlier chunks per supertile), advanced in place.  The (record, supertile) pairs of a
+ * step of 32 records are taken in (lane, cell) order, 32 pairs at a time: match.any groups the
+ * pairs of a supertile, a pair's slot is the group's cursor + its rank in the group -- the same
+ * warp-scan compaction keyed by supertile, without a mask per supertile -- and the group's first
+ * lane advances the cursor before the next 32 pairs.  Lists come out sorted by record position. */
+__global__ void __launch_bounds__(SRPD_BIN_THREADS)
+srpdBinFillWarpKernel(const __grid_constant__ SrpdBinArgs a)
+{
+	srpdGridDependencyEnter();
+	const uint32_t nSuper = a.superX * a.superY;
+	const uint32_t nStored = a.frameCounts[1];
+	const uint32_t chunkRecords = binChunkRecords(nStored, nSuper);
+	const uint32_t nChunks = (nStored + chunkRecords - 1) / chunkRecords;
+	const int lane = threadIdx.x & 31;
+	const uint32_t warpsPerGrid = gridDim.x * (SRPD_BIN_THREADS / 32);
+	const uint32_t lt = (1u << lane) - 1u;
+	for (uint32_t chunk = blockIdx.x * (SRPD_BIN_THREADS / 32) + (threadIdx.x >> 5); chunk < nChunks; chunk += warpsPerGrid)
+	{
+		uint32_t* cursor = a.chunkCounts + (size_t) chunk * nSuper;
+		const uint32_t first = chunk * chunkRecords;
+		const uint32_t last = min(first + chunkRecords, nStored);
+		for (uint32_t r0 = first; r0 < last; r0 += 32)
+		{
+			const uint32_t rec = r0 + lane;
+			const uint32_t rc = rec < last ? superRect(*(const uint2*) (a.ordered + rec), a.superX, a.superY, a.superShift) : 0x00000101u;
+			const bool empty = rectEmpty(rc);
+			const uint32_t sx0 = rc & 0xFFu, sy0 = (rc >> 8) & 0xFFu, sx1 = (rc >> 16) & 0xFFu, sy1 = rc >> 24;
+			const uint32_t w = empty ? 0u : sx1 - sx0 + 1u, cells = empty ? 0u : w * (sy1 - sy0 + 1u);
+			/* pairs in (lane, cell) order */
+			uint32_t inc = cells;
+			#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+				if (lane >= o) inc += v;
+			}
+			const uint32_t nPairs = __shfl_sync(0xFFFFFFFFu, inc, 31);
+			const uint32_t excl = inc - cells;
+			for (uint32_t p0 = 0; p0 < nPairs; p0 += 32)
+			{
+				const uint32_t p = p0 + lane;
+				/* the owner of pair p: the last lane whose first pair is <= p (lanes without cells share
+				 * their successor's value and are stepped over) */
+				int lo = 0;
+				#pragma unroll
+				for (int step = 16; step > 0; step >>= 1)
+				{
+					const uint32_t e = __shfl_sync(0xFFFFFFFFu, excl, (lo + step) & 31);
+					if (lo + step < 32 && e <= p) lo += step;
+				}
+				const uint32_t oExcl = __shfl_sync(0xFFFFFFFFu, excl, lo), oW = __shfl_sync(0xFFFFFFFFu, w, lo);
+				const uint32_t oX0 = __shfl_sync(0xFFFFFFFFu, sx0, lo), oY0 = __shfl_sync(0xFFFFFFFFu, sy0, lo);
+				const bool valid = p < nPairs;
+				uint32_t s = 0xFFFFFFFFu - (uint32_t) lane;      /* a key nobody shares */
+				if (valid)
+				{
+					const uint32_t cell = p - oExcl;
+					s = (oY0 + cell / oW) * a.superX + oX0 + cell % oW;
+				}
+				const uint32_t peers = __match_any_sync(0xFFFFFFFFu, s);
+				if (valid)
+				{
+					const int leader = __ffs(peers) - 1;
+					uint32_t cur = 0u;
+					if (lane == leader)
+						cur = a.superOffsets[s] + cursor[s];
+					cur = __shfl_sync(peers, cur, leader);
+					const uint32_t pos = cur + __popc(peers & lt);
+					if (pos < a.listCapacity)
+						a.listIds[pos] = r0 + (uint32_t) lo;
+					if (lane == leader)
+						cursor[s] += __popc(peers);
+				}
+				__syncwarp();      /* the next 32 pairs read the advanced cursors */
+			}
+		}
+	}
+}
+
 static int gBinLaunches = 0;
 int srpdBinLaunchCount(void) { return gBinLaunches; }
 
@@ -353,9 +446,16 @@ void srpdLaunchBin(const SrpdBinArgs& a, cudaStream_t stream, cudaEvent_t joinBe
 	 * dependency on the fill covers it */
 	if (joinBeforeFill)
 		cudaStreamWaitEvent(stream, joinBeforeFill, 0);
-	/* as many warps per chunk as the cursor matrix allows in shared memory */
+	/* as many warps per chunk as the cursor matrix allows in shared memory; beyond
+	 * SRPD_BIN_SMEM_SUPERS supertiles one warp per chunk with its cursors in global memory */
 	const size_t budget = 160 * 1024;
-	if (2 * 8 * (size_t) nSuper * sizeof(uint32_t) <= budget / 2)
+	if (nSuper > SRPD_BIN_SMEM_SUPERS)
+	{
+		uint32_t fillGrid = a.smCount * 4u;
+		if (fillGrid > (SRPD_BIN_WARP_CHUNKS + 7u) / 8u) fillGrid = (SRPD_BIN_WARP_CHUNKS + 7u) / 8u;
+		srpdLaunchKernel(srpdBinFillWarpKernel, fillGrid, SRPD_BIN_THREADS, 0, stream, a);
+	}
+	else if (2 * 8 * (size_t) nSuper * sizeof(uint32_t) <= budget / 2)
 	{
 		const size_t bytes = 2 * 8 * (size_t) nSuper * sizeof(uint32_t);
 		static bool configured8 = false;

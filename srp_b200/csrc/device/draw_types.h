@@ -70,7 +70,7 @@ typedef struct SrpdFrame
 	float*      depth;
 	uint8_t*    stencil;
 	uint32_t    clearPending;        /* 1: planes logically hold colour 0 / depth -1     */
-	uint32_t    pad;
+	uint32_t    pad;                 /* bit0: the planes are caller-provided device memory (srpB200NewFramebufferOnDevice) */
 } SrpdFrame;
 
 typedef struct SrpdDraw

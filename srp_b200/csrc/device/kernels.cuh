@@ -1,6 +1,7 @@
 /* srp-b200 internal -- kernel argument blocks and launch geometry shared by the CUDA
  * translation units (geom.cu, bin.cu, raster.cu, runtime.cu). */
 #pragma once
+#include <cuda.h>              /* CUtensorMap (type only: the driver entry point is fetched at run time) */
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -70,6 +71,8 @@ constexpr int SRPD_STATS_SLOTS = 1024;   /* SrpdStats[slots]: counters are sprea
 constexpr int SRPD_BIN_THREADS = 256;
 constexpr int SRPD_BIN_CHUNK = 2048;     /* records per coarse-binning CTA                  */
 constexpr uint32_t SRPD_BIN_SMALL_RECORDS = 1u << 18;   /* up to here chunks are SRPD_BIN_CHUNK / 4 (bin.cu) */
+constexpr uint32_t SRPD_BIN_SMEM_SUPERS = 1024;         /* more supertiles than this: one warp per chunk, cursors in global memory */
+constexpr uint32_t SRPD_BIN_WARP_CHUNKS = 4096;         /* chunks of that path at most (chunks grow beyond 512 records instead) */
 
 /* Per-draw zero-filled header in front of the scan state: word 0 coarse-list overflow flag, 1 abort flag,
  * 2 tile work counter, 3 records a frame needed (max over frames), 4 coarse-list entries needed,
@@ -179,6 +182,12 @@ struct SrpdTileArgs
 	const float* ckptTable;           /* barycentric checkpoints of large triangles     */
 	uint32_t smCount;
 	SrpdStats* stats;
+	/* TMA tile stores of the write-back (single-frame draws): tensor maps of frame0's planes with
+	 * a 32x8 box; tmaPlanes = planes that have one (bit0 colour, bit1 depth, bit2 stencil; 0 = none) */
+	uint32_t tmaPlanes;
+	alignas(64) CUtensorMap tmColor;
+	alignas(64) CUtensorMap tmDepth;
+	alignas(64) CUtensorMap tmStencil;
 };
 
 /* ---- programmatic dependent launch ---------------------------------------------------

@@ -295,24 +295,44 @@ constexpr int SRPD_RING = 64;            /* list entries waiting for a step (< 3
  * different banks, while a chunk stays a chunk for the 16-byte loads / stores of the write-back */
 __device__ __forceinline__ int pixelEntry(int x, int y)
 {
-	return y * SRPD_WT_W + ((((x >> 2) ^ y) & 7) << 2) + (x & 3);
+	return y * SRPD_WT_W + ((((x >> 2) ^ y) & 7) << 2) + (x & 3);      /* = CU_TENSOR_MAP_SWIZZLE_128B of a 128-byte row */
 }
 
-struct WarpTile
+/* Shared memory of a CTA: first the colour and depth planes of its warp tiles, 1024 bytes each and
+ * 1024-byte aligned (the 128-byte swizzle of the TMA tile store works on 1024-byte atoms), then
+ * one scratch block per warp.  The kernels work through these views. */
+struct WarpScratch
 {
-	alignas(16) uint32_t color[SRPD_WT_PIXELS];
-	alignas(16) float    depth[SRPD_WT_PIXELS];
-	alignas(16) uint8_t  stencil[SRPD_WT_PIXELS];
-	uint4 ring[SRPD_RING];               /* {box.x, box.y, record slot, id prefix} of the tile's next primitives */
+	alignas(16) uint8_t stencil[SRPD_WT_PIXELS];     /* row-major, 32 bytes per row */
+	uint4 ring[SRPD_RING];                           /* {box.x, box.y, record slot, id prefix} of the tile's next primitives */
 };
-struct WarpTileTri : WarpTile
+struct WarpScratchTri : WarpScratch
 {
 	uint4   frag[SRPD_QUEUE];            /* fragment queue: lambda0..2 (float bits), triangle | x << 5 | y << 10 */
 	TriInfo tri[32];                     /* [triangle of the step] */
 	uint8_t pair[SRPD_WT_H * 32];        /* work list of the row lanes: triangle * 8 + row */
 };
+template <int KIND> struct WarpScratchK { typedef WarpScratch type; };
+template <> struct WarpScratchK<SRPD_KIND_TRIANGLE> { typedef WarpScratchTri type; };
+constexpr int SRPD_PLANE_BYTES = SRPD_WT_PIXELS * 4;      /* 1024 */
+
+struct WarpTile
+{
+	uint32_t* color;      /* swizzled: pixelEntry(x, y) */
+	float*    depth;      /* swizzled: pixelEntry(x, y) */
+	uint8_t*  stencil;    /* y * 32 + x */
+	uint4*    ring;
+};
+struct WarpTileTri : WarpTile
+{
+	uint4*   frag;
+	TriInfo* tri;
+	uint8_t* pair;
+};
 template <int KIND> struct WarpTileK { typedef WarpTile type; };
 template <> struct WarpTileK<SRPD_KIND_TRIANGLE> { typedef WarpTileTri type; };
+
+__device__ __forceinline__ int stencilEntry(int x, int y) { return y * SRPD_WT_W + x; }
 
 /* top-left rule as ONE comparison per edge: the reference accepts lambda when
  * lambda > 0 || (|lambda| <= 1e-9 && edgeTL) (triangle.c:82-87).  With F = the largest float
@@ -434,7 +454,7 @@ __device__ __forceinline__ void shadeTriangleFragment(
 	const unsigned char* rec = records + (size_t) (B.w & SRPD_TRI_SLOT_MASK) * a.recStride;
 	const int p = pixelEntry(lx, ly);
 	PixelRef px;
-	px.color = wt.color + p; px.depth = wt.depth + p; px.stencil = wt.stencil + p;
+	px.color = wt.color + p; px.depth = wt.depth + p; px.stencil = wt.stencil + stencilEntry(lx, ly);
 	/* pixel centre: (float) ((double) x + 0.5) is exact, and so is the float sum for these magnitudes */
 	emitFragment<3, SIMPLE>(a.d.st, fr, px, dirty, cnt, x, y, __fadd_rn((float) x, 0.5f), __fadd_rn((float) y, 0.5f),
 	                depth, recW, recW, (B.w & SRPD_TRI_FRONT_BIT) != 0u, A.w, rec + SRPD_REC_HEADER_BYTES, wgt);
@@ -617,7 +637,7 @@ __device__ __forceinline__ void visitLines(
 			const float depth = __fadd_rn(__fmul_rn(zw0, w0), __fmul_rn(zw1, t));
 			const int p = pixelEntry(lx, ly);
 			PixelRef px;
-			px.color = wt.color + p; px.depth = wt.depth + p; px.stencil = wt.stencil + p;
+			px.color = wt.color + p; px.depth = wt.depth + p; px.stencil = wt.stencil + stencilEntry(lx, ly);
 			emitFragment<2, 0>(a.d.st, fr, px, dirty, cnt, myX, myY, (float) ((double) myX + 0.5), (float) ((double) myY + 0.5),
 			                depth, recW, recW, true, q3.w + idBase, rec + SRPD_REC_HEADER_BYTES, wgt);
 		}
@@ -684,7 +704,7 @@ __device__ __forceinline__ void visitPoints(
 						continue;
 					const int p = pixelEntry(x - tx0, y - ty0);
 					PixelRef px;
-					px.color = wt.color + p; px.depth = wt.depth + p; px.stencil = wt.stencil + p;
+					px.color = wt.color + p; px.depth = wt.depth + p; px.stencil = wt.stencil + stencilEntry(x - tx0, y - ty0);
 					emitFragment<1, 0>(a.d.st, fr, px, dirty, cnt, x, y, pcx, pcy, __uint_as_float(q2.x), 0.f, __uint_as_float(q2.y),
 					                true, q3.w + idBase, rec + SRPD_REC_HEADER_BYTES, nullptr);
 				}
@@ -768,7 +788,7 @@ __device__ __forceinline__ void loadWarpTile(const SrpdState& st, const SrpdFram
 				for (int i = 0; i < 4; i++)
 					if (x + i < st.width) v |= (uint32_t) src[i] << (8 * i);
 		}
-		*(uint32_t*) (wt.stencil + pixelEntry(col, row)) = v;
+		*(uint32_t*) (wt.stencil + stencilEntry(col, row)) = v;
 	}
 }
 
@@ -814,20 +834,13 @@ __device__ __forceinline__ void storeWarpTile(const SrpdState& st, const SrpdFra
 	{
 		if (io.vec16)
 		{
-			/* lanes 0..15: one 16-pixel half row each = four swizzled 4-byte chunks */
+			/* lanes 0..15: one 16-pixel half row each */
 			if (lane < 16)
 			{
 				const int row = lane / 2, col = (lane % 2) * 16;
 				const int x = tx0 + col, y = ty0 + row;
 				if (y < st.height && x < st.width)
-				{
-					uint4 v;
-					v.x = *(const uint32_t*) (wt.stencil + pixelEntry(col + 0, row));
-					v.y = *(const uint32_t*) (wt.stencil + pixelEntry(col + 4, row));
-					v.z = *(const uint32_t*) (wt.stencil + pixelEntry(col + 8, row));
-					v.w = *(const uint32_t*) (wt.stencil + pixelEntry(col + 12, row));
-					*(uint4*) (fr.stencil + (size_t) y * st.width + x) = v;
-				}
+					*(uint4*) (fr.stencil + (size_t) y * st.width + x) = *(const uint4*) (wt.stencil + stencilEntry(col, row));
 			}
 		}
 		else
@@ -840,7 +853,7 @@ __device__ __forceinline__ void storeWarpTile(const SrpdState& st, const SrpdFra
 				const int x = tx0 + col, y = ty0 + row;
 				if (y >= st.height || x >= st.width)
 					continue;
-				const uint32_t v = *(const uint32_t*) (wt.stencil + pixelEntry(col, row));
+				const uint32_t v = *(const uint32_t*) (wt.stencil + stencilEntry(col, row));
 				uint8_t* dst = fr.stencil + (size_t) y * st.width + x;
 				for (int i = 0; i < 4; i++)
 					if (x + i < st.width) dst[i] = (uint8_t) (v >> (8 * i));
@@ -849,10 +862,45 @@ __device__ __forceinline__ void storeWarpTile(const SrpdState& st, const SrpdFra
 	}
 }
 
+/* The same write-back as TMA tile stores (cp.async.bulk.tensor, SASS: UTMASTG): one lane hands the
+ * whole 32x8 tile of a plane to the copy engine -- the tensor map (runtime.cu) describes the
+ * row-major plane, a 32x8 box and, for colour / depth, the 128-byte swizzle the shared-memory
+ * planes are kept in; parts of the box beyond the framebuffer edge are clipped by the hardware.
+ * The generic-proxy writes of the fragments are made visible to the async proxy first; the
+ * stores are committed as one bulk group, which the warp waits for (its READ of shared memory)
+ * before it re-initialises the planes for its next tile. */
+__device__ __forceinline__ uint32_t sharedAddress(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tmaStorePlane(const CUtensorMap* map, const void* smem, int x, int y)
+{
+	asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+	             :: "l"(map), "r"(x), "r"(y), "r"(sharedAddress(smem)) : "memory");
+}
+__device__ __forceinline__ void storeWarpTileTma(const SrpdTileArgs& a, const SrpdFrame& fr, uint32_t dirty, const WarpTile& wt,
+                                                 int tx0, int ty0, int lane)
+{
+	const bool storeColor = fr.clearPending || (dirty & 1u), storeDepth = fr.clearPending || (dirty & 2u);
+	/* every lane publishes its own writes of the planes to the async proxy, then one lane issues */
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	__syncwarp();
+	if (lane == 0)
+	{
+		if (storeColor) tmaStorePlane(&a.tmColor, wt.color, tx0, ty0);
+		if (storeDepth) tmaStorePlane(&a.tmDepth, wt.depth, tx0, ty0);
+		if (dirty & 4u) tmaStorePlane(&a.tmStencil, wt.stencil, tx0, ty0);
+		asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+	}
+}
+__device__ __forceinline__ void tmaWaitSharedRead(int lane)
+{
+	if (lane == 0)
+		asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+	__syncwarp();
+}
+
 } // namespace
 
 /* One warp tile: load its state, collect the primitives that touch it, visit them in order, write it back. */
-template <int KIND, int SIMPLE>
+template <int KIND, int SIMPLE, bool BATCH_TMA>
 __device__ __forceinline__ void processWarpTile(
 	const SrpdTileArgs& a, const SrpdFrame& fr, uint32_t frame, int tileX, int tileY8, typename WarpTileK<KIND>::type& wt, FragCounters& cnt, int lane)
 {
@@ -878,6 +926,11 @@ __device__ __forceinline__ void processWarpTile(
 	const TileIO io = tileIO(st, fr);
 	uint32_t dirty = 0u;
 
+	/* TMA write-back: single-frame draws into planes of this process whose pitch keeps the tensor
+	 * maps legal (runtime.cu sets the mask); bit2 (stencil) may be missing on its own */
+	const uint32_t tma = BATCH_TMA ? a.tmaPlanes : 0u;
+	if (tma)
+		tmaWaitSharedRead(lane);      /* the previous tile's stores have read the planes */
 	loadWarpTile(st, fr, io, stencilEnabled, wt, tx0, ty0, lane);
 	__syncwarp();
 
@@ -925,7 +978,10 @@ __device__ __forceinline__ void processWarpTile(
 
 	dirty = __reduce_or_sync(0xFFFFFFFFu, dirty);
 	__syncwarp();
-	storeWarpTile(st, fr, io, dirty, wt, tx0, ty0, lane);
+	if (tma == 7u || (tma == 3u && !(dirty & 4u)))
+		storeWarpTileTma(a, fr, dirty, wt, tx0, ty0, lane);
+	else
+		storeWarpTile(st, fr, io, dirty, wt, tx0, ty0, lane);
 	__syncwarp();      /* the next tile re-initialises the state */
 }
 
@@ -969,10 +1025,21 @@ template <int KIND, bool BATCH, int SIMPLE>
 __global__ void __launch_bounds__(SRPD_TILE_THREADS, SRPD_TILE_CTAS_PER_SM)
 srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 {
-	typedef typename WarpTileK<KIND>::type Shared;
-	extern __shared__ __align__(16) unsigned char srpdTileSmem[];
+	typedef typename WarpScratchK<KIND>::type Scratch;
+	extern __shared__ __align__(1024) unsigned char srpdTileSmem[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	Shared& wt = reinterpret_cast<Shared*>(srpdTileSmem)[warp];
+	typename WarpTileK<KIND>::type wt;
+	{
+		Scratch& sc = reinterpret_cast<Scratch*>(srpdTileSmem + SRPD_TILE_WARPS * 2 * SRPD_PLANE_BYTES)[warp];
+		wt.color = reinterpret_cast<uint32_t*>(srpdTileSmem + (2 * warp + 0) * SRPD_PLANE_BYTES);
+		wt.depth = reinterpret_cast<float*>(srpdTileSmem + (2 * warp + 1) * SRPD_PLANE_BYTES);
+		wt.stencil = sc.stencil;
+		wt.ring = sc.ring;
+		if constexpr (KIND == SRPD_KIND_TRIANGLE)
+		{
+			wt.frag = sc.frag; wt.tri = sc.tri; wt.pair = sc.pair;
+		}
+	}
 
 	srpdGridDependencyEnter();
 	if (*a.abortFlag)      /* guard (never expected, runtime.cu): leave the framebuffer untouched */
@@ -1026,7 +1093,7 @@ srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 			const uint32_t tileIndex = ((uint32_t) tileY8 >> 1) * a.tilesX + (uint32_t) tileX;
 			const bool occupied = (occ[tileIndex >> 5] >> (tileIndex & 31u)) & 1u;
 			if (occupied)
-				processWarpTile<KIND, SIMPLE>(a, fr, frame, tileX, tileY8, wt, cnt, lane);
+				processWarpTile<KIND, SIMPLE, !BATCH>(a, fr, frame, tileX, tileY8, wt, cnt, lane);
 			else if (fr.clearPending)
 				clearWarpTile(a.d.st, fr, tileX, tileY8, lane);
 			if (++tileX == (int) a.tilesX)
@@ -1036,6 +1103,9 @@ srpdTileKernel(const __grid_constant__ SrpdTileArgs a)
 			}
 		}
 	}
+
+	if (!BATCH && a.tmaPlanes && lane == 0)      /* the last tile's stores have left before the CTA gives up its shared memory */
+		asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 
 	/* counters: warp reduction, then one atomic per warp into one of the slots, so the atomics
 	 * of a frame do not serialise on one L2 address */
@@ -1084,7 +1154,7 @@ template <int KIND, bool BATCH, int SIMPLE>
 static void launchTileKernelS(const SrpdTileArgs& a, unsigned grid, cudaStream_t stream)
 {
 	static bool configured = false;
-	const int bytes = (int) (sizeof(typename WarpTileK<KIND>::type) * SRPD_TILE_WARPS);
+	const int bytes = (int) ((2 * SRPD_PLANE_BYTES + sizeof(typename WarpScratchK<KIND>::type)) * SRPD_TILE_WARPS);
 	if (!configured)
 	{
 		cudaFuncSetAttribute(srpdTileKernel<KIND, BATCH, SIMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);

@@ -150,6 +150,72 @@ int envInt(const char* name, int fallback)
 
 } // namespace
 
+/* ---- TMA tensor maps of framebuffer planes (tile write-back, raster.cu) -------------------------
+ * A plane is a row-major 2-D tensor [height][width]; the box is one 32x8 warp tile.  Colour and
+ * depth use the 128-byte swizzle (the layout the tile kernel keeps them in in shared memory),
+ * stencil none.  The driver's encoder is fetched through the runtime (no link against libcuda);
+ * encoded maps are cached per (plane, size). */
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+struct CachedMap { const void* plane; int width, height, kind; CUtensorMap map; };
+std::vector<CachedMap> gTensorMaps;
+
+EncodeTiledFn encodeTiled()
+{
+	static EncodeTiledFn fn = nullptr;
+	static bool tried = false;
+	if (!tried)
+	{
+		tried = true;
+		void* p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+			fn = (EncodeTiledFn) p;
+		else
+			cudaGetLastError();
+	}
+	return fn;
+}
+
+/* kind: 0 colour (u32), 1 depth (f32), 2 stencil (u8).  false: no map (pitch / alignment / driver) */
+bool planeTensorMap(const void* plane, int width, int height, int kind, CUtensorMap* out)
+{
+	const size_t elem = kind == 2 ? 1 : 4;
+	if (getenv("SRP_B200_NO_TMA") || !plane || ((uintptr_t) plane & 15u) || ((size_t) width * elem) % 16 != 0)
+		return false;
+	for (const CachedMap& c : gTensorMaps)
+		if (c.plane == plane && c.width == width && c.height == height && c.kind == kind)
+		{
+			*out = c.map;
+			return true;
+		}
+	EncodeTiledFn enc = encodeTiled();
+	if (!enc)
+		return false;
+	const cuuint64_t dims[2] = { (cuuint64_t) width, (cuuint64_t) height };
+	const cuuint64_t strides[1] = { (cuuint64_t) width * elem };
+	const cuuint32_t box[2] = { (cuuint32_t) SRPD_WT_W, (cuuint32_t) SRPD_WT_H };
+	const cuuint32_t estr[2] = { 1, 1 };
+	CachedMap c;
+	c.plane = plane; c.width = width; c.height = height; c.kind = kind;
+	const CUresult r = enc(&c.map, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8,
+	                       2, const_cast<void*>(plane), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	                       kind == 2 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+	                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS)
+		return false;
+	if (gTensorMaps.size() >= 256)
+		gTensorMaps.clear();
+	gTensorMaps.push_back(c);
+	*out = c.map;
+	return true;
+}
+
+} // namespace
+
 extern "C" {
 
 void srpcuSetDevice(int device) { gRequestedDevice = device; }
@@ -671,6 +737,14 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	ta.ckptTable = (const float*) g.ckptTable.ptr;
 	ta.smCount = (uint32_t) g.smCount;
 	ta.stats = g.stats;
+	/* TMA tile stores for the write-back of a single frame into planes of this process */
+	if (!framesDev && !(frame0.pad & 1u))
+	{
+		const bool cd = planeTensorMap(frame0.color, st.width, st.height, 0, &ta.tmColor)
+		             && planeTensorMap(frame0.depth, st.width, st.height, 1, &ta.tmDepth);
+		if (cd)
+			ta.tmaPlanes = 3u | (planeTensorMap(frame0.stencil, st.width, st.height, 2, &ta.tmStencil) ? 4u : 0u);
+	}
 	if (ta.d.tileRow1 > tilesY) ta.d.tileRow1 = tilesY;
 	if (ta.d.tileRow0 > ta.d.tileRow1) ta.d.tileRow0 = ta.d.tileRow1;
 
@@ -687,6 +761,8 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 			const uint32_t smallChunks = (small + SRPD_BIN_CHUNK / 4 - 1) / (SRPD_BIN_CHUNK / 4);
 			if (ba.nChunksMax < smallChunks) ba.nChunksMax = smallChunks;
 		}
+		if (nSuper > SRPD_BIN_SMEM_SUPERS)      /* warp-per-chunk fill: chunks of >= 512 records, a bounded number of them */
+			ba.nChunksMax = SRPD_BIN_WARP_CHUNKS;
 		ba.smCount = (uint32_t) g.smCount;
 		ba.superX = superX;
 		ba.superY = superY;

@@ -370,7 +370,7 @@ static void submit(
 				frames[f].depth = impls[f]->dDepth;
 				frames[f].stencil = impls[f]->dStencil;
 				frames[f].clearPending = chunk == 0 && impls[f]->clearPending;
-				frames[f].pad = 0;
+				frames[f].pad = impls[f]->ownsDevicePlanes ? 0u : 1u;      /* bit0: planes are caller-provided device memory (maybe a peer GPU's) */
 			}
 			const size_t ubytes = uniforms ? prog.uniformSize : 0;
 			/* default policy: the (last sub-)draw itself may refresh the host mirror band by band,

@@ -10,8 +10,9 @@
  * view (16-byte entries, 8 bytes of box each; the records themselves are not touched):
  *   count : one CTA per chunk of 2048 records counts, per supertile, how many of the
  *           chunk's records overlap it            -> chunkCounts[chunk][supertile]
- *   scan  : per supertile an exclusive scan over the chunks, then an exclusive scan over
- *           the supertiles' totals                -> superOffsets[s] + chunkCounts[c][s] is
+ *   scan  : per supertile an exclusive scan over the chunks, then (by the CTA that finishes
+ *           last) an exclusive scan over the supertiles' totals
+ *                                                 -> superOffsets[s] + chunkCounts[c][s] is
  *                                                    the write cursor of (chunk c, supertile s)
  *   fill  : one CTA per chunk, each warp walks its share of the records 32 at a time; a
  *           record's slot in a supertile list is cursor + (number of EARLIER lanes whose box
@@ -102,12 +103,70 @@ srpdBinCountKernel(const __grid_constant__ SrpdBinArgs a)
 	}
 }
 
+/* Scan pass 2 (run by the last CTA of pass 1): exclusive scan of the supertile totals ->
+ * superOffsets (warp-shuffle scans: lanes, then the warp totals, one barrier pair per 256 supertiles) */
+constexpr int SRPD_SCAN_COL_WARPS = 8;
+__device__ __forceinline__ void scanSuperTotals(const SrpdBinArgs& a, uint32_t nSuper)
+{
+	__shared__ uint32_t sWarp[SRPD_SCAN_COL_WARPS];
+	__shared__ uint32_t sCarry;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	constexpr uint32_t T = SRPD_SCAN_COL_WARPS * 32;
+	if (threadIdx.x == 0)
+		sCarry = 0;
+	__syncthreads();
+	for (uint32_t s0 = 0; s0 < nSuper; s0 += T)
+	{
+		const uint32_t s = s0 + threadIdx.x;
+		const uint32_t run = s < nSuper ? __ldcg(a.superTotals + s) : 0;      /* (written by other CTAs: not through L1) */
+		uint32_t v = run;
+		#pragma unroll
+		for (uint32_t o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, v, o);
+			if (lane >= o) v += n;
+		}
+		if (lane == 31)
+			sWarp[warp] = v;
+		__syncthreads();
+		uint32_t before = 0, all = 0;
+		#pragma unroll
+		for (int w = 0; w < SRPD_SCAN_COL_WARPS; w++)
+		{
+			const uint32_t t = sWarp[w];
+			if ((uint32_t) w < warp) before += t;
+			all += t;
+		}
+		const uint32_t carry = sCarry;
+		const uint32_t excl = carry + before + v - run;
+		if (s < nSuper)
+			a.superOffsets[s] = excl < a.listCapacity ? excl : a.listCapacity;
+		__syncthreads();
+		if (threadIdx.x == 0)
+			sCarry = carry + all;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+	{
+		const uint32_t total = sCarry;
+		a.superOffsets[nSuper] = total < a.listCapacity ? total : a.listCapacity;
+		if (total > a.listCapacity)
+		{
+			/* the coarse lists do not fit: this draw's tiles scan all records instead (slow but
+			 * exact, no host round trip), and the host is told how large the pool has to be */
+			*a.listOverflow = 1u;
+			a.needed[1] = total;
+			*(volatile uint32_t*) (a.hostNotes + 1) = total;
+			__threadfence_system();
+		}
+	}
+}
+
 /* Scan pass 1: exclusive scan over the chunks for every supertile column, total per supertile.
  * A CTA takes 32 columns (one per lane: coalesced rows); its 8 warps split the chunk rows, sum
  * their parts (loads only, 32 in flight), exchange the 8 partial sums per column through shared
  * memory and then rewrite their rows with the running sums -- the serial depth is two batches of
  * loads per 256 chunks instead of one dependent batch per 8 (or 32) chunks. */
-constexpr int SRPD_SCAN_COL_WARPS = 8;
 __global__ void __launch_bounds__(SRPD_SCAN_COL_WARPS * 32)
 srpdBinScanColumnsKernel(const __grid_constant__ SrpdBinArgs a)
 {
@@ -151,94 +210,43 @@ srpdBinScanColumnsKernel(const __grid_constant__ SrpdBinArgs a)
 		if ((uint32_t) w < warp) run += p;
 		total += p;
 	}
-	if (!valid)
-		return;
-	uint32_t c = c0;
-	for (; c + 32 <= c1; c += 32)
+	if (valid)
 	{
-		uint32_t n[32];
-		#pragma unroll
-		for (int u = 0; u < 32; u++)
-			n[u] = col[(size_t) (c + u) * nSuper];
-		#pragma unroll
-		for (int u = 0; u < 32; u++)
+		uint32_t c = c0;
+		for (; c + 32 <= c1; c += 32)
 		{
-			col[(size_t) (c + u) * nSuper] = run;
-			run += n[u];
-		}
-	}
-	for (; c < c1; c++)
-	{
-		const uint32_t n = col[(size_t) c * nSuper];
-		col[(size_t) c * nSuper] = run;
-		run += n;
-	}
-	if (warp == 0)
-		a.superTotals[s] = total;
-}
-
-/* Scan pass 2: one CTA, exclusive scan of the supertile totals -> superOffsets (warp-shuffle
- * scans: lanes, then the 32 warp totals, one barrier pair per 1024 supertiles) */
-__global__ void __launch_bounds__(1024)
-srpdBinScanKernel(const __grid_constant__ SrpdBinArgs a)
-{
-	__shared__ uint32_t sWarp[32];
-	__shared__ uint32_t sCarry;
-	srpdGridDependencyEnter();
-	const uint32_t nSuper = a.superX * a.superY;
-	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-	if (threadIdx.x == 0)
-		sCarry = 0;
-	__syncthreads();
-	for (uint32_t s0 = 0; s0 < nSuper; s0 += 1024)
-	{
-		const uint32_t s = s0 + threadIdx.x;
-		const uint32_t run = s < nSuper ? a.superTotals[s] : 0;
-		uint32_t v = run;
-		#pragma unroll
-		for (uint32_t o = 1; o < 32; o <<= 1)
-		{
-			const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, v, o);
-			if (lane >= o) v += n;
-		}
-		if (lane == 31)
-			sWarp[warp] = v;
-		__syncthreads();
-		if (warp == 0)
-		{
-			uint32_t w = sWarp[lane];
+			uint32_t n[32];
 			#pragma unroll
-			for (uint32_t o = 1; o < 32; o <<= 1)
+			for (int u = 0; u < 32; u++)
+				n[u] = col[(size_t) (c + u) * nSuper];
+			#pragma unroll
+			for (int u = 0; u < 32; u++)
 			{
-				const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, w, o);
-				if (lane >= o) w += n;
+				col[(size_t) (c + u) * nSuper] = run;
+				run += n[u];
 			}
-			sWarp[lane] = w;      /* inclusive over the warps */
 		}
-		__syncthreads();
-		const uint32_t carry = sCarry;
-		const uint32_t excl = carry + (warp ? sWarp[warp - 1] : 0u) + v - run;
-		if (s < nSuper)
-			a.superOffsets[s] = excl < a.listCapacity ? excl : a.listCapacity;
-		__syncthreads();
-		if (threadIdx.x == 0)
-			sCarry = carry + sWarp[31];
-		__syncthreads();
-	}
-	if (threadIdx.x == 0)
-	{
-		const uint32_t total = sCarry;
-		a.superOffsets[nSuper] = total < a.listCapacity ? total : a.listCapacity;
-		if (total > a.listCapacity)
+		for (; c < c1; c++)
 		{
-			/* the coarse lists do not fit: this draw's tiles scan all records instead (slow but
-			 * exact, no host round trip), and the host is told how large the pool has to be */
-			*a.listOverflow = 1u;
-			a.needed[1] = total;
-			*(volatile uint32_t*) (a.hostNotes + 1) = total;
-			__threadfence_system();
+			const uint32_t n = col[(size_t) c * nSuper];
+			col[(size_t) c * nSuper] = run;
+			run += n;
 		}
+		if (warp == 0)
+			a.superTotals[s] = total;
 	}
+	/* the CTA that finishes last turns the supertile totals into the list offsets (this used to be
+	 * a kernel of its own: one launch and one drain less in every binned draw) */
+	__shared__ uint32_t sLast;
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0)
+		sLast = atomicAdd(a.scanTicket, 1u) == gridDim.x - 1 ? 1u : 0u;
+	__syncthreads();
+	if (!sLast)
+		return;
+	__threadfence();
+	scanSuperTotals(a, nSuper);
 }
 
 /* Fill: one CTA per chunk, FILL_WARPS warps; warp w owns the chunk's records
@@ -440,7 +448,6 @@ void srpdLaunchBin(const SrpdBinArgs& a, cudaStream_t stream, cudaEvent_t joinBe
 	if (grid == 0) grid = 1;
 	srpdLaunchKernel(srpdBinCountKernel, grid, SRPD_BIN_THREADS, nSuper * sizeof(uint32_t), stream, a);
 	srpdLaunchKernel(srpdBinScanColumnsKernel, (nSuper + 31) / 32, SRPD_SCAN_COL_WARPS * 32, 0, stream, a);
-	srpdLaunchKernel(srpdBinScanKernel, 1, 1024, 0, stream, a);
 	/* work of another stream that the kernel AFTER the fill needs (the checkpoint pre-pass, for
 	 * the tiles) joins here: the fill then starts after it, and the tile kernel's programmatic
 	 * dependency on the fill covers it */
@@ -476,5 +483,5 @@ void srpdLaunchBin(const SrpdBinArgs& a, cudaStream_t stream, cudaEvent_t joinBe
 		if (!configured2) { cudaFuncSetAttribute(srpdBinFillKernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) budget); configured2 = true; }
 		srpdLaunchKernel(srpdBinFillKernel<2>, grid, 2 * 32, bytes, stream, a);
 	}
-	gBinLaunches += 4;
+	gBinLaunches += 3;
 }

@@ -389,6 +389,16 @@ __device__ __forceinline__ void emitFanTriangle(Emitter& em, const SrpdState& st
 		emitPolygonModeTriangle<WRITE>(em, st, p, vary);
 }
 
+/* set-up of the first SRPD_FAN_CACHE fan triangles of a chunk, kept from the COUNT call for the
+ * WRITE call (filled polygons): the clipper pass is the latency of ONE warp per deferred batch, and
+ * a second set-up -- nine IEEE divisions and the f64 islands -- is a sixth of it */
+constexpr int SRPD_FAN_CACHE = 32;
+struct FanCache
+{
+	SrpdTriSetup s;
+	uint32_t stored;      /* 0 / 1; 2 = culled (no id) */
+};
+
 struct ClipResult { uint32_t nEmit, nStore; bool overflow; };
 enum { SRPD_CLIP_COUNT = 1, SRPD_CLIP_WRITE = 2 };
 
@@ -397,7 +407,7 @@ enum { SRPD_CLIP_COUNT = 1, SRPD_CLIP_WRITE = 2 };
  * their triangle produces); WRITE = emit them from idBase / storeBase of their owner, from the
  * slots the COUNT call left behind.  Called by all 32 lanes. */
 __device__ __forceinline__ ClipResult clipChunk(
-	Emitter em, const SrpdState& st, int mode, unsigned char* slots, uint32_t chunkMask,
+	Emitter em, const SrpdState& st, int mode, unsigned char* slots, FanCache* fanCache, uint32_t chunkMask,
 	const float4* vpos, const unsigned char* vvary, uint32_t slot0, uint32_t slot1, uint32_t slot2,
 	uint32_t idBase, uint32_t storeBase)
 {
@@ -416,13 +426,7 @@ __device__ __forceinline__ ClipResult clipChunk(
 		sl.origSlot[0] = (uint8_t) slot0; sl.origSlot[1] = (uint8_t) slot1; sl.origSlot[2] = (uint8_t) slot2;
 		sl.list[0][0] = 0; sl.list[0][1] = 1; sl.list[0][2] = 2;
 		int n = 3, nPool = 3, cur = 0;
-#ifdef SRPD_CLIP_ROLLED
-		/* experiment (leads for round 2): a sixth of the code on the clipper pass's path,
-		 * which stalls on instruction fetch a third of the time */
-		#pragma unroll 1
-#else
 		#pragma unroll      /* the plane becomes a constant: its distance is one add, not a jump table */
-#endif
 		for (int plane = 0; plane < 6; plane++)
 		{
 			if (n == 0)
@@ -522,9 +526,20 @@ __device__ __forceinline__ ClipResult clipChunk(
 				tv[k] = clipVary(os, ofresh, vvary, st.slotSize, v);
 			}
 			em.idBase = 0; em.storeBase = 0; em.nEmit = 0; em.nStore = 0; em.overflow = false;
+			const bool cached = st.polygonMode == SRP_POLYGON_MODE_FILL && f < (uint32_t) SRPD_FAN_CACHE;
 			if (!writing)
 			{
-				emitFanTriangle<false>(em, st, tp, tv);
+				if (cached)
+				{
+					FanCache& fc = fanCache[f];
+					bool stored = false;
+					const bool alive = setupAndClassify(st, tp, fc.s, stored);
+					fc.stored = alive ? (stored ? 1u : 0u) : 2u;
+					em.nEmit = alive ? 1u : 0u;
+					em.nStore = stored ? 1u : 0u;
+				}
+				else
+					emitFanTriangle<false>(em, st, tp, tv);
 				os.cnt[i][0] = (uint16_t) em.nEmit; os.cnt[i][1] = (uint16_t) em.nStore;
 			}
 			else if (os.cnt[i][1] != 0)
@@ -533,7 +548,13 @@ __device__ __forceinline__ ClipResult clipChunk(
 				for (int j = 0; j < i; j++) { preE += os.cnt[j][0]; preS += os.cnt[j][1]; }
 				em.idBase = os.idBase + preE;
 				em.storeBase = os.storeBase + preS;
-				emitFanTriangle<true>(em, st, tp, tv);
+				if (cached)
+				{
+					SrpdTriSetup s = fanCache[f].s;      /* (stored == 1: it has a record) */
+					writeTriangle<true>(em, st, s, true, tv);
+				}
+				else
+					emitFanTriangle<true>(em, st, tp, tv);
 				if (em.overflow) res.overflow = true;
 			}
 		}
@@ -640,9 +661,13 @@ __host__ __device__ inline size_t geomWarpBytes(int slotSize)
 {
 	return (sizeof(GeomWarpShared) + (size_t) SRPD_GEOM_MAX_VERTS * slotSize + 15) & ~(size_t) 15;
 }
+__host__ __device__ inline size_t geomClipSlotBytes(int slotSize)
+{
+	return ((size_t) SRPD_CLIP_SLOTS * clipSlotStride(slotSize) + 15) & ~(size_t) 15;
+}
 __host__ __device__ inline size_t geomCtaBytes(int slotSize, bool clipper)
 {
-	return clipper ? geomWarpBytes(slotSize) + (size_t) SRPD_CLIP_SLOTS * clipSlotStride(slotSize)
+	return clipper ? geomWarpBytes(slotSize) + geomClipSlotBytes(slotSize) + (size_t) SRPD_FAN_CACHE * sizeof(FanCache)
 	               : (size_t) SRPD_GEOM_WARPS * geomWarpBytes(slotSize);
 }
 
@@ -670,6 +695,7 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	GeomWarpShared& ws = *reinterpret_cast<GeomWarpShared*>(smem + warp * warpBytes);
 	unsigned char* vvary = reinterpret_cast<unsigned char*>(&ws + 1);
 	unsigned char* clipSlots = smem + warpBytes;      /* CLIPPER only */
+	FanCache* fanCache = reinterpret_cast<FanCache*>(clipSlots + geomClipSlotBytes(st.slotSize));
 	const uint32_t nBatches = a.batchesPerFrame * d.nFrames;
 	const int nv = (d.topology >= SRPD_TOPO_TRIANGLES) ? 3 : (d.topology == SRPD_TOPO_POINTS ? 1 : 2);
 
@@ -828,7 +854,7 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	 * as they are until the batch has written its records */
 	if (CLIPPER && clipMask != 0u)
 	{
-		const ClipResult r = clipChunk(em, st, SRPD_CLIP_COUNT, clipSlots, clipMask, ws.vpos, vvary, slot[0], slot[1], slot[2], 0u, 0u);
+		const ClipResult r = clipChunk(em, st, SRPD_CLIP_COUNT, clipSlots, fanCache, clipMask, ws.vpos, vvary, slot[0], slot[1], slot[2], 0u, 0u);
 		if (needsClip)
 		{
 			em.nEmit = r.nEmit; em.nStore = r.nStore;
@@ -862,7 +888,7 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	em.storeBase = physBase + incS - myStore;
 	if (CLIPPER && clipMask != 0u)
 	{
-		const bool ovf = clipChunk(em, st, SRPD_CLIP_WRITE, clipSlots, clipMask, ws.vpos, vvary, slot[0], slot[1], slot[2], em.idBase, em.storeBase).overflow;
+		const bool ovf = clipChunk(em, st, SRPD_CLIP_WRITE, clipSlots, fanCache, clipMask, ws.vpos, vvary, slot[0], slot[1], slot[2], em.idBase, em.storeBase).overflow;
 		if (ovf)
 		{
 			atomicAdd(&a.stats->overflow, 1ull);

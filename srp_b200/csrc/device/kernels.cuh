@@ -151,6 +151,7 @@ struct SrpdBinArgs
 	uint32_t listCapacity;
 	uint32_t* listOverflow;           /* zeroed per draw; set when the coarse lists do not fit listCapacity: the tile
 	                                     kernel then ignores them and lets every tile scan all records (slow, exact) */
+	uint32_t* scanTicket;             /* header word 5, zeroed per draw: CTAs of the column scan that have finished */
 	uint32_t* needed;
 	uint32_t* hostNotes;              /* pinned, mapped: [1] = coarse-list entries a draw needed (the host raises the pool) */
 	SrpdStats* stats;

@@ -791,10 +791,11 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		ba.listIds = (uint32_t*) g.listIds.ptr;
 		ba.listOverflow = (uint32_t*) g.scan.ptr + 0;
 		ba.needed = ga.needed;
+		ba.scanTicket = (uint32_t*) g.scan.ptr + 5;
 		ba.hostNotes = g.hostNotesDev;
 		ba.stats = g.stats;
 		srpdLaunchBin(ba, g.stream, ckptAside ? g.ckptDone : (cudaEvent_t) nullptr);     /* (ckptAside implies binned) */
-		g.launches += 4;
+		g.launches += 3;
 		CU(cudaGetLastError());
 		ta.superOffsets = ba.superOffsets;
 		ta.listIds = ba.listIds;

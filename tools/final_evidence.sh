@@ -1,17 +1,32 @@
 #!/bin/bash
-# round-end evidence in one GPU call: the driver's bench line (with the CPU baseline), the
-# reference arm, the ncu launch list, one `--set full` capture of a frame's kernels, all configs.
-# usage: gpurun -- tools/final_evidence.sh
+# round evidence in one GPU call (1 GPU): the driver's bench line (with parity + CPU baseline), the
+# reference arm, the ncu launch list and one `--set full` capture of a cfg3 frame's kernels, full
+# captures of the cfg5-batch kernels and of cfg4's binning + tile kernels, launch lists of cfg4 / cfg5 /
+# cfg2, all-config timings.   usage: gpurun -- tools/final_evidence.sh [tag]
+tag=${1:-r02}
 mkdir -p gpurun_out
-timeout 200 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
-tail -c 600 gpurun_out/bench_n1.json; echo
-timeout 120 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
-tail -c 300 gpurun_out/bench_ref.json; echo
-timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-  python bench.py --steps 20 --warmup 3 --cpu-seconds 0 > gpurun_out/launches.log 2>&1
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:srpd -s 27 -c 9 -f -o gpurun_out/full \
-  python bench.py --steps 2 --warmup 3 --cpu-seconds 0 > gpurun_out/full_ncu.log 2>&1
-tail -2 gpurun_out/full_ncu.log
-timeout 200 python tools/bench_all.py > gpurun_out/bench_all.log 2>&1
-tail -3 gpurun_out/bench_all.log | cut -c1-300
-ls -la gpurun_out
+timeout 400 python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench_cfg3_n1.json 2> gpurun_out/${tag}_bench_cfg3_n1.err
+tail -c 400 gpurun_out/${tag}_bench_cfg3_n1.json; echo
+timeout 200 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/${tag}_bench_cfg3_reference_arm.json 2>/dev/null
+tail -c 300 gpurun_out/${tag}_bench_cfg3_reference_arm.json; echo
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_cfg3_launches.csv \
+  python bench.py --steps 20 --warmup 3 --cpu-seconds 0 > /dev/null 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:srpd -s 27 -c 9 -f -o gpurun_out/${tag}_cfg3_full \
+  python bench.py --steps 2 --warmup 3 --cpu-seconds 0 > gpurun_out/${tag}_cfg3_full.log 2>&1
+tail -1 gpurun_out/${tag}_cfg3_full.log
+python tools/ncu_summary.py gpurun_out/${tag}_cfg3_full.ncu-rep gpurun_out/${tag}_cfg3_launches.csv gpurun_out/${tag}_cfg3_ncu_summary.md "Round 2 -- cfg3 (1M-triangle shell, 3840x2160): ncu evidence"
+timeout 300 ncu --set full --clock-control none -k regex:srpd -c 5 -f -o gpurun_out/${tag}_cfg5_batch_full \
+  python tools/profile_target.py cfg5 1 > gpurun_out/${tag}_cfg5_batch_full.log 2>&1
+tail -1 gpurun_out/${tag}_cfg5_batch_full.log
+python tools/ncu_summary.py gpurun_out/${tag}_cfg5_batch_full.ncu-rep /dev/null gpurun_out/${tag}_cfg5_batch_ncu_summary.md "Round 2 -- cfg5 batch (1024 teapot frames 1024x1024, one srpB200DrawBatch): ncu --set full"
+rm -f gpurun_out/${tag}_cfg5_batch_full.ncu-rep      # (gpurun_out/ travels back only below 64 MiB: the summaries are what is kept)
+timeout 400 ncu --set full --clock-control none -k 'regex:srpdBin|srpdTile|srpdBatchOrder' -c 6 -f -o gpurun_out/${tag}_cfg4_bin_full \
+  python tools/profile_target.py cfg4 1 > gpurun_out/${tag}_cfg4_bin_full.log 2>&1
+tail -1 gpurun_out/${tag}_cfg4_bin_full.log
+python tools/ncu_summary.py gpurun_out/${tag}_cfg4_bin_full.ncu-rep /dev/null gpurun_out/${tag}_cfg4_bin_ncu_summary.md "Round 2 -- cfg4 first draw (10 M sub-pixel triangles, stencil + scissor): order, binning and tile kernels, ncu --set full"
+rm -f gpurun_out/${tag}_cfg4_bin_full.ncu-rep
+tools/ncu_configs.sh $tag > gpurun_out/${tag}_launch_lists.txt 2>&1
+rm -f gpurun_out/launches_*_${tag}.csv
+timeout 400 python tools/bench_all.py > gpurun_out/${tag}_bench_all.log 2>&1
+cp gpurun_out/bench_all.json gpurun_out/${tag}_bench_all_configs.json 2>/dev/null
+ls -la gpurun_out | grep ${tag}_

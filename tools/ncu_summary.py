@@ -33,13 +33,14 @@ def main():
     title = sys.argv[4] if len(sys.argv) > 4 else rep
     lines = [f"# {title}", ""]
     # ---- launch list
-    rows = [l for l in open(launches) if not l.startswith("==")]
+    rows = [l for l in open(launches) if not l.startswith("==")] if launches != "/dev/null" else []
     agg = collections.OrderedDict()
     for r in csv.DictReader(rows):
         agg.setdefault(r["Kernel Name"].split("(")[0], []).append(float(r["Metric Value"].replace(",", "")))
     total = sum(sum(v) for k, v in agg.items() if "srpd" in k)
-    lines += ["## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare shares)", "",
-              "| kernel | launches | avg us | share of srpd* time |", "|---|---|---|---|"]
+    if rows:
+        lines += ["## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare shares)", "",
+                  "| kernel | launches | avg us | share of srpd* time |", "|---|---|---|---|"]
     for k, v in agg.items():
         share = f"{100 * sum(v) / total:.1f} %" if "srpd" in k else "-"
         lines.append(f"| `{k}` | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {share} |")

@@ -11,7 +11,7 @@ timeout 200 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/$
 tail -c 300 gpurun_out/${tag}_bench_cfg3_reference_arm.json; echo
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_cfg3_launches.csv \
   python bench.py --steps 20 --warmup 3 --cpu-seconds 0 > /dev/null 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:srpd -s 27 -c 9 -f -o gpurun_out/${tag}_cfg3_full \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:srpd -s 24 -c 8 -f -o gpurun_out/${tag}_cfg3_full \
   python bench.py --steps 2 --warmup 3 --cpu-seconds 0 > gpurun_out/${tag}_cfg3_full.log 2>&1
 tail -1 gpurun_out/${tag}_cfg3_full.log
 python tools/ncu_summary.py gpurun_out/${tag}_cfg3_full.ncu-rep gpurun_out/${tag}_cfg3_launches.csv gpurun_out/${tag}_cfg3_ncu_summary.md "Round 2 -- cfg3 (1M-triangle shell, 3840x2160): ncu evidence"

@@ -69,6 +69,20 @@ void srpB200FramebufferWait(const SRPFramebuffer* fb);
 /* stream-side counterpart of Wait: everything enqueued after this call is ordered behind the
  * framebuffer's in-flight asynchronous download (the host does not block) */
 void srpB200FramebufferFence(const SRPFramebuffer* fb);
+/* Frames in flight.  The library has srpB200LaneCount() lanes; a lane is a CUDA stream with its
+ * own scratch pools and staging.  Work enqueued on one lane runs in order; work on different lanes
+ * is independent and overlaps on the device -- the geometry and binning kernels of one frame,
+ * which leave most of the GPU idle, run under the tile kernel of another.  A frame loop under
+ * SRP_B200_SYNC_EXPLICIT that renders independent frames selects lane (frame % 2) before the
+ * frame's clear and draws, into one framebuffer per lane.  Ordering that still holds across lanes:
+ * a framebuffer used on a lane other than the one that touched it last is ordered behind that
+ * lane's work so far; srp*BufferCopyData is ordered behind every lane's earlier draws and before
+ * every lane's later ones; srpB200Finish() waits for all lanes; counters sum over lanes.
+ * Everything else (srpB200Stream, srpB200StreamSignal/Wait) refers to the current lane.
+ * Lane 0 is current at start; SetLane returns 0 on success. */
+int srpB200SetLane(int lane);
+int srpB200GetLane(void);
+int srpB200LaneCount(void);
 
 /* ---- device-resident objects -------------------------------------------------------
  * Framebuffer on caller-owned device memory (e.g. planes of a torch tensor that NCCL

@@ -38,6 +38,7 @@ struct Runtime
 	cudaStream_t auxStream = nullptr;      /* work off the critical path of a draw (checkpoint pre-pass) */
 	cudaStream_t uploadStream = nullptr;   /* srp*BufferCopyData: ordered behind the last draw that reads the buffer only */
 	cudaEvent_t uploadDone = nullptr;
+	cudaEvent_t laneFence = nullptr;       /* cross-lane ordering (srpcuOrderBehindLane, uploads) */
 	/* pinned staging ring for per-draw host data (uniform blocks, frame bindings): the caller's
 	 * memory has been read when the draw call returns, whatever kind of memory it is */
 	unsigned char* ring = nullptr;
@@ -73,8 +74,24 @@ struct Runtime
 	unsigned long long stageDraws = 0;
 };
 
-Runtime g;
+/* Lanes: independent copies of the whole submission state -- stream, scratch pools, staging ring,
+ * counters -- so that consecutive frames enqueued on different lanes overlap on the device (the
+ * low-occupancy front-end kernels of one frame run under the tile kernel of another).  Everything
+ * below addresses the current lane through `g`; srpcuSetLane selects it.  Lanes share the device
+ * and nothing else; the few cross-lane orderings (uploads, a framebuffer changing lanes) are
+ * explicit events. */
+Runtime gLanes[SRPCU_MAX_LANES];
+int gLane = 0;
+#define g gLanes[gLane]
 int gRequestedDevice = -1;
+bool gProfile = false;
+
+struct LaneScope
+{
+	int keep;
+	explicit LaneScope(int lane) : keep(gLane) { gLane = lane; }
+	~LaneScope() { gLane = keep; }
+};
 
 
 bool fail(const char* what, cudaError_t e)
@@ -276,6 +293,7 @@ int srpcuInit(void)
 	CU(cudaEventCreateWithFlags(&g.ckptDone, cudaEventDisableTiming));
 	CU(cudaStreamCreateWithFlags(&g.uploadStream, cudaStreamNonBlocking));
 	CU(cudaEventCreateWithFlags(&g.uploadDone, cudaEventDisableTiming));
+	CU(cudaEventCreateWithFlags(&g.laneFence, cudaEventDisableTiming));
 	CU(cudaEventCreateWithFlags(&g.ringWrapped, cudaEventDisableTiming));
 	g.ringBytes = (size_t) 8 << 20;
 	CU(cudaMallocHost((void**) &g.ring, g.ringBytes));
@@ -293,8 +311,41 @@ int srpcuInit(void)
 	g.forceBinning = envInt("SRP_B200_BINNING", -1);
 	g.binThreshold = (uint32_t) envInt("SRP_B200_BIN_THRESHOLD", 4096);
 	g.ckptAside = envInt("SRP_B200_CKPT_ASIDE", 1) != 0;
+	g.profile = gProfile;
+	/* buffer uploads issued on other lanes so far: this lane's draws come after them too */
+	for (int l = 0; l < SRPCU_MAX_LANES; l++)
+		if (l != gLane && gLanes[l].ready)
+			CU(cudaStreamWaitEvent(g.stream, gLanes[l].uploadDone, 0));
 	g.failed = false;
 	g.ready = true;
+	return 0;
+}
+
+int srpcuSetLane(int lane)
+{
+	if (lane < 0 || lane >= SRPCU_MAX_LANES)
+		return 1;
+	gLane = lane;
+	return 0;
+}
+int srpcuLane(void) { return gLane; }
+int srpcuLaneCount(void) { return SRPCU_MAX_LANES; }
+
+/* everything enqueued on `other` so far happens before what the current lane enqueues from now on */
+int srpcuOrderBehindLane(int other)
+{
+	if (other < 0 || other >= SRPCU_MAX_LANES || other == gLane || !gLanes[other].ready)
+		return 0;
+	if (srpcuInit()) return 1;
+	Runtime& o = gLanes[other];
+	CU(cudaEventRecord(o.laneFence, o.stream));
+	CU(cudaStreamWaitEvent(g.stream, o.laneFence, 0));
+	if (o.copyPending)
+	{
+		/* band-wise or asynchronous downloads still reading the planes */
+		CU(cudaEventRecord(o.laneFence, o.copyStream));
+		CU(cudaStreamWaitEvent(g.stream, o.laneFence, 0));
+	}
 	return 0;
 }
 
@@ -385,6 +436,14 @@ int srpcuUpload(void* dst, const void* src, size_t bytes, void* lastUse)
 	if (bytes == 0) return 0;
 	if (lastUse)
 		CU(cudaStreamWaitEvent(g.uploadStream, (cudaEvent_t) lastUse, 0));
+	/* `lastUse` was recorded on one lane; draws of the others may read the buffer as well: behind
+	 * everything they have enqueued so far */
+	for (int l = 0; l < SRPCU_MAX_LANES; l++)
+		if (l != gLane && gLanes[l].ready)
+		{
+			CU(cudaEventRecord(gLanes[l].laneFence, gLanes[l].stream));
+			CU(cudaStreamWaitEvent(g.uploadStream, gLanes[l].laneFence, 0));
+		}
 	CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, g.uploadStream));
 	cudaPointerAttributes attr;
 	bool pageable = false;
@@ -395,7 +454,9 @@ int srpcuUpload(void* dst, const void* src, size_t bytes, void* lastUse)
 	if (!pageable)
 		CU(cudaStreamSynchronize(g.uploadStream));
 	CU(cudaEventRecord(g.uploadDone, g.uploadStream));
-	CU(cudaStreamWaitEvent(g.stream, g.uploadDone, 0));
+	for (int l = 0; l < SRPCU_MAX_LANES; l++)
+		if (gLanes[l].ready)
+			CU(cudaStreamWaitEvent(gLanes[l].stream, g.uploadDone, 0));
 	g.h2d += bytes;
 	return 0;
 }
@@ -479,7 +540,7 @@ int srpcuStreamWaitEvent(void* event)
 	return 0;
 }
 
-int srpcuSynchronize(void)
+static int synchronizeLane(void)
 {
 	if (!g.ready) return 0;
 	if (g.copyPending)
@@ -498,6 +559,23 @@ int srpcuSynchronize(void)
 		return 1;
 	}
 	return 0;
+}
+/* waits for everything enqueued on every lane */
+int srpcuSynchronize(void)
+{
+	int err = synchronizeLane();
+	for (int l = 0; l < SRPCU_MAX_LANES && !err; l++)
+		if (l != gLane && gLanes[l].ready)
+		{
+			std::string message;
+			{
+				LaneScope scope(l);
+				err = synchronizeLane();
+				if (err) message = g.lastError;
+			}
+			if (err) g.lastError = message;
+		}
+	return err;
 }
 
 int srpcuClearPlanes(uint32_t* color, float* depth, size_t nPixels)
@@ -875,12 +953,11 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 	return 0;
 }
 
-void srpcuGetStats(SrpdStats* out, unsigned long long* launches, unsigned long long* h2d, unsigned long long* d2h)
+static void addLaneStats(SrpdStats* out, unsigned long long* launches, unsigned long long* h2d, unsigned long long* d2h)
 {
-	memset(out, 0, sizeof *out);
-	if (launches) *launches = g.launches;
-	if (h2d) *h2d = g.h2d;
-	if (d2h) *d2h = g.d2h;
+	if (launches) *launches += g.launches;
+	if (h2d) *h2d += g.h2d;
+	if (d2h) *d2h += g.d2h;
 	if (!g.ready)
 		return;
 	cudaMemcpyAsync(g.statsHost, g.stats, sizeof(SrpdStats) * SRPD_STATS_SLOTS, cudaMemcpyDeviceToHost, g.stream);
@@ -895,14 +972,27 @@ void srpcuGetStats(SrpdStats* out, unsigned long long* launches, unsigned long l
 		out->overflow += g.statsHost[i].overflow;
 	}
 }
+/* counters summed over the lanes */
+void srpcuGetStats(SrpdStats* out, unsigned long long* launches, unsigned long long* h2d, unsigned long long* d2h)
+{
+	memset(out, 0, sizeof *out);
+	if (launches) *launches = 0;
+	if (h2d) *h2d = 0;
+	if (d2h) *d2h = 0;
+	for (int l = 0; l < SRPCU_MAX_LANES; l++)
+	{
+		LaneScope scope(l);
+		addLaneStats(out, launches, h2d, d2h);
+	}
+}
 
 /* Guard: 1 if a draw hit a record-pool limit since the previous call (synchronises).  The pools
  * are sized for the worst case of every sub-draw, so this is never expected; a draw that does
  * trip it leaves its framebuffer (and a pending clear) untouched, and the host reports it.
  * Only slot 0 of the counter array is used for this accounting. */
-int srpcuTakeOverflow(void)
+static int takeLaneOverflow(void)
 {
-	static unsigned long long seen = 0;
+	unsigned long long& seen = g.guardSeen;
 	if (!g.ready)
 		return 0;
 	cudaMemcpyAsync(&g.statsHost[0].overflow, &g.stats[0].overflow, sizeof(unsigned long long), cudaMemcpyDeviceToHost, g.stream);
@@ -910,6 +1000,16 @@ int srpcuTakeOverflow(void)
 	const unsigned long long now = g.statsHost[0].overflow;
 	const int fresh = now > seen;
 	seen = now;
+	return fresh;
+}
+int srpcuTakeOverflow(void)
+{
+	int fresh = 0;
+	for (int l = 0; l < SRPCU_MAX_LANES; l++)
+	{
+		LaneScope scope(l);
+		fresh |= takeLaneOverflow();
+	}
 	return fresh;
 }
 
@@ -1002,9 +1102,11 @@ int srpcuStreamWaitFlag(const uint32_t* flag, uint32_t value)
 /* per-stage device time: enable, run draws, collect {geometry, binning, tiles} in ms */
 void srpcuSetProfiling(int on)
 {
-	g.profile = on != 0;
+	gProfile = on != 0;
+	for (int l = 0; l < SRPCU_MAX_LANES; l++)
+		gLanes[l].profile = gProfile;
 }
-unsigned long long srpcuCollectStageTimes(double outMs[3])
+static unsigned long long collectLaneStageTimes(double outMs[3])
 {
 	if (g.ready)
 	{
@@ -1027,18 +1129,39 @@ unsigned long long srpcuCollectStageTimes(double outMs[3])
 	g.stageDraws = 0;
 	return n;
 }
+unsigned long long srpcuCollectStageTimes(double outMs[3])
+{
+	unsigned long long n = 0;
+	outMs[0] = outMs[1] = outMs[2] = 0;
+	for (int l = 0; l < SRPCU_MAX_LANES; l++)
+	{
+		LaneScope scope(l);
+		double ms[3];
+		n += collectLaneStageTimes(ms);
+		for (int k = 0; k < 3; k++) outMs[k] += ms[k];
+	}
+	return n;
+}
 
-void srpcuResetStats(void)
+static void resetLaneStats(void)
 {
 	g.launches = 0; g.h2d = 0; g.d2h = 0;
 	if (g.ready)
 	{
 		/* keep the overflow counter monotonic (srpcuTakeOverflow compares against the
 		 * last value it saw), zero everything else */
-		srpcuTakeOverflow();
+		takeLaneOverflow();
 		cudaMemsetAsync(g.stats, 0, sizeof(SrpdStats) * SRPD_STATS_SLOTS, g.stream);
 		cudaMemcpyAsync(&g.stats[0].overflow, &g.statsHost[0].overflow, sizeof(unsigned long long), cudaMemcpyHostToDevice, g.stream);
 		cudaStreamSynchronize(g.stream);
+	}
+}
+void srpcuResetStats(void)
+{
+	for (int l = 0; l < SRPCU_MAX_LANES; l++)
+	{
+		LaneScope scope(l);
+		resetLaneStats();
 	}
 }
 

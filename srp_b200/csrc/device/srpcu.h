@@ -34,7 +34,16 @@ int srpcuUpload(void* dst, const void* src, size_t bytes, void* lastUse);
 int srpcuUploadInStream(void* dst, const void* src, size_t bytes);   /* on the submission stream; enqueue only */
 int srpcuRecordEvent(void* event);                                  /* on the submission stream */
 int srpcuDownload(void* dstHost, const void* srcDevice, size_t bytes);   /* enqueue only */
-int srpcuSynchronize(void);
+int srpcuSynchronize(void);                                         /* every lane */
+
+/* Lanes: SRPCU_MAX_LANES independent submission states (stream + scratch pools + staging).  Work
+ * enqueued on different lanes is unordered and overlaps on the device; within a lane it runs in
+ * order.  All entry points act on the current lane unless they say otherwise. */
+#define SRPCU_MAX_LANES 4
+int srpcuSetLane(int lane);                                         /* 0 on success */
+int srpcuLane(void);
+int srpcuLaneCount(void);
+int srpcuOrderBehindLane(int other);     /* what `other` has enqueued so far happens before the current lane's later work */
 
 /* Apply a pending clear to real memory: colour 0, depth -1 (stencil untouched). */
 int srpcuClearPlanes(uint32_t* color, float* depth, size_t nPixels);

@@ -22,6 +22,17 @@ size_t srpB200TileHeight(void) { return (size_t) srpcuTileHeight(); }
 const char* srpB200Version(void) { return srpcuVersion(); }
 void srpB200SetDevice(int device) { srpcuSetDevice(device); }
 void* srpB200Stream(void) { return srpcuStream(); }
+int srpB200SetLane(int lane)
+{
+	if (srpcuSetLane(lane))
+	{
+		srpMessage(SRP_MESSAGE_ERROR, SRP_MESSAGE_SEVERITY_HIGH, __func__, "lane %d does not exist (0..%d)", lane, srpcuLaneCount() - 1);
+		return 1;
+	}
+	return 0;
+}
+int srpB200GetLane(void) { return srpcuLane(); }
+int srpB200LaneCount(void) { return srpcuLaneCount(); }
 
 /* ---- multi-GPU plumbing: peer memory and stream-ordered flags (include/srp_b200.h) ---- */
 void* srpB200DeviceAlloc(size_t bytes) { return srpcuMalloc(bytes); }

@@ -43,6 +43,7 @@ static SRPFramebuffer* newFramebuffer(size_t width, size_t height, void* dColor,
 	SRPFramebufferImpl* fb = calloc(1, sizeof *fb);
 	if (!fb) abort();
 	fb->magic = SRP_FB_MAGIC;
+	fb->lane = -1;      /* nothing enqueued yet (the planes are zero-filled synchronously) */
 	fb->pub.width = width;
 	fb->pub.height = height;
 	fb->pub.size = width * height;
@@ -146,8 +147,11 @@ void srpFramebufferAfterSkippedDraw(const SRPFramebuffer* pub)
 	/* (mirrorStale stays set: only srp_io.c looks at it, and a redundant download is harmless) */
 }
 
+static void enterLane(SRPFramebufferImpl* fb);
+
 static void enqueueDownload(SRPFramebufferImpl* fb, int planes)
 {
+	enterLane(fb);
 	materializeClear(fb);
 	const size_t n = fb->pub.size;
 	int err = 0;
@@ -191,6 +195,7 @@ void srpB200FramebufferDownloadAsync(const SRPFramebuffer* pub)
 		srpFatalMessage(__func__, "%s", srpcuLastError());
 		return;
 	}
+	enterLane(fb);
 	materializeClear(fb);
 	const int planes = gMirrorPlanes;
 	const SrpcuMirror m = { (planes & SRP_B200_MIRROR_COLOR) ? fb->pub.color : NULL,
@@ -225,8 +230,22 @@ void srpB200FramebufferFence(const SRPFramebuffer* pub)
 		srpFramebufferBeforeWrite(fb);
 }
 
+/* A framebuffer belongs to the lane that touched it last; when another lane takes it over, that
+ * lane is ordered behind everything the previous one has enqueued (srp_b200.h: srpB200SetLane) */
+static void enterLane(SRPFramebufferImpl* fb)
+{
+	const int lane = srpcuLane();
+	if (fb->lane != lane)
+	{
+		if (srpcuOrderBehindLane(fb->lane))
+			srpFatalMessage("srpB200SetLane", "%s", srpcuLastError());
+		fb->lane = lane;
+	}
+}
+
 void srpFramebufferBeforeWrite(SRPFramebufferImpl* fb)
 {
+	enterLane(fb);
 	if (fb->downloadInFlight && srpcuStreamWaitEvent(fb->downloadEvent))
 		srpFatalMessage("srpDraw", "%s", srpcuLastError());
 }

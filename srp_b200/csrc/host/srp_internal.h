@@ -46,6 +46,7 @@ typedef struct SRPFramebufferImpl
 	bool stencilTouched;        /* a stencil-enabled draw ran since the last download */
 	bool downloadInFlight;      /* srpB200FramebufferDownloadAsync not yet waited for */
 	void* downloadEvent;        /* recorded behind the asynchronous download's copies */
+	int lane;                   /* lane whose stream the last work on the planes was enqueued on */
 } SRPFramebufferImpl;
 #define SRP_FB_MAGIC 0x53524246u   /* "SRBF" */
 

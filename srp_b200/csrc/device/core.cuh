@@ -427,15 +427,37 @@ SRP_HD void srpdLineSegment(const SrpdState& st, const SrpdLineSetup& ln, float&
 	seg.w[6] = srpdF2U(ln.zw[0]); seg.w[7] = srpdF2U(ln.zw[1]);
 	seg.w[8] = srpdF2U(ln.invW[0]); seg.w[9] = srpdF2U(ln.invW[1]);
 	seg.w[10] = srpdF2U(t);
-	int x0 = 1 << 30, y0 = 1 << 30, x1 = -1, y1 = -1;
-	const long long W = st.width, total = (long long) st.width * st.height;
-	/* a fixed trip count with the body under `k < n`: the lanes of a warp (one line each, of
-	 * different lengths) stay together instead of peeling off one by one (measured: two lanes
-	 * active in the data-dependent loop) */
+	/* The chain: n - 1 float additions per axis (line.c:72-74).  Adding one constant over and over
+	 * is monotone, and so is rounding: every fragment's pixel lies between the pixels of the
+	 * segment's first and last fragment, so the exact box needs two roundings per axis instead of
+	 * one per fragment.  A fixed trip count with the body under `k < n`: the lanes of a warp (one
+	 * line each, of different lengths) stay together. */
+	const float xs = x, ys = y;
+	float xl = x, yl = y;
 	for (int k = 0; k < SRPD_LINE_SEG; k++)
 		if (k < n)
 		{
-			const int ix = srpdRoundToInt(x), iy = srpdRoundToInt(y);
+			xl = x; yl = y;
+			x = SRP_FADD(x, ln.xInc);
+			y = SRP_FADD(y, ln.yInc);
+			t = SRP_FADD(t, ln.tInc);
+		}
+	int x0, y0, x1, y1;
+	{
+		const int ax = srpdRoundToInt(xs), ay = srpdRoundToInt(ys), bx = srpdRoundToInt(xl), by = srpdRoundToInt(yl);
+		x0 = ax < bx ? ax : bx; x1 = ax < bx ? bx : ax;
+		y0 = ay < by ? ay : by; y1 = ay < by ? by : ay;
+	}
+	if (x0 < 0 || y0 < 0 || x1 >= st.width || y1 >= st.height)
+	{
+		/* the segment touches the framebuffer's border: fragment by fragment, with the reference's
+		 * unchecked y*W + x index (a fragment with x == width lands on the next row, App. B-1) */
+		x0 = 1 << 30; y0 = 1 << 30; x1 = -1; y1 = -1;
+		const long long W = st.width, total = (long long) st.width * st.height;
+		float fx = xs, fy = ys;
+		for (int k = 0; k < n; k++)
+		{
+			const int ix = srpdRoundToInt(fx), iy = srpdRoundToInt(fy);
 			const long long idx = (long long) iy * W + ix;
 			if (idx >= 0 && idx < total)
 			{
@@ -445,10 +467,10 @@ SRP_HD void srpdLineSegment(const SrpdState& st, const SrpdLineSetup& ln, float&
 				x0 = px < x0 ? px : x0; x1 = px > x1 ? px : x1;
 				y0 = py < y0 ? py : y0; y1 = py > y1 ? py : y1;
 			}
-			x = SRP_FADD(x, ln.xInc);
-			y = SRP_FADD(y, ln.yInc);
-			t = SRP_FADD(t, ln.tInc);
+			fx = SRP_FADD(fx, ln.xInc);
+			fy = SRP_FADD(fy, ln.yInc);
 		}
+	}
 	seg.any = x1 >= 0;
 	seg.minX = (uint16_t) (seg.any ? x0 : 0); seg.maxX = (uint16_t) (seg.any ? x1 + 1 : 0);
 	seg.minY = (uint16_t) (seg.any ? y0 : 0); seg.maxY = (uint16_t) (seg.any ? y1 + 1 : 0);

@@ -567,49 +567,74 @@ __device__ __forceinline__ void visitTriangles(
 }
 
 /* rasterizeLine for the warp tile, reference line.c:34-77.  A record is a segment of
- * <= SRPD_LINE_SEG (16) consecutive DDA fragments with the chain state at its first one.  A pass
- * takes TWO records: lanes 0..15 hold the fragments of the first, lanes 16..31 of the second.
- * Lane k of a half walks the chain to fragment k -- k float additions per coordinate, exactly
- * the reference's sequence, all fragments side by side -- and rounds it to its pixel once.  A
- * fragment that lands in this warp's tile is shaded by the lane that walked to it, on the pixel's
- * state in shared memory; a fragment is placed through its linear index y*W + x, which is also
- * how the reference's unchecked indexing wraps x == width onto the next row (App. B-1).
- * Fragments of the pass that share a pixel run in lane order = (record, DDA) order.  Must be
- * called by all 32 lanes; `recB` may be null. */
-static_assert(SRPD_LINE_SEG <= 16, "two segments per pass: one lane per fragment of a segment");
+ * <= SRPD_LINE_SEG (16) consecutive DDA fragments with the chain state at its first one.  A step
+ * is up to 32 records; their fragments -- 1 to 16 each -- are numbered in (record, DDA) order by a
+ * warp scan over the records' fragment counts and taken 32 per pass, ONE LANE PER FRAGMENT
+ * whichever records they belong to (a million two-pixel lines fill the warp as well as a few long
+ * ones).  A lane finds its fragment's record by bisection over the scan, walks the chain to its
+ * fragment -- k float additions per coordinate, exactly the reference's sequence -- and rounds it
+ * to its pixel once.  A fragment that lands in this warp's tile is shaded by the lane that
+ * walked to it, on the pixel's state in shared memory; a fragment is placed through its linear
+ * index y*W + x, which is also how the reference's unchecked indexing wraps x == width onto the
+ * next row (App. B-1).  Fragments of a pass that share a pixel run in lane order = (record, DDA)
+ * order.  Must be called by all 32 lanes. */
 __device__ __forceinline__ void visitLines(
-	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* recA, uint32_t idBaseA, const unsigned char* recB, uint32_t idBaseB,
-	WarpTile& wt, int tx0, int ty0, uint32_t& dirty, FragCounters& cnt, int lane)
+	const SrpdTileArgs& a, const SrpdFrame& fr, const unsigned char* records, WarpTile& wt, int head, int n,
+	int tx0, int ty0, uint32_t& dirty, FragCounters& cnt, int lane)
 {
-	const unsigned char* rec = lane < 16 ? recA : recB;
-	const uint32_t idBase = lane < 16 ? idBaseA : idBaseB;
-	const int k = lane & 15;
-	bool inTile = false;
-	int lx = 0, ly = 0, myX = 0, myY = 0;
-	float t = 0.f;
-	uint4 q1 = make_uint4(0u, 0u, 0u, 0u), q2 = q1, q3 = q1;
-	if (rec != nullptr)
+	uint32_t myCount = 0u;
+	if (lane < n)
+		myCount = __ldg((const uint32_t*) (records + (size_t) wt.ring[(head + lane) & (SRPD_RING - 1)].z * a.recStride) + 5);
+	uint32_t incl = myCount;
+	#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
 	{
-		const uint4* h = (const uint4*) rec;
-		const uint4 q0 = __ldg(h + 0);
-		q1 = __ldg(h + 1); q2 = __ldg(h + 2); q3 = __ldg(h + 3);
-		float fx = __uint_as_float(q0.x), fy = __uint_as_float(q0.y);
-		const float xInc = __uint_as_float(q0.z), yInc = __uint_as_float(q0.w);
-		const float tInc = __uint_as_float(q1.x);
-		const int count = (int) q1.y;
-		t = __uint_as_float(q2.z);
-		const long long W = a.d.st.width;
-		/* lane k of the half: k steps of the chain */
-		for (int i = 0; i < k && i + 1 < count; i++)
+		const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+		if (lane >= d) incl += v;
+	}
+	const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+	const long long W = a.d.st.width;
+	for (uint32_t f0 = 0; f0 < total; f0 += 32u)
+	{
+		const uint32_t f = f0 + (uint32_t) lane;
+		const bool have = f < total;
+		/* the record of fragment f: the first one whose inclusive count exceeds f */
+		int e = 0;
+		#pragma unroll
+		for (int step = 16; step > 0; step >>= 1)
 		{
-			fx = __fadd_rn(fx, xInc);
-			fy = __fadd_rn(fy, yInc);
-			t = __fadd_rn(t, tInc);
+			const uint32_t v = __shfl_sync(0xFFFFFFFFu, incl, e + step - 1);
+			if (v <= f) e += step;
 		}
-		myX = srpdRoundToInt(fx); myY = srpdRoundToInt(fy);
-		/* does my fragment land in this warp's tile? */
-		if (k < count)
+		e = min(e, 31);
+		const uint32_t inclE = __shfl_sync(0xFFFFFFFFu, incl, e), countE = __shfl_sync(0xFFFFFFFFu, myCount, e);
+		bool inTile = false;
+		int lx = 0, ly = 0, myX = 0, myY = 0;
+		float t = 0.f;
+		uint4 q1 = make_uint4(0u, 0u, 0u, 0u), q2 = q1, q3 = q1;
+		const unsigned char* rec = nullptr;
+		uint32_t idBase = 0u;
+		if (have)
 		{
+			const int k = (int) (f - (inclE - countE));      /* my fragment's place in its segment */
+			const uint4 ent = wt.ring[(head + e) & (SRPD_RING - 1)];
+			rec = records + (size_t) ent.z * a.recStride;
+			idBase = ent.w;
+			const uint4* h = (const uint4*) rec;
+			const uint4 q0 = __ldg(h + 0);
+			q1 = __ldg(h + 1); q2 = __ldg(h + 2); q3 = __ldg(h + 3);
+			float fx = __uint_as_float(q0.x), fy = __uint_as_float(q0.y);
+			const float xInc = __uint_as_float(q0.z), yInc = __uint_as_float(q0.w);
+			const float tInc = __uint_as_float(q1.x);
+			t = __uint_as_float(q2.z);
+			for (int i = 0; i < k; i++)
+			{
+				fx = __fadd_rn(fx, xInc);
+				fy = __fadd_rn(fy, yInc);
+				t = __fadd_rn(t, tInc);
+			}
+			myX = srpdRoundToInt(fx); myY = srpdRoundToInt(fy);
+			/* does my fragment land in this warp's tile? */
 			const long long idx = (long long) myY * W + myX;
 			if (idx >= 0 && idx < W * (long long) a.d.st.height)
 			{
@@ -619,30 +644,31 @@ __device__ __forceinline__ void visitLines(
 				lx = pxl - tx0; ly = pyl - ty0;
 			}
 		}
-	}
-	if (!__any_sync(0xFFFFFFFFu, inTile))
-		return;
-	uint32_t turns;
-	const uint32_t turn = fragmentTurn(inTile ? (uint32_t) (ly * SRPD_WT_W + lx) : (uint32_t) (SRPD_WT_PIXELS + lane), lane, turns);
-	for (uint32_t r = 0; r < turns; r++)
-	{
-		if (inTile && turn == r)
+		if (!__any_sync(0xFFFFFFFFu, inTile))
+			continue;
+		uint32_t turns;
+		const uint32_t turn = fragmentTurn(inTile ? (uint32_t) (ly * SRPD_WT_W + lx) : (uint32_t) (SRPD_WT_PIXELS + lane), lane, turns);
+		for (uint32_t r = 0; r < turns; r++)
 		{
-			const float zw0 = __uint_as_float(q1.z), zw1 = __uint_as_float(q1.w);
-			const float iw0 = __uint_as_float(q2.x), iw1 = __uint_as_float(q2.y);
-			const float w0 = __fsub_rn(1.0f, t);
-			const float wgt[2] = { w0, t };
-			/* interpolateDepthAndWLine, interpolation.c:49-60 */
-			const float recW = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(iw0, w0), __fmul_rn(iw1, t)));
-			const float depth = __fadd_rn(__fmul_rn(zw0, w0), __fmul_rn(zw1, t));
-			const int p = pixelEntry(lx, ly);
-			PixelRef px;
-			px.color = wt.color + p; px.depth = wt.depth + p; px.stencil = wt.stencil + stencilEntry(lx, ly);
-			emitFragment<2, 0>(a.d.st, fr, px, dirty, cnt, myX, myY, (float) ((double) myX + 0.5), (float) ((double) myY + 0.5),
-			                depth, recW, recW, true, q3.w + idBase, rec + SRPD_REC_HEADER_BYTES, wgt);
+			if (inTile && turn == r)
+			{
+				const float zw0 = __uint_as_float(q1.z), zw1 = __uint_as_float(q1.w);
+				const float iw0 = __uint_as_float(q2.x), iw1 = __uint_as_float(q2.y);
+				const float w0 = __fsub_rn(1.0f, t);
+				const float wgt[2] = { w0, t };
+				/* interpolateDepthAndWLine, interpolation.c:49-60 */
+				const float recW = __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(iw0, w0), __fmul_rn(iw1, t)));
+				const float depth = __fadd_rn(__fmul_rn(zw0, w0), __fmul_rn(zw1, t));
+				const int p = pixelEntry(lx, ly);
+				PixelRef px;
+				px.color = wt.color + p; px.depth = wt.depth + p; px.stencil = wt.stencil + stencilEntry(lx, ly);
+				emitFragment<2, 0>(a.d.st, fr, px, dirty, cnt, myX, myY, (float) ((double) myX + 0.5), (float) ((double) myY + 0.5),
+				                depth, recW, recW, true, q3.w + idBase, rec + SRPD_REC_HEADER_BYTES, wgt);
+			}
+			if (turns > 1u)
+				__syncwarp();
 		}
-		if (turns > 1u)
-			__syncwarp();
+		__syncwarp();      /* the next pass sees these fragments' pixels */
 	}
 }
 
@@ -961,15 +987,7 @@ __device__ __forceinline__ void processWarpTile(
 		if constexpr (KIND == SRPD_KIND_TRIANGLE)
 			visitTriangles<SIMPLE>(a, fr, records, wt, head, n, tx0, ty0, dirty, cnt, lane);
 		else if constexpr (KIND == SRPD_KIND_LINE)
-			for (int k = 0; k < n; k += 2)
-			{
-				const uint4 eA = wt.ring[(head + k) & (SRPD_RING - 1)];
-				const uint4 eB = wt.ring[(head + k + 1) & (SRPD_RING - 1)];
-				const unsigned char* recA = records + (size_t) eA.z * a.recStride;
-				const unsigned char* recB = k + 1 < n ? records + (size_t) eB.z * a.recStride : nullptr;
-				visitLines(a, fr, recA, eA.w, recB, eB.w, wt, tx0, ty0, dirty, cnt, lane);
-				__syncwarp();      /* the next primitives see these ones' pixels */
-			}
+			visitLines(a, fr, records, wt, head, n, tx0, ty0, dirty, cnt, lane);
 		else
 			visitPoints(a, fr, records, wt, head, n, tx0, ty0, dirty, cnt, lane);
 		head = (head + n) & (SRPD_RING - 1);

@@ -361,8 +361,10 @@ struct ClipSlot
 	uint8_t cur, pad[3];                        /* which list holds it                                 */
 };                                              /* followed by SRPD_CLIP_NEW_VERTS varyings blobs       */
 
+struct LineSlot;
 __host__ __device__ inline size_t clipSlotStride(int slotSize)
 {
+	/* (a line's slot -- LineSlot + two blobs -- fits as well: static_assert below) */
 	size_t b = (sizeof(ClipSlot) + (size_t) SRPD_CLIP_NEW_VERTS * slotSize + 15) & ~(size_t) 15;
 	if (b % 128 == 0) b += 16;                  /* keep the slots of neighbouring lanes on different banks */
 	return b;
@@ -565,18 +567,18 @@ __device__ __forceinline__ ClipResult clipChunk(
 	return res;
 }
 
-/* clipLine (Liang-Barsky) + setup, reference clipping.c:139-183 */
-template <bool WRITE>
-__device__ void processLine(Emitter& em, const SrpdState& st, const SrpdPos p[2], const unsigned char* const vary[2])
+/* clipLine (Liang-Barsky), reference clipping.c:139-183: false if nothing of the line is left;
+ * otherwise cp / cv are the end points to set up (originals, or blends kept in `a` / `b`) */
+__device__ __forceinline__ bool clipLineEnds(const SrpdState& st, const SrpdPos p[2], const unsigned char* const vary[2],
+                                             ClipVert& a, ClipVert& b, SrpdPos cp[2], const unsigned char* cv[2])
 {
+	cp[0] = p[0]; cp[1] = p[1];
+	cv[0] = vary[0]; cv[1] = vary[1];
 	const uint32_t c0 = srpdClipCode(p[0]), c1 = srpdClipCode(p[1]);
 	if ((c0 | c1) == 0)
-	{
-		emitLine<WRITE>(em, st, p, vary);
-		return;
-	}
+		return true;
 	if ((c0 & c1) != 0)
-		return;
+		return false;
 
 	float t0 = 0.f, t1 = 1.f;
 	for (int plane = 0; plane < 6; plane++)
@@ -584,7 +586,7 @@ __device__ void processLine(Emitter& em, const SrpdState& st, const SrpdPos p[2]
 		const float da = srpdPlaneDistance(p[0], plane);
 		const float db = srpdPlaneDistance(p[1], plane);
 		if (da < 0 && db < 0)
-			return;
+			return false;
 		if (da < 0 || db < 0)
 		{
 			const float diff = SRP_FSUB(da, db);
@@ -596,12 +598,9 @@ __device__ void processLine(Emitter& em, const SrpdState& st, const SrpdPos p[2]
 			else
 				t1 = (t1 > t) ? t : t1;     /* MIN(t1, t) */
 			if (t0 > t1)
-				return;
+				return false;
 		}
 	}
-	ClipVert a, b;
-	SrpdPos cp[2] = { p[0], p[1] };
-	const unsigned char* cv[2] = { vary[0], vary[1] };
 	if (t0 > 0)
 	{
 		a.p = srpdBlendPos(p[0], p[1], t0);
@@ -614,8 +613,149 @@ __device__ void processLine(Emitter& em, const SrpdState& st, const SrpdPos p[2]
 		srpdBlendVaryings(st, vary[0], vary[1], SRP_FSUB(1.0f, t1), t1, b.vary);
 		cp[1] = b.p; cv[1] = b.vary;
 	}
+	return true;
+}
+
+template <bool WRITE>
+__device__ void processLine(Emitter& em, const SrpdState& st, const SrpdPos p[2], const unsigned char* const vary[2])
+{
+	ClipVert a, b;
+	SrpdPos cp[2];
+	const unsigned char* cv[2];
+	if (!clipLineEnds(st, p, vary, a, b, cp, cv))
+		return;
 	const unsigned char* const cvc[2] = { cv[0], cv[1] };
 	emitLine<WRITE>(em, st, cp, cvc);
+}
+
+/* ---- lines in the clipper pass ------------------------------------------------------------
+ * A line is one lane's work in the main pass: its DDA chain is serial (float additions,
+ * line.c:72-74) and so is the lane's walk over its 16-fragment segments.  That is fine for the
+ * short lines a mesh is made of and hopeless for a line that crosses the screen (240 segments
+ * while the other lanes of the warp wait): batches with a long line go to the clipper pass,
+ * where the line's segments are spread over the 32 lanes.  Every lane first clips and sets up
+ * its own line into a slot in shared memory (set-up + both varyings blobs as the records will
+ * hold them); short lines are then emitted by their lanes side by side, long lines one after
+ * the other by the whole warp: all lanes walk the chain through 32 segments together (the same
+ * additions in the same order -- what is serial stays serial, it is 3 FADDs per fragment), lane
+ * j keeps the state at the start of segment j and then boxes and writes that segment on its
+ * own.  Record slots and ids are the owner lane's, segment order is kept by a ballot. */
+struct LineSlot
+{
+	SrpdLineSetup ln;
+	uint32_t valid, pad;
+};                                              /* followed by the two varyings blobs of the records */
+constexpr int SRPD_LINE_SHORT_SEGS = 2;         /* lines of up to this many segments stay with their lane */
+static_assert(sizeof(LineSlot) <= sizeof(ClipSlot) && sizeof(LineSlot) % 8 == 0, "a line's slot lives in a clip slot");
+
+__device__ __forceinline__ int lineSegments(const SrpdLineSetup& ln) { return (ln.steps + 1 + SRPD_LINE_SEG - 1) / SRPD_LINE_SEG; }
+
+__device__ void prepareLine(const SrpdState& st, const SrpdPos p[2], const unsigned char* const vary[2], LineSlot& sl)
+{
+	ClipVert a, b;
+	SrpdPos cp[2];
+	const unsigned char* cv[2];
+	if (!clipLineEnds(st, p, vary, a, b, cp, cv))
+		return;
+	srpdSetupLine(st, cp, sl.ln);
+	unsigned char* blobs = reinterpret_cast<unsigned char*>(&sl + 1);
+	for (int k = 0; k < 2; k++)
+		storeBlob(st, cv[k], sl.ln.invW[k], true, blobs + k * st.slotSize);
+	sl.valid = 1u;
+}
+
+template <bool WRITE>
+__device__ __forceinline__ bool emitLineSegment(const Emitter& em, const SrpdState& st, const SrpdLineSegment& seg, const unsigned char* blobs,
+                                                uint32_t id, uint32_t slot)
+{
+	if (!WRITE)
+		return false;
+	Emitter one = em;
+	one.idBase = id; one.nEmit = 0u;
+	one.storeBase = slot; one.nStore = 0u;
+	one.overflow = false;
+	unsigned char* dst = beginRecord<true>(one, seg.w, seg.minX, seg.minY, seg.maxX, seg.maxY);
+	if (dst)
+		copyBlobWords(blobs, dst, 2 * st.slotSize);
+	return one.overflow;
+}
+
+/* count (WRITE = false: em.nEmit / em.nStore of the owner lanes) or write (em.idBase / em.storeBase
+ * are the owners' bases) the prepared lines of a batch; all 32 lanes */
+template <bool WRITE>
+__device__ __noinline__ void emitPreparedLines(Emitter& em, const SrpdState& st, const unsigned char* slots, size_t stride, int lane)
+{
+	const LineSlot& mine = *reinterpret_cast<const LineSlot*>(slots + (size_t) lane * stride);
+	const bool valid = mine.valid != 0u;
+	const bool isShort = valid && lineSegments(mine.ln) <= SRPD_LINE_SHORT_SEGS;
+	if (isShort)
+	{
+		const SrpdLineSetup ln = mine.ln;
+		const unsigned char* blobs = reinterpret_cast<const unsigned char*>(&mine + 1);
+		float x = ln.x0, y = ln.y0, t = 0.f;
+		const int total = ln.steps + 1;
+		uint32_t stored = 0u;
+		for (int i = 0; i < total; i += SRPD_LINE_SEG)
+		{
+			SrpdLineSegment seg;
+			const int n = total - i < SRPD_LINE_SEG ? total - i : SRPD_LINE_SEG;
+			srpdLineSegment(st, ln, x, y, t, n, seg);
+			if (!seg.any || (int) seg.maxY <= st.stripY0 || (int) seg.minY >= st.stripY1)
+				continue;
+			if (emitLineSegment<WRITE>(em, st, seg, blobs, em.idBase, em.storeBase + stored))
+				em.overflow = true;
+			stored++;
+		}
+		em.nEmit = 1u; em.nStore = stored;
+	}
+	__syncwarp();
+	for (uint32_t m = __ballot_sync(0xFFFFFFFFu, valid && !isShort); m != 0u; m &= m - 1u)
+	{
+		const int owner = __ffs(m) - 1;
+		const LineSlot& sl = *reinterpret_cast<const LineSlot*>(slots + (size_t) owner * stride);
+		const unsigned char* blobs = reinterpret_cast<const unsigned char*>(&sl + 1);
+		const SrpdLineSetup ln = sl.ln;
+		const uint32_t ownerId = __shfl_sync(0xFFFFFFFFu, em.idBase, owner), ownerStore = __shfl_sync(0xFFFFFFFFu, em.storeBase, owner);
+		const int total = ln.steps + 1;
+		const int nSeg = lineSegments(ln);
+		float x = ln.x0, y = ln.y0, t = 0.f;      /* the chain at the first fragment of the round's first segment: the same in every lane */
+		uint32_t stored = 0u;
+		bool overflow = false;
+		for (int s0 = 0; s0 < nSeg; s0 += 32)
+		{
+			const int here = nSeg - s0 < 32 ? nSeg - s0 : 32;
+			const int walk = (s0 + 32 < nSeg ? here : here - 1) * SRPD_LINE_SEG;      /* to the next round, or to the last segment's start */
+			float mx = x, my = y, mt = t;
+			for (int k = 0; ; k++)
+			{
+				if (k == lane * SRPD_LINE_SEG) { mx = x; my = y; mt = t; }
+				if (k == walk)
+					break;
+				x = SRP_FADD(x, ln.xInc);
+				y = SRP_FADD(y, ln.yInc);
+				t = SRP_FADD(t, ln.tInc);
+			}
+			bool keep = false;
+			SrpdLineSegment seg;
+			if (lane < here)
+			{
+				const int i = (s0 + lane) * SRPD_LINE_SEG;
+				const int n = total - i < SRPD_LINE_SEG ? total - i : SRPD_LINE_SEG;
+				srpdLineSegment(st, ln, mx, my, mt, n, seg);
+				keep = seg.any && !((int) seg.maxY <= st.stripY0 || (int) seg.minY >= st.stripY1);
+			}
+			const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, keep);
+			if (keep)
+				overflow |= emitLineSegment<WRITE>(em, st, seg, blobs, ownerId, ownerStore + stored + (uint32_t) __popc(ballot & ((1u << lane) - 1u)));
+			stored += (uint32_t) __popc(ballot);
+		}
+		if (__any_sync(0xFFFFFFFFu, overflow))
+			em.overflow = true;
+		if (lane == owner)
+		{
+			em.nEmit = 1u; em.nStore = stored;
+		}
+	}
 }
 
 /* Lines, points and unclipped triangles in polygon modes LINE / POINT go through here.  Deliberately NOT inlined
@@ -821,14 +961,42 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	}
 	const bool needsClip = active && nv == 3 && codeAnd == 0u && codeOr != 0u;
 	const uint32_t clipMask = __ballot_sync(0xFFFFFFFFu, needsClip);
-	if (!CLIPPER && clipMask != 0u)
+	/* a line that is clipped or long (an estimate is enough: either pass emits the same records) */
+	bool longLine = false;
+	if (!CLIPPER && nv == 2 && active && codeAnd == 0u)
 	{
-		/* a triangle of this batch crosses a clip plane: the whole batch goes to the clipper pass */
+		longLine = codeOr != 0u;
+		if (!longLine)
+		{
+			const float ax = __fdividef(p[0].x, p[0].w), ay = __fdividef(p[0].y, p[0].w);
+			const float bx = __fdividef(p[1].x, p[1].w), by = __fdividef(p[1].y, p[1].w);
+			const float len = fmaxf(fabsf(bx - ax) * (float) st.width, fabsf(by - ay) * (float) st.height) * 0.5f;
+			longLine = !(len <= (float) (SRPD_LINE_SHORT_SEGS * SRPD_LINE_SEG));
+		}
+	}
+	if (!CLIPPER && (clipMask != 0u || __any_sync(0xFFFFFFFFu, longLine)))
+	{
+		/* a triangle of this batch crosses a clip plane, or one of its lines is long: the whole
+		 * batch goes to the clipper pass */
 		if (lane == 0)
 			a.deferList[atomicAdd(a.deferCount, 1u)] = batch;
 		continue;
 	}
-	if (active && codeAnd == 0u && !needsClip)
+	constexpr bool LINES_BY_WARP = CLIPPER;      /* emitPreparedLines */
+	if (LINES_BY_WARP && nv == 2)
+	{
+		LineSlot& sl = *reinterpret_cast<LineSlot*>(clipSlots + (size_t) lane * clipSlotStride(st.slotSize));
+		sl.valid = 0u;
+		if (active && codeAnd == 0u)
+		{
+			const SrpdPos sp[2] = { p[0], p[1] };
+			const unsigned char* const sv[2] = { vary[0], vary[1] };
+			prepareLine(st, sp, sv, sl);
+		}
+		__syncwarp();
+		emitPreparedLines<false>(em, st, clipSlots, clipSlotStride(st.slotSize), lane);
+	}
+	else if (active && codeAnd == 0u && !needsClip)
 	{
 		if (nv == 3 && st.polygonMode == SRP_POLYGON_MODE_FILL)
 		{
@@ -895,7 +1063,17 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 			atomicExch(a.abortFlag, 1u);
 		}
 	}
-	if (active && myStore > 0 && !needsClip)
+	if (LINES_BY_WARP && nv == 2)
+	{
+		em.nEmit = 0; em.nStore = 0;
+		emitPreparedLines<true>(em, st, clipSlots, clipSlotStride(st.slotSize), lane);
+		if (em.overflow)
+		{
+			atomicAdd(&a.stats->overflow, 1ull);
+			atomicExch(a.abortFlag, 1u);
+		}
+	}
+	else if (active && myStore > 0 && !needsClip)
 	{
 		em.nEmit = 0; em.nStore = 0;
 		if (fast.valid)

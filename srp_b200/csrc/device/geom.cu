@@ -111,7 +111,13 @@ struct Emitter
 	uint32_t nEmit, nStore;
 	uint32_t frame;
 	bool overflow;
+	/* tile-occupancy bits: normally set record by record (beginRecord); a lane that writes ONE record
+	 * in a converged warp may leave its (word, mask) here instead, and the warp then sets the bits of
+	 * all its lanes with one reduction per distinct word (srpdGeomKernel, step 5) */
+	bool deferOcc;
+	uint32_t occWord, occMask;
 };
+constexpr uint32_t SRPD_OCC_NONE = 0xFFFFFFFFu;
 
 __device__ __forceinline__ void copyBlobWords(const unsigned char* src, unsigned char* dst, int bytes)
 {
@@ -178,6 +184,14 @@ __device__ __forceinline__ unsigned char* beginRecord(Emitter& em, const uint32_
 	{
 		const uint32_t tx0 = x0 / SRPD_TILE_W, tx1 = (uint32_t) (x1 - 1) / SRPD_TILE_W;
 		const uint32_t ty0 = y0 / SRPD_TILE_H, ty1 = (uint32_t) (y1 - 1) / SRPD_TILE_H;
+		const uint32_t first = ty0 * em.a->tilesX + tx0, last = ty0 * em.a->tilesX + (tx1 < em.a->tilesX ? tx1 : em.a->tilesX - 1);
+		if (em.deferOcc && ty0 == ty1 && ty0 < em.a->tilesY && (first >> 5) == (last >> 5))
+		{
+			const uint32_t lo = first & 31u, hi = last & 31u;
+			em.occWord = first >> 5;
+			em.occMask = (hi == 31u ? 0xFFFFFFFFu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+		}
+		else
 		for (uint32_t ty = ty0; ty <= ty1 && ty < em.a->tilesY; ty++)
 		{
 			const uint32_t b0 = ty * em.a->tilesX + tx0, b1 = ty * em.a->tilesX + (tx1 < em.a->tilesX ? tx1 : em.a->tilesX - 1);
@@ -945,6 +959,7 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	em.bboxes = a.bboxes + (size_t) frame * a.recCapacity;
 	em.occupancy = a.occupancy + (size_t) frame * a.occWordsPerFrame;
 	em.idBase = 0; em.storeBase = 0; em.nEmit = 0; em.nStore = 0; em.overflow = false;
+	em.deferOcc = false; em.occWord = SRPD_OCC_NONE; em.occMask = 0u;
 	em.frame = frame;
 	FastTriangle fast;
 	fast.valid = false; fast.stored = false;
@@ -1077,7 +1092,10 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 	{
 		em.nEmit = 0; em.nStore = 0;
 		if (fast.valid)
+		{
+			em.deferOcc = true;
 			writeTriangle<true>(em, st, fast.s, fast.stored, vary);
+		}
 		else
 		{
 			Emitter slow = em;
@@ -1091,6 +1109,15 @@ srpdGeomKernel(const __grid_constant__ SrpdGeomArgs a)
 			atomicAdd(&a.stats->overflow, 1ull);
 			atomicExch(a.abortFlag, 1u);
 		}
+	}
+	/* occupancy bits of the batch's unclipped filled triangles: the triangles of a batch are
+	 * neighbours, so the lanes' bits fall into a word or two -- one reduction per distinct word and
+	 * nothing to wait for (a load-and-test per record stalled every batch for an L2 round trip) */
+	{
+		const uint32_t peers = __match_any_sync(0xFFFFFFFFu, em.occWord);
+		const uint32_t bits = __reduce_or_sync(peers, em.occMask);
+		if (em.occWord != SRPD_OCC_NONE && lane == __ffs(peers) - 1)
+			atomicOr(&em.occupancy[em.occWord], bits);
 	}
 	}   /* batch */
 }

@@ -319,6 +319,11 @@ srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 		if (__ballot_sync(0xFFFFFFFFu, !empty) == 0)
 			continue;
 		const uint32_t sx0 = rc & 0xFFu, sy0 = (rc >> 8) & 0xFFu, sx1 = (rc >> 16) & 0xFFu, sy1 = rc >> 24;
+		/* a list entry is the record's entry of the ordered view itself (box, slot, id prefix): the
+		 * tile kernel's scan of a list is then one coalesced stream, not a gather behind an index */
+		uint4 ent = make_uint4(0u, 0u, 0u, 0u);
+		if (!empty)
+			ent = a.ordered[rec];
 		/* which lanes of this step cover supertile s: one bit per lane */
 		if (!empty)
 			for (uint32_t sy = sy0; sy <= sy1; sy++)
@@ -333,7 +338,7 @@ srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 					const uint32_t s = sy * a.superX + sx;
 					const uint32_t pos = sCnt[s] + __popc(sMask[s] & ((1u << lane) - 1u));
 					if (pos < a.listCapacity)
-						a.listIds[pos] = rec;
+						a.listEntries[pos] = ent;
 				}
 		__syncwarp();
 		/* the last covering lane advances the cursor and clears the mask for the next step */
@@ -427,7 +432,7 @@ srpdBinFillWarpKernel(const __grid_constant__ SrpdBinArgs a)
 					cur = __shfl_sync(peers, cur, leader);
 					const uint32_t pos = cur + __popc(peers & lt);
 					if (pos < a.listCapacity)
-						a.listIds[pos] = r0 + (uint32_t) lo;
+						a.listEntries[pos] = a.ordered[r0 + (uint32_t) lo];
 					if (lane == leader)
 						cursor[s] += __popc(peers);
 				}

@@ -147,7 +147,7 @@ struct SrpdBinArgs
 	uint32_t* superTotals;            /* [nSuper] entries per supertile (scan pass 1 -> 2)*/
 	uint32_t* chunkCounts;            /* [nChunksMax][nSuper]                            */
 	uint32_t* superOffsets;           /* [nSuper + 1]                                    */
-	uint32_t* listIds;                /* [listCapacity] record indices, id order per supertile */
+	uint4* listEntries;               /* [listCapacity] copies of the ordered view's entries {box, slot, id prefix}, id order per supertile */
 	uint32_t listCapacity;
 	uint32_t* listOverflow;           /* zeroed per draw; set when the coarse lists do not fit listCapacity: the tile
 	                                     kernel then ignores them and lets every tile scan all records (slow, exact) */
@@ -169,7 +169,7 @@ struct SrpdTileArgs
 	uint32_t recStride;
 	const uint32_t* frameCounts;
 	const uint32_t* superOffsets;     /* nullptr: direct path, every tile scans all records */
-	const uint32_t* listIds;
+	const uint4* listEntries;
 	const uint32_t* listOverflow;     /* != 0: the coarse lists are incomplete, scan all records instead */
 	uint32_t superX;
 	uint32_t superShift;

@@ -935,13 +935,13 @@ __device__ __forceinline__ void processWarpTile(
 
 	/* candidate list of this tile */
 	uint32_t begin = 0, end;
-	const uint32_t* ids = nullptr;
+	const uint4* list = nullptr;      /* the supertile's list: copies of ordered-view entries */
 	if (a.superOffsets && *a.listOverflow == 0u)
 	{
 		const uint32_t s = ((uint32_t) tileY8 >> (a.superShift + 1)) * a.superX + ((uint32_t) tileX >> a.superShift);
 		begin = a.superOffsets[s];
 		end = a.superOffsets[s + 1];
-		ids = a.listIds;
+		list = a.listEntries;
 	}
 	else
 		end = a.frameCounts[2 * frame + 1];
@@ -969,8 +969,7 @@ __device__ __forceinline__ void processWarpTile(
 		uint4 ent = make_uint4(0u, 0u, 0u, 0u);
 		if (i < end)
 		{
-			const uint32_t rid = ids ? ids[i] : i;          /* position in primitive order */
-			ent = ordered[rid];                              /* {box, record slot, id prefix} */
+			ent = list ? list[i] : ordered[i];              /* {box, record slot, id prefix}, in primitive order */
 			const int x0 = (int) (ent.x & 0xFFFFu), y0b = (int) (ent.x >> 16);
 			const int x1 = (int) (ent.y & 0xFFFFu), y1b = (int) (ent.y >> 16);
 			hit = x0 < tx0 + SRPD_WT_W && x1 > tx0 && y0b < ty0 + SRPD_WT_H && y1b > ty0;

@@ -862,11 +862,11 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		if (!grow(g.chunkCounts, sizeof(uint32_t) * (size_t) ba.nChunksMax * nSuper)) return 1;
 		if (!grow(g.superOffsets, sizeof(uint32_t) * (nSuper + 1))) return 1;
 		if (!grow(g.superTotals, sizeof(uint32_t) * nSuper)) return 1;
-		if (!grow(g.listIds, sizeof(uint32_t) * (size_t) ba.listCapacity)) return 1;
+		if (!grow(g.listIds, sizeof(uint4) * (size_t) ba.listCapacity)) return 1;
 		ba.chunkCounts = (uint32_t*) g.chunkCounts.ptr;
 		ba.superOffsets = (uint32_t*) g.superOffsets.ptr;
 		ba.superTotals = (uint32_t*) g.superTotals.ptr;
-		ba.listIds = (uint32_t*) g.listIds.ptr;
+		ba.listEntries = (uint4*) g.listIds.ptr;
 		ba.listOverflow = (uint32_t*) g.scan.ptr + 0;
 		ba.needed = ga.needed;
 		ba.scanTicket = (uint32_t*) g.scan.ptr + 5;
@@ -876,7 +876,7 @@ int srpcuDraw(const SrpdDraw* dIn, const SrpdFrame* framesHost,
 		g.launches += 3;
 		CU(cudaGetLastError());
 		ta.superOffsets = ba.superOffsets;
-		ta.listIds = ba.listIds;
+		ta.listEntries = ba.listEntries;
 	}
 
 	{

@@ -105,7 +105,7 @@ srpdBinCountKernel(const __grid_constant__ SrpdBinArgs a)
 
 /* Scan pass 2 (run by the last CTA of pass 1): exclusive scan of the supertile totals ->
  * superOffsets (warp-shuffle scans: lanes, then the warp totals, one barrier pair per 256 supertiles) */
-constexpr int SRPD_SCAN_COL_WARPS = 8;
+constexpr int SRPD_SCAN_COL_WARPS = 16;
 __device__ __forceinline__ void scanSuperTotals(const SrpdBinArgs& a, uint32_t nSuper)
 {
 	__shared__ uint32_t sWarp[SRPD_SCAN_COL_WARPS];

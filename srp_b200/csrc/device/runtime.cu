@@ -301,9 +301,10 @@ int srpcuInit(void)
 	memset(g.hostNotes, 0, 64);
 	CU(cudaHostGetDevicePointer((void**) &g.hostNotesDev, g.hostNotes, 0));
 	{
-		/* scratch budget of one sub-draw: an eighth of the device memory unless told otherwise */
+		/* scratch budget of one sub-draw: a sixth of the device memory unless told otherwise (the
+		 * worst case of a million lines on a 4K framebuffer, 243 segment records each, is 29 GB) */
 		const int mb = envInt("SRP_B200_POOL_BUDGET_MB", 0);
-		g.poolBudget = mb > 0 ? (size_t) mb << 20 : prop.totalGlobalMem / 8;
+		g.poolBudget = mb > 0 ? (size_t) mb << 20 : prop.totalGlobalMem / 6;
 	}
 	CU(cudaMalloc(&g.stats, sizeof(SrpdStats) * SRPD_STATS_SLOTS));
 	CU(cudaMemset(g.stats, 0, sizeof(SrpdStats) * SRPD_STATS_SLOTS));

@@ -286,22 +286,33 @@ def strips(lib, torch, dist, stream, world, rank, prep, scene, steps, warm, sing
         prep.fb = fb
         prep.draw_all()
 
-    # (a) fused peer write
-    target = M.StripTarget(lib, scene.width, scene.height, ring=3, root=0)
+    # (a) fused peer write, consecutive frames on alternating lanes (the replicated geometry
+    # front-end of frame k+1 runs under frame k's tiles)
+    strip_lanes = max(1, min(4, int(lib.dll.srpB200LaneCount())))
+    target = M.StripTarget(lib, scene.width, scene.height, ring=strip_lanes, root=0, lanes=strip_lanes)
+    lane_streams = []
+    for l in range(strip_lanes):
+        lib.dll.srpB200SetLane(l)
+        lane_streams.append(torch.cuda.ExternalStream(lib.dll.srpB200Stream()))
+    lib.dll.srpB200SetLane(0)
     def run(n):
         for _ in range(n):
             target.render(draw_into)
             if rank == 0:
                 target.complete()
-    run(warm)
+    run(max(warm, 2 * strip_lanes))
     lib.dll.srpB200Finish()
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        e0.record(stream); run(steps); e1.record(stream)
+    s_ev = [torch.cuda.Event(enable_timing=True) for _ in lane_streams]
+    e_ev = [torch.cuda.Event(enable_timing=True) for _ in lane_streams]
+    for ev, st_ in zip(s_ev, lane_streams):
+        ev.record(st_)
+    run(steps)
+    for ev, st_ in zip(e_ev, lane_streams):
+        ev.record(st_)
     lib.dll.srpB200Finish()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    ms = max(a.elapsed_time(b) for a in s_ev for b in e_ev)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     exact = None
@@ -317,7 +328,7 @@ def strips(lib, torch, dist, stream, world, rank, prep, scene, steps, warm, sing
     out["fused_peer_write"] = {"frames_per_s": steps / (float(t[0]) / 1e3), "ms_per_frame": float(t[0]) / steps,
                                "bit_exact_vs_single_gpu": exact, "nvlink_bytes_per_frame": int(tb[0]),
                                "what": "tile kernels of ranks 1.. store their strips into rank 0's planes (CUDA IPC peer memory) as part of the tile "
-                                       "write-back; per frame and rank one flag store in rank 0's memory signals completion, ring of 3 framebuffers"}
+                                       f"write-back; per frame and rank one flag store in rank 0's memory signals completion; {strip_lanes} frames in flight (lanes), one framebuffer each", "frames_in_flight": strip_lanes}
 
     # (b) NCCL gather baseline
     th = int(lib.dll.srpB200TileHeight())

@@ -103,22 +103,29 @@ def device_plane_tensor(lib, fb, which: int) -> torch.Tensor:
 class StripTarget:
     """A ring of `ring` root-owned framebuffers that every rank renders its strip into.
 
-    Root: creates the framebuffers and a block of 32-bit flags -- flags[r] = frames rank r has
-    finished writing, flags[world] = frames the root has consumed -- and exports the three planes
-    of every framebuffer and the flags as CUDA IPC handles (srpB200IpcExport); `exchange` is any
-    function that hands the root's bytes to all ranks (a torch.distributed broadcast of objects,
-    over NCCL or gloo).  Other ranks: open the handles and wrap the mapped planes in
-    framebuffers of their own (srpB200NewFramebufferOnDevice): the tile kernel's write-back then
-    stores into the root's memory.
+    Root: creates the framebuffers and a block of 32-bit flags per ring slot -- flags[slot][r] =
+    frames rank r has finished writing into the slot (as frame number + 1), flags[slot][world] =
+    frames the root has consumed from it -- and exports the three planes of every framebuffer and
+    the flags as CUDA IPC handles (srpB200IpcExport); `exchange` is any function that hands the
+    root's bytes to all ranks (a torch.distributed broadcast of objects, over NCCL or gloo).
+    Other ranks: open the handles and wrap the mapped planes in framebuffers of their own
+    (srpB200NewFramebufferOnDevice): the tile kernel's write-back then stores into the root's
+    memory.
 
-    Frame k (every rank):  wait until the root has consumed frame k - ring (its slot is free),
-    srpB200SetRowRange(own rows), clear + draw into slot k % ring, signal flags[rank] = k + 1.
-    Root, additionally: wait for flags[r] >= k + 1 of every rank -- the frame is complete in
-    its memory --, run `consume` (e.g. an asynchronous download), signal flags[world] = k + 1.
-    Everything is enqueued on the library's stream; nothing blocks the host."""
+    Frame k (every rank), on lane k % lanes and in slot k % ring (`ring` is a multiple of `lanes`,
+    so a slot always lives on one lane and its flags only ever grow): wait until the root has
+    consumed the slot's previous frame, srpB200SetRowRange(own rows), clear + draw into the slot,
+    signal flags[slot][rank] = k + 1.  Root, additionally: wait for flags[slot][r] >= k + 1 of
+    every rank -- the frame is complete in its memory --, run `consume` (e.g. an asynchronous
+    download), signal flags[slot][world] = k + 1.  With lanes > 1 consecutive frames are in flight
+    side by side: the geometry front-end, which every rank runs in full, overlaps the previous
+    frame's tiles.  Everything is enqueued on the lanes' streams; nothing blocks the host."""
 
-    def __init__(self, lib, width, height, ring=2, root=0, group=None, exchange=None):
+    def __init__(self, lib, width, height, ring=2, root=0, group=None, exchange=None, lanes=1):
+        if lanes < 1 or ring % lanes:
+            raise ValueError("ring must be a multiple of lanes")
         self.lib, self.width, self.height, self.ring, self.root, self.group = lib, width, height, ring, root, group
+        self.lanes = lanes
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.tile_h = int(lib.dll.srpB200TileHeight())
@@ -128,7 +135,7 @@ class StripTarget:
         payload = None
         if self.rank == root:
             self.fbs = [lib.framebuffer(width, height) for _ in range(ring)]
-            self.flags = d.srpB200DeviceAlloc(4 * (self.world + 1))
+            self.flags = d.srpB200DeviceAlloc(4 * (self.world + 1) * ring)
             if not self.flags:
                 raise RuntimeError("srpB200DeviceAlloc failed")
             handles = []
@@ -169,38 +176,50 @@ class StripTarget:
         self._mapped.append(p)
         return p
 
-    def flag_ptr(self, index: int) -> int:
-        return int(self.flags) + 4 * index
+    def flag_ptr(self, slot: int, index: int) -> int:
+        return int(self.flags) + 4 * (slot * (self.world + 1) + index)
 
     def render(self, draw):
         """enqueue one frame: `draw(fb)` issues srpFramebufferClear + the frame's draws into fb.
         Returns the framebuffer that will hold the complete frame on the root."""
         d = self.lib.dll
         k = self.frame
-        fb = self.fbs[k % self.ring]
-        if k >= self.ring:
-            d.srpB200StreamWait(self.flag_ptr(self.world), k - self.ring + 1)      # the slot's previous frame was consumed
-        d.srpB200SetRowRange(self.rows[0], self.rows[1])
+        slot = k % self.ring
+        fb = self.fbs[slot]
+        keep = d.srpB200GetLane()
+        d.srpB200SetLane(k % self.lanes)
         try:
-            draw(fb)
+            if k >= self.ring:
+                d.srpB200StreamWait(self.flag_ptr(slot, self.world), k - self.ring + 1)      # the slot's previous frame was consumed
+            d.srpB200SetRowRange(self.rows[0], self.rows[1])
+            try:
+                draw(fb)
+            finally:
+                d.srpB200SetRowRange(0, 2 ** 64 - 1)
+            d.srpB200StreamSignal(self.flag_ptr(slot, self.rank), k + 1)
         finally:
-            d.srpB200SetRowRange(0, 2 ** 64 - 1)
-        d.srpB200StreamSignal(self.flag_ptr(self.rank), k + 1)
+            d.srpB200SetLane(keep)
         self.frame = k + 1
         return fb
 
     def complete(self, consume=None):
-        """root only: order the stream behind every rank's strip of the frame enqueued last, run
-        `consume(fb)` (enqueue-only work on the complete frame), release the slot"""
+        """root only: order the frame's lane behind every rank's strip of the frame enqueued last,
+        run `consume(fb)` (enqueue-only work on the complete frame), release the slot"""
         assert self.rank == self.root
         d = self.lib.dll
         k = self.frame - 1
-        for r in range(self.world):
-            if r != self.rank:
-                d.srpB200StreamWait(self.flag_ptr(r), k + 1)
-        if consume is not None:
-            consume(self.fbs[k % self.ring])
-        d.srpB200StreamSignal(self.flag_ptr(self.world), k + 1)
+        slot = k % self.ring
+        keep = d.srpB200GetLane()
+        d.srpB200SetLane(k % self.lanes)
+        try:
+            for r in range(self.world):
+                if r != self.rank:
+                    d.srpB200StreamWait(self.flag_ptr(slot, r), k + 1)
+            if consume is not None:
+                consume(self.fbs[slot])
+            d.srpB200StreamSignal(self.flag_ptr(slot, self.world), k + 1)
+        finally:
+            d.srpB200SetLane(keep)
 
     def free(self):
         d = self.lib.dll

@@ -14,16 +14,16 @@ import torch.multiprocessing as mp
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, ring, lanes):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SRP_B200_DEVICE="0")
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from srp_b200 import host as H, multigpu as M, scenes as S
         lib = H.load_product()
-        frames = [S.cfg3_shell(640, 360, n=96, radius=r) for r in (3.0, 1.4, 2.2, 1.2, 2.6)]
+        frames = [S.cfg3_shell(640, 360, n=96, radius=r) for r in (3.0, 1.4, 2.2, 1.2, 2.6, 1.7, 2.9, 1.3, 2.0)]
         want = [S.render(lib, sc) for sc in frames] if rank == 0 else None
         lib.dll.srpB200SetSyncMode(H.SRP_B200_SYNC_EXPLICIT)
-        target = M.StripTarget(lib, 640, 360, ring=2, root=0)
+        target = M.StripTarget(lib, 640, 360, ring=ring, root=0, lanes=lanes)
         preps = [S.Prepared(lib, sc) for sc in frames]
         got = []
         for k, p in enumerate(preps):
@@ -58,11 +58,12 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_strips_written_into_the_roots_framebuffer_over_ipc():
+@pytest.mark.parametrize("ring,lanes", [(2, 1), (4, 2)], ids=["one_lane", "two_frames_in_flight"])
+def test_strips_written_into_the_roots_framebuffer_over_ipc(ring, lanes):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     manager = mp.Manager()
     out = manager.dict()
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, out, ring, lanes), nprocs=2, join=True)
     assert dict(out) == {0: True, 1: True}

@@ -37,10 +37,13 @@ def main():
             continue
         f, g = d["strips"]["fused_peer_write"], d["strips"]["nccl_gather"]
         single = d.get("one_frame_in_flight", {}).get("value", d["value"]) / n      # one GPU rendering one frame at a time
-        L.append(f"| {n} | {f['frames_per_s']:.0f} frames/s ({f['ms_per_frame']:.3f} ms) = {f['frames_per_s'] / single:.2f}x one GPU | "
+        flight = f.get("frames_in_flight", 1)
+        L.append(f"| {n} | {f['frames_per_s']:.0f} frames/s ({f['ms_per_frame']:.3f} ms; {flight} frame(s) in flight) = {f['frames_per_s'] / single:.2f}x one GPU one frame at a time"
+                 + (f", {f['frames_per_s'] / (d['value'] / n):.2f}x one GPU with 4 frames in flight" if flight > 1 else "") + " | "
                  f"{g['frames_per_s']:.0f} frames/s ({g['ms_per_frame']:.3f} ms) | {f['bit_exact_vs_single_gpu']} / {g['bit_exact_vs_single_gpu']} | {f['nvlink_bytes_per_frame'] / 1e6:.1f} MB |")
-    L += ["", "The geometry front-end (~0.12 ms) is replicated on every rank by construction (identical primitive ids and barycentric chains), "
-          "so it bounds the strips' speed-up; the tile kernel's share shrinks with N and the peer write-back costs no extra pass.", "",
+    L += ["", "The geometry front-end (~0.12 ms one frame at a time) is replicated on every rank by construction (identical primitive ids and "
+          "barycentric chains), so it bounds the strips' speed-up; the tile kernel's share shrinks with N and the peer write-back costs no extra pass.  "
+          "With frames in flight (StripTarget(lanes=4): frame k on lane k % 4, per-slot flags) the front-end of one frame runs under the tiles of another.", "",
           "## End to end (host buffers in, host-visible planes out, every step's copies timed) against the host link's ceiling", "",
           f"`tools/pcie_ceiling.py` copies one frame's traffic (28 MB up, 66 MB down, pinned) on every rank at once: `{tag}_pcie_ceiling_n*.json`.  "
           f"The box is a KVM guest with ONE virtual NUMA node (`{tag}_topology_n8.txt`: every GPU reports the same CPU affinity / NUMA 0), so there is "

@@ -148,7 +148,7 @@ size_t srpB200TileHeight(void);
  *           srpB200SetRowRange(own strip), then the usual srpFramebufferClear + srpDraw*Buffer.
  * Completion is signalled through 32-bit flags in (peer) device memory with two stream-ordered
  * calls: srpB200StreamSignal stores `value` once everything enqueued before it has finished and
- * its writes are visible system-wide; srpB200StreamWait holds this process's stream until the
+ * its writes are visible system-wide; srpB200StreamWait holds the current lane's stream until the
  * flag is >= value.  srpB200DeviceAlloc gives zero-filled device memory that can be exported. */
 typedef struct SRPB200IpcHandle { unsigned char bytes[64]; } SRPB200IpcHandle;
 void* srpB200DeviceAlloc(size_t bytes);
@@ -188,7 +188,7 @@ const char* srpB200Version(void);
 /* select the CUDA device for the calling process (before any other call); default:
  * environment SRP_B200_DEVICE, else LOCAL_RANK, else 0 */
 void srpB200SetDevice(int device);
-/* raw CUDA stream (cudaStream_t) all work is enqueued on, for event timing */
+/* raw CUDA stream (cudaStream_t) the current lane's work is enqueued on, for event timing */
 void* srpB200Stream(void);
 
 #ifdef __cplusplus

@@ -519,6 +519,7 @@ __device__ __forceinline__ void visitTriangles(
 			out[r] = (uint8_t) (lane * SRPD_WT_H + rowLo + r);
 	}
 	__syncwarp();
+	int carried = 0;      /* fragments at the front of the queue that wait for a full pass (< 32) */
 	for (int q0 = 0; q0 < nPairs; q0 += 32)
 	{
 		/* coverage: one lane per (triangle, row) */
@@ -535,7 +536,7 @@ __device__ __forceinline__ void visitTriangles(
 		}
 		/* do two triangles meet in this round?  (only then can two fragments share a pixel) */
 		const uint32_t firstTri = __shfl_sync(0xFFFFFFFFu, tRow / SRPD_WT_H, 0);
-		const bool several = __any_sync(0xFFFFFFFFu, left != 0 && tRow / SRPD_WT_H != firstTri);
+		const bool several = carried > 0 || __any_sync(0xFFFFFFFFu, left != 0 && tRow / SRPD_WT_H != firstTri);
 		uint32_t meta = (tRow / SRPD_WT_H) | ((uint32_t) x << 5) | ((tRow % SRPD_WT_H) << 10);
 		while (__any_sync(0xFFFFFFFFu, left != 0))
 		{
@@ -546,9 +547,11 @@ __device__ __forceinline__ void visitTriangles(
 			const uint32_t want = (uint32_t) left;
 			const uint32_t incF = warpInclusiveScan(want, lane);
 			const uint32_t excl = incF - want;
-			const int nFrags = min((int) __shfl_sync(0xFFFFFFFFu, incF, 31), SRPD_QUEUE);
-			const int k = excl >= (uint32_t) SRPD_QUEUE ? 0 : min((int) want, SRPD_QUEUE - (int) excl);
-			uint4* out = wt.frag + excl;
+			const int room = SRPD_QUEUE - carried;
+			const int total = (int) __shfl_sync(0xFFFFFFFFu, incF, 31);
+			const int nFrags = carried + min(total, room);
+			const int k = excl >= (uint32_t) room ? 0 : min((int) want, room - (int) excl);
+			uint4* out = wt.frag + carried + excl;
 			for (int j = 0; j < k; j++)
 			{
 				/* lambda at the covered pixels: the chain goes on with the same additions */
@@ -558,10 +561,31 @@ __device__ __forceinline__ void visitTriangles(
 			}
 			left -= k;
 			__syncwarp();
-			for (int f0 = 0; f0 < nFrags; f0 += 32)
-				shadePass<SIMPLE>(a, fr, records, wt, f0, nFrags, several, tx0, ty0, dirty, cnt, lane);
+			/* full passes only while more fragments of this step are to come: what is left over
+			 * (< 32) moves to the front of the queue and is shaded with the next turn's fragments,
+			 * so that a pass has 32 fragments whichever rows and triangles they come from */
+			const bool more = total > room || q0 + 32 < nPairs;
+			const int nShade = more ? (nFrags & ~31) : nFrags;
+			for (int f0 = 0; f0 < nShade; f0 += 32)
+				shadePass<SIMPLE>(a, fr, records, wt, f0, nShade, several, tx0, ty0, dirty, cnt, lane);
 			__syncwarp();      /* the next turn overwrites the queue */
+			carried = nFrags - nShade;
+			if (carried > 0 && nShade > 0)
+			{
+				uint4 keep = make_uint4(0u, 0u, 0u, 0u);
+				if (lane < carried)
+					keep = wt.frag[nShade + lane];
+				__syncwarp();
+				if (lane < carried)
+					wt.frag[lane] = keep;
+				__syncwarp();
+			}
 		}
+	}
+	if (carried > 0)      /* (the last rounds of the step had no fragments of their own) */
+	{
+		shadePass<SIMPLE>(a, fr, records, wt, 0, carried, true, tx0, ty0, dirty, cnt, lane);
+		__syncwarp();
 	}
 	__syncwarp();      /* the next step overwrites the triangle data and the pair list */
 }

@@ -58,6 +58,12 @@ WORKLOADS = {
                  width=3840, height=2160),
     "cfg2": dict(desc="cfg2: Utah teapot 1920x1080, Gouraud VS, depth test + back-face culling", width=1920, height=1080),
     "cfg1": dict(desc="cfg1: textured cube 800x600, depth test, perspective-correct UVs", width=800, height=600),
+    # multi-draw / batch configs: timed on the GPU by tools/bench_all.py; here only the reference arm
+    # (the CPU figures that stand next to them: profiles/r02_reference_arm_all_configs.jsonl)
+    "cfg4": dict(desc="cfg4: 10 M sub-pixel triangles (two passes) + 1 M lines + 1 M points, stencil + scissor, 3840x2160", width=3840, height=2160,
+                 reference_only=True),
+    "cfg5": dict(desc="cfg5: one 1024x1024 frame of the teapot batch (frame-parallel: frames/s scale with the workers)", width=1024, height=1024,
+                 reference_only=True),
 }
 
 
@@ -69,6 +75,10 @@ def make_scene(workload):
         return S.cfg2_teapot()
     if workload == "cfg1":
         return S.cfg1_textured_cube()
+    if workload == "cfg4":
+        return S.cfg4_subpixel()
+    if workload == "cfg5":
+        return S.cfg5_frame(0)
     raise SystemExit(f"unknown workload {workload}")
 
 
@@ -418,6 +428,9 @@ def main():
         return
 
     # ---------------------------------------------------------------- ours
+    if wl.get("reference_only"):
+        raise SystemExit(f"--workload {args.workload} is a multi-draw / batch config: its GPU timings come from tools/bench_all.py; "
+                         "bench.py runs it with --impl reference only")
     os.environ["SRP_B200_DEVICE"] = str(local_rank)
     # NUMA placement of this rank's host side BEFORE anything pins memory: the pinned framebuffer
     # mirrors and staging buffers then live next to the rank's GPU (srp_b200/numa.py)

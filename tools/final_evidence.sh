@@ -9,6 +9,12 @@ timeout 400 python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench_cfg3
 tail -c 400 gpurun_out/${tag}_bench_cfg3_n1.json; echo
 timeout 200 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/${tag}_bench_cfg3_reference_arm.json 2>/dev/null
 tail -c 300 gpurun_out/${tag}_bench_cfg3_reference_arm.json; echo
+# the CPU figures that stand next to the other configs (same arm, other workloads)
+: > gpurun_out/${tag}_reference_arm_all_configs.jsonl
+for w in cfg1 cfg2 cfg4 cfg5; do
+  timeout 300 python bench.py --impl reference --workload $w --steps 3 --warmup 1 2>/dev/null | tail -1 >> gpurun_out/${tag}_reference_arm_all_configs.jsonl
+done
+cut -c1-160 gpurun_out/${tag}_reference_arm_all_configs.jsonl
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_cfg3_launches.csv \
   python bench.py --steps 20 --warmup 3 --cpu-seconds 0 > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:srpd -s 24 -c 8 -f -o gpurun_out/${tag}_cfg3_full \

@@ -46,6 +46,42 @@ def time_scene(lib, scene, steps=10, warm=3):
             "gfrag_per_s": stats["fragsEmitted"] / steps / ms / 1e6, "launches_per_frame": stats["kernelLaunches"] / steps}
 
 
+def time_in_flight(lib, scene, lanes=4, steps=40):
+    """the same frames with `lanes` of them in flight (srpB200SetLane): one interval over all steps,
+    events on every lane's stream, one Prepared (buffers + framebuffer) per lane"""
+    lib.dll.srpB200SetSyncMode(H.SRP_B200_SYNC_EXPLICIT)
+    lanes = min(lanes, int(lib.dll.srpB200LaneCount()))
+    ring = [S.Prepared(lib, scene) for _ in range(lanes)]
+    streams = []
+    for l in range(lanes):
+        lib.dll.srpB200SetLane(l)
+        streams.append(torch.cuda.ExternalStream(lib.dll.srpB200Stream()))
+    def run(n):
+        for k in range(n):
+            lib.dll.srpB200SetLane(k % lanes)
+            lib.new_context()
+            ring[k % lanes].draw_all()
+        lib.dll.srpB200SetLane(0)
+    run(2 * lanes)
+    lib.dll.srpB200Finish()
+    s_ev = [torch.cuda.Event(enable_timing=True) for _ in streams]
+    e_ev = [torch.cuda.Event(enable_timing=True) for _ in streams]
+    for ev, st in zip(s_ev, streams):
+        ev.record(st)
+    run(steps)
+    for ev, st in zip(e_ev, streams):
+        ev.record(st)
+    lib.dll.srpB200Finish()
+    torch.cuda.synchronize()
+    ms = max(a.elapsed_time(b) for a in s_ev for b in e_ev) / steps
+    first = ring[0].planes()
+    same = all(bool(np.array_equal(x, y)) for p in ring[1:] for x, y in zip(p.planes(), first))
+    for p in ring:
+        p.free()
+    lib.dll.srpB200SetSyncMode(H.SRP_B200_SYNC_DRAW)
+    return {"frames_in_flight": lanes, "ms_per_frame": ms, "frames_per_s": 1e3 / ms, "planes_equal_across_lanes": same}
+
+
 def time_batch(lib, n_frames=1024, size=1024, steps=3):
     mesh = S.teapot_mesh()
     draws = [S.teapot_draw(f, mesh) for f in range(n_frames)]
@@ -92,7 +128,10 @@ def main():
     for name, make in makers.items():
         if only and name not in only:
             continue
-        r = time_scene(lib, make())
+        scene = make()
+        r = time_scene(lib, scene)
+        if name != "cfg4":      # (cfg4's worst-case scratch pools are 36 GB per lane)
+            r["in_flight"] = time_in_flight(lib, scene)
         print(json.dumps(r)); out["results"].append(r)
     if not only or "cfg5" in only:
         r = time_batch(lib)

@@ -46,7 +46,7 @@ def time_scene(lib, scene, steps=10, warm=3):
             "gfrag_per_s": stats["fragsEmitted"] / steps / ms / 1e6, "launches_per_frame": stats["kernelLaunches"] / steps}
 
 
-def time_in_flight(lib, scene, lanes=4, steps=40):
+def time_in_flight(lib, scene, lanes=4, steps=200):
     """the same frames with `lanes` of them in flight (srpB200SetLane): one interval over all steps,
     events on every lane's stream, one Prepared (buffers + framebuffer) per lane"""
     lib.dll.srpB200SetSyncMode(H.SRP_B200_SYNC_EXPLICIT)
@@ -59,8 +59,7 @@ def time_in_flight(lib, scene, lanes=4, steps=40):
     def run(n):
         for k in range(n):
             lib.dll.srpB200SetLane(k % lanes)
-            lib.new_context()
-            ring[k % lanes].draw_all()
+            ring[k % lanes].draw_all()      # (every frame sets the same state: no fresh context needed in between)
         lib.dll.srpB200SetLane(0)
     run(2 * lanes)
     lib.dll.srpB200Finish()

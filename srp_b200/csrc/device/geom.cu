@@ -20,9 +20,10 @@
  *   4. warp scan of both counts; the batch takes a contiguous range of record slots from the
  *      frame's bump allocator (arrival order) and publishes its totals;
  *   5. records are written with batch-local primitive ids.
- * A batch that contains a triangle crossing a clip plane is not processed by the main pass at
- * all: it is appended to a deferred list and a second launch (`CLIPPER`: one warp per CTA, more
- * registers, clip slots in shared memory) takes all deferred batches at once (clipChunk).
+ * A batch that contains a triangle crossing a clip plane, or a line that is clipped or longer
+ * than two 16-fragment segments, is not processed by the main pass at all: it is appended to a
+ * deferred list and a second launch (`CLIPPER`: one warp per CTA, more registers, scratch slots in
+ * shared memory) takes all deferred batches at once (clipChunk, emitPreparedLines).
  * srpdBatchOrderKernel then restores the reference's serial order (primitive_assembly.c:64,
  * 90-91: `primitiveID++` over emitted primitives): it prefix-sums the batch totals in batch order
  * and writes the id-ordered view -- per stored primitive its bounding box, its record slot and

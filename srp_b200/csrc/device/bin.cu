@@ -341,7 +341,7 @@ srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 						a.listEntries[pos] = ent;
 				}
 		__syncwarp();
-		/* the last covering lane advances the cursor and clears the mask for the next step */
+		/* the last covering lane advances the cursor (nobody reads the cursors in this phase) ... */
 		if (!empty)
 			for (uint32_t sy = sy0; sy <= sy1; sy++)
 				for (uint32_t sx = sx0; sx <= sx1; sx++)
@@ -349,11 +349,15 @@ srpdBinFillKernel(const __grid_constant__ SrpdBinArgs a)
 					const uint32_t s = sy * a.superX + sx;
 					const uint32_t m = sMask[s];
 					if ((m >> lane) == 1u)
-					{
 						sCnt[s] += __popc(m);
-						sMask[s] = 0;
-					}
 				}
+		__syncwarp();
+		/* ... and every lane takes its own bit out of the masks again for the next step (atomically:
+		 * the covering lanes of a supertile do it side by side) */
+		if (!empty)
+			for (uint32_t sy = sy0; sy <= sy1; sy++)
+				for (uint32_t sx = sx0; sx <= sx1; sx++)
+					atomicAnd(&sMask[sy * a.superX + sx], ~(1u << lane));
 		__syncwarp();
 	}
 	__syncthreads();      /* the next chunk re-initialises the cursors */

@@ -158,6 +158,9 @@ void* srpB200IpcOpen(const SRPB200IpcHandle* handle);                     /* NUL
 void srpB200IpcClose(void* mappedPtr);
 void srpB200StreamSignal(uint32_t* flag, uint32_t value);
 void srpB200StreamWait(const uint32_t* flag, uint32_t value);
+/* the same for a run of consecutive flags: the stream goes on once ALL of flags[0 .. count) are >= value
+ * (one launch instead of count; count <= 1024) */
+void srpB200StreamWaitAll(const uint32_t* flags, uint32_t count, uint32_t value);
 
 /* ---- counters ----------------------------------------------------------------------
  * Accumulated since the last reset over all draws (deterministic; equal to the

@@ -1043,6 +1043,7 @@ __global__ void srpdSignalKernel(uint32_t* flag, uint32_t value)
 __global__ void srpdWaitFlagKernel(const uint32_t* flag, uint32_t value, uint32_t* hostNotes)
 {
 	srpdGridDependencyEnter();
+	flag += threadIdx.x;      /* (srpcuStreamWaitFlags: one thread per flag of a consecutive run) */
 	/* bounded: a peer that died must not hang this GPU for good (~10 s, then the stream moves on
 	 * and the host is told through hostNotes[2]) */
 	for (uint32_t spins = 0; *(volatile const uint32_t*) flag < value; spins++)
@@ -1093,8 +1094,15 @@ int srpcuStreamSignal(uint32_t* flag, uint32_t value)
 }
 int srpcuStreamWaitFlag(const uint32_t* flag, uint32_t value)
 {
+	return srpcuStreamWaitFlags(flag, 1u, value);
+}
+/* one kernel that holds the stream until ALL of flag[0 .. count) are >= value (count <= 1024) */
+int srpcuStreamWaitFlags(const uint32_t* flag, uint32_t count, uint32_t value)
+{
 	if (srpcuInit()) return 1;
-	srpdWaitFlagKernel<<<1, 1, 0, g.stream>>>(flag, value, g.hostNotesDev);
+	if (count == 0u) return 0;
+	if (count > 1024u) { g.lastError = "srp-b200: at most 1024 flags per wait"; return 1; }
+	srpdWaitFlagKernel<<<1, count, 0, g.stream>>>(flag, value, g.hostNotesDev);
 	g.launches++;
 	CU(cudaGetLastError());
 	return 0;

@@ -94,6 +94,7 @@ void* srpcuIpcOpen(const unsigned char handle[64]);
 int srpcuIpcClose(void* mapped);
 int srpcuStreamSignal(uint32_t* flag, uint32_t value);
 int srpcuStreamWaitFlag(const uint32_t* flag, uint32_t value);
+int srpcuStreamWaitFlags(const uint32_t* flag, uint32_t count, uint32_t value);      /* all of flag[0 .. count) >= value, one kernel */
 
 void srpcuSetProfiling(int on);
 unsigned long long srpcuCollectStageTimes(double outMs[3]);

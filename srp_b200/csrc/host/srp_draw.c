@@ -68,6 +68,11 @@ void srpB200StreamWait(const uint32_t* flag, uint32_t value)
 	if (srpcuStreamWaitFlag(flag, value))
 		srpFatalMessage(__func__, "%s", srpcuLastError());
 }
+void srpB200StreamWaitAll(const uint32_t* flags, uint32_t count, uint32_t value)
+{
+	if (srpcuStreamWaitFlags(flags, count, value))
+		srpFatalMessage(__func__, "%s", srpcuLastError());
+}
 
 void srpB200GetStats(SRPB200Stats* out)
 {

@@ -234,6 +234,7 @@ class SrpLibrary:
             "srpB200CollectStageTimes": (C.c_ulonglong, [C.POINTER(C.c_double)]),
             "srpB200Version": (C.c_char_p, []), "srpB200SetDevice": (None, [i32]),
             "srpB200Stream": (vp, []),
+            "srpB200StreamWaitAll": (None, [vp, C.c_uint32, C.c_uint32]),
             "srpB200SetLane": (i32, [i32]), "srpB200GetLane": (i32, []), "srpB200LaneCount": (i32, []),
         }
         if self.is_product:

@@ -212,9 +212,8 @@ class StripTarget:
         keep = d.srpB200GetLane()
         d.srpB200SetLane(k % self.lanes)
         try:
-            for r in range(self.world):
-                if r != self.rank:
-                    d.srpB200StreamWait(self.flag_ptr(slot, r), k + 1)
+            # every rank's flag of the slot in one launch (the root's own was signalled on this lane just before)
+            d.srpB200StreamWaitAll(self.flag_ptr(slot, 0), self.world, k + 1)
             if consume is not None:
                 consume(self.fbs[slot])
             d.srpB200StreamSignal(self.flag_ptr(slot, self.world), k + 1)
